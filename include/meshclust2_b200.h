@@ -1,0 +1,242 @@
+/* meshclust2_b200.h — C ABI of the B200-native MeShClust2 hot path.
+ *
+ * The reference (BioinformaticsToolsmith/MeShClust2 2.3.0) has no FFI layer: its boundary for this
+ * path is a C++ template API linked statically.  This header is what a cgo/JNI/ctypes
+ * style binding — or the C++ shim classes in meshclust2_b200/host/ that keep the reference's own class
+ * names — binds instead.  Each entry point cites the reference interface it replaces (paths relative to
+ * the reference root).
+ *
+ * Conventions: plain C types only; every function returns MC2_OK (0) or a negative mc2_status;
+ * mc2_last_error() gives a thread-local message; no C++ exception ever crosses this boundary;
+ * outputs are caller-allocated.  One mc2_ctx per GPU; a ctx and the objects made from it may be used
+ * from one host thread at a time (create one ctx per thread for concurrent use).
+ * There is NO CPU fallback: every compute entry point fails with MC2_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef MESHCLUST2_B200_H
+#define MESHCLUST2_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC2_ABI_VERSION 1
+
+typedef enum {
+	MC2_OK = 0,
+	MC2_ERR_ARG = -1,        /* bad argument (k, elem_bytes, NULL, index out of range ...) */
+	MC2_ERR_CUDA = -2,       /* CUDA runtime / no device / wrong architecture */
+	MC2_ERR_INPUT = -3,      /* the reference would throw InvalidInputException (code outside 0..3 in a segment) */
+	MC2_ERR_FEATURE = -4,    /* the reference would throw while scoring (length 0 for length_difference, NaN after normalise) */
+	MC2_ERR_UNSUPPORTED = -5,/* feature flag / combination outside the hot-path scope */
+	MC2_ERR_IO = -6          /* weights file unreadable / malformed */
+} mc2_status;
+
+/* single-feature flags: src/predict/Feature.h:31-64 (same bit values) */
+#define MC2_FEAT_MANHATTAN           (1ULL << 2)
+#define MC2_FEAT_EUCLIDEAN           (1ULL << 3)
+#define MC2_FEAT_NORMALIZED_VECTORS  (1ULL << 5)
+#define MC2_FEAT_JEFFEREY_DIV        (1ULL << 7)
+#define MC2_FEAT_PEARSON_COEFF       (1ULL << 9)
+#define MC2_FEAT_INTERSECTION        (1ULL << 13)
+#define MC2_FEAT_EMD                 (1ULL << 18)
+#define MC2_FEAT_LENGTHD             (1ULL << 21)
+#define MC2_FEAT_KULCZYNSKI2         (1ULL << 27)
+#define MC2_FEAT_SIMRATIO            (1ULL << 28)
+#define MC2_FEAT_JENSEN_SHANNON      (1ULL << 29)
+/* src/predict/Predictor.h:23-24 */
+#define MC2_PRED_FEAT_FAST (MC2_FEAT_EUCLIDEAN | MC2_FEAT_MANHATTAN | MC2_FEAT_INTERSECTION | MC2_FEAT_KULCZYNSKI2 | \
+			    MC2_FEAT_SIMRATIO | MC2_FEAT_NORMALIZED_VECTORS | MC2_FEAT_PEARSON_COEFF | MC2_FEAT_EMD | MC2_FEAT_LENGTHD)
+#define MC2_PRED_FEAT_DIV (MC2_FEAT_JEFFEREY_DIV | MC2_FEAT_JENSEN_SHANNON)
+
+/* combo codes as stored in weights.txt: src/predict/Predictor.cpp:96-110 (enum class Combo, Feature.h:66-71) */
+#define MC2_COMBO_XY   0
+#define MC2_COMBO_XY2  1
+#define MC2_COMBO_X2Y  2
+#define MC2_COMBO_X2Y2 3
+
+#define MC2_MAX_SINGLES 16
+#define MC2_MAX_COMBOS 16
+#define MC2_MAX_COMBO_IDX 4
+
+/* A trained Feature<T> + GLM weight column, i.e. what Predictor::get_class() hands to Trainer
+ * (src/predict/Predictor.h:57, src/cluster/Trainer.cpp:160-182) and what weights.txt stores. */
+typedef struct {
+	int32_t n_singles;                                   /* Feature::lookup.size() */
+	uint64_t single_flag[MC2_MAX_SINGLES];               /* Feature::lookup, in add_feature order */
+	double single_min[MC2_MAX_SINGLES];                  /* Feature::mins */
+	double single_max[MC2_MAX_SINGLES];                  /* Feature::maxs */
+	int32_t n_combos;                                    /* Feature::size() */
+	int32_t combo_kind[MC2_MAX_COMBOS];                  /* MC2_COMBO_* */
+	int32_t combo_nidx[MC2_MAX_COMBOS];
+	int32_t combo_idx[MC2_MAX_COMBOS][MC2_MAX_COMBO_IDX];/* indices into singles, ascending flag bit */
+	double weight[MC2_MAX_COMBOS + 1];                   /* GLM weights, [0] = intercept */
+	double bias;                                         /* Predictor::set_bias (src/predict/Predictor.cpp:307-313) */
+	int32_t regression;                                  /* 0: classifier (logistic + cutoff); 1: Predictor::p_predict clamp */
+} mc2_model_desc;
+
+typedef struct mc2_ctx mc2_ctx;     /* one GPU: device id, stream, scratch, pinned result slots */
+typedef struct mc2_seqs mc2_seqs;   /* device-resident 2-bit packed sequences + segment lists */
+typedef struct mc2_hset mc2_hset;   /* device-resident histogram matrix n x 4^k (elem_bytes wide) + side-band SoA */
+typedef struct mc2_model mc2_model; /* device-side copy of a mc2_model_desc */
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int mc2_abi_version(void);
+const char *mc2_last_error(void);
+int mc2_device_count(void);
+int mc2_ctx_create(int device, mc2_ctx **out);
+void mc2_ctx_destroy(mc2_ctx *ctx);
+int mc2_ctx_sync(mc2_ctx *ctx);
+int mc2_ctx_device(const mc2_ctx *ctx);
+int mc2_ctx_sm_count(const mc2_ctx *ctx);
+void *mc2_ctx_stream(mc2_ctx *ctx);                 /* the cudaStream_t every launch of this ctx goes to */
+/* CUDA-event stopwatch on the ctx stream (bench.py times kernels with it, not wall clock) */
+int mc2_timer_start(mc2_ctx *ctx);
+int mc2_timer_stop(mc2_ctx *ctx, float *ms);
+/* count of this library's kernel launches on this ctx since creation (bench.py's gpu_launches) */
+uint64_t mc2_ctx_launch_count(const mc2_ctx *ctx);
+/* write `bytes` of zeros to a scratch buffer (L2 flush between timed iterations) */
+int mc2_ctx_flush_l2(mc2_ctx *ctx, size_t bytes);
+
+/* ---- host-side input contract (no GPU involved) ------------------------------------------------ */
+/* For callers that do not already hold a reference ChromosomeOneDigit: raw DNA text -> one-digit codes + inclusive
+ * segments + effective size, exactly as Chromosome::help + ChromosomeOneDigit::encode produce them
+ * (src/nonltr/Chromosome.cpp:130-154, 263-385; src/nonltr/ChromosomeOneDigit.cpp:79-133;
+ * src/nonltr/ChromosomeOneDigitDna.cpp:48-68).  Stays on the host, as in the reference.
+ * MC2_ERR_INPUT where the reference throws InvalidInputException. */
+int mc2_encode_dna(const char *text, uint64_t len, char *codes_out, int32_t *segs_out, uint64_t max_segs,
+		   uint64_t *n_segs, uint64_t *effective_size);
+/* n sequences at text[off[i]..off[i+1]); codes_out has off[n]-off[0] bytes; segs_out 2*max_segs ints (sequence-relative);
+ * seg_off_out n+1; effective_sizes n (may be NULL). OpenMP over sequences with `threads` threads. */
+int mc2_encode_dna_batch(const char *text, const uint64_t *off, uint64_t n, char *codes_out, int32_t *segs_out,
+			 uint64_t max_segs, uint64_t *seg_off_out, uint64_t *effective_sizes, int threads);
+
+/* ---- K1: k-mer histograms ---------------------------------------------------------------------- */
+/* Input contract = ChromosomeOneDigit after finalize() (src/nonltr/ChromosomeOneDigit.cpp:79-133):
+ * codes[seq_off[i] .. seq_off[i+1]) is sequence i, one byte per base, values 0..3 inside segments
+ * (anything outside); segs holds inclusive [start,end] pairs relative to the sequence start, sequence i
+ * owning segs[2*seg_off[i] .. 2*seg_off[i+1]).  Replaces the std::string base + vector<vector<int>*>* segment
+ * that Loader<T>::fill_table reads (src/clutil/Loader.cpp:42-49). Copies host->device and packs to 2 bits/base. */
+int mc2_seqs_upload(mc2_ctx *ctx, const char *codes, const uint64_t *seq_off, uint64_t n, const int32_t *segs,
+		    const uint64_t *seg_off, mc2_seqs **out);
+void mc2_seqs_free(mc2_seqs *s);
+uint64_t mc2_seqs_count(const mc2_seqs *s);
+uint64_t mc2_seqs_total_bases(const mc2_seqs *s);
+
+/* Loader<T>::get_point for a whole batch (src/clutil/Loader.cpp:138-179): per sequence a 4^k histogram of
+ * elem_bytes-wide counts initialised to 1 and saturating at max(T) (KmerHashTable::wholesaleIncrementNoOverflow,
+ * src/nonltr/KmerHashTable.cpp:236-256), the k=1 table (u64, init 1), mag = sum of bins
+ * (DivergencePoint ctor, src/clutil/DivergencePoint.cpp:99-110), length = sum of segment lengths
+ * (Chromosome::getEffectiveSize), stddev (Loader.cpp:162-171) and the number of overflowing segments
+ * (Loader.cpp:55-56).  elem_bytes in {1,2,4,8} = --datatype 8/16/32/64 (src/cluster/CRunner.cpp:278-291). */
+int mc2_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, mc2_hset **out);
+
+/* KmerHashTable<unsigned long,V>(k, init).wholesaleIncrementNoOverflow(codes, first, last) on ONE sequence
+ * (src/nonltr/KmerHashTable.h:20-79): values_out receives the 4^k table; *ret = 0 or -1 (saturation).
+ * MC2_ERR_INPUT where the reference throws InvalidInputException. */
+int mc2_kmer_table_increment(mc2_ctx *ctx, const char *codes, int32_t first_kmer_start, int32_t last_kmer_start, int k,
+			     int elem_bytes, uint64_t init_value, void *values_out, int32_t *ret);
+
+/* ---- histogram sets ----------------------------------------------------------------------------- */
+/* Build a set from host DivergencePoint<T> state: bins (n x 4^k, row-major), pseudo-magnitude and length per
+ * point (src/clutil/DivergencePoint.h:80-88).  mag may be NULL (= sum of bins, as the ctor computes) or carry
+ * the host object's possibly stale value (DivergencePoint::set does not refresh it, DivergencePoint.cpp:182-190). */
+int mc2_hset_from_host(mc2_ctx *ctx, const void *bins, uint64_t n, int k, int elem_bytes, const uint64_t *mag,
+		       const uint64_t *len, mc2_hset **out);
+void mc2_hset_free(mc2_hset *h);
+uint64_t mc2_hset_count(const mc2_hset *h);
+int mc2_hset_k(const mc2_hset *h);
+int mc2_hset_elem_bytes(const mc2_hset *h);
+/* device pointers (for NCCL all-gather of shards through torch tensors; rows are contiguous, stride 4^k elements) */
+void *mc2_hset_device_bins(const mc2_hset *h);
+/* copy rows [first, first+count) back: any output pointer may be NULL. mers1: count x 4; n_overflow: count */
+int mc2_hset_download(mc2_ctx *ctx, const mc2_hset *h, uint64_t first, uint64_t count, void *bins, uint64_t *mag,
+		      uint64_t *len, uint64_t *mers1, double *stddev, int32_t *n_overflow, uint32_t *max_count);
+/* overwrite pseudo-magnitudes / lengths of selected rows (mirror of host objects mutated by set()/set_length()) */
+int mc2_hset_set_sideband(mc2_ctx *ctx, mc2_hset *h, uint64_t count, const uint64_t *rows, const uint64_t *mag,
+			  const uint64_t *len);
+/* copy row `src_row` of `src` over row `dst_row` of `dst` the way DivergencePoint::set does: bins + length, NOT mag */
+int mc2_hset_set_row(mc2_ctx *ctx, mc2_hset *dst, uint64_t dst_row, const mc2_hset *src, uint64_t src_row);
+
+/* ---- model -------------------------------------------------------------------------------------- */
+int mc2_model_create(mc2_ctx *ctx, const mc2_model_desc *desc, mc2_model **out);
+void mc2_model_free(mc2_model *m);
+/* Parse a weights file written by Predictor::save (src/predict/Predictor.cpp:28-44, 82-121) the way the file ctor
+ * does (Predictor.cpp:47-79, 125-185). which = 0: classifier block, 1: regression block.
+ * k/id/elem_bytes/mode outputs may be NULL. */
+int mc2_model_desc_from_file(const char *path, int which, mc2_model_desc *desc, int *k, double *id, int *elem_bytes,
+			     int *mode);
+
+/* ---- K2: pair features + GLM -------------------------------------------------------------------- */
+/* What to score.  first/second follow the reference's argument order of Feature::compute(first, second). */
+typedef struct {
+	const mc2_hset *set_a;     /* rows ia[] index into set_a */
+	const mc2_hset *set_b;     /* rows ib[] index into set_b (may equal set_a) */
+	uint64_t n_pairs;
+	const uint64_t *ia;        /* host array, or NULL: ia[j] = a_begin + (a_broadcast ? 0 : j) */
+	const uint64_t *ib;        /* host array, or NULL: ib[j] = b_begin + (b_broadcast ? 0 : j) */
+	uint64_t a_begin, b_begin;
+	int32_t a_broadcast, b_broadcast;
+	/* length prefilter of Trainer::get_close/merge/filter (src/cluster/Trainer.cpp:39-48, 82-91, 126-130):
+	 * when len_filter != 0 a pair is skipped (close=0, score=dist=NaN, skipped=1) unless the NON-anchor length lies in
+	 * [(u64)(len_anchor*cutoff), (u64)(len_anchor/cutoff)]; anchor = side b if anchor_is_b else side a. */
+	int32_t len_filter;
+	int32_t anchor_is_b;
+	double cutoff;
+} mc2_pairs;
+
+/* Feature<T>::compute + operator() + Trainer<T>::classify / Predictor<T>::p_close / p_predict
+ * (src/predict/Feature.h:197-239, src/cluster/Trainer.cpp:112-120, src/predict/Predictor.cpp:284-333).
+ * Outputs (host, each may be NULL): score[n_pairs] = logistic(sum)+bias (or the clamped sum for a regression model),
+ * dist[n_pairs] = first combo value, close[n_pairs] = round(score) > 0, cache[n_pairs x n_singles] = normalised singles,
+ * raw[n_pairs x n_singles] = raw singles (what Feature::normalize / BestFirstSelector::calculate_table consume),
+ * skipped[n_pairs] = 1 where the length prefilter dropped the pair. */
+int mc2_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs, double *score, double *dist,
+		    uint8_t *close, double *cache, double *raw, uint8_t *skipped);
+
+/* Trainer<T>::get_close (src/cluster/Trainer.cpp:23-71): query row `q` of set_q against candidate rows cand[0..n_cand)
+ * of set_c (cand NULL = rows cand_begin .. cand_begin+n_cand).  Feature order compute(candidate, query).
+ * *best = position in the candidate list of the max first-combo value over all in-window candidates (first such position on
+ * ties, -1 if none in window), *best_dist its value (-1 if none), *is_min = no candidate classified close,
+ * marks[n_cand] = 1 for candidates classified close (the reference sets (*i).second = true). */
+int mc2_get_close(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, uint64_t q, const mc2_hset *set_c,
+		  const uint64_t *cand, uint64_t cand_begin, uint64_t n_cand, double cutoff, int64_t *best,
+		  double *best_dist, int32_t *is_min, uint8_t *marks);
+
+/* Trainer<T>::filter (src/cluster/Trainer.cpp:123-141): keep[j] = 1 iff member j survives (in window and
+ * round(classify(center, member)) != 0). Feature order compute(center, member). */
+int mc2_filter(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint64_t center, const mc2_hset *set_m,
+	       const uint64_t *members, uint64_t n_members, double id, uint8_t *keep);
+
+/* Trainer<T>::merge (src/cluster/Trainer.cpp:74-109): center row rows[cur] vs rows[begin..last] of `centers`;
+ * *out = chosen index in [begin,last] or 0 when none is close. */
+int mc2_merge(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *centers, const uint64_t *rows, int64_t cur,
+	      int64_t begin, int64_t last, double id, int64_t *out);
+
+/* All-pairs / query-vs-database sweep with the length prefilter, as fastcar's work() does
+ * (src/fastcar/FC_Runner.cpp:427-470): for every query row r in [q_begin,q_end) of set_q and database row c in
+ * [d_begin,d_end) of set_d with len_c in [(size_t)(len_r*cutoff), (size_t)(len_r/cutoff)] evaluate close(c, r);
+ * upper_only != 0 restricts to c > r (set_q == set_d, unordered pairs).  Survivors (close pairs) are appended to
+ * out_q/out_d/out_score (capacity max_out); *n_out returns the TOTAL number of survivors (may exceed max_out),
+ * *n_scored the number of pairs that passed the prefilter and were scored. Order of survivors is unspecified. */
+int mc2_all_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, uint64_t q_begin, uint64_t q_end,
+		  const mc2_hset *set_d, uint64_t d_begin, uint64_t d_end, int32_t upper_only, double cutoff,
+		  uint64_t max_out, uint64_t *out_q, uint64_t *out_d, double *out_score, uint64_t *n_out,
+		  uint64_t *n_scored);
+
+/* DivergencePoint<T>::distance (src/clutil/DivergencePoint.cpp:70-82) for pairs of rows */
+int mc2_distance(mc2_ctx *ctx, const mc2_pairs *pairs, uint64_t *out);
+
+/* Device-timed variants used by bench.py: run the scoring kernel `iters` times on inputs already resident
+ * (pair lists uploaded once), return the average milliseconds per launch measured with CUDA events on the ctx stream. */
+int mc2_bench_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs, int iters, int flush_l2,
+			  float *avg_ms, uint64_t *n_close);
+int mc2_bench_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, int iters, int flush_l2,
+			  float *avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

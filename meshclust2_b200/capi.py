@@ -1,0 +1,444 @@
+"""ctypes binding of the C ABI in include/meshclust2_b200.h (lib/libmeshclust2_b200.so).
+
+This is the Python face of the drop-in boundary: thin wrappers, numpy in / numpy out, no compute.
+There is no CPU fallback — if the CUDA library is missing or no sm_100 device is present every
+entry point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmeshclust2_b200.so")
+
+MAX_SINGLES, MAX_COMBOS, MAX_COMBO_IDX = 16, 16, 4
+DTYPES = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
+
+FEAT_MANHATTAN = 1 << 2
+FEAT_EUCLIDEAN = 1 << 3
+FEAT_NORMALIZED_VECTORS = 1 << 5
+FEAT_JEFFEREY_DIV = 1 << 7
+FEAT_PEARSON_COEFF = 1 << 9
+FEAT_INTERSECTION = 1 << 13
+FEAT_EMD = 1 << 18
+FEAT_LENGTHD = 1 << 21
+FEAT_KULCZYNSKI2 = 1 << 27
+FEAT_SIMRATIO = 1 << 28
+FEAT_JENSEN_SHANNON = 1 << 29
+PRED_FEAT_FAST = (FEAT_EUCLIDEAN | FEAT_MANHATTAN | FEAT_INTERSECTION | FEAT_KULCZYNSKI2 | FEAT_SIMRATIO |
+                  FEAT_NORMALIZED_VECTORS | FEAT_PEARSON_COEFF | FEAT_EMD | FEAT_LENGTHD)
+PRED_FEAT_DIV = FEAT_JEFFEREY_DIV | FEAT_JENSEN_SHANNON
+
+# every symbol include/meshclust2_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "mc2_abi_version", "mc2_last_error", "mc2_device_count", "mc2_ctx_create", "mc2_ctx_destroy", "mc2_ctx_sync",
+    "mc2_ctx_device", "mc2_ctx_sm_count", "mc2_ctx_stream", "mc2_timer_start", "mc2_timer_stop",
+    "mc2_ctx_launch_count", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_free", "mc2_seqs_count",
+    "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_free",
+    "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download",
+    "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
+    "mc2_score_pairs", "mc2_get_close", "mc2_filter", "mc2_merge", "mc2_all_pairs", "mc2_distance",
+    "mc2_bench_score_pairs", "mc2_bench_count_kmers", "mc2_encode_dna", "mc2_encode_dna_batch",
+]
+
+
+class Mc2Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("mc2 status %d: %s" % (status, msg))
+        self.status = status
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("n_singles", C.c_int32),
+        ("single_flag", C.c_uint64 * MAX_SINGLES),
+        ("single_min", C.c_double * MAX_SINGLES),
+        ("single_max", C.c_double * MAX_SINGLES),
+        ("n_combos", C.c_int32),
+        ("combo_kind", C.c_int32 * MAX_COMBOS),
+        ("combo_nidx", C.c_int32 * MAX_COMBOS),
+        ("combo_idx", (C.c_int32 * MAX_COMBO_IDX) * MAX_COMBOS),
+        ("weight", C.c_double * (MAX_COMBOS + 1)),
+        ("bias", C.c_double),
+        ("regression", C.c_int32),
+    ]
+
+
+class Pairs(C.Structure):
+    _fields_ = [
+        ("set_a", C.c_void_p), ("set_b", C.c_void_p), ("n_pairs", C.c_uint64),
+        ("ia", C.c_void_p), ("ib", C.c_void_p),
+        ("a_begin", C.c_uint64), ("b_begin", C.c_uint64),
+        ("a_broadcast", C.c_int32), ("b_broadcast", C.c_int32),
+        ("len_filter", C.c_int32), ("anchor_is_b", C.c_int32),
+        ("cutoff", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(meshclust2_b200 has no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.mc2_last_error.restype = C.c_char_p
+        L.mc2_ctx_stream.restype = C.c_void_p
+        L.mc2_ctx_launch_count.restype = C.c_uint64
+        L.mc2_seqs_count.restype = C.c_uint64
+        L.mc2_seqs_total_bases.restype = C.c_uint64
+        L.mc2_hset_count.restype = C.c_uint64
+        L.mc2_hset_device_bins.restype = C.c_void_p
+        L.mc2_ctx_flush_l2.argtypes = [C.c_void_p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise Mc2Error(rc, lib().mc2_last_error().decode(errors="replace"))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _u64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def device_count():
+    return lib().mc2_device_count()
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().mc2_ctx_create(device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().mc2_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _check(lib().mc2_ctx_sync(self.h))
+
+    @property
+    def sm_count(self):
+        return lib().mc2_ctx_sm_count(self.h)
+
+    @property
+    def launches(self):
+        return lib().mc2_ctx_launch_count(self.h)
+
+    def stream(self):
+        return lib().mc2_ctx_stream(self.h)
+
+    def timer_start(self):
+        _check(lib().mc2_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _check(lib().mc2_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self, nbytes=256 << 20):
+        _check(lib().mc2_ctx_flush_l2(self.h, nbytes))
+
+    # ---- K1 ----
+    def upload_seqs(self, codes, seq_off, segs, seg_off):
+        """codes: int8/uint8 concatenated; seq_off uint64[n+1]; segs int32[total,2] sequence-relative inclusive;
+        seg_off uint64[n+1]."""
+        codes = np.ascontiguousarray(codes).view(np.int8)
+        seq_off = _u64(seq_off)
+        seg_off = _u64(seg_off)
+        segs = np.ascontiguousarray(segs, dtype=np.int32)
+        out = C.c_void_p()
+        _check(lib().mc2_seqs_upload(self.h, _p(codes), _p(seq_off), C.c_uint64(len(seq_off) - 1), _p(segs),
+                                     _p(seg_off), C.byref(out)))
+        return Seqs(self, out)
+
+    def count_kmers(self, seqs, k, elem_bytes):
+        out = C.c_void_p()
+        _check(lib().mc2_count_kmers(self.h, seqs.h, k, elem_bytes, C.byref(out)))
+        return HistSet(self, out)
+
+    def kmer_table_increment(self, codes, first, last, k, elem_bytes, init=1):
+        codes = np.ascontiguousarray(codes).view(np.int8)
+        vals = np.zeros(4 ** k, dtype=DTYPES[elem_bytes])
+        ret = C.c_int32()
+        _check(lib().mc2_kmer_table_increment(self.h, _p(codes), first, last, k, elem_bytes, C.c_uint64(init),
+                                              _p(vals), C.byref(ret)))
+        return vals, ret.value
+
+    def hset_from_host(self, bins, k, mag=None, length=None):
+        bins = np.ascontiguousarray(bins)
+        n = bins.shape[0]
+        assert bins.ndim == 2 and bins.shape[1] == 4 ** k
+        length = _u64(length if length is not None else np.ones(n))
+        mag = _u64(mag)
+        out = C.c_void_p()
+        _check(lib().mc2_hset_from_host(self.h, _p(bins), C.c_uint64(n), k, bins.dtype.itemsize, _p(mag), _p(length),
+                                        C.byref(out)))
+        return HistSet(self, out)
+
+    def model(self, desc):
+        out = C.c_void_p()
+        _check(lib().mc2_model_create(self.h, C.byref(desc), C.byref(out)))
+        return Model(self, out, desc)
+
+    def model_from_file(self, path, which=0):
+        desc, meta = model_desc_from_file(path, which)
+        m = self.model(desc)
+        m.meta = meta
+        return m
+
+    # ---- K2 ----
+    def _pairs(self, set_a, set_b, ia, ib, n_pairs, a_begin=0, b_begin=0, a_bc=0, b_bc=0, len_filter=0,
+               anchor_is_b=0, cutoff=0.0):
+        ia = _u64(ia)
+        ib = _u64(ib)
+        p = Pairs(set_a.h.value, set_b.h.value, n_pairs, ia.ctypes.data if ia is not None else None,
+                  ib.ctypes.data if ib is not None else None, a_begin, b_begin, a_bc, b_bc, len_filter, anchor_is_b,
+                  cutoff)
+        p._keep = (ia, ib)
+        return p
+
+    def score_pairs(self, model, set_a, set_b, ia=None, ib=None, n_pairs=None, a_begin=0, b_begin=0, a_bc=0, b_bc=0,
+                    len_filter=0, anchor_is_b=0, cutoff=0.0, want=("score", "dist", "close", "cache", "raw", "skipped")):
+        if n_pairs is None:
+            n_pairs = len(ia) if ia is not None else len(ib)
+        p = self._pairs(set_a, set_b, ia, ib, n_pairs, a_begin, b_begin, a_bc, b_bc, len_filter, anchor_is_b, cutoff)
+        S = model.desc.n_singles
+        out = {}
+        out["score"] = np.zeros(n_pairs) if "score" in want else None
+        out["dist"] = np.zeros(n_pairs) if "dist" in want else None
+        out["close"] = np.zeros(n_pairs, dtype=np.uint8) if "close" in want else None
+        out["cache"] = np.zeros((n_pairs, S)) if "cache" in want else None
+        out["raw"] = np.zeros((n_pairs, S)) if "raw" in want else None
+        out["skipped"] = np.zeros(n_pairs, dtype=np.uint8) if "skipped" in want else None
+        _check(lib().mc2_score_pairs(self.h, model.h, C.byref(p), _p(out["score"]), _p(out["dist"]), _p(out["close"]),
+                                     _p(out["cache"]), _p(out["raw"]), _p(out["skipped"])))
+        return out
+
+    def get_close(self, model, set_q, q, set_c, cand=None, cand_begin=0, n_cand=None, cutoff=0.9):
+        cand = _u64(cand)
+        if n_cand is None:
+            n_cand = len(cand)
+        best, bd, ismin = C.c_int64(), C.c_double(), C.c_int32()
+        marks = np.zeros(n_cand, dtype=np.uint8)
+        _check(lib().mc2_get_close(self.h, model.h, set_q.h, C.c_uint64(q), set_c.h, _p(cand), C.c_uint64(cand_begin),
+                                   C.c_uint64(n_cand), C.c_double(cutoff), C.byref(best), C.byref(bd), C.byref(ismin),
+                                   _p(marks)))
+        return best.value, bd.value, bool(ismin.value), marks
+
+    def filter(self, model, set_c, center, set_m, members, ident):
+        members = _u64(members)
+        keep = np.zeros(len(members), dtype=np.uint8)
+        _check(lib().mc2_filter(self.h, model.h, set_c.h, C.c_uint64(center), set_m.h, _p(members),
+                                C.c_uint64(len(members)), C.c_double(ident), _p(keep)))
+        return keep
+
+    def merge(self, model, centers, rows, cur, begin, last, ident):
+        rows = _u64(rows)
+        out = C.c_int64()
+        _check(lib().mc2_merge(self.h, model.h, centers.h, _p(rows), C.c_int64(cur), C.c_int64(begin), C.c_int64(last),
+                               C.c_double(ident), C.byref(out)))
+        return out.value
+
+    def all_pairs(self, model, set_q, set_d, cutoff, q_range=None, d_range=None, upper_only=False, max_out=1 << 20):
+        q0, q1 = q_range if q_range else (0, len(set_q))
+        d0, d1 = d_range if d_range else (0, len(set_d))
+        oq = np.zeros(max_out, dtype=np.uint64)
+        od = np.zeros(max_out, dtype=np.uint64)
+        osc = np.zeros(max_out)
+        n_out, n_scored = C.c_uint64(), C.c_uint64()
+        _check(lib().mc2_all_pairs(self.h, model.h, set_q.h, C.c_uint64(q0), C.c_uint64(q1), set_d.h, C.c_uint64(d0),
+                                   C.c_uint64(d1), int(upper_only), C.c_double(cutoff), C.c_uint64(max_out), _p(oq),
+                                   _p(od), _p(osc), C.byref(n_out), C.byref(n_scored)))
+        got = min(n_out.value, max_out)
+        return dict(q=oq[:got], d=od[:got], score=osc[:got], n_out=n_out.value, n_scored=n_scored.value)
+
+    def distance(self, set_a, set_b, ia, ib):
+        p = self._pairs(set_a, set_b, ia, ib, len(ia))
+        out = np.zeros(len(ia), dtype=np.uint64)
+        _check(lib().mc2_distance(self.h, C.byref(p), _p(out)))
+        return out
+
+    def bench_score_pairs(self, model, set_a, set_b, ia=None, ib=None, n_pairs=None, iters=10, flush_l2=True, **kw):
+        if n_pairs is None:
+            n_pairs = len(ia) if ia is not None else len(ib)
+        p = self._pairs(set_a, set_b, ia, ib, n_pairs, **kw)
+        ms, nc = C.c_float(), C.c_uint64()
+        _check(lib().mc2_bench_score_pairs(self.h, model.h, C.byref(p), iters, int(flush_l2), C.byref(ms), C.byref(nc)))
+        return ms.value, nc.value
+
+    def bench_count_kmers(self, seqs, k, elem_bytes, iters=10, flush_l2=True):
+        ms = C.c_float()
+        _check(lib().mc2_bench_count_kmers(self.h, seqs.h, k, elem_bytes, iters, int(flush_l2), C.byref(ms)))
+        return ms.value
+
+
+class Seqs:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def __len__(self):
+        return lib().mc2_seqs_count(self.h)
+
+    @property
+    def total_bases(self):
+        return lib().mc2_seqs_total_bases(self.h)
+
+    def free(self):
+        if self.h:
+            lib().mc2_seqs_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class HistSet:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def __len__(self):
+        return lib().mc2_hset_count(self.h)
+
+    @property
+    def k(self):
+        return lib().mc2_hset_k(self.h)
+
+    @property
+    def elem_bytes(self):
+        return lib().mc2_hset_elem_bytes(self.h)
+
+    def device_bins(self):
+        return lib().mc2_hset_device_bins(self.h)
+
+    def download(self, first=0, count=None):
+        n = len(self)
+        count = n - first if count is None else count
+        N = 4 ** self.k
+        out = dict(
+            hist=np.zeros((count, N), dtype=DTYPES[self.elem_bytes]),
+            mag=np.zeros(count, dtype=np.uint64), len=np.zeros(count, dtype=np.uint64),
+            mers1=np.zeros((count, 4), dtype=np.uint64), stddev=np.zeros(count),
+            n_overflow=np.zeros(count, dtype=np.int32), max_count=np.zeros(count, dtype=np.uint32))
+        _check(lib().mc2_hset_download(self.ctx.h, self.h, C.c_uint64(first), C.c_uint64(count), _p(out["hist"]),
+                                       _p(out["mag"]), _p(out["len"]), _p(out["mers1"]), _p(out["stddev"]),
+                                       _p(out["n_overflow"]), _p(out["max_count"])))
+        return out
+
+    def set_sideband(self, rows, mag=None, length=None):
+        rows = _u64(rows)
+        _check(lib().mc2_hset_set_sideband(self.ctx.h, self.h, C.c_uint64(len(rows)), _p(rows), _p(_u64(mag)),
+                                           _p(_u64(length))))
+
+    def set_row(self, dst_row, src, src_row):
+        _check(lib().mc2_hset_set_row(self.ctx.h, self.h, C.c_uint64(dst_row), src.h, C.c_uint64(src_row)))
+
+    def free(self):
+        if self.h:
+            lib().mc2_hset_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Model:
+    def __init__(self, ctx, h, desc):
+        self.ctx, self.h, self.desc = ctx, h, desc
+        self.meta = {}
+
+    def free(self):
+        if self.h:
+            lib().mc2_model_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def encode_dna(text):
+    """raw DNA text (bytes) -> (codes int8[len], segs int32[nseg,2], effective_size); host-only (input contract a1)."""
+    n = len(text)
+    codes = np.zeros(max(n, 1), dtype=np.int8)
+    max_segs = n // 2 + 2
+    segs = np.zeros((max_segs, 2), dtype=np.int32)
+    nseg, eff = C.c_uint64(), C.c_uint64()
+    _check(lib().mc2_encode_dna(text, C.c_uint64(n), _p(codes), _p(segs), C.c_uint64(max_segs), C.byref(nseg),
+                                C.byref(eff)))
+    return codes[:n], segs[:nseg.value].copy(), eff.value
+
+
+def encode_batch(texts, threads=0):
+    """list of raw DNA bytes -> dict(codes, seq_off, segs, seg_off, eff) ready for Context.upload_seqs."""
+    n = len(texts)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    if n:
+        off[1:] = np.cumsum([len(t) for t in texts])
+    blob = b"".join(texts)
+    total = int(off[n])
+    codes = np.zeros(max(total, 1), dtype=np.int8)
+    max_segs = total // 20 + 2 * n + 16
+    segs = np.zeros((max_segs, 2), dtype=np.int32)
+    seg_off = np.zeros(n + 1, dtype=np.uint64)
+    eff = np.zeros(max(n, 1), dtype=np.uint64)
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    _check(lib().mc2_encode_dna_batch(blob, _p(off), C.c_uint64(n), _p(codes), _p(segs), C.c_uint64(max_segs),
+                                      _p(seg_off), _p(eff), threads))
+    return dict(codes=codes[:total], seq_off=off, segs=segs[:int(seg_off[n])].copy(), seg_off=seg_off, eff=eff[:n])
+
+
+def model_desc_from_file(path, which=0):
+    """Parse a reference weights.txt (Predictor::save format). Pure host parsing inside the C library; needs no GPU."""
+    d = ModelDesc()
+    k, ident, eb, mode = C.c_int(), C.c_double(), C.c_int(), C.c_int()
+    _check(lib().mc2_model_desc_from_file(os.fsencode(path), which, C.byref(d), C.byref(k), C.byref(ident), C.byref(eb),
+                                          C.byref(mode)))
+    return d, dict(k=k.value, id=ident.value, elem_bytes=eb.value, mode=mode.value)
+
+
+def make_desc(singles, combos, weights, bias=0.0, regression=0):
+    """singles: [(flag, min, max)], combos: [(kind_code, [single indices])], weights: C+1 doubles."""
+    d = ModelDesc()
+    d.n_singles = len(singles)
+    for i, (f, lo, hi) in enumerate(singles):
+        d.single_flag[i], d.single_min[i], d.single_max[i] = f, lo, hi
+    d.n_combos = len(combos)
+    for c, (kind, idx) in enumerate(combos):
+        d.combo_kind[c] = kind
+        d.combo_nidx[c] = len(idx)
+        for j, ix in enumerate(idx):
+            d.combo_idx[c][j] = ix
+    for i, w in enumerate(weights):
+        d.weight[i] = w
+    d.bias = bias
+    d.regression = regression
+    return d

@@ -1,0 +1,469 @@
+// kmer_count.cu — K1: batched k-mer histograms (sm_100a).
+//
+// Replaces, for a whole batch of sequences, the reference chain
+//   Loader<T>::get_point            src/clutil/Loader.cpp:138-179
+//   Loader<T>::fill_table           src/clutil/Loader.cpp:42-86
+//   KmerHashTable::hash / wholesaleIncrementNoOverflow   src/nonltr/KmerHashTable.cpp:108-160, 236-256
+//   DivergencePoint ctor (mag)      src/clutil/DivergencePoint.cpp:99-110
+// hist[h] = min(max(T), init + #occurrences of k-mer h inside the segments), order independent, so the
+// sequential rolling hash becomes: one thread per 16-base packed word, the k-mer index is a funnel shift
+// of two consecutive big-endian 2-bit words, counts go to a shared-memory u32 histogram with atomics and
+// are narrowed (saturating) to T on the way out, fused with the side-band sums K2 needs.
+#include "mc2_internal.cuh"
+
+namespace mc2 {
+
+// ------------------------------------------------------------------------------------------------
+// pack: 1 byte/base codes -> 2 bits/base, big-endian inside each 32-bit word (base j of a sequence sits in
+// word j/16 at bits [31-2(j%16)-1, 31-2(j%16)]), validating that every in-segment byte is a code 0..3
+// (KmerHashTable.cpp:138-149 throws InvalidInputException otherwise).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pack_kernel(const char *__restrict__ codes, const u64 *__restrict__ seq_off,
+						   const u64 *__restrict__ word_off, const int *__restrict__ segs,
+						   const u64 *__restrict__ seg_off, u64 n, u32 *__restrict__ packed, int *err)
+{
+	for (u64 s = blockIdx.x; s < n; s += gridDim.x) {
+		const u64 b0 = seq_off[s];
+		const u64 len = seq_off[s + 1] - b0;
+		const u64 w0 = word_off[s];
+		const u64 nw = word_off[s + 1] - w0;
+		const u64 sg0 = seg_off[s], sg1 = seg_off[s + 1];
+		const unsigned char *src = reinterpret_cast<const unsigned char *>(codes) + b0;
+		for (u64 w = threadIdx.x; w < nw; w += blockDim.x) {
+			u32 word = 0;
+			u32 badmask = 0;
+			const u64 j0 = w * 16;
+#pragma unroll
+			for (int t = 0; t < 16; t++) {
+				u64 j = j0 + t;
+				u32 c = j < len ? src[j] : 0;
+				badmask |= (c > 3 ? 1u : 0u) << t;
+				word |= (c & 3u) << (30 - 2 * t);
+			}
+			packed[w0 + w] = word;
+			if (badmask) {
+				// only bytes inside a segment matter; binary search the (sorted, disjoint) segment list
+				for (int t = 0; t < 16; t++) {
+					if (!(badmask >> t & 1)) {
+						continue;
+					}
+					long long j = (long long)(j0 + t);
+					u64 lo = sg0, hi = sg1;
+					while (lo < hi) {
+						u64 mid = (lo + hi) >> 1;
+						if (segs[2 * mid + 1] < j) {
+							lo = mid + 1;
+						} else {
+							hi = mid;
+						}
+					}
+					if (lo < sg1 && segs[2 * lo] <= j && j <= segs[2 * lo + 1]) {
+						atomicOr(err, 4);
+					}
+				}
+			}
+		}
+	}
+}
+
+int launch_pack(mc2_ctx *ctx, const char *d_codes, const u64 *d_seq_off, mc2_seqs *s)
+{
+	if (s->n == 0) {
+		return MC2_OK;
+	}
+	u64 cap = (u64)ctx->sm_count * 16;
+	int grid = (int)(s->n < cap ? s->n : cap);
+	pack_kernel<<<grid, 128, 0, ctx->stream>>>(d_codes, d_seq_off, s->word_off, s->segs, s->seg_off, s->n, s->packed,
+						      ctx->d_err);
+	ctx->launches++;
+	MC2_CUDA(cudaGetLastError());
+	return MC2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// counting
+// ------------------------------------------------------------------------------------------------
+struct CountArgs {
+	const u32 *packed;
+	const u64 *word_off;
+	const int *segs;
+	const u64 *seg_off;
+	u64 n;
+	u64 seq_begin;  // first sequence of this launch (global path batches)
+	int k;
+	int eb;
+	u64 N;
+	u64 init;
+	void *bins;
+	u64 *mag, *sum, *sumsq, *len, *mers1;
+	double *stddev;
+	int *novf;
+	u32 *maxc;
+	u32 *gscratch;  // global path: [batch x N] u32 counts, zeroed
+};
+
+// group = the threads cooperating on one sequence: a warp (WARP=true, several sequences per CTA) or the CTA
+template <bool WARP>
+__device__ __forceinline__ void group_sync()
+{
+	if (WARP) {
+		__syncwarp();
+	} else {
+		__syncthreads();
+	}
+}
+template <bool WARP>
+__device__ __forceinline__ int group_or(int v)
+{
+	if (WARP) {
+		return __any_sync(0xffffffffu, v);
+	}
+	return __syncthreads_or(v);
+}
+
+__device__ __forceinline__ u64 block_sum_u64(u64 v, u64 *sh)
+{
+	// CTA-wide sum; sh: 32 u64
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		v += __shfl_xor_sync(0xffffffffu, v, d);
+	}
+	__syncthreads();
+	if (lane == 0) {
+		sh[warp] = v;
+	}
+	__syncthreads();
+	u64 t = 0;
+	for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+		t += sh[w];
+	}
+	return t;
+}
+__device__ __forceinline__ u64 warp_sum_u64_shfl(u64 v)
+{
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		v += __shfl_xor_sync(0xffffffffu, v, d);
+	}
+	return v;
+}
+
+template <bool WARP>
+__device__ __forceinline__ u64 group_sum(u64 v, u64 *sh)
+{
+	if (WARP) {
+		return warp_sum_u64_shfl(v);
+	}
+	return block_sum_u64(v, sh);
+}
+template <bool WARP>
+__device__ __forceinline__ u32 group_max(u32 v, u64 *sh)
+{
+	v = __reduce_max_sync(0xffffffffu, v);
+	if (WARP) {
+		return v;
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0) {
+		sh[warp] = v;
+	}
+	__syncthreads();
+	u32 t = 0;
+	for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+		t = max(t, (u32)sh[w]);
+	}
+	return t;
+}
+
+// count one sequence's k-mers into `hist` (shared or global u32 counters) and its 1-mers; returns per-thread partials
+template <bool WARP, bool GLOBAL>
+__device__ __forceinline__ void count_sequence(const CountArgs &a, u64 seq, u32 *hist, int gt, int gs, u64 tmax,
+					       u64 (&m1)[4], u64 &eff_len, int &novf)
+{
+	const u64 w0 = a.word_off[seq];
+	const u64 nw = a.word_off[seq + 1] - w0;
+	const u32 *pk = a.packed + w0;
+	const int k = a.k;
+	const int sh_r = 32 - 2 * k;
+	m1[0] = m1[1] = m1[2] = m1[3] = 0;
+	eff_len = 0;
+	novf = 0;
+	for (u64 sg = a.seg_off[seq]; sg < a.seg_off[seq + 1]; sg++) {
+		const long long s0 = a.segs[2 * sg], e0 = a.segs[2 * sg + 1];
+		eff_len += (u64)(e0 - s0 + 1);
+		const long long last = e0 - k + 1; // last k-mer start; k-mers counted only if the segment holds >= k bases
+		const bool do_k = (e0 - s0 + 1 >= k);
+		int ovf = 0;
+		for (long long w = s0 / 16 + gt; w <= e0 / 16; w += gs) {
+			const u32 cur = pk[w];
+			const u32 nxt = ((u64)(w + 1) < nw) ? pk[w + 1] : 0u;
+			const long long j0 = w * 16;
+			// 1-mers over [s0, e0] (the k=1 table, Loader.cpp:144,150)
+			{
+				int lo_t = (int)max(0LL, s0 - j0), hi_t = (int)min(15LL, e0 - j0);
+				// valid fields mask on the low bit of each 2-bit field; field t sits at bits (31-2t, 30-2t)
+				u32 vm = 0x55555555u;
+				vm &= 0xFFFFFFFFu >> (2 * lo_t);
+				vm &= hi_t >= 15 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> (2 * (hi_t + 1)));
+				u32 lo = cur & 0x55555555u, hi = (cur >> 1) & 0x55555555u;
+				m1[0] += __popc(~hi & ~lo & vm);
+				m1[1] += __popc(~hi & lo & vm);
+				m1[2] += __popc(hi & ~lo & vm);
+				m1[3] += __popc(hi & lo & vm);
+			}
+			if (do_k && j0 <= last) {
+#pragma unroll
+				for (int t = 0; t < 16; t++) {
+					const long long j = j0 + t;
+					if (j >= s0 && j <= last) {
+						u32 idx = __funnelshift_l(nxt, cur, 2 * t) >> sh_r;
+						u32 old = atomicAdd(&hist[idx], 1u);
+						ovf |= (a.init + (u64)old >= tmax);
+					}
+				}
+			}
+		}
+		// one -1 return per overflowing segment (Loader.cpp:54-56); needs every increment of the segment done
+		if (group_or<WARP>(ovf)) {
+			novf++;
+		}
+	}
+	(void)GLOBAL;
+}
+
+// narrow counts -> T with saturation, 4 bins per thread per step; accumulate side-band partials
+template <typename T>
+__device__ __forceinline__ void emit4(const u32 *cnt4, u64 init, u64 tmax, T *dst, u64 &sum, u64 &sumsq, u32 &mx)
+{
+	T v[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		u64 x = init + (u64)cnt4[i];
+		x = x > tmax ? tmax : x;
+		v[i] = (T)x;
+		sum += x;
+		sumsq += x * x;
+		mx = max(mx, cnt4[i]);
+	}
+	if constexpr (sizeof(T) == 1) {
+		*reinterpret_cast<uchar4 *>(dst) = make_uchar4(v[0], v[1], v[2], v[3]);
+	} else if constexpr (sizeof(T) == 2) {
+		*reinterpret_cast<ushort4 *>(dst) = make_ushort4(v[0], v[1], v[2], v[3]);
+	} else if constexpr (sizeof(T) == 4) {
+		*reinterpret_cast<uint4 *>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+	} else {
+		reinterpret_cast<ulonglong2 *>(dst)[0] = make_ulonglong2(v[0], v[1]);
+		reinterpret_cast<ulonglong2 *>(dst)[1] = make_ulonglong2(v[2], v[3]);
+	}
+}
+
+template <typename T, bool WARP, bool GLOBAL>
+__global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ CountArgs a)
+{
+	extern __shared__ __align__(16) u32 sh_hist[];
+	__shared__ u64 sh_red[32];
+	const int warps = blockDim.x >> 5;
+	const int gt = WARP ? (threadIdx.x & 31) : threadIdx.x;
+	const int gs = WARP ? 32 : blockDim.x;
+	const u64 group = WARP ? (u64)blockIdx.x * warps + (threadIdx.x >> 5) : blockIdx.x;
+	const u64 groups = WARP ? (u64)gridDim.x * warps : gridDim.x;
+	const u64 tmax = sizeof(T) == 8 ? ~0ULL : ((1ULL << (8 * sizeof(T))) - 1);
+	const u64 N = a.N;
+	u32 *hist = GLOBAL ? nullptr : (WARP ? sh_hist + (u64)(threadIdx.x >> 5) * N : sh_hist);
+	// WARP mode: every warp of the CTA iterates the same number of times (no CTA-wide barriers are used)
+	for (u64 seq = a.seq_begin + group; seq < a.n; seq += groups) {
+		if (GLOBAL) {
+			hist = a.gscratch + (seq - a.seq_begin) * N; // zeroed by the host before the launch
+		} else {
+			for (u64 b = gt * 4; b < N; b += (u64)gs * 4) {
+				*reinterpret_cast<uint4 *>(hist + b) = make_uint4(0, 0, 0, 0);
+			}
+			group_sync<WARP>();
+		}
+		u64 m1[4], eff_len;
+		int novf;
+		count_sequence<WARP, GLOBAL>(a, seq, hist, gt, gs, tmax, m1, eff_len, novf);
+		if (GLOBAL) {
+			__threadfence();
+		}
+		group_sync<WARP>();
+		// narrow + side-band
+		u64 sum = 0, sumsq = 0;
+		u32 mx = 0;
+		T *dst = reinterpret_cast<T *>(a.bins) + seq * N;
+		for (u64 b = (u64)gt * 4; b < N; b += (u64)gs * 4) {
+			uint4 c = GLOBAL ? __ldcg(reinterpret_cast<const uint4 *>(hist + b)) : *reinterpret_cast<const uint4 *>(hist + b);
+			u32 c4[4] = {c.x, c.y, c.z, c.w};
+			emit4<T>(c4, a.init, tmax, dst + b, sum, sumsq, mx);
+		}
+		sum = group_sum<WARP>(sum, sh_red);
+		sumsq = group_sum<WARP>(sumsq, sh_red);
+		mx = group_max<WARP>(mx, sh_red);
+		u64 t0 = group_sum<WARP>(m1[0], sh_red), t1 = group_sum<WARP>(m1[1], sh_red);
+		u64 t2 = group_sum<WARP>(m1[2], sh_red), t3 = group_sum<WARP>(m1[3], sh_red);
+		if (gt == 0) {
+			a.mag[seq] = sum;
+			a.sum[seq] = sum;
+			a.sumsq[seq] = sumsq;
+			a.len[seq] = eff_len;
+			a.mers1[4 * seq + 0] = 1 + t0;
+			a.mers1[4 * seq + 1] = 1 + t1;
+			a.mers1[4 * seq + 2] = 1 + t2;
+			a.mers1[4 * seq + 3] = 1 + t3;
+			a.novf[seq] = novf;
+			a.maxc[seq] = mx;
+			// Loader.cpp:162-171: sqrt(sum((p_i - mag/N)^2)/N) == sqrt(N*sumsq - sum^2)/N, exact integer numerator
+			unsigned __int128 num = (unsigned __int128)N * sumsq - (unsigned __int128)sum * sum;
+			double numd = (double)(u64)(num >> 64) * 18446744073709551616.0 + (double)(u64)num;
+			a.stddev[seq] = sqrt(numd) / (double)N;
+		}
+		group_sync<WARP>();
+	}
+}
+
+// sums / sums of squares for a set uploaded from the host (mc2_hset_from_host)
+template <typename T>
+__global__ void __launch_bounds__(256) sideband_kernel(const T *__restrict__ bins, u64 n, u64 N, u64 *sum, u64 *sumsq,
+						       u64 *mag, int set_mag)
+{
+	const int lane = threadIdx.x & 31;
+	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
+	for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps_total) {
+		const T *row = bins + r * N;
+		u64 s = 0, q = 0;
+		for (u64 i = lane; i < N; i += 32) {
+			u64 v = row[i];
+			s += v;
+			q += v * v;
+		}
+		s = warp_sum_u64_shfl(s);
+		q = warp_sum_u64_shfl(q);
+		if (lane == 0) {
+			sum[r] = s;
+			sumsq[r] = q;
+			if (set_mag) {
+				mag[r] = s;
+			}
+		}
+	}
+}
+
+int launch_sideband(mc2_ctx *ctx, mc2_hset *h, bool set_mag)
+{
+	if (h->n == 0) {
+		return MC2_OK;
+	}
+	u64 want = (h->n + 7) / 8, cap = (u64)ctx->sm_count * 8;
+	int grid = (int)(want < cap ? want : cap);
+	switch (h->eb) {
+	case 1: sideband_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t *)h->bins, h->n, h->N, h->sum, h->sumsq, h->mag, set_mag); break;
+	case 2: sideband_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t *)h->bins, h->n, h->N, h->sum, h->sumsq, h->mag, set_mag); break;
+	case 4: sideband_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>((const uint32_t *)h->bins, h->n, h->N, h->sum, h->sumsq, h->mag, set_mag); break;
+	case 8: sideband_kernel<u64><<<grid, 256, 0, ctx->stream>>>((const u64 *)h->bins, h->n, h->N, h->sum, h->sumsq, h->mag, set_mag); break;
+	default: set_error("elem_bytes must be 1, 2, 4 or 8"); return MC2_ERR_ARG;
+	}
+	ctx->launches++;
+	MC2_CUDA(cudaGetLastError());
+	return MC2_OK;
+}
+
+template <typename T>
+static int launch_count_t(mc2_ctx *ctx, const mc2_seqs *s, CountArgs &a)
+{
+	const u64 N = a.N;
+	const u64 hist_bytes = N * 4;
+	const u64 avg_len = s->n ? s->total_bases / s->n : 0;
+	if (hist_bytes <= 64 * 1024) {
+		// shared-memory histograms
+		const bool warp_mode = hist_bytes <= 16 * 1024 && avg_len <= 4096;
+		if (warp_mode) {
+			int warps = (int)(48 * 1024 / hist_bytes);
+			warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
+			size_t smem = (size_t)warps * hist_bytes;
+			u64 want = (s->n + warps - 1) / warps, cap = (u64)ctx->sm_count * 8;
+			int grid = (int)(want < cap ? want : cap);
+			MC2_CUDA(cudaFuncSetAttribute(count_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+			count_kernel<T, true, false><<<grid, warps * 32, smem, ctx->stream>>>(a);
+		} else {
+			u64 cap = (u64)ctx->sm_count * 4;
+			int grid = (int)(s->n < cap ? s->n : cap);
+			MC2_CUDA(cudaFuncSetAttribute(count_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+			count_kernel<T, false, false><<<grid, 256, hist_bytes, ctx->stream>>>(a);
+		}
+		ctx->launches++;
+		MC2_CUDA(cudaGetLastError());
+		return MC2_OK;
+	}
+	// global-memory counters, batched so the scratch stays <= 1 GiB
+	u64 batch = (1ULL << 30) / hist_bytes;
+	batch = batch < 1 ? 1 : batch;
+	batch = batch > s->n ? s->n : batch;
+	u32 *scratch = nullptr;
+	MC2_CUDA(cudaMalloc(&scratch, batch * hist_bytes));
+	int rc = MC2_OK;
+	for (u64 b0 = 0; b0 < s->n && rc == MC2_OK; b0 += batch) {
+		u64 cnt = s->n - b0 < batch ? s->n - b0 : batch;
+		cudaError_t e = cudaMemsetAsync(scratch, 0, cnt * hist_bytes, ctx->stream);
+		if (e != cudaSuccess) {
+			rc = cuda_fail(e, "cudaMemsetAsync", __FILE__, __LINE__);
+			break;
+		}
+		CountArgs b = a;
+		b.seq_begin = b0;
+		b.n = b0 + cnt;
+		b.gscratch = scratch;
+		u64 cap = (u64)ctx->sm_count * 4;
+		int grid = (int)(cnt < cap ? cnt : cap);
+		// sequences b0.. are reached by offsetting the group index through seq_begin
+		b.packed = a.packed;
+		count_kernel<T, false, true><<<grid, 256, 0, ctx->stream>>>(b);
+		ctx->launches++;
+		e = cudaGetLastError();
+		if (e != cudaSuccess) {
+			rc = cuda_fail(e, "count_kernel(global)", __FILE__, __LINE__);
+		}
+	}
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(scratch);
+	return rc;
+}
+
+int launch_count(mc2_ctx *ctx, const mc2_seqs *s, int k, int eb, mc2_hset *h, u64 init_value)
+{
+	if (s->n == 0) {
+		return MC2_OK;
+	}
+	CountArgs a;
+	a.packed = s->packed;
+	a.word_off = s->word_off;
+	a.segs = s->segs;
+	a.seg_off = s->seg_off;
+	a.n = s->n;
+	a.seq_begin = 0;
+	a.k = k;
+	a.eb = eb;
+	a.N = 1ULL << (2 * k);
+	a.init = init_value;
+	a.bins = h->bins;
+	a.mag = h->mag;
+	a.sum = h->sum;
+	a.sumsq = h->sumsq;
+	a.len = h->len;
+	a.mers1 = h->mers1;
+	a.stddev = h->stddev;
+	a.novf = h->novf;
+	a.maxc = h->maxc;
+	a.gscratch = nullptr;
+	switch (eb) {
+	case 1: return launch_count_t<uint8_t>(ctx, s, a);
+	case 2: return launch_count_t<uint16_t>(ctx, s, a);
+	case 4: return launch_count_t<uint32_t>(ctx, s, a);
+	case 8: return launch_count_t<u64>(ctx, s, a);
+	}
+	set_error("elem_bytes must be 1, 2, 4 or 8");
+	return MC2_ERR_ARG;
+}
+
+} // namespace mc2

@@ -1,0 +1,1179 @@
+// mc2_api.cu — the C ABI declared in include/meshclust2_b200.h: contexts, device-resident objects, host glue.
+// No compute happens on the host here; every entry point launches the sm_100a kernels in kmer_count.cu /
+// pair_score.cu / pair_tile.cu or fails loudly.
+#include "mc2_internal.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace mc2 {
+
+static thread_local std::string g_err;
+
+void set_error(const std::string &msg)
+{
+	g_err = msg;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+	char buf[512];
+	snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+	g_err = buf;
+	return MC2_ERR_CUDA;
+}
+
+// growable device / pinned scratch
+struct Buf {
+	void *p = nullptr;
+	size_t cap = 0;
+	bool pinned = false;
+};
+
+static int ensure(Buf &b, size_t bytes, bool pinned)
+{
+	if (bytes <= b.cap) {
+		return MC2_OK;
+	}
+	if (b.p) {
+		if (b.pinned) {
+			cudaFreeHost(b.p);
+		} else {
+			cudaFree(b.p);
+		}
+		b.p = nullptr;
+		b.cap = 0;
+	}
+	size_t want = bytes + bytes / 4 + 256;
+	if (pinned) {
+		MC2_CUDA(cudaMallocHost(&b.p, want));
+	} else {
+		MC2_CUDA(cudaMalloc(&b.p, want));
+	}
+	b.cap = want;
+	b.pinned = pinned;
+	return MC2_OK;
+}
+
+static void release(Buf &b)
+{
+	if (b.p) {
+		if (b.pinned) {
+			cudaFreeHost(b.p);
+		} else {
+			cudaFree(b.p);
+		}
+	}
+	b.p = nullptr;
+	b.cap = 0;
+}
+
+enum { B_IA = 0, B_IB, B_SCORE, B_DIST, B_CLOSE, B_SKIP, B_CACHE, B_RAW, B_MISC, B_OUTQ, B_OUTD, B_OUTS, B_COUNT };
+
+struct CtxExtra {
+	Buf d[B_COUNT];
+};
+
+static int model_need(const mc2_model_desc &d, DevModel &dm)
+{
+	memset(&dm, 0, sizeof dm);
+	if (d.n_singles < 1 || d.n_singles > MC2_MAX_SINGLES || d.n_combos < 1 || d.n_combos > MC2_MAX_COMBOS) {
+		set_error("model: n_singles / n_combos out of range");
+		return MC2_ERR_ARG;
+	}
+	dm.n_singles = d.n_singles;
+	dm.n_combos = d.n_combos;
+	int need = 0;
+	for (int i = 0; i < d.n_singles; i++) {
+		int code, sim;
+		switch (d.single_flag[i]) {
+		case MC2_FEAT_MANHATTAN: code = SC_MANHATTAN; sim = 0; need |= NEED_MIN; break;
+		case MC2_FEAT_EUCLIDEAN: code = SC_EUCLIDEAN; sim = 0; need |= NEED_DOT; break;
+		case MC2_FEAT_NORMALIZED_VECTORS: code = SC_NORMALIZED_VECTORS; sim = 1; need |= NEED_DOT; break;
+		case MC2_FEAT_JEFFEREY_DIV: code = SC_JEFFEREY; sim = 0; need |= NEED_LOG; break;
+		case MC2_FEAT_PEARSON_COEFF: code = SC_PEARSON; sim = 1; need |= NEED_DOT; break;
+		case MC2_FEAT_INTERSECTION: code = SC_INTERSECTION; sim = 1; need |= NEED_MIN; break;
+		case MC2_FEAT_EMD: code = SC_EMD; sim = 0; need |= NEED_EMD; break;
+		case MC2_FEAT_LENGTHD: code = SC_LENGTHD; sim = 0; break;
+		case MC2_FEAT_KULCZYNSKI2: code = SC_KULCZYNSKI2; sim = 1; need |= NEED_MIN; break;
+		case MC2_FEAT_SIMRATIO: code = SC_SIMRATIO; sim = 1; need |= NEED_DOT; break;
+		case MC2_FEAT_JENSEN_SHANNON: code = SC_JENSEN_SHANNON; sim = 0; need |= NEED_LOG; break;
+		default: {
+			char buf[160];
+			snprintf(buf, sizeof buf,
+				 "model: single feature flag %llu is outside the hot-path scope (fast + slow sets only)",
+				 (unsigned long long)d.single_flag[i]);
+			set_error(buf);
+			return MC2_ERR_UNSUPPORTED;
+		}
+		}
+		dm.code[i] = code;
+		dm.is_sim[i] = sim; // Feature::feat_is_sim, src/predict/Feature.cpp:549-663
+		dm.smin[i] = d.single_min[i];
+		dm.smax[i] = d.single_max[i];
+	}
+	for (int c = 0; c < d.n_combos; c++) {
+		int kind = d.combo_kind[c], n = d.combo_nidx[c];
+		if (kind < 0 || kind > 3 || n < 1 || n > MC2_MAX_COMBO_IDX) {
+			set_error("model: bad combo kind / index count");
+			return MC2_ERR_ARG;
+		}
+		if ((kind == MC2_COMBO_XY2 || kind == MC2_COMBO_X2Y) && n != 2) {
+			// Feature::operator() throws "invalid" (Feature.h:221-235)
+			set_error("model: xy2 / x2y combos need exactly two singles");
+			return MC2_ERR_ARG;
+		}
+		dm.kind[c] = kind;
+		dm.nidx[c] = n;
+		for (int t = 0; t < n; t++) {
+			int ix = d.combo_idx[c][t];
+			if (ix < 0 || ix >= d.n_singles) {
+				set_error("model: combo index out of range");
+				return MC2_ERR_ARG;
+			}
+			dm.idx[c][t] = ix;
+		}
+	}
+	for (int c = 0; c <= d.n_combos; c++) {
+		dm.weight[c] = d.weight[c];
+	}
+	dm.bias = d.bias;
+	dm.regression = d.regression;
+	dm.need = need;
+	return MC2_OK;
+}
+
+static CtxExtra *extra(mc2_ctx *ctx)
+{
+	return reinterpret_cast<CtxExtra *>(ctx->extra);
+}
+
+static int check_err(mc2_ctx *ctx)
+{
+	int e = *ctx->h_err;
+	if (e == 0) {
+		return MC2_OK;
+	}
+	if (e & 4) {
+		set_error("invalid nucleotide code inside a segment (reference: InvalidInputException, KmerHashTable.cpp:138-149)");
+		return MC2_ERR_INPUT;
+	}
+	if (e & 1) {
+		set_error("a single feature failed the way the reference throws (zero length in length_difference or NaN after normalisation)");
+		return MC2_ERR_FEATURE;
+	}
+	set_error("internal: unknown single-feature code on device");
+	return MC2_ERR_FEATURE;
+}
+
+static int reset_err(mc2_ctx *ctx)
+{
+	MC2_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+	return MC2_OK;
+}
+
+static int fetch_err(mc2_ctx *ctx)
+{
+	MC2_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	return MC2_OK;
+}
+
+static int alloc_hset(mc2_ctx *ctx, u64 n, int k, int eb, mc2_hset **out)
+{
+	mc2_hset *h = new (std::nothrow) mc2_hset();
+	if (!h) {
+		set_error("out of host memory");
+		return MC2_ERR_ARG;
+	}
+	memset(h, 0, sizeof *h);
+	h->ctx = ctx;
+	h->n = n;
+	h->k = k;
+	h->N = 1ULL << (2 * k);
+	h->eb = eb;
+	u64 nn = n ? n : 1;
+	cudaError_t e;
+#define A(ptr, bytes)                                                \
+	e = cudaMalloc((void **)&(ptr), (bytes));                    \
+	if (e != cudaSuccess) {                                      \
+		mc2_hset_free(h);                                    \
+		return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); \
+	}
+	A(h->bins, nn * h->N * (u64)eb);
+	A(h->mag, nn * 8);
+	A(h->sum, nn * 8);
+	A(h->sumsq, nn * 8);
+	A(h->len, nn * 8);
+	A(h->mers1, nn * 32);
+	A(h->stddev, nn * 8);
+	A(h->novf, nn * 4);
+	A(h->maxc, nn * 4);
+#undef A
+	*out = h;
+	return MC2_OK;
+}
+
+static int refresh_max_sum(mc2_ctx *ctx, mc2_hset *h)
+{
+	// host-side bound used to pick the 32-bit fast paths; one small D2H per set creation
+	std::vector<u64> s(h->n);
+	if (h->n) {
+		MC2_CUDA(cudaMemcpyAsync(s.data(), h->sum, h->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	u64 m = 0;
+	for (u64 v : s) {
+		m = v > m ? v : m;
+	}
+	h->max_sum = m;
+	return MC2_OK;
+}
+
+} // namespace mc2
+
+using namespace mc2;
+
+extern "C" {
+
+int mc2_abi_version(void)
+{
+	return MC2_ABI_VERSION;
+}
+
+const char *mc2_last_error(void)
+{
+	return g_err.c_str();
+}
+
+int mc2_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int mc2_ctx_create(int device, mc2_ctx **out)
+{
+	MC2_REQUIRE(out != nullptr, "mc2_ctx_create: out is NULL");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		set_error("no CUDA device available: libmeshclust2_b200 has no CPU fallback");
+		return MC2_ERR_CUDA;
+	}
+	MC2_REQUIRE(device >= 0 && device < n, "mc2_ctx_create: device index out of range");
+	cudaDeviceProp prop;
+	MC2_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) {
+		char buf[200];
+		snprintf(buf, sizeof buf, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+			 prop.minor);
+		set_error(buf);
+		return MC2_ERR_CUDA;
+	}
+	MC2_CUDA(cudaSetDevice(device));
+	mc2_ctx *c = new (std::nothrow) mc2_ctx();
+	MC2_REQUIRE(c != nullptr, "out of host memory");
+	memset(c, 0, sizeof *c);
+	c->device = device;
+	c->sm_count = prop.multiProcessorCount;
+	MC2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	MC2_CUDA(cudaEventCreate(&c->ev0));
+	MC2_CUDA(cudaEventCreate(&c->ev1));
+	MC2_CUDA(cudaMalloc((void **)&c->d_err, 64));
+	MC2_CUDA(cudaMallocHost((void **)&c->h_err, 64));
+	MC2_CUDA(cudaMallocHost(&c->h_slot, 4096));
+	MC2_CUDA(cudaMalloc(&c->d_slot, 4096));
+	memset(c->h_slot, 0, 4096);
+	*c->h_err = 0;
+	CtxExtra *x = new (std::nothrow) CtxExtra();
+	c->extra = x;
+	*out = c;
+	return MC2_OK;
+}
+
+void mc2_ctx_destroy(mc2_ctx *ctx)
+{
+	if (!ctx) {
+		return;
+	}
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	CtxExtra *x = extra(ctx);
+	if (x) {
+		for (auto &b : x->d) {
+			release(b);
+		}
+		delete x;
+	}
+	if (ctx->flush_buf) {
+		cudaFree(ctx->flush_buf);
+	}
+	cudaFree(ctx->d_err);
+	cudaFreeHost(ctx->h_err);
+	cudaFreeHost(ctx->h_slot);
+	cudaFree(ctx->d_slot);
+	cudaEventDestroy(ctx->ev0);
+	cudaEventDestroy(ctx->ev1);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+int mc2_ctx_sync(mc2_ctx *ctx)
+{
+	MC2_REQUIRE(ctx != nullptr, "ctx is NULL");
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC2_OK;
+}
+
+int mc2_ctx_device(const mc2_ctx *ctx)
+{
+	return ctx ? ctx->device : -1;
+}
+
+int mc2_ctx_sm_count(const mc2_ctx *ctx)
+{
+	return ctx ? ctx->sm_count : 0;
+}
+
+void *mc2_ctx_stream(mc2_ctx *ctx)
+{
+	return ctx ? (void *)ctx->stream : nullptr;
+}
+
+int mc2_timer_start(mc2_ctx *ctx)
+{
+	MC2_REQUIRE(ctx != nullptr, "ctx is NULL");
+	MC2_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+	return MC2_OK;
+}
+
+int mc2_timer_stop(mc2_ctx *ctx, float *ms)
+{
+	MC2_REQUIRE(ctx != nullptr && ms != nullptr, "ctx / ms is NULL");
+	MC2_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+	MC2_CUDA(cudaEventSynchronize(ctx->ev1));
+	MC2_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+	return MC2_OK;
+}
+
+uint64_t mc2_ctx_launch_count(const mc2_ctx *ctx)
+{
+	return ctx ? ctx->launches : 0;
+}
+
+int mc2_ctx_flush_l2(mc2_ctx *ctx, size_t bytes)
+{
+	MC2_REQUIRE(ctx != nullptr, "ctx is NULL");
+	if (bytes > ctx->flush_bytes) {
+		if (ctx->flush_buf) {
+			cudaFree(ctx->flush_buf);
+			ctx->flush_buf = nullptr;
+			ctx->flush_bytes = 0;
+		}
+		MC2_CUDA(cudaMalloc(&ctx->flush_buf, bytes));
+		ctx->flush_bytes = bytes;
+	}
+	MC2_CUDA(cudaMemsetAsync(ctx->flush_buf, 0, bytes, ctx->stream));
+	return MC2_OK;
+}
+
+/* ---- sequences -------------------------------------------------------------------------------- */
+int mc2_seqs_upload(mc2_ctx *ctx, const char *codes, const uint64_t *seq_off, uint64_t n, const int32_t *segs,
+		    const uint64_t *seg_off, mc2_seqs **out)
+{
+	MC2_REQUIRE(ctx && seq_off && seg_off && out, "mc2_seqs_upload: NULL argument");
+	MC2_REQUIRE(n == 0 || codes != nullptr, "mc2_seqs_upload: codes is NULL");
+	*out = nullptr;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	const u64 total_bases = seq_off[n] - seq_off[0];
+	const u64 total_segs = seg_off[n] - seg_off[0];
+	MC2_REQUIRE(total_segs == 0 || segs != nullptr, "mc2_seqs_upload: segs is NULL");
+	// host-side shape checks only (no per-base work on the host)
+	std::vector<u64> word_off(n + 1), len(n), soff(n + 1), boff(n + 1);
+	u64 w = 0, max_len = 0;
+	for (u64 i = 0; i < n; i++) {
+		MC2_REQUIRE(seq_off[i + 1] >= seq_off[i] && seg_off[i + 1] >= seg_off[i], "mc2_seqs_upload: offsets must be non-decreasing");
+		u64 L = seq_off[i + 1] - seq_off[i];
+		MC2_REQUIRE(L < (1ULL << 31), "mc2_seqs_upload: a sequence is longer than 2^31-1 bases (reference positions are int)");
+		len[i] = L;
+		max_len = L > max_len ? L : max_len;
+		word_off[i] = w;
+		boff[i] = seq_off[i] - seq_off[0];
+		soff[i] = seg_off[i] - seg_off[0];
+		u64 nw = (L + 15) / 16 + 1; // one spare word so the k-mer window may read past the end
+		w += (nw + 3) & ~3ULL;
+		for (u64 s = seg_off[i]; s < seg_off[i + 1]; s++) {
+			long long s0 = segs[2 * s], e0 = segs[2 * s + 1];
+			MC2_REQUIRE(s0 >= 0 && e0 >= s0 && (u64)e0 < L, "mc2_seqs_upload: segment outside its sequence");
+			MC2_REQUIRE(s == seg_off[i] || s0 > segs[2 * s - 1], "mc2_seqs_upload: segments must be sorted and disjoint");
+		}
+	}
+	word_off[n] = w;
+	boff[n] = total_bases;
+	soff[n] = total_segs;
+	mc2_seqs *s = new (std::nothrow) mc2_seqs();
+	MC2_REQUIRE(s != nullptr, "out of host memory");
+	memset(s, 0, sizeof *s);
+	s->ctx = ctx;
+	s->n = n;
+	s->total_bases = total_bases;
+	s->max_len = max_len;
+	s->total_segs = total_segs;
+	s->total_words = w;
+	char *d_codes = nullptr;
+	u64 *d_boff = nullptr;
+	cudaError_t e = cudaSuccess;
+	auto fail = [&](const char *what) {
+		int rc = cuda_fail(e, what, __FILE__, __LINE__);
+		if (d_codes) cudaFree(d_codes);
+		if (d_boff) cudaFree(d_boff);
+		mc2_seqs_free(s);
+		return rc;
+	};
+	if ((e = cudaMalloc((void **)&s->packed, (w ? w : 1) * 4)) != cudaSuccess) return fail("cudaMalloc packed");
+	if ((e = cudaMalloc((void **)&s->word_off, (n + 1) * 8)) != cudaSuccess) return fail("cudaMalloc word_off");
+	if ((e = cudaMalloc((void **)&s->len, (n ? n : 1) * 8)) != cudaSuccess) return fail("cudaMalloc len");
+	if ((e = cudaMalloc((void **)&s->segs, (total_segs ? total_segs : 1) * 8)) != cudaSuccess) return fail("cudaMalloc segs");
+	if ((e = cudaMalloc((void **)&s->seg_off, (n + 1) * 8)) != cudaSuccess) return fail("cudaMalloc seg_off");
+	if ((e = cudaMalloc((void **)&d_codes, total_bases ? total_bases : 1)) != cudaSuccess) return fail("cudaMalloc codes");
+	if ((e = cudaMalloc((void **)&d_boff, (n + 1) * 8)) != cudaSuccess) return fail("cudaMalloc boff");
+	cudaStream_t st = ctx->stream;
+	if ((e = cudaMemcpyAsync(s->word_off, word_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D word_off");
+	if (n && (e = cudaMemcpyAsync(s->len, len.data(), n * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D len");
+	if (total_segs && (e = cudaMemcpyAsync(s->segs, segs + 2 * seg_off[0], total_segs * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D segs");
+	if ((e = cudaMemcpyAsync(s->seg_off, soff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D seg_off");
+	if (total_bases && (e = cudaMemcpyAsync(d_codes, codes + seq_off[0], total_bases, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D codes");
+	if ((e = cudaMemcpyAsync(d_boff, boff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D boff");
+	int rc = reset_err(ctx);
+	if (rc == MC2_OK) rc = launch_pack(ctx, d_codes, d_boff, s);
+	if (rc == MC2_OK) rc = fetch_err(ctx);
+	e = cudaStreamSynchronize(st);
+	cudaFree(d_codes);
+	cudaFree(d_boff);
+	d_codes = nullptr;
+	d_boff = nullptr;
+	if (rc == MC2_OK && e != cudaSuccess) return fail("pack");
+	if (rc == MC2_OK) rc = check_err(ctx);
+	if (rc != MC2_OK) {
+		mc2_seqs_free(s);
+		return rc;
+	}
+	*out = s;
+	return MC2_OK;
+}
+
+void mc2_seqs_free(mc2_seqs *s)
+{
+	if (!s) {
+		return;
+	}
+	cudaFree(s->packed);
+	cudaFree(s->word_off);
+	cudaFree(s->len);
+	cudaFree(s->segs);
+	cudaFree(s->seg_off);
+	delete s;
+}
+
+uint64_t mc2_seqs_count(const mc2_seqs *s)
+{
+	return s ? s->n : 0;
+}
+
+uint64_t mc2_seqs_total_bases(const mc2_seqs *s)
+{
+	return s ? s->total_bases : 0;
+}
+
+static int check_k_eb(int k, int eb)
+{
+	MC2_REQUIRE(k >= 1 && k <= 12, "k must be in 1..12");
+	MC2_REQUIRE(eb == 1 || eb == 2 || eb == 4 || eb == 8, "elem_bytes must be 1, 2, 4 or 8 (--datatype 8/16/32/64)");
+	return MC2_OK;
+}
+
+static int count_into(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int eb, u64 init, mc2_hset *h)
+{
+	int rc = reset_err(ctx);
+	if (rc == MC2_OK) rc = launch_count(ctx, seqs, k, eb, h, init);
+	if (rc == MC2_OK) rc = fetch_err(ctx);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	return check_err(ctx);
+}
+
+int mc2_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, mc2_hset **out)
+{
+	MC2_REQUIRE(ctx && seqs && out, "mc2_count_kmers: NULL argument");
+	*out = nullptr;
+	int rc = check_k_eb(k, elem_bytes);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	mc2_hset *h = nullptr;
+	rc = alloc_hset(ctx, seqs->n, k, elem_bytes, &h);
+	if (rc != MC2_OK) return rc;
+	rc = count_into(ctx, seqs, k, elem_bytes, 1, h);
+	if (rc == MC2_OK) rc = refresh_max_sum(ctx, h);
+	if (rc != MC2_OK) {
+		mc2_hset_free(h);
+		return rc;
+	}
+	*out = h;
+	return MC2_OK;
+}
+
+int mc2_kmer_table_increment(mc2_ctx *ctx, const char *codes, int32_t first, int32_t last, int k, int elem_bytes,
+			     uint64_t init_value, void *values_out, int32_t *ret)
+{
+	MC2_REQUIRE(ctx && codes && values_out && ret, "mc2_kmer_table_increment: NULL argument");
+	int rc = check_k_eb(k, elem_bytes);
+	if (rc != MC2_OK) return rc;
+	MC2_REQUIRE(first >= 0 && last >= first, "mc2_kmer_table_increment: need 0 <= first <= last");
+	// the k-mers with starts first..last span codes[first .. last+k-1]: one sequence, one segment
+	uint64_t seq_off[2] = {0, (uint64_t)last + (uint64_t)k};
+	int32_t seg[2] = {first, last + k - 1};
+	uint64_t seg_off[2] = {0, 1};
+	mc2_seqs *s = nullptr;
+	rc = mc2_seqs_upload(ctx, codes, seq_off, 1, seg, seg_off, &s);
+	if (rc != MC2_OK) return rc;
+	mc2_hset *h = nullptr;
+	rc = alloc_hset(ctx, 1, k, elem_bytes, &h);
+	if (rc == MC2_OK) rc = count_into(ctx, s, k, elem_bytes, init_value, h);
+	int32_t novf = 0;
+	if (rc == MC2_OK) rc = mc2_hset_download(ctx, h, 0, 1, values_out, nullptr, nullptr, nullptr, nullptr, &novf, nullptr);
+	*ret = novf ? -1 : 0;
+	mc2_hset_free(h);
+	mc2_seqs_free(s);
+	return rc;
+}
+
+/* ---- histogram sets --------------------------------------------------------------------------- */
+int mc2_hset_from_host(mc2_ctx *ctx, const void *bins, uint64_t n, int k, int elem_bytes, const uint64_t *mag,
+		       const uint64_t *len, mc2_hset **out)
+{
+	MC2_REQUIRE(ctx && out && (n == 0 || (bins && len)), "mc2_hset_from_host: NULL argument");
+	*out = nullptr;
+	int rc = check_k_eb(k, elem_bytes);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	mc2_hset *h = nullptr;
+	rc = alloc_hset(ctx, n, k, elem_bytes, &h);
+	if (rc != MC2_OK) return rc;
+	cudaError_t e = cudaSuccess;
+	if (n) {
+		e = cudaMemcpyAsync(h->bins, bins, n * h->N * (u64)elem_bytes, cudaMemcpyHostToDevice, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(h->len, len, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+		if (e == cudaSuccess && mag) e = cudaMemcpyAsync(h->mag, mag, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(h->mers1, 0, n * 32, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(h->stddev, 0, n * 8, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(h->novf, 0, n * 4, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(h->maxc, 0, n * 4, ctx->stream);
+	}
+	if (e != cudaSuccess) {
+		mc2_hset_free(h);
+		return cuda_fail(e, "mc2_hset_from_host copies", __FILE__, __LINE__);
+	}
+	rc = launch_sideband(ctx, h, mag == nullptr);
+	if (rc == MC2_OK) rc = refresh_max_sum(ctx, h);
+	if (rc != MC2_OK) {
+		mc2_hset_free(h);
+		return rc;
+	}
+	*out = h;
+	return MC2_OK;
+}
+
+void mc2_hset_free(mc2_hset *h)
+{
+	if (!h) {
+		return;
+	}
+	cudaFree(h->bins);
+	cudaFree(h->mag);
+	cudaFree(h->sum);
+	cudaFree(h->sumsq);
+	cudaFree(h->len);
+	cudaFree(h->mers1);
+	cudaFree(h->stddev);
+	cudaFree(h->novf);
+	cudaFree(h->maxc);
+	delete h;
+}
+
+uint64_t mc2_hset_count(const mc2_hset *h)
+{
+	return h ? h->n : 0;
+}
+
+int mc2_hset_k(const mc2_hset *h)
+{
+	return h ? h->k : 0;
+}
+
+int mc2_hset_elem_bytes(const mc2_hset *h)
+{
+	return h ? h->eb : 0;
+}
+
+void *mc2_hset_device_bins(const mc2_hset *h)
+{
+	return h ? h->bins : nullptr;
+}
+
+int mc2_hset_download(mc2_ctx *ctx, const mc2_hset *h, uint64_t first, uint64_t count, void *bins, uint64_t *mag,
+		      uint64_t *len, uint64_t *mers1, double *stddev, int32_t *n_overflow, uint32_t *max_count)
+{
+	MC2_REQUIRE(ctx && h, "mc2_hset_download: NULL argument");
+	MC2_REQUIRE(first <= h->n && count <= h->n - first, "mc2_hset_download: row range out of bounds");
+	if (count == 0) {
+		return MC2_OK;
+	}
+	cudaStream_t st = ctx->stream;
+	const u64 rb = h->N * (u64)h->eb;
+	if (bins) MC2_CUDA(cudaMemcpyAsync(bins, (const char *)h->bins + first * rb, count * rb, cudaMemcpyDeviceToHost, st));
+	if (mag) MC2_CUDA(cudaMemcpyAsync(mag, h->mag + first, count * 8, cudaMemcpyDeviceToHost, st));
+	if (len) MC2_CUDA(cudaMemcpyAsync(len, h->len + first, count * 8, cudaMemcpyDeviceToHost, st));
+	if (mers1) MC2_CUDA(cudaMemcpyAsync(mers1, h->mers1 + 4 * first, count * 32, cudaMemcpyDeviceToHost, st));
+	if (stddev) MC2_CUDA(cudaMemcpyAsync(stddev, h->stddev + first, count * 8, cudaMemcpyDeviceToHost, st));
+	if (n_overflow) MC2_CUDA(cudaMemcpyAsync(n_overflow, h->novf + first, count * 4, cudaMemcpyDeviceToHost, st));
+	if (max_count) MC2_CUDA(cudaMemcpyAsync(max_count, h->maxc + first, count * 4, cudaMemcpyDeviceToHost, st));
+	MC2_CUDA(cudaStreamSynchronize(st));
+	return MC2_OK;
+}
+
+int mc2_hset_set_sideband(mc2_ctx *ctx, mc2_hset *h, uint64_t count, const uint64_t *rows, const uint64_t *mag,
+			  const uint64_t *len)
+{
+	MC2_REQUIRE(ctx && h && (count == 0 || rows), "mc2_hset_set_sideband: NULL argument");
+	for (u64 i = 0; i < count; i++) {
+		MC2_REQUIRE(rows[i] < h->n, "mc2_hset_set_sideband: row out of range");
+		if (mag) MC2_CUDA(cudaMemcpyAsync(h->mag + rows[i], mag + i, 8, cudaMemcpyHostToDevice, ctx->stream));
+		if (len) MC2_CUDA(cudaMemcpyAsync(h->len + rows[i], len + i, 8, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC2_OK;
+}
+
+int mc2_hset_set_row(mc2_ctx *ctx, mc2_hset *dst, uint64_t dst_row, const mc2_hset *src, uint64_t src_row)
+{
+	MC2_REQUIRE(ctx && dst && src, "mc2_hset_set_row: NULL argument");
+	MC2_REQUIRE(dst->k == src->k && dst->eb == src->eb, "mc2_hset_set_row: sets differ in k or width");
+	MC2_REQUIRE(dst_row < dst->n && src_row < src->n, "mc2_hset_set_row: row out of range");
+	cudaStream_t st = ctx->stream;
+	const u64 rb = dst->N * (u64)dst->eb;
+	// DivergencePoint::set (src/clutil/DivergencePoint.cpp:182-190): points + length (+header/id), NOT mag
+	MC2_CUDA(cudaMemcpyAsync((char *)dst->bins + dst_row * rb, (const char *)src->bins + src_row * rb, rb, cudaMemcpyDeviceToDevice, st));
+	MC2_CUDA(cudaMemcpyAsync(dst->len + dst_row, src->len + src_row, 8, cudaMemcpyDeviceToDevice, st));
+	MC2_CUDA(cudaMemcpyAsync(dst->sum + dst_row, src->sum + src_row, 8, cudaMemcpyDeviceToDevice, st));
+	MC2_CUDA(cudaMemcpyAsync(dst->sumsq + dst_row, src->sumsq + src_row, 8, cudaMemcpyDeviceToDevice, st));
+	MC2_CUDA(cudaStreamSynchronize(st));
+	if (src->max_sum > dst->max_sum) {
+		dst->max_sum = src->max_sum;
+	}
+	return MC2_OK;
+}
+
+/* ---- model ------------------------------------------------------------------------------------ */
+int mc2_model_create(mc2_ctx *ctx, const mc2_model_desc *desc, mc2_model **out)
+{
+	MC2_REQUIRE(ctx && desc && out, "mc2_model_create: NULL argument");
+	*out = nullptr;
+	DevModel dm;
+	int rc = model_need(*desc, dm);
+	if (rc != MC2_OK) return rc;
+	mc2_model *m = new (std::nothrow) mc2_model();
+	MC2_REQUIRE(m != nullptr, "out of host memory");
+	m->ctx = ctx;
+	m->desc = *desc;
+	m->dm = dm;
+	*out = m;
+	return MC2_OK;
+}
+
+void mc2_model_free(mc2_model *m)
+{
+	delete m;
+}
+
+int mc2_model_desc_from_file(const char *path, int which, mc2_model_desc *desc, int *k_out, double *id_out,
+			     int *elem_bytes_out, int *mode_out)
+{
+	MC2_REQUIRE(path && desc, "mc2_model_desc_from_file: NULL argument");
+	MC2_REQUIRE(which == 0 || which == 1, "mc2_model_desc_from_file: which must be 0 (classifier) or 1 (regression)");
+	std::ifstream in(path);
+	if (!in) {
+		set_error(std::string("cannot open weights file ") + path);
+		return MC2_ERR_IO;
+	}
+	// header, Predictor.cpp:47-66
+	std::string buf, datatype;
+	int k = 0, max_feat = 0;
+	unsigned mode = 0;
+	double id = 0;
+	uint64_t feats64 = 0;
+	in >> buf >> k;
+	in >> buf >> mode;
+	in >> buf >> max_feat;
+	in >> buf >> id;
+	in >> buf >> datatype;
+	in >> buf >> feats64;
+	if (!in) {
+		set_error("weights file: malformed header");
+		return MC2_ERR_IO;
+	}
+	const bool has_c = mode & 1, has_r = mode & 2;
+	if ((which == 0 && !has_c) || (which == 1 && !has_r)) {
+		set_error("weights file does not contain the requested model block");
+		return MC2_ERR_IO;
+	}
+	int blocks_to_skip = (which == 1 && has_c) ? 1 : 0;
+	for (int blk = 0; blk <= blocks_to_skip; blk++) {
+		// read_from, Predictor.cpp:125-185
+		mc2_model_desc d;
+		memset(&d, 0, sizeof d);
+		int nc = 0;
+		in >> buf >> nc;
+		if (!in || nc < 1 || nc > MC2_MAX_COMBOS) {
+			set_error("weights file: bad n_combos");
+			return MC2_ERR_IO;
+		}
+		d.n_combos = nc;
+		in >> d.weight[0];
+		uint64_t have = 0;
+		for (int c = 0; c < nc; c++) {
+			int cmb;
+			uint64_t flags;
+			double wv;
+			in >> cmb >> flags >> wv;
+			if (!in || cmb < 0 || cmb > 3) {
+				set_error("weights file: bad combo line");
+				return MC2_ERR_IO;
+			}
+			d.weight[c + 1] = wv;
+			d.combo_kind[c] = cmb;
+			// Feature::add_feature, Feature.cpp:102-127: new singles appended in ascending flag-bit order
+			int ni = 0;
+			for (int b = 0; b < 64; b++) {
+				uint64_t f = 1ULL << b;
+				if (!(flags & f)) {
+					continue;
+				}
+				if (!(have & f)) {
+					if (d.n_singles >= MC2_MAX_SINGLES) {
+						set_error("weights file: too many singles");
+						return MC2_ERR_IO;
+					}
+					d.single_flag[d.n_singles++] = f;
+					have |= f;
+				}
+				int ix = -1;
+				for (int s = 0; s < d.n_singles; s++) {
+					if (d.single_flag[s] == f) {
+						ix = s;
+					}
+				}
+				if (ni >= MC2_MAX_COMBO_IDX) {
+					set_error("weights file: combo with too many singles");
+					return MC2_ERR_IO;
+				}
+				d.combo_idx[c][ni++] = ix;
+			}
+			d.combo_nidx[c] = ni;
+		}
+		int ns = 0;
+		in >> buf >> ns;
+		if (!in || ns < 0 || ns > MC2_MAX_SINGLES) {
+			set_error("weights file: bad n_singles");
+			return MC2_ERR_IO;
+		}
+		for (int s = 0; s < ns; s++) {
+			uint64_t f;
+			double lo, hi;
+			in >> f >> lo >> hi;
+			if (!in) {
+				set_error("weights file: bad single line");
+				return MC2_ERR_IO;
+			}
+			for (int t = 0; t < d.n_singles; t++) { // Feature::set_normal, Feature.cpp:173-180
+				if (d.single_flag[t] == f) {
+					d.single_min[t] = lo;
+					d.single_max[t] = hi;
+				}
+			}
+		}
+		d.bias = 0;
+		d.regression = (blk == 1 || (which == 1 && !has_c)) ? 1 : 0;
+		if (blk == blocks_to_skip) {
+			*desc = d;
+		}
+	}
+	if (k_out) *k_out = k;
+	if (id_out) *id_out = id;
+	if (mode_out) *mode_out = (int)mode;
+	if (elem_bytes_out) {
+		*elem_bytes_out = datatype == "uint8_t" ? 1 : datatype == "uint16_t" ? 2 : datatype == "uint32_t" ? 4 : datatype == "uint64_t" ? 8 : 0;
+	}
+	return MC2_OK;
+}
+
+/* ---- scoring ----------------------------------------------------------------------------------- */
+static int fill_pair_args(mc2_ctx *ctx, const mc2_pairs *p, PairArgs &a, CtxExtra *x)
+{
+	MC2_REQUIRE(p->set_a && p->set_b, "pairs: set_a / set_b is NULL");
+	const mc2_hset *A = p->set_a, *B = p->set_b;
+	MC2_REQUIRE(A->k == B->k && A->eb == B->eb, "pairs: the two sets differ in k or histogram width");
+	memset(&a, 0, sizeof a);
+	a.binsA = A->bins;
+	a.binsB = B->bins;
+	a.sbA = Sideband{A->mag, A->sum, A->sumsq, A->len};
+	a.sbB = Sideband{B->mag, B->sum, B->sumsq, B->len};
+	a.N = A->N;
+	a.eb = A->eb;
+	a.n_pairs = p->n_pairs;
+	a.a_begin = p->a_begin;
+	a.b_begin = p->b_begin;
+	a.a_bc = p->a_broadcast;
+	a.b_bc = p->b_broadcast;
+	a.len_filter = p->len_filter;
+	a.anchor_is_b = p->anchor_is_b;
+	a.cutoff = p->cutoff;
+	a.err = ctx->d_err;
+	a.max_sum = A->max_sum > B->max_sum ? A->max_sum : B->max_sum;
+	const u64 m = p->n_pairs;
+	if (p->ia) {
+		for (u64 j = 0; j < m; j++) {
+			MC2_REQUIRE(p->ia[j] < A->n, "pairs: ia index out of range");
+		}
+		int rc = ensure(x->d[B_IA], m * 8, false);
+		if (rc != MC2_OK) return rc;
+		MC2_CUDA(cudaMemcpyAsync(x->d[B_IA].p, p->ia, m * 8, cudaMemcpyHostToDevice, ctx->stream));
+		a.ia = (const u64 *)x->d[B_IA].p;
+	} else {
+		MC2_REQUIRE(m == 0 || (p->a_broadcast ? p->a_begin < A->n : (p->a_begin <= A->n && m <= A->n - p->a_begin)), "pairs: a range out of bounds");
+	}
+	if (p->ib) {
+		for (u64 j = 0; j < m; j++) {
+			MC2_REQUIRE(p->ib[j] < B->n, "pairs: ib index out of range");
+		}
+		int rc = ensure(x->d[B_IB], m * 8, false);
+		if (rc != MC2_OK) return rc;
+		MC2_CUDA(cudaMemcpyAsync(x->d[B_IB].p, p->ib, m * 8, cudaMemcpyHostToDevice, ctx->stream));
+		a.ib = (const u64 *)x->d[B_IB].p;
+	} else {
+		MC2_REQUIRE(m == 0 || (p->b_broadcast ? p->b_begin < B->n : (p->b_begin <= B->n && m <= B->n - p->b_begin)), "pairs: b range out of bounds");
+	}
+	if (p->len_filter) {
+		MC2_REQUIRE(p->cutoff > 0, "pairs: cutoff must be > 0 when len_filter is set");
+	}
+	return MC2_OK;
+}
+
+int mc2_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs, double *score, double *dist,
+		    uint8_t *close, double *cache, double *raw, uint8_t *skipped)
+{
+	MC2_REQUIRE(ctx && model && pairs, "mc2_score_pairs: NULL argument");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	CtxExtra *x = extra(ctx);
+	PairArgs a;
+	int rc = fill_pair_args(ctx, pairs, a, x);
+	if (rc != MC2_OK) return rc;
+	const u64 m = pairs->n_pairs;
+	if (m == 0) return MC2_OK;
+	const u64 S = (u64)model->dm.n_singles;
+	if (score) { rc = ensure(x->d[B_SCORE], m * 8, false); if (rc) return rc; a.score = (double *)x->d[B_SCORE].p; }
+	if (dist) { rc = ensure(x->d[B_DIST], m * 8, false); if (rc) return rc; a.dist = (double *)x->d[B_DIST].p; }
+	if (close) { rc = ensure(x->d[B_CLOSE], m, false); if (rc) return rc; a.close = (uint8_t *)x->d[B_CLOSE].p; }
+	if (skipped) { rc = ensure(x->d[B_SKIP], m, false); if (rc) return rc; a.skipped = (uint8_t *)x->d[B_SKIP].p; }
+	if (cache) { rc = ensure(x->d[B_CACHE], m * S * 8, false); if (rc) return rc; a.cache = (double *)x->d[B_CACHE].p; MC2_CUDA(cudaMemsetAsync(a.cache, 0, m * S * 8, ctx->stream)); }
+	if (raw) { rc = ensure(x->d[B_RAW], m * S * 8, false); if (rc) return rc; a.raw = (double *)x->d[B_RAW].p; MC2_CUDA(cudaMemsetAsync(a.raw, 0, m * S * 8, ctx->stream)); }
+	rc = reset_err(ctx);
+	if (rc == MC2_OK) rc = launch_pair_score(ctx, model->dm, a);
+	if (rc == MC2_OK) rc = fetch_err(ctx);
+	if (rc != MC2_OK) return rc;
+	cudaStream_t st = ctx->stream;
+	if (score) MC2_CUDA(cudaMemcpyAsync(score, a.score, m * 8, cudaMemcpyDeviceToHost, st));
+	if (dist) MC2_CUDA(cudaMemcpyAsync(dist, a.dist, m * 8, cudaMemcpyDeviceToHost, st));
+	if (close) MC2_CUDA(cudaMemcpyAsync(close, a.close, m, cudaMemcpyDeviceToHost, st));
+	if (skipped) MC2_CUDA(cudaMemcpyAsync(skipped, a.skipped, m, cudaMemcpyDeviceToHost, st));
+	if (cache) MC2_CUDA(cudaMemcpyAsync(cache, a.cache, m * S * 8, cudaMemcpyDeviceToHost, st));
+	if (raw) MC2_CUDA(cudaMemcpyAsync(raw, a.raw, m * S * 8, cudaMemcpyDeviceToHost, st));
+	MC2_CUDA(cudaStreamSynchronize(st));
+	return check_err(ctx);
+}
+
+struct ArgOutHost {
+	long long best;
+	double best_dist;
+	int is_min;
+	int has;
+};
+
+// shared by get_close / merge / filter: score on device, reduce on device, copy back only what the caller reads
+static int score_and_reduce(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs, int reduce_mode, ArgOutHost *red,
+			    uint8_t *close_out, uint8_t *skipped_out)
+{
+	CtxExtra *x = extra(ctx);
+	PairArgs a;
+	int rc = fill_pair_args(ctx, pairs, a, x);
+	if (rc != MC2_OK) return rc;
+	const u64 m = pairs->n_pairs;
+	rc = ensure(x->d[B_DIST], m * 8, false); if (rc) return rc;
+	rc = ensure(x->d[B_CLOSE], m, false); if (rc) return rc;
+	rc = ensure(x->d[B_SKIP], m, false); if (rc) return rc;
+	a.dist = (double *)x->d[B_DIST].p;
+	a.close = (uint8_t *)x->d[B_CLOSE].p;
+	a.skipped = (uint8_t *)x->d[B_SKIP].p;
+	rc = reset_err(ctx);
+	if (rc == MC2_OK) rc = launch_pair_score(ctx, model->dm, a);
+	if (rc == MC2_OK && reduce_mode >= 0) rc = launch_argmax(ctx, a.dist, a.skipped, a.close, m, reduce_mode, ctx->d_slot);
+	if (rc == MC2_OK) rc = fetch_err(ctx);
+	if (rc != MC2_OK) return rc;
+	cudaStream_t st = ctx->stream;
+	if (reduce_mode >= 0) MC2_CUDA(cudaMemcpyAsync(ctx->h_slot, ctx->d_slot, sizeof(ArgOutHost), cudaMemcpyDeviceToHost, st));
+	if (close_out) MC2_CUDA(cudaMemcpyAsync(close_out, a.close, m, cudaMemcpyDeviceToHost, st));
+	if (skipped_out) MC2_CUDA(cudaMemcpyAsync(skipped_out, a.skipped, m, cudaMemcpyDeviceToHost, st));
+	MC2_CUDA(cudaStreamSynchronize(st));
+	if (reduce_mode >= 0) *red = *reinterpret_cast<ArgOutHost *>(ctx->h_slot);
+	return check_err(ctx);
+}
+
+int mc2_get_close(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, uint64_t q, const mc2_hset *set_c,
+		  const uint64_t *cand, uint64_t cand_begin, uint64_t n_cand, double cutoff, int64_t *best,
+		  double *best_dist, int32_t *is_min, uint8_t *marks)
+{
+	MC2_REQUIRE(ctx && model && set_q && set_c && best && best_dist && is_min, "mc2_get_close: NULL argument");
+	MC2_REQUIRE(q < set_q->n, "mc2_get_close: query row out of range");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	*best = -1;
+	*best_dist = -1;
+	*is_min = 1;
+	if (n_cand == 0) return MC2_OK;
+	mc2_pairs p;
+	memset(&p, 0, sizeof p);
+	p.set_a = set_c; // compute(candidate, query): candidate is the first argument (Trainer.cpp:49)
+	p.set_b = set_q;
+	p.n_pairs = n_cand;
+	p.ia = cand;
+	p.a_begin = cand_begin;
+	p.b_begin = q;
+	p.b_broadcast = 1;
+	p.len_filter = 1;
+	p.anchor_is_b = 1;
+	p.cutoff = cutoff;
+	ArgOutHost r;
+	int rc = score_and_reduce(ctx, model, &p, 0, &r, marks, nullptr);
+	if (rc != MC2_OK) return rc;
+	*best = r.best;
+	*best_dist = r.best_dist;
+	*is_min = r.is_min;
+	return MC2_OK;
+}
+
+int mc2_filter(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint64_t center, const mc2_hset *set_m,
+	       const uint64_t *members, uint64_t n_members, double id, uint8_t *keep)
+{
+	MC2_REQUIRE(ctx && model && set_c && set_m && (n_members == 0 || (members && keep)), "mc2_filter: NULL argument");
+	MC2_REQUIRE(center < set_c->n, "mc2_filter: center row out of range");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	if (n_members == 0) return MC2_OK;
+	mc2_pairs p;
+	memset(&p, 0, sizeof p);
+	p.set_a = set_c; // classify(center, member), Trainer.cpp:133
+	p.set_b = set_m;
+	p.n_pairs = n_members;
+	p.a_begin = center;
+	p.a_broadcast = 1;
+	p.ib = members;
+	p.len_filter = 1;
+	p.anchor_is_b = 0;
+	p.cutoff = id;
+	// keep <=> in window and round(score) != 0 ; the kernel's close flag is round(score) > 0 and score >= 0 always
+	// holds for logistic(sum)+bias with bias >= -0.5; for generality fetch the scores when bias is negative.
+	if (model->dm.bias < 0) {
+		std::vector<double> sc(n_members);
+		std::vector<uint8_t> sk(n_members);
+		int rc = mc2_score_pairs(ctx, model, &p, sc.data(), nullptr, nullptr, nullptr, nullptr, sk.data());
+		if (rc != MC2_OK) return rc;
+		for (u64 j = 0; j < n_members; j++) {
+			keep[j] = !sk[j] && std::round(sc[j]) != 0;
+		}
+		return MC2_OK;
+	}
+	return score_and_reduce(ctx, model, &p, -1, nullptr, keep, nullptr);
+}
+
+int mc2_merge(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *centers, const uint64_t *rows, int64_t cur,
+	      int64_t begin, int64_t last, double id, int64_t *out)
+{
+	MC2_REQUIRE(ctx && model && centers && rows && out, "mc2_merge: NULL argument");
+	MC2_REQUIRE(cur >= 0 && begin >= 0, "mc2_merge: negative index");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	*out = 0;
+	if (last < begin) return MC2_OK;
+	mc2_pairs p;
+	memset(&p, 0, sizeof p);
+	p.set_a = centers; // compute(*cen, *p): the other center first (Trainer.cpp:93)
+	p.set_b = centers;
+	p.n_pairs = (u64)(last - begin + 1);
+	p.ia = rows + begin;
+	p.b_begin = rows[cur];
+	p.b_broadcast = 1;
+	p.len_filter = 1;
+	p.anchor_is_b = 1;
+	p.cutoff = id;
+	MC2_REQUIRE(rows[cur] < centers->n, "mc2_merge: current center row out of range");
+	ArgOutHost r;
+	int rc = score_and_reduce(ctx, model, &p, 1, &r, nullptr, nullptr);
+	if (rc != MC2_OK) return rc;
+	// mode 1 returns the position inside [begin,last] of the winner; has == 0 when no candidate is close
+	*out = r.has ? begin + r.best : 0;
+	return MC2_OK;
+}
+
+int mc2_all_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, uint64_t q_begin, uint64_t q_end,
+		  const mc2_hset *set_d, uint64_t d_begin, uint64_t d_end, int32_t upper_only, double cutoff,
+		  uint64_t max_out, uint64_t *out_q, uint64_t *out_d, double *out_score, uint64_t *n_out,
+		  uint64_t *n_scored)
+{
+	MC2_REQUIRE(ctx && model && set_q && set_d && n_out, "mc2_all_pairs: NULL argument");
+	MC2_REQUIRE(q_begin <= q_end && q_end <= set_q->n && d_begin <= d_end && d_end <= set_d->n, "mc2_all_pairs: row range out of bounds");
+	MC2_REQUIRE(set_q->k == set_d->k && set_q->eb == set_d->eb, "mc2_all_pairs: the two sets differ in k or histogram width");
+	MC2_REQUIRE(cutoff > 0, "mc2_all_pairs: cutoff must be > 0");
+	MC2_REQUIRE(!model->dm.regression, "mc2_all_pairs: needs a classifier model");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	*n_out = 0;
+	if (n_scored) *n_scored = 0;
+	if (q_begin == q_end || d_begin == d_end) return MC2_OK;
+	CtxExtra *x = extra(ctx);
+	int rc;
+	u64 cap = max_out ? max_out : 1;
+	rc = ensure(x->d[B_OUTQ], cap * 8, false); if (rc) return rc;
+	rc = ensure(x->d[B_OUTD], cap * 8, false); if (rc) return rc;
+	rc = ensure(x->d[B_OUTS], cap * 8, false); if (rc) return rc;
+	rc = ensure(x->d[B_MISC], 64, false); if (rc) return rc;
+	u64 *d_counters = (u64 *)x->d[B_MISC].p;
+	MC2_CUDA(cudaMemsetAsync(d_counters, 0, 64, ctx->stream));
+	rc = reset_err(ctx);
+	if (rc == MC2_OK)
+		rc = launch_all_pairs(ctx, model->dm, set_q, q_begin, q_end, set_d, d_begin, d_end, upper_only, cutoff, max_out,
+				      (u64 *)x->d[B_OUTQ].p, (u64 *)x->d[B_OUTD].p, (double *)x->d[B_OUTS].p, d_counters);
+	if (rc == MC2_OK) rc = fetch_err(ctx);
+	if (rc != MC2_OK) return rc;
+	cudaStream_t st = ctx->stream;
+	MC2_CUDA(cudaMemcpyAsync(ctx->h_slot, d_counters, 16, cudaMemcpyDeviceToHost, st));
+	MC2_CUDA(cudaStreamSynchronize(st));
+	u64 total = ((u64 *)ctx->h_slot)[0];
+	if (n_scored) *n_scored = ((u64 *)ctx->h_slot)[1];
+	*n_out = total;
+	u64 got = total < max_out ? total : max_out;
+	if (got) {
+		if (out_q) MC2_CUDA(cudaMemcpyAsync(out_q, x->d[B_OUTQ].p, got * 8, cudaMemcpyDeviceToHost, st));
+		if (out_d) MC2_CUDA(cudaMemcpyAsync(out_d, x->d[B_OUTD].p, got * 8, cudaMemcpyDeviceToHost, st));
+		if (out_score) MC2_CUDA(cudaMemcpyAsync(out_score, x->d[B_OUTS].p, got * 8, cudaMemcpyDeviceToHost, st));
+		MC2_CUDA(cudaStreamSynchronize(st));
+	}
+	return check_err(ctx);
+}
+
+int mc2_distance(mc2_ctx *ctx, const mc2_pairs *pairs, uint64_t *out)
+{
+	MC2_REQUIRE(ctx && pairs && out, "mc2_distance: NULL argument");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	CtxExtra *x = extra(ctx);
+	PairArgs a;
+	int rc = fill_pair_args(ctx, pairs, a, x);
+	if (rc != MC2_OK) return rc;
+	const u64 m = pairs->n_pairs;
+	if (m == 0) return MC2_OK;
+	rc = ensure(x->d[B_MISC], m * 8 + 64, false); if (rc) return rc;
+	rc = launch_distance(ctx, a, (u64 *)x->d[B_MISC].p);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaMemcpyAsync(out, x->d[B_MISC].p, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC2_OK;
+}
+
+/* ---- device-timed bench helpers ---------------------------------------------------------------- */
+int mc2_bench_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs, int iters, int flush_l2,
+			  float *avg_ms, uint64_t *n_close)
+{
+	MC2_REQUIRE(ctx && model && pairs && avg_ms && iters > 0, "mc2_bench_score_pairs: bad argument");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	CtxExtra *x = extra(ctx);
+	PairArgs a;
+	int rc = fill_pair_args(ctx, pairs, a, x);
+	if (rc != MC2_OK) return rc;
+	const u64 m = pairs->n_pairs;
+	rc = ensure(x->d[B_SCORE], m * 8, false); if (rc) return rc;
+	rc = ensure(x->d[B_CLOSE], m, false); if (rc) return rc;
+	rc = ensure(x->d[B_MISC], 64, false); if (rc) return rc;
+	a.score = (double *)x->d[B_SCORE].p;
+	a.close = (uint8_t *)x->d[B_CLOSE].p;
+	a.n_close = (u64 *)x->d[B_MISC].p;
+	rc = reset_err(ctx);
+	if (rc != MC2_OK) return rc;
+	double total = 0;
+	for (int it = 0; it < iters; it++) {
+		if (flush_l2) {
+			rc = mc2_ctx_flush_l2(ctx, 256u << 20);
+			if (rc != MC2_OK) return rc;
+		}
+		MC2_CUDA(cudaMemsetAsync(a.n_close, 0, 8, ctx->stream));
+		MC2_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+		rc = launch_pair_score(ctx, model->dm, a);
+		if (rc != MC2_OK) return rc;
+		MC2_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+		MC2_CUDA(cudaEventSynchronize(ctx->ev1));
+		float ms = 0;
+		MC2_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		total += ms;
+	}
+	*avg_ms = (float)(total / iters);
+	rc = fetch_err(ctx);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaMemcpyAsync(ctx->h_slot, a.n_close, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (n_close) *n_close = *(u64 *)ctx->h_slot;
+	return check_err(ctx);
+}
+
+int mc2_bench_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, int iters, int flush_l2,
+			  float *avg_ms)
+{
+	MC2_REQUIRE(ctx && seqs && avg_ms && iters > 0, "mc2_bench_count_kmers: bad argument");
+	int rc = check_k_eb(k, elem_bytes);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	mc2_hset *h = nullptr;
+	rc = alloc_hset(ctx, seqs->n, k, elem_bytes, &h);
+	if (rc != MC2_OK) return rc;
+	double total = 0;
+	rc = reset_err(ctx);
+	for (int it = 0; it < iters && rc == MC2_OK; it++) {
+		if (flush_l2) rc = mc2_ctx_flush_l2(ctx, 256u << 20);
+		if (rc != MC2_OK) break;
+		cudaEventRecord(ctx->ev0, ctx->stream);
+		rc = launch_count(ctx, seqs, k, elem_bytes, h, 1);
+		cudaEventRecord(ctx->ev1, ctx->stream);
+		cudaEventSynchronize(ctx->ev1);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+		total += ms;
+	}
+	mc2_hset_free(h);
+	if (rc != MC2_OK) return rc;
+	*avg_ms = (float)(total / iters);
+	return MC2_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,167 @@
+// mc2_internal.cuh — shared device/host structures of libmeshclust2_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/meshclust2_b200.h"
+
+typedef unsigned long long u64;
+typedef long long s64;
+typedef unsigned int u32;
+
+namespace mc2 {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define MC2_CUDA(expr)                                                         \
+	do {                                                                   \
+		cudaError_t _e = (expr);                                       \
+		if (_e != cudaSuccess) {                                       \
+			return mc2::cuda_fail(_e, #expr, __FILE__, __LINE__);  \
+		}                                                              \
+	} while (0)
+
+#define MC2_REQUIRE(cond, msg)                         \
+	do {                                           \
+		if (!(cond)) {                         \
+			mc2::set_error(msg);           \
+			return MC2_ERR_ARG;            \
+		}                                      \
+	} while (0)
+
+// internal single-feature codes (dense, so the kernel can switch on a small int)
+enum SingleCode : int {
+	SC_MANHATTAN = 0,
+	SC_EUCLIDEAN,
+	SC_NORMALIZED_VECTORS,
+	SC_JEFFEREY,
+	SC_PEARSON,
+	SC_INTERSECTION,
+	SC_EMD,
+	SC_LENGTHD,
+	SC_KULCZYNSKI2,
+	SC_SIMRATIO,
+	SC_JENSEN_SHANNON,
+	SC_COUNT
+};
+
+// which reductions over the bins a model needs
+enum NeedBits : int { NEED_MIN = 1, NEED_DOT = 2, NEED_EMD = 4, NEED_LOG = 8 };
+
+struct DevModel {
+	int n_singles;
+	int code[MC2_MAX_SINGLES];
+	int is_sim[MC2_MAX_SINGLES];
+	double smin[MC2_MAX_SINGLES];
+	double smax[MC2_MAX_SINGLES];
+	int n_combos;
+	int kind[MC2_MAX_COMBOS];
+	int nidx[MC2_MAX_COMBOS];
+	int idx[MC2_MAX_COMBOS][MC2_MAX_COMBO_IDX];
+	double weight[MC2_MAX_COMBOS + 1];
+	double bias;
+	int regression;
+	int need;
+};
+
+// side-band SoA of a histogram set (device pointers)
+struct Sideband {
+	const u64 *mag;   // pseudo-magnitude as the host object reports it (may be stale, quirk Q4)
+	const u64 *sum;   // true sum of the bins
+	const u64 *sumsq; // true sum of squared bins (exact for u8/u16; wraps like the reference's u64 for wider)
+	const u64 *len;   // get_length()
+};
+
+} // namespace mc2
+
+struct mc2_ctx {
+	int device;
+	int sm_count;
+	cudaStream_t stream;
+	cudaEvent_t ev0, ev1;
+	u64 launches;
+	// scratch
+	void *flush_buf;
+	size_t flush_bytes;
+	int *d_err;       // device error word (sticky per call)
+	int *h_err;       // pinned mirror
+	void *h_slot;     // pinned result slot (4 KB)
+	void *d_slot;     // device result slot (4 KB)
+	void *extra;      // CtxExtra (growable scratch buffers), owned by mc2_api.cu
+};
+
+struct mc2_seqs {
+	mc2_ctx *ctx;
+	u64 n;
+	u64 total_bases;
+	u64 max_len;
+	u32 *packed;      // 2-bit packed, big-endian within each 32-bit word; every sequence starts on a 16-byte boundary
+	u64 *word_off;    // [n+1] word offset of each sequence
+	u64 *len;         // [n] bases
+	int *segs;        // [2*total_segs] inclusive, sequence-relative
+	u64 *seg_off;     // [n+1]
+	u64 total_segs;
+	u64 total_words;
+};
+
+struct mc2_hset {
+	mc2_ctx *ctx;
+	u64 n;
+	int k;
+	u64 N;
+	int eb;
+	void *bins;       // n x N elements
+	u64 *mag, *sum, *sumsq, *len;
+	u64 *mers1;       // n x 4 (0 when built from host)
+	double *stddev;   // n
+	int *novf;        // n
+	u32 *maxc;        // n : largest unsaturated count+1
+	u64 max_sum;      // host-known upper bound of sum[] (selects fast paths)
+};
+
+struct mc2_model {
+	mc2_ctx *ctx;
+	mc2_model_desc desc;
+	mc2::DevModel dm;
+};
+
+namespace mc2 {
+
+// launchers implemented in the .cu files
+struct PairArgs {
+	const void *binsA;
+	const void *binsB;
+	Sideband sbA, sbB;
+	u64 N;
+	int eb;
+	u64 n_pairs;
+	const u64 *ia; // device or NULL
+	const u64 *ib;
+	u64 a_begin, b_begin;
+	int a_bc, b_bc;
+	int len_filter, anchor_is_b;
+	double cutoff;
+	double *score;
+	double *dist;
+	uint8_t *close;
+	double *cache;
+	double *raw;
+	uint8_t *skipped;
+	u64 *n_close;  // optional device counter
+	int *err;      // device error word
+	u64 max_sum;   // bound on bin sums of both sets
+};
+
+int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a);
+int launch_argmax(mc2_ctx *ctx, const double *dist, const uint8_t *skipped, const uint8_t *close, u64 n, int mode,
+		  void *d_out);
+int launch_count(mc2_ctx *ctx, const mc2_seqs *s, int k, int eb, mc2_hset *h, u64 init_value);
+int launch_sideband(mc2_ctx *ctx, mc2_hset *h, bool set_mag);
+int launch_pack(mc2_ctx *ctx, const char *d_codes, const u64 *d_seq_off, mc2_seqs *s);
+int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0, u64 q1, const mc2_hset *d, u64 d0, u64 d1,
+		     int upper_only, double cutoff, u64 max_out, u64 *d_out_q, u64 *d_out_d, double *d_out_score,
+		     u64 *d_counters);
+int launch_distance(mc2_ctx *ctx, const PairArgs &a, u64 *d_out);
+
+} // namespace mc2

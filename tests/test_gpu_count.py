@@ -1,0 +1,127 @@
+"""GPU: K1 (k-mer histograms) through the C ABI vs the oracle and the reference-generated golden vectors. Bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import port
+from meshclust2_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _upload(capi, ctx, seqs):
+    enc = capi.encode_batch(seqs, threads=4)
+    return ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
+
+
+def _check_against_oracle(got, seqs, k, eb):
+    for i, s in enumerate(seqs):
+        w = port.get_point(s, k, eb)
+        assert np.array_equal(got["hist"][i], w["hist"]), (k, eb, i)
+        assert np.array_equal(got["mers1"][i], w["mers1"]), (k, eb, i)
+        assert got["mag"][i] == w["mag"] and got["len"][i] == w["len"], (k, eb, i)
+        assert got["n_overflow"][i] == w["n_overflow"], (k, eb, i)
+        assert abs(got["stddev"][i] - w["stddev"]) <= 1e-12 * max(1.0, w["stddev"]), (k, eb, i)
+
+
+@pytest.mark.parametrize("k,eb", [(5, 1), (3, 2), (2, 4), (4, 8), (6, 1), (3, 1)])
+def test_golden_histograms(built_lib, ctx, golden, golden_seqs, k, eb):
+    tag = "k%d_eb%d" % (k, eb)
+    hs = ctx.count_kmers(_upload(built_lib, ctx, golden_seqs), k, eb)
+    got = hs.download()
+    assert np.array_equal(got["hist"], golden["hist_" + tag])
+    assert np.array_equal(got["mers1"], golden["mers1_" + tag])
+    assert np.array_equal(got["mag"], golden["mag_" + tag])
+    assert np.array_equal(got["len"], golden["len_" + tag])
+    assert np.abs(got["stddev"] - golden["stddev_" + tag]).max() <= 1e-12 * max(1.0, golden["stddev_" + tag].max())
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("eb", [1, 2, 4, 8])
+def test_random_and_adversarial_vs_oracle(built_lib, ctx, k, eb):
+    rng = np.random.default_rng(100 * k + eb)
+    n = 40 if k <= 7 else 6
+    seqs, _ = synth.make_set(n, 600, 5, 0.1, seed=k * 10 + eb)
+    seqs = list(seqs)
+    a = bytearray(seqs[0]); a[100:130] = b"N" * 30; a[300:305] = b"N" * 5; seqs[0] = bytes(a)     # split + bridged gaps
+    seqs[1] = seqs[1].lower()
+    seqs[2] = b"A" * 900                                                                          # saturation for u8/u16? (u8 only)
+    seqs[3] = b"ACGT"[: max(1, k - 1)] * 1                                                        # shorter than k
+    seqs[4] = b"ACG" + b"N" * 40 + b"ACGTACGTACGTACGTACGTACGTAC" + b"N" * 12 + b"TTTTTTTTTTTTTTTTTTTTTTTTTGA"
+    seqs[5] = bytes(rng.choice(list(b"ACGTRYMKSWHBVD"), size=500).tolist())                       # IUPAC
+    hs = ctx.count_kmers(_upload(built_lib, ctx, seqs), k, eb)
+    _check_against_oracle(hs.download(), seqs, k, eb)
+
+
+def test_long_sequences_cta_path(built_lib, ctx):
+    # > 4096 bases on average: CTA-per-sequence path; multi-segment like --single-file (50 N between contigs)
+    seqs = synth.make_single_file(6, 4, 3000, seed=3)
+    for k, eb in ((5, 1), (7, 2), (8, 2)):
+        hs = ctx.count_kmers(_upload(built_lib, ctx, seqs), k, eb)
+        _check_against_oracle(hs.download(), seqs, k, eb)
+
+
+def test_u8_saturation_and_overflow_count(built_lib, ctx):
+    seqs = [b"A" * 2000, b"AC" * 400 + b"N" * 30 + b"AC" * 400, b"ACGT" * 100]
+    hs = ctx.count_kmers(_upload(built_lib, ctx, seqs), 2, 1)
+    got = hs.download()
+    assert got["hist"].max() == 255
+    _check_against_oracle(got, seqs, 2, 1)
+    assert got["n_overflow"][0] == 1 and got["n_overflow"][1] == 2 and got["n_overflow"][2] == 0
+
+
+def test_empty_batch_and_empty_sequence(built_lib, ctx):
+    hs = ctx.count_kmers(_upload(built_lib, ctx, []), 3, 1)
+    assert len(hs) == 0
+    seqs = [b"N" * 30, b"ACGTACGTACGTACGTACGTACGT"]
+    hs = ctx.count_kmers(_upload(built_lib, ctx, seqs), 3, 2)
+    got = hs.download()
+    assert (got["hist"][0] == 1).all() and got["len"][0] == 0
+    _check_against_oracle(got, seqs, 3, 2)
+
+
+def test_invalid_code_inside_segment_is_an_error(built_lib, ctx):
+    codes = np.array([0, 1, 2, 3, 7, 1, 2, 3, 0, 1], dtype=np.int8)
+    with pytest.raises(built_lib.Mc2Error) as e:
+        ctx.upload_seqs(codes, [0, 10], np.array([[0, 9]], dtype=np.int32), [0, 1])
+    assert e.value.status == -3
+    # the same byte outside every segment is fine (the reference leaves 'N' there)
+    sq = ctx.upload_seqs(codes, [0, 10], np.array([[0, 3], [5, 9]], dtype=np.int32), [0, 2])
+    got = ctx.count_kmers(sq, 2, 1).download()
+    want, m1, _ = port.count(codes, np.array([[0, 3], [5, 9]]), 2, 1)
+    assert np.array_equal(got["hist"][0], want)
+
+
+@pytest.mark.parametrize("eb", [1, 2, 4, 8])
+def test_kmer_hash_table_increment(built_lib, ctx, eb):
+    """KmerHashTable<unsigned long,V>(k, init).wholesaleIncrementNoOverflow(seq, first, last)"""
+    rng = np.random.default_rng(eb)
+    codes = rng.integers(0, 4, 300).astype(np.int8)
+    for k, first, last, init in ((3, 0, 297, 1), (5, 10, 200, 1), (2, 5, 5, 0), (4, 0, 296, 250)):
+        vals, ret = ctx.kmer_table_increment(codes, first, last, k, eb, init)
+        want = np.full(4 ** k, init, dtype=np.uint64)
+        tmax = np.iinfo(port.DTYPES[eb]).max
+        wret = 0
+        for p in range(first, last + 1):
+            h = 0
+            for t in range(k):
+                h = h * 4 + int(codes[p + t])
+            if want[h] < tmax:
+                want[h] += 1
+            else:
+                wret = -1
+        assert np.array_equal(vals.astype(np.uint64), want) and ret == wret
+
+
+def test_full_size_property_cfg2_shape(built_lib, ctx):
+    """At a BASELINE size (10k x 1.5 kb) check size-independent invariants: mag == N + #k-mers, 1-mers sum to len + 4,
+    and a checksum of histograms equals the oracle's on a strided sample."""
+    seqs, _ = synth.make_set(10000, 1500, 200, 0.03, seed=42)
+    hs = ctx.count_kmers(_upload(built_lib, ctx, seqs), 5, 1)
+    got = hs.download()
+    lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+    assert np.array_equal(got["len"], lens)
+    unsat = got["hist"].max(axis=1) < 255
+    assert np.array_equal(got["mag"][unsat], (1024 + lens - 4)[unsat])
+    assert np.array_equal(got["mers1"].sum(axis=1), lens + 4)
+    for i in range(0, 10000, 397):
+        assert np.array_equal(got["hist"][i], port.get_point(seqs[i], 5, 1)["hist"])

@@ -1,0 +1,329 @@
+"""GPU: K2 (pair features + GLM + cutoff) through the C ABI vs the oracle and the reference-generated golden vectors.
+Integer-valued singles bit-exact; floating-point singles, caches and scores within REL_TOL = 1e-9 (north_star: 1e-6);
+close flags identical except pairs whose score sits within 1e-9 of the 0.5 decision boundary."""
+import numpy as np
+import pytest
+
+from conftest import weights_path, weights_text
+from helpers import FAST, SLOW, REL_TOL, all_singles_model, assert_close_rel, assert_flags_match, synth_hist, to_desc
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+INT_SINGLES = {port.FEAT["manhattan"], port.FEAT["emd"], port.FEAT["length_difference"]}
+
+
+def _side(H, rng, stale=False):
+    n = H.shape[0]
+    mag = H.sum(axis=1, dtype=np.uint64)
+    if stale:
+        mag = mag.copy()
+        mag[::3] += 13
+        mag[1::5] -= 3
+    ln = rng.integers(800, 1300, n).astype(np.uint64)
+    return mag, ln
+
+
+@pytest.mark.parametrize("wname", ["weights_cfg1_id90", "weights_appendixD_id90"])
+def test_golden_classifier(built_lib, ctx, golden, wname):
+    H, ln, mag = golden["hist_k5_eb1"], golden["len_k5_eb1"], golden["mag_k5_eb1"]
+    hs = ctx.hset_from_host(H, 5, mag=None, length=ln)
+    gm = ctx.model_from_file(weights_path(wname))
+    ja, jb = golden["score_ia"], golden["score_ib"]
+    g = ctx.score_pairs(gm, hs, hs, ja, jb)
+    assert np.abs(g["score"] - golden[wname + "_score"]).max() <= 1e-9
+    assert_close_rel(g["cache"], golden[wname + "_cache"], REL_TOL, "cache")
+    assert_close_rel(g["dist"], golden[wname + "_dist"], 1e-8, "dist")
+    assert_flags_match(g["close"], golden[wname + "_close"], golden[wname + "_score"])
+    assert g["close"].any()
+    # stale pseudo-magnitudes (quirk Q4): host-supplied mag is what intersection/kulczynski2/pearson must read
+    hs2 = ctx.hset_from_host(H, 5, mag=golden["stale_mag_k5_eb1"], length=ln)
+    g2 = ctx.score_pairs(gm, hs2, hs2, ja, jb, want=("score", "close"))
+    assert np.abs(g2["score"] - golden[wname + "_stale_score"]).max() <= 1e-9
+    assert_flags_match(g2["close"], golden[wname + "_stale_close"], golden[wname + "_stale_score"])
+    # callers
+    cand = golden["cand"]
+    for t, q in enumerate(golden[wname + "_gc_q"]):
+        best, bd, ismin, marks = ctx.get_close(gm, hs, int(q), hs, cand=cand, cutoff=0.9)
+        assert best == golden[wname + "_gc_best"][t]
+        assert abs(bd - golden[wname + "_gc_dist"][t]) <= 1e-9
+        assert ismin == bool(golden[wname + "_gc_ismin"][t])
+        assert np.array_equal(marks, golden[wname + "_gc_marks"][t])
+        keep = ctx.filter(gm, hs, int(q), hs, cand, 0.9)
+        assert np.array_equal(keep, golden[wname + "_filter_keep"][t])
+        rows = cand[(np.arange(8) + int(q)) % len(cand)]
+        assert ctx.merge(gm, hs, rows, 0, 1, 7, 0.9) == golden[wname + "_merge"][t]
+
+
+@pytest.mark.parametrize("k,eb", [(5, 1), (3, 2), (2, 4), (4, 8)])
+def test_golden_raw_singles(built_lib, ctx, golden, k, eb):
+    """every in-scope raw single for every width against the reference's own static Feature<T>::xxx outputs"""
+    tag = "k%d_eb%d" % (k, eb)
+    H, ln = golden["hist_" + tag], golden["len_" + tag]
+    names = [str(x) for x in golden["single_names"]]
+    ia, ib = golden["pair_ia"], golden["pair_ib"]
+    ok = (ln[ia] > 0) & (ln[ib] > 0)           # zero lengths make length_difference throw; tested separately
+    ia, ib, want = ia[ok], ib[ok], golden["raw_" + tag][ok]
+    hs = ctx.hset_from_host(H, k, length=ln)
+    flags = [port.FEAT[n] for n in names]
+    singles = [(f, 0.0, 1.0) for f in flags]
+    combos = [(0, [i]) for i in range(len(flags))]
+    gm = ctx.model(built_lib.make_desc(singles, combos, [0.0] * (len(flags) + 1)))
+    g = ctx.score_pairs(gm, hs, hs, ia, ib, want=("raw",))
+    for c, nm in enumerate(names):
+        fin = np.isfinite(want[:, c])
+        if nm in ("manhattan", "emd", "length_difference"):
+            assert np.array_equal(g["raw"][fin, c], want[fin, c]), nm
+        else:
+            assert_close_rel(g["raw"][fin, c], want[fin, c], REL_TOL, tag + " " + nm)
+
+
+def test_golden_raw_singles_stale(built_lib, ctx, golden):
+    H, ln, mag = golden["hist_k5_eb1"], golden["len_k5_eb1"], golden["stale_mag_k5_eb1"]
+    names = [str(x) for x in golden["single_names"]]
+    ia, ib = golden["pair_ia"], golden["pair_ib"]
+    ok = (ln[ia] > 0) & (ln[ib] > 0)
+    ia, ib, want = ia[ok], ib[ok], golden["raw_stale_k5_eb1"][ok]
+    hs = ctx.hset_from_host(H, 5, mag=mag, length=ln)
+    flags = [port.FEAT[n] for n in names]
+    gm = ctx.model(built_lib.make_desc([(f, 0.0, 1.0) for f in flags], [(0, [i]) for i in range(len(flags))],
+                                       [0.0] * (len(flags) + 1)))
+    g = ctx.score_pairs(gm, hs, hs, ia, ib, want=("raw",))
+    fin = np.isfinite(want)
+    assert_close_rel(np.where(fin, g["raw"], 0), np.where(fin, want, 0), REL_TOL, "stale raw")
+
+
+@pytest.mark.parametrize("k,eb,flags", [
+    (5, 1, FAST), (6, 1, FAST), (4, 1, FAST), (2, 1, FAST), (1, 1, FAST),     # fast u8 path (k>=5) and generic (small k)
+    (5, 2, FAST), (4, 2, FAST), (3, 2, FAST), (7, 2, FAST),                  # fast u16 path (k>=4) and generic
+    (3, 4, FAST), (5, 4, FAST), (3, 8, FAST), (4, 8, FAST),                  # wide types: reference's wrap-around arithmetic
+    (5, 1, SLOW), (4, 2, SLOW), (3, 4, SLOW), (2, 8, SLOW),                  # + jefferey / jensen-shannon
+])
+def test_random_models_vs_oracle(built_lib, ctx, k, eb, flags):
+    rng = np.random.default_rng(1000 * k + 10 * eb + len(flags))
+    n = 96
+    hi = {1: 255, 2: 3000, 4: 100000, 8: 100000}[eb]
+    H = synth_hist(rng, n, k, eb, hi=hi if k <= 5 else min(hi, 40))
+    mag, ln = _side(H, rng, stale=True)
+    model = all_singles_model(flags, H, mag, ln, rng)
+    hs = ctx.hset_from_host(H, k, mag=mag, length=ln)
+    gm = ctx.model(to_desc(built_lib, model))
+    m = 700
+    ia, ib = rng.integers(0, n, m), rng.integers(0, n, m)
+    g = ctx.score_pairs(gm, hs, hs, ia, ib)
+    o = port.score_pairs(model, H, mag, ln, ia, ib)
+    what = "k=%d eb=%d S=%d" % (k, eb, len(flags))
+    assert_close_rel(g["cache"], o["cache"], 1e-8, what + " cache")
+    assert np.abs(g["score"] - o["score"]).max() <= 1e-8, what
+    assert_flags_match(g["close"], o["close"], o["score"], tol=1e-8, what=what)
+    assert not g["skipped"].any()
+
+
+@pytest.mark.parametrize("eb", [1, 2])
+def test_extreme_histograms(built_lib, ctx, eb):
+    """all-ones, saturated, one-hot rows: exact integer reductions must survive the extremes"""
+    k, N = 5, 1024
+    dt = port.DTYPES[eb]
+    top = int(np.iinfo(dt).max)
+    H = np.ones((6, N), dtype=dt)
+    H[1, :] = top                       # saturated everywhere
+    H[2, 0] = top                       # one-hot first bin
+    H[3, N - 1] = top                   # one-hot last bin (largest EMD)
+    H[4, ::2] = top
+    H[5, :] = np.arange(N) % 200 + 1
+    ln = np.full(6, 1000, dtype=np.uint64)
+    names = ["manhattan", "euclidean", "normalized_vectors", "intersection", "emd", "kulczynski2", "simratio"]
+    flags = [port.FEAT[n] for n in names]
+    hs = ctx.hset_from_host(H, k, length=ln)
+    gm = ctx.model(built_lib.make_desc([(f, 0.0, 1.0) for f in flags], [(0, [i]) for i in range(len(flags))],
+                                       [0.0] * (len(flags) + 1)))
+    ia, ib = np.repeat(np.arange(6), 6), np.tile(np.arange(6), 6)
+    g = ctx.score_pairs(gm, hs, hs, ia, ib, want=("raw",))
+    mag = H.sum(axis=1, dtype=np.uint64)
+    for j, (a, b) in enumerate(zip(ia, ib)):
+        for c, nm in enumerate(names):
+            want = port.raw_single(port.FEAT[nm], H[a], H[b], int(mag[a]), int(mag[b]), 1000, 1000)
+            got = g["raw"][j, c]
+            if nm in ("manhattan", "emd"):
+                assert got == want, (nm, a, b, got, want)
+            else:
+                assert abs(got - want) <= REL_TOL * max(abs(want), 1e-300) or (np.isnan(got) and np.isnan(want)), (nm, a, b)
+
+
+def test_length_filter_and_broadcast_forms(built_lib, ctx, golden):
+    H, ln, mag = golden["hist_k5_eb1"], golden["len_k5_eb1"], golden["mag_k5_eb1"]
+    cand = golden["cand"]
+    Hc, lnc, magc = H[cand], ln[cand].copy(), mag[cand]
+    lnc[::4] = (lnc[::4] * 0.7).astype(np.uint64)          # push a quarter of the lengths out of the 0.9 window
+    lnc[1::6] = (lnc[1::6] * 1.3).astype(np.uint64)
+    hs = ctx.hset_from_host(Hc, 5, length=lnc)
+    m = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    gm = ctx.model_from_file(weights_path("weights_cfg1_id90"))
+    n = len(cand)
+    for q in (0, 5, 11):
+        # contiguous candidate range (no index list) and explicit list must agree with the oracle's get_close
+        for kw in (dict(cand=None, cand_begin=0, n_cand=n), dict(cand=np.arange(n))):
+            best, bd, ismin, marks = ctx.get_close(gm, hs, q, hs, cutoff=0.9, **kw)
+            ob = port.get_close(m, Hc, magc, lnc, q, np.arange(n), 0.9)
+            assert best == ob[0] and abs(bd - ob[1]) <= 1e-9 and ismin == ob[2] and np.array_equal(marks, ob[3])
+        r = ctx.score_pairs(gm, hs, hs, ia=np.arange(n), b_begin=q, b_bc=1, len_filter=1, anchor_is_b=1, cutoff=0.9)
+        lo, hi = int(float(lnc[q]) * 0.9), int(float(lnc[q]) / 0.9)
+        want_skip = (lnc < lo) | (lnc > hi)
+        assert np.array_equal(r["skipped"].astype(bool), want_skip) and want_skip.any() and not want_skip.all()
+        assert np.isnan(r["score"][want_skip]).all() and not r["close"][want_skip].any()
+        keep = ctx.filter(gm, hs, q, hs, np.arange(n), 0.9)
+        assert np.array_equal(keep, port.filter_members(m, Hc, magc, lnc, q, np.arange(n), 0.9))
+
+
+def test_get_close_none_in_window_and_empty(built_lib, ctx, golden):
+    H, ln = golden["hist_k5_eb1"][:8], golden["len_k5_eb1"][:8].copy()
+    ln[0] = 5000
+    hs = ctx.hset_from_host(H, 5, length=ln)
+    gm = ctx.model_from_file(weights_path("weights_cfg1_id90"))
+    best, bd, ismin, marks = ctx.get_close(gm, hs, 0, hs, cand=np.arange(1, 8), cutoff=0.9)
+    assert best == -1 and bd == -1 and ismin and not marks.any()
+    best, bd, ismin, marks = ctx.get_close(gm, hs, 0, hs, cand=np.zeros(0, dtype=np.uint64), cutoff=0.9)
+    assert best == -1 and ismin
+    assert ctx.merge(gm, hs, np.arange(8), 0, 1, 7, 0.9) == 0
+
+
+def test_zero_length_and_nan_are_errors(built_lib, ctx, golden):
+    H, ln = golden["hist_k5_eb1"][:4], golden["len_k5_eb1"][:4].copy()
+    gm = ctx.model_from_file(weights_path("weights_cfg1_id90"))       # uses length_difference and pearson
+    ln0 = ln.copy(); ln0[1] = 0
+    hs = ctx.hset_from_host(H, 5, length=ln0)
+    with pytest.raises(built_lib.Mc2Error) as e:                      # Feature::length_difference throws 123
+        ctx.score_pairs(gm, hs, hs, [0], [1])
+    assert e.value.status == -4
+    Hc = H.copy(); Hc[2, :] = 1                                        # zero variance -> pearson NaN -> reference throws
+    hs = ctx.hset_from_host(Hc, 5, length=ln)
+    with pytest.raises(built_lib.Mc2Error) as e:
+        ctx.score_pairs(gm, hs, hs, [0], [2])
+    assert e.value.status == -4
+
+
+def test_unsupported_feature_flag_is_rejected(built_lib, ctx):
+    d = built_lib.make_desc([(1 << 1, 0.0, 1.0)], [(0, [0])], [0.0, 1.0])      # FEAT_HELLINGER: out of scope (a9)
+    with pytest.raises(built_lib.Mc2Error) as e:
+        ctx.model(d)
+    assert e.value.status == -5
+
+
+def test_regression_model_clamps(built_lib, ctx, golden):
+    """Predictor::p_predict (similarity): sum clamped to [0,1], no logistic"""
+    H, ln, mag = golden["hist_k5_eb1"], golden["len_k5_eb1"], golden["mag_k5_eb1"]
+    m = port.Model.from_text(weights_text("weights_appendixD_id90"))
+    hs = ctx.hset_from_host(H, 5, length=ln)
+    gm = ctx.model(to_desc(built_lib, m, regression=1))
+    ja, jb = golden["score_ia"][:100], golden["score_ib"][:100]
+    g = ctx.score_pairs(gm, hs, hs, ja, jb, want=("score",))
+    want = np.array([port.predict_pair(m, H[a], H[b], int(mag[a]), int(mag[b]), int(ln[a]), int(ln[b])) for a, b in zip(ja, jb)])
+    assert np.abs(g["score"] - want).max() <= 1e-9 and (want == 0).any() and (want > 0).any()
+
+
+def test_bias_shifts_decisions(built_lib, ctx, golden):
+    H, ln, mag = golden["hist_k5_eb1"], golden["len_k5_eb1"], golden["mag_k5_eb1"]
+    m = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    m.bias = 0.3
+    hs = ctx.hset_from_host(H, 5, length=ln)
+    gm = ctx.model(to_desc(built_lib, m))
+    ja, jb = golden["score_ia"], golden["score_ib"]
+    g = ctx.score_pairs(gm, hs, hs, ja, jb, want=("score", "close"))
+    o = port.score_pairs(m, H, mag, ln, ja, jb)
+    assert np.abs(g["score"] - o["score"]).max() <= 1e-9 and np.array_equal(g["close"], o["close"])
+    assert g["close"].sum() > golden["weights_cfg1_id90_close"].sum()
+
+
+def test_distance(built_lib, ctx, golden):
+    H = golden["hist_k5_eb1"]
+    hs = ctx.hset_from_host(H, 5, length=golden["len_k5_eb1"])
+    got = ctx.distance(hs, hs, golden["pair_ia"], golden["pair_ib"])
+    assert np.array_equal(got, golden["distance_k5_eb1"])
+
+
+def test_symmetry_and_batch_equals_single(built_lib, ctx, golden):
+    H, ln = golden["hist_k5_eb1"], golden["len_k5_eb1"]
+    hs = ctx.hset_from_host(H, 5, length=ln)
+    gm = ctx.model_from_file(weights_path("weights_appendixD_id90"))
+    ja, jb = golden["score_ia"][:64], golden["score_ib"][:64]
+    ab = ctx.score_pairs(gm, hs, hs, ja, jb, want=("score", "raw"))
+    ba = ctx.score_pairs(gm, hs, hs, jb, ja, want=("score", "raw"))
+    assert_close_rel(ab["raw"], ba["raw"], 1e-12, "symmetric singles")
+    one = np.array([ctx.score_pairs(gm, hs, hs, [a], [b], want=("score",))["score"][0] for a, b in zip(ja, jb)])
+    assert np.array_equal(one, ab["score"])          # batched == one-by-one, bitwise
+
+
+def test_set_row_keeps_stale_mag(built_lib, ctx, golden):
+    """DivergencePoint::set copies bins + length but not mag (quirk Q4): mc2_hset_set_row mirrors that"""
+    H, ln = golden["hist_k5_eb1"][:6], golden["len_k5_eb1"][:6]
+    hs = ctx.hset_from_host(H, 5, length=ln)
+    centers = ctx.hset_from_host(H[:2], 5, length=ln[:2])
+    centers.set_row(0, hs, 4)
+    got = centers.download()
+    assert np.array_equal(got["hist"][0], H[4]) and got["len"][0] == ln[4]
+    assert got["mag"][0] == H[0].sum()                # still the old point's magnitude
+    m = port.Model.from_text(weights_text("weights_appendixD_id90"))
+    gm = ctx.model_from_file(weights_path("weights_appendixD_id90"))
+    g = ctx.score_pairs(gm, centers, hs, [0], [3], want=("score",))
+    Hc, magc = np.stack([H[4], H[3]]), np.array([H[0].sum(), H[3].sum()], dtype=np.uint64)
+    o = port.score_pairs(m, Hc, magc, np.array([ln[4], ln[3]]), [0], [1])
+    assert abs(g["score"][0] - o["score"][0]) <= 1e-9
+
+
+def test_all_pairs_sweep_vs_oracle(built_lib, ctx, golden):
+    """fastcar-style query-vs-database sweep with the length window and fused cutoff (FC_Runner.cpp:427-470)"""
+    H, ln, mag = golden["hist_k5_eb1"], golden["len_k5_eb1"], golden["mag_k5_eb1"]
+    cand = golden["cand"]
+    Hc, lnc, magc = H[cand], ln[cand], mag[cand]
+    n = len(cand)
+    hs = ctx.hset_from_host(Hc, 5, length=lnc)
+    m = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    gm = ctx.model_from_file(weights_path("weights_cfg1_id90"))
+    r = ctx.all_pairs(gm, hs, hs, 0.9, upper_only=True, max_out=n * n)
+    want = set()
+    scored = 0
+    ia, ib = [], []
+    for q in range(n):
+        lo, hi = int(float(lnc[q]) * 0.9), int(float(lnc[q]) / 0.9)
+        for c in range(q + 1, n):
+            if lo <= lnc[c] <= hi:
+                ia.append(c), ib.append(q)
+    o = port.score_pairs(m, Hc, magc, lnc, ia, ib)          # close(pts[i], query): database row first
+    want = {(b, a) for a, b, cl in zip(ia, ib, o["close"]) if cl}
+    got = set(zip(r["q"].tolist(), r["d"].tolist()))
+    assert r["n_scored"] == len(ia) and got == want and len(want) > 0
+    # capacity smaller than the survivor count: count still exact, payload truncated
+    r2 = ctx.all_pairs(gm, hs, hs, 0.9, upper_only=True, max_out=3)
+    assert r2["n_out"] == len(want) and len(r2["q"]) == 3
+    # rectangular block, not upper-only
+    r3 = ctx.all_pairs(gm, hs, hs, 0.9, q_range=(2, 9), d_range=(0, n), upper_only=False, max_out=n * n)
+    want3 = set()
+    for q in range(2, 9):
+        lo, hi = int(float(lnc[q]) * 0.9), int(float(lnc[q]) / 0.9)
+        cs = [c for c in range(n) if lo <= lnc[c] <= hi]
+        oo = port.score_pairs(m, Hc, magc, lnc, cs, [q] * len(cs))
+        want3 |= {(q, c) for c, cl in zip(cs, oo["close"]) if cl}
+    assert set(zip(r3["q"].tolist(), r3["d"].tolist())) == want3
+
+
+def test_full_size_properties_100k_one_vs_many(built_lib, ctx):
+    """BASELINE-size candidate scan (1 query x 100k candidates, k=5, u8): batch result equals chunked results bitwise,
+    scores symmetric under swapping sides, and a strided sample agrees with the oracle."""
+    rng = np.random.default_rng(9)
+    n = 100000
+    H = synth_hist(rng, n, 5, 1, hi=40)
+    ln = rng.integers(950, 1050, n).astype(np.uint64)
+    hs = ctx.hset_from_host(H, 5, length=ln)
+    m = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    gm = ctx.model_from_file(weights_path("weights_cfg1_id90"))
+    full = ctx.score_pairs(gm, hs, hs, a_begin=0, n_pairs=n, b_begin=7, b_bc=1, want=("score", "close"))
+    parts = [ctx.score_pairs(gm, hs, hs, a_begin=s, n_pairs=25000, b_begin=7, b_bc=1, want=("score",))["score"]
+             for s in range(0, n, 25000)]
+    assert np.array_equal(np.concatenate(parts), full["score"])
+    idx = np.arange(0, n, 997)
+    mag = H.sum(axis=1, dtype=np.uint64)
+    o = port.score_pairs(m, H, mag, ln, idx, np.full(len(idx), 7))
+    assert np.abs(full["score"][idx] - o["score"]).max() <= 1e-9
+    assert_flags_match(full["close"][idx], o["close"], o["score"])
+    best = ctx.get_close(gm, hs, 7, hs, cand_begin=0, n_cand=n, cutoff=0.9)
+    assert best[3][7] == 1            # the query itself is in the candidate range and is close to itself
