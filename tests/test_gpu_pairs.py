@@ -62,8 +62,11 @@ def test_golden_raw_singles(built_lib, ctx, golden, k, eb):
     H, ln = golden["hist_" + tag], golden["len_" + tag]
     names = [str(x) for x in golden["single_names"]]
     ia, ib = golden["pair_ia"], golden["pair_ib"]
-    ok = (ln[ia] > 0) & (ln[ib] > 0)           # zero lengths make length_difference throw; tested separately
+    # zero lengths make length_difference throw and all-ones histograms make pearson NaN (then the reference throws
+    # in normalize_cache); both are tested separately as error cases
+    ok = np.isfinite(golden["raw_" + tag]).all(axis=1)
     ia, ib, want = ia[ok], ib[ok], golden["raw_" + tag][ok]
+    assert ok.sum() > 100
     hs = ctx.hset_from_host(H, k, length=ln)
     flags = [port.FEAT[n] for n in names]
     singles = [(f, 0.0, 1.0) for f in flags]
@@ -82,7 +85,7 @@ def test_golden_raw_singles_stale(built_lib, ctx, golden):
     H, ln, mag = golden["hist_k5_eb1"], golden["len_k5_eb1"], golden["stale_mag_k5_eb1"]
     names = [str(x) for x in golden["single_names"]]
     ia, ib = golden["pair_ia"], golden["pair_ib"]
-    ok = (ln[ia] > 0) & (ln[ib] > 0)
+    ok = np.isfinite(golden["raw_stale_k5_eb1"]).all(axis=1)
     ia, ib, want = ia[ok], ib[ok], golden["raw_stale_k5_eb1"][ok]
     hs = ctx.hset_from_host(H, 5, mag=mag, length=ln)
     flags = [port.FEAT[n] for n in names]
@@ -124,7 +127,9 @@ def test_extreme_histograms(built_lib, ctx, eb):
     """all-ones, saturated, one-hot rows: exact integer reductions must survive the extremes"""
     k, N = 5, 1024
     dt = port.DTYPES[eb]
-    top = int(np.iinfo(dt).max)
+    # uint16: the reference squares T-promoted ints, so bins > 46340 overflow `int` there (undefined behaviour, SURVEY E1);
+    # the CUDA path returns the exact value instead, so the extreme case stops just below that line
+    top = int(np.iinfo(dt).max) if eb == 1 else 46000
     H = np.ones((6, N), dtype=dt)
     H[1, :] = top                       # saturated everywhere
     H[2, 0] = top                       # one-hot first bin
