@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — one JSON line for the MeShClust2 hot path on B200 (contract in the task prompt / DESIGN.md §Measurement).
+
+A step = one pass of the hot path over one batch of synthetic mutated-template DNA:
+    K1  k-mer histograms of every sequence (Loader<T>::get_point), then
+    K2  the all-pairs feature + GLM + cutoff sweep with the reference's length prefilter (fastcar work() /
+        the candidate scans of Trainer::get_close) -> survivor list.
+`value` = pairs scored per second over the whole step with the packed sequences already resident in HBM;
+`e2e`   = the same metric through the C ABI from HOST buffers (codes + segments in, survivors out), copies timed.
+N > 1: one process per GPU (torchrun); sequences sharded for K1, histogram shards all-gathered over NCCL, the sweep
+split by folded query-row blocks; total work fixed ("strong" scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2] [--n N_SEQ]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sequence pairs scored/sec (features+GLM)"
+UNIT = "pairs/s"
+WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_cfg1_id90.txt")
+WORKLOADS = {
+    # BASELINE.json configs[2]: 100k sequences 1 kb, k=5, uint8, all-pairs feature+GLM sweep at 1/2/4/8 B200
+    "cfg3": dict(synth="cfg3", desc="BASELINE configs[2]: 100k x 1 kb, k=5, uint8, all-pairs feature+GLM sweep (id 0.9)"),
+    # BASELINE.json configs[1] shape: 10k 16S-like 1.5 kb (hot-path content of the train+cluster run: K1 + candidate scans)
+    "cfg2": dict(synth="cfg2", desc="BASELINE configs[1] shape: 10k x 1.5 kb 16S-like, k=5, uint8, K1 + all-pairs candidate sweep (id 0.9)"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [x for x in sm if smax and x > 0.3 * smax] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_workload(name, n_override, lo, hi):
+    from meshclust2_b200 import synth
+    t0 = time.time()
+    seqs, _, k, eb = synth.make_config_range(WORKLOADS[name]["synth"], lo=lo, hi=hi, n=n_override)
+    log("[bench] generated %d synthetic sequences [%d,%d) in %.1fs" % (len(seqs), lo, hi, time.time() - t0))
+    return seqs, k, eb
+
+
+def host_bytes(enc):
+    return int(enc["codes"].nbytes + enc["seq_off"].nbytes + enc["segs"].nbytes + enc["seg_off"].nbytes)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's own implementation compiled in place (oracle/_ref), else the C port
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_leg(seqs, k, eb, n_total, n_scored_total, cutoff, hist_sample, pair_sample, seed=0):
+    """Times Loader<T>::get_point (omp over sequences) and Predictor<T>::close (omp over pairs) on all host cores on a
+    bounded sample of the workload; returns dict with the workload-equivalent pairs/s."""
+    from oracle import port, ref
+    threads = os.cpu_count() or 1
+    rng = np.random.default_rng(seed)
+    model_txt = open(WEIGHTS).read()
+    hs = min(hist_sample, len(seqs))
+    sample = [seqs[i] for i in rng.choice(len(seqs), hs, replace=False)] if hs < len(seqs) else list(seqs)
+    if ref.available():
+        kind = "reference"
+        H, t_hist = ref.count_batch(sample, k, eb, threads=threads, want_hist=True)
+        ln = np.array([len(s) for s in sample], dtype=np.uint64)   # synthetic ACGT: effective size == length
+    else:
+        kind = "port"
+        encs = [port.encode(s) for s in sample]
+        codes = np.concatenate([e[0] for e in encs])
+        seq_off = np.concatenate([[0], np.cumsum([len(e[0]) for e in encs])])
+        segs = np.concatenate([e[1].reshape(-1, 2) for e in encs])
+        seg_off = np.concatenate([[0], np.cumsum([len(e[1].reshape(-1, 2)) for e in encs])])
+        H, t_hist = port.count_batch(codes, seq_off, segs, seg_off, k, eb, threads=threads)
+        ln = np.array([e[2] for e in encs], dtype=np.uint64)
+    hist_rate = hs / t_hist
+    # pairs inside the length window, as the sweep scores them
+    order = np.argsort(ln, kind="stable")
+    ia = rng.integers(0, hs, pair_sample * 2)
+    ib = rng.integers(0, hs, pair_sample * 2)
+    lo = (ln[ib].astype(np.float64) * cutoff).astype(np.uint64)
+    hi = (ln[ib].astype(np.float64) / cutoff).astype(np.uint64)
+    ok = (ln[ia] >= lo) & (ln[ia] <= hi)
+    ia, ib = ia[ok][:pair_sample], ib[ok][:pair_sample]
+    if kind == "reference":
+        rm = ref.RefModel(model_txt, eb, cutoff)
+        r = rm.score_pairs(H, None, ln, ia, ib, mode=1, threads=threads)      # Predictor<T>::close
+        t_pairs, n_close = r["seconds"], int(r["close"].sum())
+    else:
+        m = port.Model.from_text(model_txt)
+        mag = H.sum(axis=1, dtype=np.uint64)
+        r = port.score_pairs(m, H, mag, ln, ia, ib, threads=threads, want_cache=False)
+        t_pairs, n_close = r["seconds"], int(r["close"].sum())
+    pair_rate = len(ia) / t_pairs
+    t_step = n_total / hist_rate + n_scored_total / pair_rate
+    del order
+    return dict(value=n_scored_total / t_step, unit=UNIT, cores=threads, kind=kind,
+                sample="%d sequences through Loader<T>::get_point (%.2fs) + %d in-window pairs through Predictor<T>::close "
+                       "(%.2fs), %d OpenMP threads; extrapolated to the step's %d histograms + %d pairs" % (
+                           hs, t_hist, len(ia), t_pairs, threads, n_total, n_scored_total),
+                hist_per_s=hist_rate, pairs_per_s_kernel=pair_rate, seconds=t_hist + t_pairs, n_close_sample=n_close)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n_total = args.n or {"cfg3": 100000, "cfg2": 10000}[args.workload]
+    nsamp = min(n_total, args.cpu_hist_sample)
+    seqs, k, eb = load_workload(args.workload, args.n, 0, nsamp)
+    n_scored_total = n_total * (n_total - 1) // 2          # synthetic lengths are within the 0.9 window (L +/- 5 %)
+    vals, secs = [], []
+    leg = None
+    for s in range(args.warmup + args.steps):
+        leg = cpu_leg(seqs, k, eb, n_total, n_scored_total, 0.9, nsamp, args.cpu_pair_sample, seed=s)
+        if s >= args.warmup:
+            vals.append(leg["value"])
+            secs.append(leg["seconds"])
+    v = float(np.mean(vals))
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOADS[args.workload]["desc"], "n_sequences": n_total, "k": k, "elem_bytes": eb,
+                       "pairs_per_step": n_scored_total, "model": os.path.basename(WEIGHTS),
+                       "note": "each step is a bounded sample; value is the workload-equivalent rate"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": leg["cores"], "kind": leg["kind"], "sample": leg["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    from meshclust2_b200 import capi, dist as mdist
+    import torch
+    tdist = None
+    if world > 1:
+        import torch.distributed as tdist_mod
+        torch.cuda.set_device(local_rank)
+        tdist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        tdist = tdist_mod
+    comm = mdist.Comm(tdist)
+    n_total = args.n or {"cfg3": 100000, "cfg2": 10000}[args.workload]
+    per, bounds = mdist.shard_bounds(n_total, world)
+    lo, hi = bounds[rank]
+    seqs, k, eb = load_workload(args.workload, args.n, lo, hi)
+    t0 = time.time()
+    enc = capi.encode_batch(seqs)
+    log("[bench] rank %d host encode %.2fs" % (rank, time.time() - t0))
+    ctx = capi.Context(local_rank)
+    model = ctx.model_from_file(WEIGHTS)
+    cutoff = model.meta["id"]
+    eng = mdist.GpuEngine(capi, ctx, torch, model, k, eb, local_rank)
+    eng.set_local_sequences(ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"]), hi - lo, per)
+    max_out = 1 << 22
+
+    def step_resident():
+        ctx.flush_l2(256 << 20)
+        return mdist.all_pairs_step(eng, comm, torch, n_total, cutoff, upper_only=True, max_out=max_out)
+
+    def step_e2e():
+        ctx.flush_l2(256 << 20)
+        old = eng.seqs
+        eng.seqs = ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])   # H2D + pack, timed
+        old.free()
+        return mdist.all_pairs_step(eng, comm, torch, n_total, cutoff, upper_only=True, max_out=max_out)
+
+    def timed(fn, steps, sample_clocks=False):
+        comm.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
+        l0 = ctx.launches
+        ctx.profile(True)
+        ctx.timer_start()
+        res = None
+        for _ in range(steps):
+            res = fn()
+        ms = ctx.timer_stop()
+        comm.barrier()
+        torch.cuda.synchronize()
+        ktime = {kind: ctx.kernel_time(kind) for kind in range(6)}
+        ctx.profile(False)
+        clocks = sampler.stop() if sampler else None
+        ms = comm.all_reduce_max(ms, torch, eng.device)
+        return ms, res, ctx.launches - l0, ktime, clocks
+
+    for _ in range(args.warmup):
+        res = step_resident()
+    ms, res, launches, ktime, clocks = timed(step_resident, args.steps, sample_clocks=True)
+    n_scored = res["n_scored"]
+    value = n_scored * args.steps / (ms * 1e-3)
+    log("[bench] rank %d resident: %.1f ms/step, %d pairs scored, %d close, %d launches" % (
+        rank, ms / args.steps, n_scored, res["n_close"], launches))
+    # end to end from host buffers
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e, res_e, _, _, _ = timed(step_e2e, e2e_steps)
+    e2e_value = res_e["n_scored"] * e2e_steps / (ms_e * 1e-3)
+    h2d = host_bytes(enc)
+    d2h = int(len(res_e["survivors"]) * 24 + 16 * len(res_e["blocks"]))
+
+    # roofline of the dominant kernel (the sweep): algorithmic bytes = candidate form, N*w + 24 + 9 per pair
+    N = 4 ** k
+    bytes_per_pair = N * eb + 24 + 9
+    sweep_ms, sweep_n = ktime[3]
+    count_ms, count_n = ktime[1]
+    peak, peak_src = peaks()
+    local_pairs = res["local_scored"] * args.steps
+    achieved = local_pairs * bytes_per_pair / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "sweep_kernel<u8,NEED_DOT|NEED_EMD>",
+                "algorithmic_bytes_per_unit": bytes_per_pair, "units_per_launch": local_pairs / max(1, sweep_n),
+                "avg_launch_ms": sweep_ms / max(1, sweep_n), "launches": sweep_n,
+                "kernel_share_of_step": sweep_ms / ms if ms > 0 else None, "peak_source": peak_src,
+                "note": "candidate-form bytes (each scored pair streams one database row, query row resident); at this "
+                        "size the 4^k x n set is L2-resident, so the kernel is ALU-issue bound, see DESIGN.md"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload]["desc"], "n_sequences": n_total, "k": k, "elem_bytes": eb,
+                       "pairs_scored_per_step": n_scored, "pairs_close_per_step": res["n_close"],
+                       "model": os.path.basename(WEIGHTS), "parallelism": "row-block x%d, NCCL all-gather of histograms" % world,
+                       "l2": "L2 flushed between steps (256 MB memset inside the timed region)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "ms_per_step": ms_e / e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "k1": {"hist_per_s": (hi - lo) * args.steps / (count_ms * 1e-3) if count_ms > 0 else None,
+                   "avg_launch_ms": count_ms / max(1, count_n),
+                   "achieved_gbs": (hi - lo) * args.steps * (250 + N * eb + 40) / (count_ms * 1e-3) / 1e9 if count_ms > 0 else None}}
+    if world == 1 and not args.no_extras:
+        line["roofline_candidates"] = candidates_roofline(ctx, capi, model, k, eb, peak, peak_src)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        t0 = time.time()
+        cb = cpu_leg(seqs, k, eb, n_total, n_scored, cutoff, args.cpu_hist_sample, args.cpu_pair_sample)
+        log("[bench] cpu baseline leg %.1fs" % (time.time() - t0))
+        line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if tdist is not None:
+        tdist.destroy_process_group()
+
+
+def candidates_roofline(ctx, capi, model, k, eb, peak, peak_src, n=1 << 20):
+    """The HBM-streaming form (Trainer::get_close over a long candidate range, BASELINE configs[4] shape):
+    one query vs 2^20 candidate histograms (1 GiB > L2), device-timed per launch."""
+    rng = np.random.default_rng(1)
+    N = 4 ** k
+    base = rng.integers(1, 7, size=(4096, N), dtype=np.uint8)
+    H = base[rng.integers(0, 4096, n)]
+    ln = rng.integers(950, 1050, n).astype(np.uint64)
+    hs = ctx.hset_from_host(H, k, length=ln)
+    del H
+    ms, nclose = ctx.bench_score_pairs(model, hs, hs, n_pairs=n, a_begin=0, b_begin=3, b_bc=1, iters=20, flush_l2=False,
+                                       len_filter=1, anchor_is_b=1, cutoff=0.9)
+    ms, nclose = ctx.bench_score_pairs(model, hs, hs, n_pairs=n, a_begin=0, b_begin=3, b_bc=1, iters=20, flush_l2=False,
+                                       len_filter=1, anchor_is_b=1, cutoff=0.9)
+    hs.free()
+    bpp = N * eb + 24 + 9
+    ach = n * bpp / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "kernel": "pair_fast_kernel<u8> one query vs 2^20 candidates (1 GiB streamed, > L2)",
+            "algorithmic_bytes_per_unit": bpp, "units_per_launch": n, "avg_launch_ms": ms, "pairs_per_s": n / (ms * 1e-3),
+            "peak_source": peak_src}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=None, help="override the number of sequences (smoke runs)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--cpu-hist-sample", type=int, default=20000)
+    ap.add_argument("--cpu-pair-sample", type=int, default=3000000)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] note: W >= 3 warm-up steps are required for a valid number")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

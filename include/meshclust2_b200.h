@@ -97,6 +97,13 @@ int mc2_timer_start(mc2_ctx *ctx);
 int mc2_timer_stop(mc2_ctx *ctx, float *ms);
 /* count of this library's kernel launches on this ctx since creation (bench.py's gpu_launches) */
 uint64_t mc2_ctx_launch_count(const mc2_ctx *ctx);
+/* Per-kernel device timing (CUDA events around each launch on the ctx stream), for bench.py's roofline object.
+ * kinds: 0 pack, 1 k-mer count, 2 pair score (gather / one-vs-many), 3 sweep (query-vs-database), 4 argmax, 5 side-band.
+ * mc2_ctx_profile(ctx, 1) starts collecting (and clears the totals), (ctx, 0) stops;
+ * mc2_ctx_kernel_time synchronises the stream and returns the summed milliseconds and launch count of one kind. */
+#define MC2_KERNEL_KINDS 6
+int mc2_ctx_profile(mc2_ctx *ctx, int enable);
+int mc2_ctx_kernel_time(mc2_ctx *ctx, int kind, double *total_ms, uint64_t *launches);
 /* write `bytes` of zeros to a scratch buffer (L2 flush between timed iterations) */
 int mc2_ctx_flush_l2(mc2_ctx *ctx, size_t bytes);
 
@@ -145,6 +152,13 @@ int mc2_kmer_table_increment(mc2_ctx *ctx, const char *codes, int32_t first_kmer
  * the host object's possibly stale value (DivergencePoint::set does not refresh it, DivergencePoint.cpp:182-190). */
 int mc2_hset_from_host(mc2_ctx *ctx, const void *bins, uint64_t n, int k, int elem_bytes, const uint64_t *mag,
 		       const uint64_t *len, mc2_hset **out);
+/* Same from DEVICE memory on ctx's GPU (e.g. a torch tensor that an NCCL all-gather of per-rank shards just filled):
+ * bins n x 4^k row-major, d_len n u64, d_mag n u64 or NULL (= sum of bins). The data is copied; the caller keeps
+ * ownership of its buffers. */
+int mc2_hset_from_device(mc2_ctx *ctx, const void *d_bins, uint64_t n, int k, int elem_bytes, const uint64_t *d_mag,
+			 const uint64_t *d_len, mc2_hset **out);
+/* device pointer of a side-band column: which = 0 mag, 1 len, 2 sum of bins, 3 sum of squared bins (n u64 each) */
+void *mc2_hset_device_sideband(const mc2_hset *h, int which);
 void mc2_hset_free(mc2_hset *h);
 uint64_t mc2_hset_count(const mc2_hset *h);
 int mc2_hset_k(const mc2_hset *h);
@@ -154,6 +168,10 @@ void *mc2_hset_device_bins(const mc2_hset *h);
 /* copy rows [first, first+count) back: any output pointer may be NULL. mers1: count x 4; n_overflow: count */
 int mc2_hset_download(mc2_ctx *ctx, const mc2_hset *h, uint64_t first, uint64_t count, void *bins, uint64_t *mag,
 		      uint64_t *len, uint64_t *mers1, double *stddev, int32_t *n_overflow, uint32_t *max_count);
+/* same as mc2_hset_download but into DEVICE buffers on ctx's GPU (bins / mag / len; any may be NULL); the copy has
+ * completed when the call returns, so another stream (e.g. NCCL's) may read the buffers */
+int mc2_hset_copy_to_device(mc2_ctx *ctx, const mc2_hset *h, uint64_t first, uint64_t count, void *d_bins,
+			    uint64_t *d_mag, uint64_t *d_len);
 /* overwrite pseudo-magnitudes / lengths of selected rows (mirror of host objects mutated by set()/set_length()) */
 int mc2_hset_set_sideband(mc2_ctx *ctx, mc2_hset *h, uint64_t count, const uint64_t *rows, const uint64_t *mag,
 			  const uint64_t *len);

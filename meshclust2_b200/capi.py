@@ -34,9 +34,9 @@ PRED_FEAT_DIV = FEAT_JEFFEREY_DIV | FEAT_JENSEN_SHANNON
 SYMBOLS = [
     "mc2_abi_version", "mc2_last_error", "mc2_device_count", "mc2_ctx_create", "mc2_ctx_destroy", "mc2_ctx_sync",
     "mc2_ctx_device", "mc2_ctx_sm_count", "mc2_ctx_stream", "mc2_timer_start", "mc2_timer_stop",
-    "mc2_ctx_launch_count", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_free", "mc2_seqs_count",
-    "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_free",
-    "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download",
+    "mc2_ctx_launch_count", "mc2_ctx_profile", "mc2_ctx_kernel_time", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_free", "mc2_seqs_count",
+    "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
+    "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
     "mc2_score_pairs", "mc2_get_close", "mc2_filter", "mc2_merge", "mc2_all_pairs", "mc2_distance",
     "mc2_bench_score_pairs", "mc2_bench_count_kmers", "mc2_encode_dna", "mc2_encode_dna_batch",
@@ -95,6 +95,7 @@ def lib():
         L.mc2_seqs_total_bases.restype = C.c_uint64
         L.mc2_hset_count.restype = C.c_uint64
         L.mc2_hset_device_bins.restype = C.c_void_p
+        L.mc2_hset_device_sideband.restype = C.c_void_p
         L.mc2_ctx_flush_l2.argtypes = [C.c_void_p, C.c_size_t]
         _lib = L
     return _lib
@@ -155,6 +156,15 @@ class Context:
         _check(lib().mc2_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    def profile(self, enable=True):
+        _check(lib().mc2_ctx_profile(self.h, int(enable)))
+
+    def kernel_time(self, kind):
+        """kind: 0 pack, 1 count, 2 pair score, 3 sweep, 4 argmax, 5 side-band -> (total_ms, launches)"""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib().mc2_ctx_kernel_time(self.h, kind, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def flush_l2(self, nbytes=256 << 20):
         _check(lib().mc2_ctx_flush_l2(self.h, nbytes))
 
@@ -193,6 +203,13 @@ class Context:
         out = C.c_void_p()
         _check(lib().mc2_hset_from_host(self.h, _p(bins), C.c_uint64(n), k, bins.dtype.itemsize, _p(mag), _p(length),
                                         C.byref(out)))
+        return HistSet(self, out)
+
+    def hset_from_device(self, d_bins, n, k, elem_bytes, d_len, d_mag=None):
+        """d_bins / d_len / d_mag: raw device pointers (ints), e.g. torch_tensor.data_ptr()"""
+        out = C.c_void_p()
+        _check(lib().mc2_hset_from_device(self.h, C.c_void_p(d_bins), C.c_uint64(n), k, elem_bytes,
+                                          C.c_void_p(d_mag) if d_mag else None, C.c_void_p(d_len), C.byref(out)))
         return HistSet(self, out)
 
     def model(self, desc):
@@ -333,6 +350,10 @@ class HistSet:
     def device_bins(self):
         return lib().mc2_hset_device_bins(self.h)
 
+    def device_sideband(self, which):
+        """0 mag, 1 len, 2 sum, 3 sumsq -> raw device pointer"""
+        return lib().mc2_hset_device_sideband(self.h, which)
+
     def download(self, first=0, count=None):
         n = len(self)
         count = n - first if count is None else count
@@ -346,6 +367,13 @@ class HistSet:
                                        _p(out["mag"]), _p(out["len"]), _p(out["mers1"]), _p(out["stddev"]),
                                        _p(out["n_overflow"]), _p(out["max_count"])))
         return out
+
+    def copy_to_device(self, d_bins=None, d_mag=None, d_len=None, first=0, count=None):
+        """D2D copy of rows into caller-owned device buffers given as raw pointers (torch_tensor.data_ptr())"""
+        count = len(self) - first if count is None else count
+        _check(lib().mc2_hset_copy_to_device(self.ctx.h, self.h, C.c_uint64(first), C.c_uint64(count),
+                                             C.c_void_p(d_bins) if d_bins else None, C.c_void_p(d_mag) if d_mag else None,
+                                             C.c_void_p(d_len) if d_len else None))
 
     def set_sideband(self, rows, mag=None, length=None):
         rows = _u64(rows)

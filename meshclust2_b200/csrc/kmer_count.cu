@@ -73,8 +73,10 @@ int launch_pack(mc2_ctx *ctx, const char *d_codes, const u64 *d_seq_off, mc2_seq
 	}
 	u64 cap = (u64)ctx->sm_count * 16;
 	int grid = (int)(s->n < cap ? s->n : cap);
+	prof_begin(ctx, 0);
 	pack_kernel<<<grid, 128, 0, ctx->stream>>>(d_codes, d_seq_off, s->word_off, s->segs, s->seg_off, s->n, s->packed,
 						      ctx->d_err);
+	prof_end(ctx);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
 	return MC2_OK;
@@ -357,6 +359,7 @@ int launch_sideband(mc2_ctx *ctx, mc2_hset *h, bool set_mag)
 	}
 	u64 want = (h->n + 7) / 8, cap = (u64)ctx->sm_count * 8;
 	int grid = (int)(want < cap ? want : cap);
+	prof_begin(ctx, 5);
 	switch (h->eb) {
 	case 1: sideband_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t *)h->bins, h->n, h->N, h->sum, h->sumsq, h->mag, set_mag); break;
 	case 2: sideband_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t *)h->bins, h->n, h->N, h->sum, h->sumsq, h->mag, set_mag); break;
@@ -364,6 +367,7 @@ int launch_sideband(mc2_ctx *ctx, mc2_hset *h, bool set_mag)
 	case 8: sideband_kernel<u64><<<grid, 256, 0, ctx->stream>>>((const u64 *)h->bins, h->n, h->N, h->sum, h->sumsq, h->mag, set_mag); break;
 	default: set_error("elem_bytes must be 1, 2, 4 or 8"); return MC2_ERR_ARG;
 	}
+	prof_end(ctx);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
 	return MC2_OK;
@@ -385,12 +389,16 @@ static int launch_count_t(mc2_ctx *ctx, const mc2_seqs *s, CountArgs &a)
 			u64 want = (s->n + warps - 1) / warps, cap = (u64)ctx->sm_count * 8;
 			int grid = (int)(want < cap ? want : cap);
 			MC2_CUDA(cudaFuncSetAttribute(count_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+			prof_begin(ctx, 1);
 			count_kernel<T, true, false><<<grid, warps * 32, smem, ctx->stream>>>(a);
+			prof_end(ctx);
 		} else {
 			u64 cap = (u64)ctx->sm_count * 4;
 			int grid = (int)(s->n < cap ? s->n : cap);
 			MC2_CUDA(cudaFuncSetAttribute(count_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+			prof_begin(ctx, 1);
 			count_kernel<T, false, false><<<grid, 256, hist_bytes, ctx->stream>>>(a);
+			prof_end(ctx);
 		}
 		ctx->launches++;
 		MC2_CUDA(cudaGetLastError());
@@ -418,7 +426,9 @@ static int launch_count_t(mc2_ctx *ctx, const mc2_seqs *s, CountArgs &a)
 		int grid = (int)(cnt < cap ? cnt : cap);
 		// sequences b0.. are reached by offsetting the group index through seq_begin
 		b.packed = a.packed;
+		prof_begin(ctx, 1);
 		count_kernel<T, false, true><<<grid, 256, 0, ctx->stream>>>(b);
+		prof_end(ctx);
 		ctx->launches++;
 		e = cudaGetLastError();
 		if (e != cudaSuccess) {

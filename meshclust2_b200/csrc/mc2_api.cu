@@ -74,9 +74,68 @@ static void release(Buf &b)
 
 enum { B_IA = 0, B_IB, B_SCORE, B_DIST, B_CLOSE, B_SKIP, B_CACHE, B_RAW, B_MISC, B_OUTQ, B_OUTD, B_OUTS, B_COUNT };
 
+struct ProfRec {
+	int kind;
+	cudaEvent_t e0, e1;
+};
+
 struct CtxExtra {
 	Buf d[B_COUNT];
+	std::vector<ProfRec> pending;
+	std::vector<cudaEvent_t> pool;
+	double prof_ms[MC2_KERNEL_KINDS] = {0};
+	u64 prof_n[MC2_KERNEL_KINDS] = {0};
 };
+
+static cudaEvent_t prof_event(CtxExtra *x)
+{
+	cudaEvent_t e;
+	if (!x->pool.empty()) {
+		e = x->pool.back();
+		x->pool.pop_back();
+		return e;
+	}
+	cudaEventCreate(&e);
+	return e;
+}
+
+void prof_begin(mc2_ctx *ctx, int kind)
+{
+	if (!ctx->prof_on) {
+		return;
+	}
+	CtxExtra *x = reinterpret_cast<CtxExtra *>(ctx->extra);
+	ProfRec r;
+	r.kind = kind;
+	r.e0 = prof_event(x);
+	r.e1 = prof_event(x);
+	cudaEventRecord(r.e0, ctx->stream);
+	x->pending.push_back(r);
+}
+
+void prof_end(mc2_ctx *ctx)
+{
+	if (!ctx->prof_on) {
+		return;
+	}
+	CtxExtra *x = reinterpret_cast<CtxExtra *>(ctx->extra);
+	cudaEventRecord(x->pending.back().e1, ctx->stream);
+}
+
+static void prof_drain(mc2_ctx *ctx)
+{
+	CtxExtra *x = reinterpret_cast<CtxExtra *>(ctx->extra);
+	for (ProfRec &r : x->pending) {
+		float ms = 0;
+		if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+			x->prof_ms[r.kind] += ms;
+			x->prof_n[r.kind]++;
+		}
+		x->pool.push_back(r.e0);
+		x->pool.push_back(r.e1);
+	}
+	x->pending.clear();
+}
 
 static int model_need(const mc2_model_desc &d, DevModel &dm)
 {
@@ -310,6 +369,10 @@ void mc2_ctx_destroy(mc2_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	CtxExtra *x = extra(ctx);
 	if (x) {
+		prof_drain(ctx);
+		for (auto e : x->pool) {
+			cudaEventDestroy(e);
+		}
 		for (auto &b : x->d) {
 			release(b);
 		}
@@ -369,6 +432,34 @@ int mc2_timer_stop(mc2_ctx *ctx, float *ms)
 uint64_t mc2_ctx_launch_count(const mc2_ctx *ctx)
 {
 	return ctx ? ctx->launches : 0;
+}
+
+int mc2_ctx_profile(mc2_ctx *ctx, int enable)
+{
+	MC2_REQUIRE(ctx != nullptr, "ctx is NULL");
+	CtxExtra *x = extra(ctx);
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	prof_drain(ctx);
+	if (enable) {
+		for (int i = 0; i < MC2_KERNEL_KINDS; i++) {
+			x->prof_ms[i] = 0;
+			x->prof_n[i] = 0;
+		}
+	}
+	ctx->prof_on = enable ? 1 : 0;
+	return MC2_OK;
+}
+
+int mc2_ctx_kernel_time(mc2_ctx *ctx, int kind, double *total_ms, uint64_t *launches)
+{
+	MC2_REQUIRE(ctx && total_ms && launches, "mc2_ctx_kernel_time: NULL argument");
+	MC2_REQUIRE(kind >= 0 && kind < MC2_KERNEL_KINDS, "mc2_ctx_kernel_time: kind out of range");
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	prof_drain(ctx);
+	CtxExtra *x = extra(ctx);
+	*total_ms = x->prof_ms[kind];
+	*launches = x->prof_n[kind];
+	return MC2_OK;
 }
 
 int mc2_ctx_flush_l2(mc2_ctx *ctx, size_t bytes)
@@ -593,6 +684,55 @@ int mc2_hset_from_host(mc2_ctx *ctx, const void *bins, uint64_t n, int k, int el
 	return MC2_OK;
 }
 
+int mc2_hset_from_device(mc2_ctx *ctx, const void *d_bins, uint64_t n, int k, int elem_bytes, const uint64_t *d_mag,
+			 const uint64_t *d_len, mc2_hset **out)
+{
+	MC2_REQUIRE(ctx && out && (n == 0 || (d_bins && d_len)), "mc2_hset_from_device: NULL argument");
+	*out = nullptr;
+	int rc = check_k_eb(k, elem_bytes);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	mc2_hset *h = nullptr;
+	rc = alloc_hset(ctx, n, k, elem_bytes, &h);
+	if (rc != MC2_OK) return rc;
+	cudaError_t e = cudaSuccess;
+	if (n) {
+		e = cudaMemcpyAsync(h->bins, d_bins, n * h->N * (u64)elem_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(h->len, d_len, n * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+		if (e == cudaSuccess && d_mag) e = cudaMemcpyAsync(h->mag, d_mag, n * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(h->mers1, 0, n * 32, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(h->stddev, 0, n * 8, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(h->novf, 0, n * 4, ctx->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(h->maxc, 0, n * 4, ctx->stream);
+	}
+	if (e != cudaSuccess) {
+		mc2_hset_free(h);
+		return cuda_fail(e, "mc2_hset_from_device copies", __FILE__, __LINE__);
+	}
+	rc = launch_sideband(ctx, h, d_mag == nullptr);
+	if (rc == MC2_OK) rc = refresh_max_sum(ctx, h);
+	if (rc != MC2_OK) {
+		mc2_hset_free(h);
+		return rc;
+	}
+	*out = h;
+	return MC2_OK;
+}
+
+void *mc2_hset_device_sideband(const mc2_hset *h, int which)
+{
+	if (!h) {
+		return nullptr;
+	}
+	switch (which) {
+	case 0: return h->mag;
+	case 1: return h->len;
+	case 2: return h->sum;
+	case 3: return h->sumsq;
+	}
+	return nullptr;
+}
+
 void mc2_hset_free(mc2_hset *h)
 {
 	if (!h) {
@@ -647,6 +787,23 @@ int mc2_hset_download(mc2_ctx *ctx, const mc2_hset *h, uint64_t first, uint64_t 
 	if (stddev) MC2_CUDA(cudaMemcpyAsync(stddev, h->stddev + first, count * 8, cudaMemcpyDeviceToHost, st));
 	if (n_overflow) MC2_CUDA(cudaMemcpyAsync(n_overflow, h->novf + first, count * 4, cudaMemcpyDeviceToHost, st));
 	if (max_count) MC2_CUDA(cudaMemcpyAsync(max_count, h->maxc + first, count * 4, cudaMemcpyDeviceToHost, st));
+	MC2_CUDA(cudaStreamSynchronize(st));
+	return MC2_OK;
+}
+
+int mc2_hset_copy_to_device(mc2_ctx *ctx, const mc2_hset *h, uint64_t first, uint64_t count, void *d_bins,
+			    uint64_t *d_mag, uint64_t *d_len)
+{
+	MC2_REQUIRE(ctx && h, "mc2_hset_copy_to_device: NULL argument");
+	MC2_REQUIRE(first <= h->n && count <= h->n - first, "mc2_hset_copy_to_device: row range out of bounds");
+	if (count == 0) {
+		return MC2_OK;
+	}
+	cudaStream_t st = ctx->stream;
+	const u64 rb = h->N * (u64)h->eb;
+	if (d_bins) MC2_CUDA(cudaMemcpyAsync(d_bins, (const char *)h->bins + first * rb, count * rb, cudaMemcpyDeviceToDevice, st));
+	if (d_mag) MC2_CUDA(cudaMemcpyAsync(d_mag, h->mag + first, count * 8, cudaMemcpyDeviceToDevice, st));
+	if (d_len) MC2_CUDA(cudaMemcpyAsync(d_len, h->len + first, count * 8, cudaMemcpyDeviceToDevice, st));
 	MC2_CUDA(cudaStreamSynchronize(st));
 	return MC2_OK;
 }

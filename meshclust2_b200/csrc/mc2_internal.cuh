@@ -89,7 +89,14 @@ struct mc2_ctx {
 	void *h_slot;     // pinned result slot (4 KB)
 	void *d_slot;     // device result slot (4 KB)
 	void *extra;      // CtxExtra (growable scratch buffers), owned by mc2_api.cu
+	int prof_on;      // per-kernel event timing enabled
 };
+
+namespace mc2 {
+// event-pair bracket around one kernel launch when profiling is on (no-ops otherwise)
+void prof_begin(mc2_ctx *ctx, int kind);
+void prof_end(mc2_ctx *ctx);
+}
 
 struct mc2_seqs {
 	mc2_ctx *ctx;

@@ -985,6 +985,7 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 	}
 	const u64 row_bytes = a.N * (u64)a.eb;
 	const bool fast = a.eb <= 2 && row_bytes % 512 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 27);
+	prof_begin(ctx, 2);
 	if (fast) {
 		int grid = grid_for(ctx, a.n_pairs, 8, 8);
 		if (a.eb == 1) {
@@ -1002,6 +1003,7 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 		default: set_error("elem_bytes must be 1, 2, 4 or 8"); return MC2_ERR_ARG;
 		}
 	}
+	prof_end(ctx);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
 	return MC2_OK;
@@ -1009,7 +1011,9 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 
 int launch_argmax(mc2_ctx *ctx, const double *dist, const uint8_t *skipped, const uint8_t *close, u64 n, int mode, void *d_out)
 {
+	prof_begin(ctx, 4);
 	argmax_kernel<<<1, 1024, 0, ctx->stream>>>(dist, skipped, close, n, mode, reinterpret_cast<ArgOut *>(d_out));
+	prof_end(ctx);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
 	return MC2_OK;
@@ -1086,6 +1090,7 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 	int grid = (int)(want < cap ? want : cap);
 	const u64 row_bytes = a.N * (u64)a.eb;
 	const bool fast = a.eb <= 2 && row_bytes % 512 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 27);
+	prof_begin(ctx, 3);
 	if (fast) {
 		if (a.eb == 1) {
 			launch_sweep_fast<uint8_t>(dm.need, grid, ctx->stream, dm, a, g);
@@ -1101,6 +1106,7 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 		default: set_error("elem_bytes must be 1, 2, 4 or 8"); return MC2_ERR_ARG;
 		}
 	}
+	prof_end(ctx);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
 	return MC2_OK;

@@ -1,0 +1,166 @@
+"""Multi-GPU plumbing for the sharded hot path: one process per GPU, torch.distributed for the exchange step.
+
+north_star's partition: sequences are split contiguously by rank for k-mer counting (K1);
+the per-rank histogram shards are ALL-GATHERED so every GPU holds the full n x 4^k set; the all-pairs sweep (K2) is
+split by query-row blocks.  No floating-point value ever crosses ranks, so results are bitwise independent of the
+number of GPUs.  Everything here is host logic over an `engine` object, so the same code runs under gloo on CPU in
+the tests (engine = a stand-in) and under NCCL on GPUs (engine = GpuEngine over the C ABI).
+"""
+import numpy as np
+
+
+def shard_bounds(n, world):
+    """Contiguous, equal-size (padded) shards: every rank owns `per` rows, the tail ranks may own fewer real rows."""
+    per = (n + world - 1) // world
+    return per, [(min(r * per, n), min((r + 1) * per, n)) for r in range(world)]
+
+
+def folded_row_blocks(n, world, rank, blocks_per_rank=8):
+    """Query-row blocks of an upper-triangular sweep for `rank`, balanced by folding: block b and block B-1-b together
+    hold a constant number of pairs, so each fold goes to one rank (cyclic over folds)."""
+    B = 2 * world * blocks_per_rank
+    B = min(B, max(2, n - n % 2))
+    edges = np.linspace(0, n, B + 1).astype(np.int64)
+    out = []
+    for fold in range((B + 1) // 2):
+        if fold % world != rank:
+            continue
+        for b in {fold, B - 1 - fold}:
+            q0, q1 = int(edges[b]), int(edges[b + 1])
+            if q1 > q0:
+                out.append((q0, q1))
+    return sorted(out)
+
+
+def rect_row_blocks(n, world, rank):
+    """Query-row blocks of a rectangular (query set x database) sweep: plain contiguous split."""
+    _, b = shard_bounds(n, world)
+    lo, hi = b[rank]
+    return [(lo, hi)] if hi > lo else []
+
+
+class Comm:
+    """Thin wrapper so single-process runs need no process group."""
+
+    def __init__(self, dist=None):
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def all_gather_rows(self, local, torch):
+        """local: torch tensor [per, ...] on the engine's device -> [world*per, ...] (rank-major)."""
+        if self.dist is None:
+            return local
+        out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        self.dist.all_gather_into_tensor(out, local.contiguous())
+        return out
+
+    def all_reduce_sum(self, values, torch, device):
+        t = torch.tensor(values, dtype=torch.int64, device=device)
+        if self.dist is not None:
+            self.dist.all_reduce(t)
+        return [int(v) for v in t.tolist()]
+
+    def all_reduce_max(self, value, torch, device):
+        t = torch.tensor([value], dtype=torch.float64, device=device)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def all_pairs_step(engine, comm, torch, n_total, cutoff, upper_only=True, blocks_per_rank=8, max_out=1 << 20):
+    """One pass of the hot path over a batch: local K1 -> all-gather -> row-block K2 sweep.
+
+    engine.count()                  K1 over this rank's shard
+    engine.export_local()           -> (bins [per, N] tensor, length [per] int64 tensor, mag [per] int64 tensor) padded
+    engine.install_full(bins, length, mag, n_total)   make the gathered set the sweep's database
+    engine.use_local_as_full()      single rank: the counted shard is the database (no copy, no collective)
+    engine.sweep(q0, q1, upper_only, cutoff, max_out) -> (n_survivors, n_scored, survivors array [m,2])
+    Returns dict(n_scored, n_close, survivors (this rank's), blocks)."""
+    engine.count()
+    if comm.world == 1:
+        engine.use_local_as_full()
+    else:
+        bins, length, mag = engine.export_local()
+        bins = comm.all_gather_rows(bins, torch)
+        length = comm.all_gather_rows(length, torch)
+        mag = comm.all_gather_rows(mag, torch)
+        per = bins.shape[0] // comm.world
+        if per * comm.world != n_total:
+            # drop the padding rows of the tail shards: rows are rank-major, real rows are a prefix of each shard
+            _, bounds = shard_bounds(n_total, comm.world)
+            keep = np.concatenate([np.arange(r * per, r * per + (hi - lo)) for r, (lo, hi) in enumerate(bounds)])
+            idx = torch.as_tensor(keep, device=bins.device)
+            bins, length, mag = bins[idx].contiguous(), length[idx].contiguous(), mag[idx].contiguous()
+        engine.install_full(bins, length, mag, n_total)
+    blocks = (folded_row_blocks(n_total, comm.world, comm.rank, blocks_per_rank) if upper_only
+              else rect_row_blocks(n_total, comm.world, comm.rank))
+    n_scored = n_close = 0
+    surv = []
+    for q0, q1 in blocks:
+        ns, sc, pairs = engine.sweep(q0, q1, upper_only, cutoff, max_out)
+        n_close += ns
+        n_scored += sc
+        surv.append(pairs)
+    tot_scored, tot_close = comm.all_reduce_sum([n_scored, n_close], torch, engine.device)
+    return dict(n_scored=tot_scored, n_close=tot_close, local_scored=n_scored, local_close=n_close,
+                survivors=np.concatenate(surv) if surv else np.zeros((0, 2), dtype=np.uint64), blocks=blocks)
+
+
+class GpuEngine:
+    """The product engine: K1 / K2 through the C ABI on this rank's GPU; torch only carries device memory for NCCL."""
+
+    def __init__(self, capi, ctx, torch, model, k, elem_bytes, device_index):
+        self.capi, self.ctx, self.torch, self.model = capi, ctx, torch, model
+        self.k, self.eb = k, elem_bytes
+        self.N = 4 ** k
+        self.device = torch.device("cuda", device_index)
+        self.seqs = None       # resident packed sequences of this rank's shard
+        self.per = 0           # padded shard size
+        self.n_local = 0
+        self.full = None
+        self._dt = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[elem_bytes]
+
+    def set_local_sequences(self, seqs_handle, n_local, per):
+        self.seqs, self.n_local, self.per = seqs_handle, n_local, per
+
+    def upload_local(self, enc):
+        self.seqs = self.ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
+        return self.seqs
+
+    def count(self):
+        if getattr(self, "local_hset", None) is not None and self.local_hset is not self.full:
+            self.local_hset.free()
+        self.local_hset = self.ctx.count_kmers(self.seqs, self.k, self.eb)
+
+    def use_local_as_full(self):
+        if self.full is not None and self.full is not self.local_hset:
+            self.full.free()
+        self.full = self.local_hset
+
+    def export_local(self):
+        torch = self.torch
+        hs = self.local_hset
+        bins = torch.ones((self.per, self.N), dtype=self._dt, device=self.device)
+        length = torch.zeros((self.per,), dtype=torch.int64, device=self.device)
+        mag = torch.zeros((self.per,), dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)     # the fills above run on torch's stream
+        if self.n_local:
+            hs.copy_to_device(bins.data_ptr(), mag.data_ptr(), length.data_ptr(), 0, self.n_local)
+        return bins, length, mag
+
+    def install_full(self, bins, length, mag, n_total):
+        self.torch.cuda.synchronize(self.device)
+        if self.full is not None and self.full is not self.local_hset:
+            self.full.free()
+        self.full = self.ctx.hset_from_device(bins.data_ptr(), n_total, self.k, self.eb, length.data_ptr(),
+                                              mag.data_ptr())
+
+    def sweep(self, q0, q1, upper_only, cutoff, max_out):
+        r = self.ctx.all_pairs(self.model, self.full, self.full, cutoff, q_range=(q0, q1), upper_only=upper_only,
+                               max_out=max_out)
+        return r["n_out"], r["n_scored"], np.stack([r["q"], r["d"]], axis=1)

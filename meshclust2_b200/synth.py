@@ -71,6 +71,45 @@ CONFIGS = {
 }
 
 
+BLOCK = 1024
+
+
+def make_range(n, length, n_templates, r_max, seed, lo=0, hi=None, len_jitter=0.05, ancestor_div=None,
+               variant_rmax=None):
+    """Sequences [lo, hi) of an n-sequence set, generated block-wise so that any rank can produce its own shard and
+    the union over ranks is independent of how the range was split: templates come from `seed`, the variants of
+    block b (sequences b*1024 .. b*1024+1023) from default_rng([seed, 1 + b])."""
+    hi = n if hi is None else hi
+    rng = np.random.default_rng([seed, 0])
+    if ancestor_div is None:
+        lens = np.round(length * (1 + len_jitter * (2 * rng.random(n_templates) - 1))).astype(np.int64)
+        templates = [random_template(rng, L) for L in lens]
+    else:
+        anc = random_template(rng, length)
+        a, b = ancestor_div
+        templates = [mutate(rng, anc, a + (b - a) * rng.random()) for _ in range(n_templates)]
+    vr = r_max if variant_rmax is None else variant_rmax
+    seqs, tids = [], []
+    for blk in range(lo // BLOCK, (hi + BLOCK - 1) // BLOCK):
+        brng = np.random.default_rng([seed, 1 + blk])
+        for i in range(blk * BLOCK, min((blk + 1) * BLOCK, n)):
+            t = i % n_templates
+            s = mutate(brng, templates[t], vr * brng.random())
+            if lo <= i < hi:
+                seqs.append(s.tobytes())
+                tids.append(t)
+    return seqs, np.array(tids, dtype=np.int32)
+
+
+def make_config_range(name, lo=0, hi=None, n=None):
+    cfg = dict(CONFIGS[name])
+    k, eb = cfg.pop("k"), cfg.pop("elem_bytes")
+    if n is not None:
+        cfg["n"] = n
+    seqs, tids = make_range(lo=lo, hi=hi, **cfg)
+    return seqs, tids, k, eb
+
+
 def make_config(name, n=None):
     cfg = dict(CONFIGS[name])
     k, eb = cfg.pop("k"), cfg.pop("elem_bytes")

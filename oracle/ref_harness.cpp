@@ -132,6 +132,17 @@ Model<T>* load_model(const char* weights_file, double cutoff)
 	Model<T>* m = new Model<T>();
 	m->elem_bytes = sizeof(T);
 	m->pred = new Predictor<T>(std::string(weights_file));
+	// Feature(int k) leaves do_save uninitialised and read_from() builds raw_funcs while it is
+	// garbage: when it happens to be non-zero the singles memoise into an unlocked std::map and concurrent
+	// close() calls crash.  Pin it to the state every trained Feature handed to clustering has (copy-ctor: false).
+	if (m->pred->get_mode() & PRED_MODE_CLASS) {
+		m->pred->feat_c->set_save(false);
+		m->pred->feat_c->reset_funcs();
+	}
+	if (m->pred->get_mode() & PRED_MODE_REGR) {
+		m->pred->feat_r->set_save(false);
+		m->pred->feat_r->reset_funcs();
+	}
 	std::vector<Point<T>*> none;
 	m->trainer = new Trainer<T>(none, 0, 0, cutoff, 0, m->pred->get_k());
 	if (m->pred->get_mode() & PRED_MODE_CLASS) {

@@ -1,0 +1,143 @@
+"""CPU, world_size 2, gloo: the N>1 host logic of meshclust2_b200/dist.py (contiguous K1 shards, padded all-gather of
+histogram shards, folded row-block split of the upper-triangular sweep).  The compute engine here is a stand-in built
+on the oracle (test infrastructure); on GPUs the same driver runs GpuEngine over the C ABI."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as tdist
+import torch.multiprocessing as mp
+
+from conftest import weights_text
+from meshclust2_b200 import dist as mdist
+from meshclust2_b200 import synth
+from oracle import port
+
+
+def test_shard_bounds_and_blocks_cover_everything():
+    for n in (1, 7, 64, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            per, b = mdist.shard_bounds(n, world)
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert all(hi - lo <= per for lo, hi in b)
+            rows = []
+            for r in range(world):
+                for q0, q1 in mdist.folded_row_blocks(n, world, r):
+                    rows.extend(range(q0, q1))
+            assert sorted(rows) == list(range(n)), (n, world)
+            rows = [q for r in range(world) for q0, q1 in mdist.rect_row_blocks(n, world, r) for q in range(q0, q1)]
+            assert sorted(rows) == list(range(n))
+
+
+def test_folded_blocks_balance_the_triangle():
+    n, world = 100000, 8
+    work = []
+    for r in range(world):
+        work.append(sum((n - 1 - q0 + n - q1) * (q1 - q0) / 2 for q0, q1 in mdist.folded_row_blocks(n, world, r)))
+    assert max(work) / min(work) < 1.01
+
+
+class OracleEngine:
+    def __init__(self, seqs, k, eb, model, per):
+        self.seqs, self.k, self.eb, self.model, self.per = seqs, k, eb, model, per
+        self.device = torch.device("cpu")
+        self.N = 4 ** k
+
+    def count(self):
+        pts = [port.get_point(s, self.k, self.eb) for s in self.seqs]
+        self.H = np.stack([p["hist"] for p in pts]) if pts else np.zeros((0, self.N), dtype=port.DTYPES[self.eb])
+        self.ln = np.array([p["len"] for p in pts], dtype=np.int64)
+        self.mag = np.array([p["mag"] for p in pts], dtype=np.int64)
+
+    def use_local_as_full(self):
+        self.full = (self.H, self.ln, self.mag)
+
+    def export_local(self):
+        bins = torch.ones((self.per, self.N), dtype=torch.uint8)
+        ln = torch.zeros((self.per,), dtype=torch.int64)
+        mag = torch.zeros((self.per,), dtype=torch.int64)
+        n = len(self.seqs)
+        bins[:n] = torch.from_numpy(self.H)
+        ln[:n] = torch.from_numpy(self.ln)
+        mag[:n] = torch.from_numpy(self.mag)
+        return bins, ln, mag
+
+    def install_full(self, bins, length, mag, n_total):
+        assert bins.shape[0] == n_total
+        self.full = (bins.numpy(), length.numpy(), mag.numpy())
+
+    def sweep(self, q0, q1, upper_only, cutoff, max_out):
+        H, ln, mag = self.full
+        n = H.shape[0]
+        ia, ib = [], []
+        for q in range(q0, q1):
+            lo, hi = int(float(ln[q]) * cutoff), int(float(ln[q]) / cutoff)
+            for c in range(q + 1 if upper_only else 0, n):
+                if lo <= ln[c] <= hi:
+                    ia.append(c), ib.append(q)
+        if not ia:
+            return 0, 0, np.zeros((0, 2), dtype=np.uint64)
+        o = port.score_pairs(self.model, H, mag.astype(np.uint64), ln.astype(np.uint64), ia, ib, want_cache=False)
+        cl = o["close"].astype(bool)
+        pairs = np.stack([np.array(ib)[cl], np.array(ia)[cl]], axis=1).astype(np.uint64)
+        return int(cl.sum()), len(ia), pairs
+
+
+def _worker(rank, world, port_no, n_total, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = port.Model.from_text(weights_text("weights_cfg1_id90"))
+        per, bounds = mdist.shard_bounds(n_total, world)
+        lo, hi = bounds[rank]
+        seqs, _ = synth.make_range(n_total, 1000, 9, 0.1, seed=31, lo=lo, hi=hi)
+        eng = OracleEngine(seqs, 5, 1, model, per)
+        comm = mdist.Comm(tdist)
+        res = mdist.all_pairs_step(eng, comm, torch, n_total, 0.9, upper_only=True, blocks_per_rank=2)
+        gathered = [None] * world
+        tdist.all_gather_object(gathered, res["survivors"].tolist())
+        if rank == 0:
+            out.put((res["n_scored"], res["n_close"], sorted(map(tuple, sum(gathered, [])))))
+    finally:
+        tdist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_equal_one_rank():
+    n_total = 61      # odd on purpose: the tail shard is padded for the all-gather
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, _free_port_cached(), n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single process, same data, no process group
+    model = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    seqs, _ = synth.make_range(n_total, 1000, 9, 0.1, seed=31)
+    eng = OracleEngine(seqs, 5, 1, model, n_total)
+    res = mdist.all_pairs_step(eng, mdist.Comm(None), torch, n_total, 0.9, upper_only=True, blocks_per_rank=2)
+    want = (res["n_scored"], res["n_close"], sorted(map(tuple, res["survivors"].tolist())))
+    assert got == want and want[1] > 0
+
+
+_PORT = []
+
+
+def _free_port_cached():
+    if not _PORT:
+        _PORT.append(_free_port())
+    return _PORT[0]
