@@ -387,157 +387,403 @@ __device__ __forceinline__ bool resolve_pair(const PairArgs &a, u64 j, u64 &ra, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// fast path: 8/16-bit bins, rows a multiple of 512 bytes, bin sums < 2^27
+// fast path: 8/16-bit bins, rows a multiple of 1 KiB, bin sums < 2^26.
+// A warp walks a row in 1 KiB slabs; lane l owns the 32 CONTIGUOUS bytes [32l, 32l+32) of the slab (one 256-bit
+// load, the warp reads 1 KiB contiguous), so the EMD prefix needs ONE warp scan per slab:
+//   tot_l   = sum_lane(p) - sum_lane(q)                 (IDP with all-ones / all-minus-ones byte masks)
+//   off_l   = exclusive warp scan of tot + carry        (5 SHFL.UP with predicated add)
+//   c_{i+1} = c_i + p_i - q_i  starting at off_l        (PRMT interleave + IDP with +1/-1 masks, 2 bins per dependent step)
+//   emd    += |c_i|                                      (VABSDIFF with accumulate)
 // ------------------------------------------------------------------------------------------------
-template <int NEED>
-__device__ __forceinline__ void slab_u8(const uint4 &pv, const uint4 &qv, u32 &sad, u32 &dot, int (&l)[16], int &tot)
+struct Row8 {
+	u32 w[8];
+};
+
+__device__ __forceinline__ Row8 ld_row_stream(const void *p)
 {
-	const u32 pw[4] = {pv.x, pv.y, pv.z, pv.w};
-	const u32 qw[4] = {qv.x, qv.y, qv.z, qv.w};
-	int c = 0;
-#pragma unroll
-	for (int w = 0; w < 4; w++) {
-		u32 p = pw[w], q = qw[w];
-		if (NEED & NEED_MIN) {
-			sad = vabsdiff4_acc(p, q, sad);
-		}
-		if (NEED & NEED_DOT) {
-			dot = __dp4a(p, q, dot);
-		}
-		if (NEED & NEED_EMD) {
-			u32 w01 = __byte_perm(p, q, 0x5140); // p0 q0 p1 q1
-			u32 w23 = __byte_perm(p, q, 0x7362); // p2 q2 p3 q3
-			l[4 * w + 0] = dp4a_us(w01, 0x0000FF01u, c);
-			l[4 * w + 1] = dp4a_us(w01, 0xFF01FF01u, c);
-			c = l[4 * w + 1];
-			l[4 * w + 2] = dp4a_us(w23, 0x0000FF01u, c);
-			l[4 * w + 3] = dp4a_us(w23, 0xFF01FF01u, c);
-			c = l[4 * w + 3];
-		}
-	}
-	tot = c;
+	Row8 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+		     : "l"(p));
+	return r;
+}
+__device__ __forceinline__ Row8 ld_row_keep(const void *p)
+{
+	Row8 r;
+	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+		     : "l"(p));
+	return r;
 }
 
-template <int NEED>
-__device__ __forceinline__ void slab_u16(const uint4 &pv, const uint4 &qv, u32 &smin, u32 &dlo, u32 &dhi, int (&l)[8],
-					 int &tot)
+// inclusive scan step: x += shfl_up(x, d) where the source lane exists
+__device__ __forceinline__ void scan_step(int &x, int d)
 {
-	const u32 pw[4] = {pv.x, pv.y, pv.z, pv.w};
-	const u32 qw[4] = {qv.x, qv.y, qv.z, qv.w};
-	int c = 0;
-#pragma unroll
-	for (int w = 0; w < 4; w++) {
-		u32 p = pw[w], q = qw[w];
-		if (NEED & NEED_MIN) {
-			u32 mn = __vminu2(p, q);
-			smin = dp2a_lo_uu(mn, 0x0101u, smin);
-		}
-		if (NEED & NEED_DOT) {
-			u32 qp = __byte_perm(q, q, 0x3120); // q0.lo q1.lo q0.hi q1.hi
-			dlo = dp2a_lo_uu(p, qp, dlo);
-			dhi = dp2a_hi_uu(p, qp, dhi);
-		}
-		if (NEED & NEED_EMD) {
-			l[2 * w + 0] = dp2a_lo_us(q, 0x00FFu, (int)dp2a_lo_uu(p, 0x0001u, (u32)c));
-			l[2 * w + 1] = dp2a_lo_us(q, 0xFFFFu, (int)dp2a_lo_uu(p, 0x0101u, (u32)c));
-			c = l[2 * w + 1];
-		}
-	}
-	tot = c;
+	asm volatile("{\n\t.reg .s32 t;\n\t.reg .pred p;\n\tshfl.sync.up.b32 t|p, %0, %1, 0x0, 0xffffffff;\n\t@p add.s32 %0, %0, t;\n\t}"
+		     : "+r"(x)
+		     : "r"(d));
 }
-
-// exclusive prefix of `tot` across lanes, plus the warp total
-__device__ __forceinline__ int warp_excl_scan(int tot, int lane, int &warp_total)
+__device__ __forceinline__ int warp_excl_scan(int tot, int &warp_total)
 {
 	int x = tot;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		int y = __shfl_up_sync(0xffffffffu, x, d);
-		if (lane >= d) {
-			x += y;
-		}
-	}
+	scan_step(x, 1);
+	scan_step(x, 2);
+	scan_step(x, 4);
+	scan_step(x, 8);
+	scan_step(x, 16);
 	warp_total = __shfl_sync(0xffffffffu, x, 31);
 	return x - tot;
 }
 
+// sum over the lane's 32 bytes of q, as the (negative) constant the scan needs; hoisted when q is the fixed query
+template <typename T>
+__device__ __forceinline__ int lane_sum(const Row8 &q)
+{
+	u32 s = 0;
+#pragma unroll
+	for (int w = 0; w < 8; w++) {
+		if (sizeof(T) == 1) {
+			s = __dp4a(q.w[w], 0x01010101u, s);
+		} else {
+			s = dp2a_lo_uu(q.w[w], 0x0101u, s);
+		}
+	}
+	return (int)s;
+}
+
+// one 1 KiB slab: per-lane partial sums; `carry` is the running cumP-cumQ at the start of the slab
+template <typename T, int NEED>
+__device__ __forceinline__ void slab_reduce(const Row8 &p, const Row8 &q, int qsum, int &carry, u32 &a_min, u32 &a_dot_lo,
+					    u32 &a_dot_hi, u32 &a_emd)
+{
+	if (NEED & NEED_MIN) {
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			if (sizeof(T) == 1) {
+				a_min = vabsdiff4_acc(p.w[w], q.w[w], a_min);   // sum |p-q| (converted to S_min by the caller)
+			} else {
+				a_min = dp2a_lo_uu(__vminu2(p.w[w], q.w[w]), 0x0101u, a_min);
+			}
+		}
+	}
+	if (NEED & NEED_DOT) {
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			if (sizeof(T) == 1) {
+				a_dot_lo = __dp4a(p.w[w], q.w[w], a_dot_lo);
+			} else {
+				u32 qp = __byte_perm(q.w[w], q.w[w], 0x3120); // q0.lo q1.lo q0.hi q1.hi
+				a_dot_lo = dp2a_lo_uu(p.w[w], qp, a_dot_lo);
+				a_dot_hi = dp2a_hi_uu(p.w[w], qp, a_dot_hi);
+			}
+		}
+	}
+	if (NEED & NEED_EMD) {
+		int tot = lane_sum<T>(p) - qsum;
+		int wt;
+		int c = warp_excl_scan(tot, wt) + carry;
+		carry += wt;
+		u32 e = a_emd;
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			if (sizeof(T) == 1) {
+				u32 w01 = __byte_perm(p.w[w], q.w[w], 0x5140); // p0 q0 p1 q1
+				u32 w23 = __byte_perm(p.w[w], q.w[w], 0x7362); // p2 q2 p3 q3
+				int l0 = dp4a_us(w01, 0x0000FF01u, c);
+				int l1 = dp4a_us(w01, 0xFF01FF01u, c);
+				int l2 = dp4a_us(w23, 0x0000FF01u, l1);
+				int l3 = dp4a_us(w23, 0xFF01FF01u, l1);
+				c = l3;
+				e = __sad(l0, 0, e);
+				e = __sad(l1, 0, e);
+				e = __sad(l2, 0, e);
+				e = __sad(l3, 0, e);
+			} else {
+				u32 w0 = __byte_perm(p.w[w], q.w[w], 0x5410); // p0 (16 bit) | q0 (16 bit)
+				u32 w1 = __byte_perm(p.w[w], q.w[w], 0x7632); // p1 | q1
+				int l0 = dp2a_lo_us(w0, 0xFF01u, c);
+				int l1 = dp2a_lo_us(w1, 0xFF01u, l0);
+				c = l1;
+				e = __sad(l0, 0, e);
+				e = __sad(l1, 0, e);
+			}
+		}
+		a_emd = e;
+	}
+}
+
+// whole row pair, any number of slabs; q rows come through L1 (hot when q is the broadcast side)
 template <typename T, int NEED>
 __device__ __forceinline__ RedN reduce_rows_fast(const T *__restrict__ P, const T *__restrict__ Q, u32 slabs, int lane,
 						 bool q_hot)
 {
-	u64 a_min = 0, a_dot = 0, a_emd = 0;
+	u64 t_min = 0, t_dot = 0, t_emd = 0;
 	int carry = 0;
-	const char *pp = reinterpret_cast<const char *>(P) + lane * 16;
-	const char *qq = reinterpret_cast<const char *>(Q) + lane * 16;
-	uint4 pv = ldg_stream(pp);
-	uint4 qv = q_hot ? ldg_keep(qq) : ldg_stream(qq);
+	const char *pp = reinterpret_cast<const char *>(P) + lane * 32;
+	const char *qq = reinterpret_cast<const char *>(Q) + lane * 32;
+	Row8 pv = ld_row_stream(pp);
+	Row8 qv = q_hot ? ld_row_keep(qq) : ld_row_stream(qq);
 #pragma unroll 1
 	for (u32 s = 0; s < slabs; s++) {
-		uint4 pn = pv, qn = qv;
-		if (s + 1 < slabs) { // prefetch the next slab before the ALU work of this one
-			pn = ldg_stream(pp + (size_t)(s + 1) * 512);
-			qn = q_hot ? ldg_keep(qq + (size_t)(s + 1) * 512) : ldg_stream(qq + (size_t)(s + 1) * 512);
+		Row8 pn = pv, qn = qv;
+		if (s + 1 < slabs) { // next slab in flight during this slab's ALU work
+			pn = ld_row_stream(pp + (size_t)(s + 1) * 1024);
+			qn = q_hot ? ld_row_keep(qq + (size_t)(s + 1) * 1024) : ld_row_stream(qq + (size_t)(s + 1) * 1024);
 		}
-		int tot = 0;
-		if constexpr (sizeof(T) == 1) {
-			u32 sad = 0, dot = 0;
-			int l[16];
-			slab_u8<NEED>(pv, qv, sad, dot, l, tot);
-			a_min += sad; // holds sum|p-q| for u8; converted after the loop
-			a_dot += dot;
-			if (NEED & NEED_EMD) {
-				int wt;
-				int off = warp_excl_scan(tot, lane, wt) + carry;
-				carry += wt;
-				u32 e = 0;
-#pragma unroll
-				for (int i = 0; i < 16; i++) {
-					e = __sad(l[i], -off, e);
-				}
-				a_emd += e;
-			}
-		} else {
-			u32 smin = 0, dlo = 0, dhi = 0;
-			int l[8];
-			slab_u16<NEED>(pv, qv, smin, dlo, dhi, l, tot);
-			a_min += smin;
-			a_dot += (u64)dlo + ((u64)dhi << 8);
-			if (NEED & NEED_EMD) {
-				int wt;
-				int off = warp_excl_scan(tot, lane, wt) + carry;
-				carry += wt;
-				u32 e = 0;
-#pragma unroll
-				for (int i = 0; i < 8; i++) {
-					e = __sad(l[i], -off, e);
-				}
-				a_emd += e;
-			}
-		}
+		u32 a_min = 0, lo = 0, hi = 0, e = 0;
+		slab_reduce<T, NEED>(pv, qv, (NEED & NEED_EMD) ? lane_sum<T>(qv) : 0, carry, a_min, lo, hi, e);
+		t_min += a_min;
+		t_dot += (u64)lo + ((u64)hi << 8);
+		t_emd += e;
 		pv = pn;
 		qv = qn;
 	}
 	RedN r;
-	r.smin = (NEED & NEED_MIN) ? warp_sum_u64(a_min) : 0;
-	r.dot = (NEED & NEED_DOT) ? warp_sum_u64(a_dot) : 0;
-	r.emd = (NEED & NEED_EMD) ? warp_sum_u64(a_emd) : 0;
+	r.smin = (NEED & NEED_MIN) ? warp_sum_u64(t_min) : 0;
+	r.dot = (NEED & NEED_DOT) ? warp_sum_u64(t_dot) : 0;
+	r.emd = (NEED & NEED_EMD) ? warp_sum_u64(t_emd) : 0;
 	r.jeff = r.js = 0;
 	return r;
 }
 
-template <typename T, int NEED>
-__global__ void __launch_bounds__(256) pair_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a)
+// ------------------------------------------------------------------------------------------------
+// single-slab rows (k=5 uint8: 1 KiB, the BASELINE shape) against a FIXED row q (the query of a candidate scan, or the
+// query row of one sweep group).  Everything that depends only on q is hoisted into registers once:
+//   q.w[8]   the lane's 32 bins (for the dot / min terms)
+//   bq[32]   the lane-local inclusive prefix sums of q, so that  |cumP_i - cumQ_i| = |(off + prefixP_i) - bq_i|
+//            is ONE VABSDIFF whose operands are an IDP result and a register: no byte interleave (PRMT) at all.
+// Per streamed row and lane: 8 IDP (dot) + 8 IDP (lane total of p) + 32 IDP (prefixes) on the full-rate FMA pipe,
+// 32 VABSDIFF on the half-rate ALU pipe, one 5-step warp scan, one REDUX per needed sum.
+// ------------------------------------------------------------------------------------------------
+struct FixedQ {
+	Row8 q;
+	int bq[32];
+	int qsum;
+};
+
+template <int NEED>
+__device__ __forceinline__ void fixed_q_setup(FixedQ &f, const void *row, int lane)
+{
+	f.q = ld_row_keep(reinterpret_cast<const char *>(row) + lane * 32);
+	int base = 0;
+#pragma unroll
+	for (int w = 0; w < 8; w++) {
+		if (NEED & NEED_EMD) {
+			f.bq[4 * w + 0] = (int)__dp4a(f.q.w[w], 0x00000001u, (u32)base);
+			f.bq[4 * w + 1] = (int)__dp4a(f.q.w[w], 0x00000101u, (u32)base);
+			f.bq[4 * w + 2] = (int)__dp4a(f.q.w[w], 0x00010101u, (u32)base);
+			f.bq[4 * w + 3] = (int)__dp4a(f.q.w[w], 0x01010101u, (u32)base);
+			base = f.bq[4 * w + 3];
+		}
+	}
+	f.qsum = base;
+}
+
+template <int NEED>
+__device__ __forceinline__ void reduce_row1(const Row8 &p, const FixedQ &f, u32 &smin, u32 &dot, u32 &emd)
+{
+	u32 a_min = 0, a_dot = 0, e = 0;
+	if (NEED & NEED_MIN) {
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			a_min = vabsdiff4_acc(p.w[w], f.q.w[w], a_min); // sum |p-q| (converted to S_min by the caller)
+		}
+	}
+	if (NEED & NEED_DOT) {
+		u32 d0 = 0, d1 = 0; // two chains for ILP
+#pragma unroll
+		for (int w = 0; w < 8; w += 2) {
+			d0 = __dp4a(p.w[w], f.q.w[w], d0);
+			d1 = __dp4a(p.w[w + 1], f.q.w[w + 1], d1);
+		}
+		a_dot = d0 + d1;
+	}
+	if (NEED & NEED_EMD) {
+		u32 t0 = 0, t1 = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w += 2) {
+			t0 = __dp4a(p.w[w], 0x01010101u, t0);
+			t1 = __dp4a(p.w[w + 1], 0x01010101u, t1);
+		}
+		int wt;
+		int base = warp_excl_scan((int)(t0 + t1) - f.qsum, wt);
+		u32 e0 = 0, e1 = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			int a0 = (int)__dp4a(p.w[w], 0x00000001u, (u32)base);
+			int a1 = (int)__dp4a(p.w[w], 0x00000101u, (u32)base);
+			int a2 = (int)__dp4a(p.w[w], 0x00010101u, (u32)base);
+			int a3 = (int)__dp4a(p.w[w], 0x01010101u, (u32)base);
+			base = a3;
+			e0 = __sad(a0, f.bq[4 * w + 0], e0);
+			e1 = __sad(a1, f.bq[4 * w + 1], e1);
+			e0 = __sad(a2, f.bq[4 * w + 2], e0);
+			e1 = __sad(a3, f.bq[4 * w + 3], e1);
+		}
+		e = e0 + e1;
+	}
+	// N*w = 1 KiB: every warp total fits 32 bits (dot <= 2^26, emd <= 2^28), one REDUX each
+	smin = (NEED & NEED_MIN) ? __reduce_add_sync(0xffffffffu, a_min) : 0;
+	dot = (NEED & NEED_DOT) ? __reduce_add_sync(0xffffffffu, a_dot) : 0;
+	emd = (NEED & NEED_EMD) ? __reduce_add_sync(0xffffffffu, e) : 0;
+}
+
+// two streamed rows against the same fixed row, written side by side so the two dependency chains (lane totals ->
+// warp scan -> prefix chain -> |.| accumulation -> REDUX) interleave and hide each other's latencies
+template <int NEED>
+__device__ __forceinline__ void reduce_row2(const Row8 &pa, const Row8 &pb, const FixedQ &f, u32 (&oa)[3], u32 (&ob)[3])
+{
+	u32 mina = 0, minb = 0, dota = 0, dotb = 0, ea = 0, eb = 0;
+	if (NEED & NEED_MIN) {
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			mina = vabsdiff4_acc(pa.w[w], f.q.w[w], mina);
+			minb = vabsdiff4_acc(pb.w[w], f.q.w[w], minb);
+		}
+	}
+	if (NEED & NEED_DOT) {
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			dota = __dp4a(pa.w[w], f.q.w[w], dota);
+			dotb = __dp4a(pb.w[w], f.q.w[w], dotb);
+		}
+	}
+	if (NEED & NEED_EMD) {
+		u32 ta = 0, tb = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			ta = __dp4a(pa.w[w], 0x01010101u, ta);
+			tb = __dp4a(pb.w[w], 0x01010101u, tb);
+		}
+		int xa = (int)ta - f.qsum, xb = (int)tb - f.qsum;
+		const int ta0 = xa, tb0 = xb;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			scan_step(xa, d);
+			scan_step(xb, d);
+		}
+		int basea = xa - ta0, baseb = xb - tb0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			int a0 = (int)__dp4a(pa.w[w], 0x00000001u, (u32)basea);
+			int b0 = (int)__dp4a(pb.w[w], 0x00000001u, (u32)baseb);
+			int a1 = (int)__dp4a(pa.w[w], 0x00000101u, (u32)basea);
+			int b1 = (int)__dp4a(pb.w[w], 0x00000101u, (u32)baseb);
+			int a2 = (int)__dp4a(pa.w[w], 0x00010101u, (u32)basea);
+			int b2 = (int)__dp4a(pb.w[w], 0x00010101u, (u32)baseb);
+			int a3 = (int)__dp4a(pa.w[w], 0x01010101u, (u32)basea);
+			int b3 = (int)__dp4a(pb.w[w], 0x01010101u, (u32)baseb);
+			basea = a3;
+			baseb = b3;
+			ea = __sad(a0, f.bq[4 * w + 0], ea);
+			eb = __sad(b0, f.bq[4 * w + 0], eb);
+			ea = __sad(a1, f.bq[4 * w + 1], ea);
+			eb = __sad(b1, f.bq[4 * w + 1], eb);
+			ea = __sad(a2, f.bq[4 * w + 2], ea);
+			eb = __sad(b2, f.bq[4 * w + 2], eb);
+			ea = __sad(a3, f.bq[4 * w + 3], ea);
+			eb = __sad(b3, f.bq[4 * w + 3], eb);
+		}
+	}
+	oa[0] = (NEED & NEED_MIN) ? __reduce_add_sync(0xffffffffu, mina) : 0;
+	ob[0] = (NEED & NEED_MIN) ? __reduce_add_sync(0xffffffffu, minb) : 0;
+	oa[1] = (NEED & NEED_DOT) ? __reduce_add_sync(0xffffffffu, dota) : 0;
+	ob[1] = (NEED & NEED_DOT) ? __reduce_add_sync(0xffffffffu, dotb) : 0;
+	oa[2] = (NEED & NEED_EMD) ? __reduce_add_sync(0xffffffffu, ea) : 0;
+	ob[2] = (NEED & NEED_EMD) ? __reduce_add_sync(0xffffffffu, eb) : 0;
+}
+
+// predicated 256-bit streaming load: the destination keeps its old contents when pred is false, so the register
+// ring below never needs a copy that would wait on a load still in flight
+__device__ __forceinline__ void ld_row_stream_if(Row8 &r, const void *p, int pred)
+{
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %9, 0;\n\t"
+		     "@q ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+		     : "+r"(r.w[0]), "+r"(r.w[1]), "+r"(r.w[2]), "+r"(r.w[3]), "+r"(r.w[4]), "+r"(r.w[5]), "+r"(r.w[6]), "+r"(r.w[7])
+		     : "l"(p), "r"(pred));
+}
+
+// stream the rows of up to 32 pairs (bit mask `active`, row index of pair i held by lane i in `rs`, or consecutive rows
+// first_row + i when contig) against the fixed row, two rows per step.  Two buffer pairs alternate by loop unrolling
+// (no register copies): while one pair of rows is reduced the next pair is in flight.
+template <int NEED>
+__device__ __forceinline__ void scan_group(const unsigned char *S, u64 row_bytes, unsigned active, u64 rs, bool contig,
+					   u64 first_row, const FixedQ &f, int lane, u32 &my_min, u32 &my_dot, u32 &my_emd)
+{
+	auto next_idx = [&]() -> int {
+		int pi = active ? __ffs(active) - 1 : -1;
+		active &= active ? active - 1 : 0;
+		return pi;
+	};
+	auto fetch = [&](Row8 &r, int pi) {
+		// the shuffle must be executed by the whole warp: clamp the source lane instead of predicating it
+		u64 x = contig ? first_row + (u64)(pi < 0 ? 0 : pi) : __shfl_sync(0xffffffffu, rs, pi < 0 ? 0 : pi);
+		ld_row_stream_if(r, S + x * row_bytes + lane * 32, pi >= 0);
+	};
+	auto reduce = [&](const Row8 &ra, int ia, const Row8 &rb, int ib) {
+		u32 oa[3], ob[3];
+		reduce_row2<NEED>(ra, rb, f, oa, ob); // an absent second row (ib < 0) reduces stale data that nobody keeps
+		if (lane == ia) {
+			my_min = oa[0];
+			my_dot = oa[1];
+			my_emd = oa[2];
+		}
+		if (lane == ib) {
+			my_min = ob[0];
+			my_dot = ob[1];
+			my_emd = ob[2];
+		}
+	};
+	Row8 a0 = {}, b0 = {}, a1 = {}, b1 = {};
+	int ia0 = next_idx();
+	if (ia0 < 0) {
+		return;
+	}
+	int ib0 = next_idx();
+	fetch(a0, ia0);
+	fetch(b0, ib0);
+	int ia1 = next_idx(), ib1 = next_idx();
+	fetch(a1, ia1);
+	fetch(b1, ib1);
+	while (true) {
+		reduce(a0, ia0, b0, ib0);
+		if (ia1 < 0) {
+			break;
+		}
+		ia0 = next_idx();
+		ib0 = next_idx();
+		fetch(a0, ia0);
+		fetch(b0, ib0);
+		reduce(a1, ia1, b1, ib1);
+		if (ia0 < 0) {
+			break;
+		}
+		ia1 = next_idx();
+		ib1 = next_idx();
+		fetch(a1, ia1);
+		fetch(b1, ib1);
+	}
+}
+
+template <typename T, int NEED, bool ONE>
+__global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) pair_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a)
 {
 	const int lane = threadIdx.x & 31;
 	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
 	const u64 warp_id = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	const u32 slabs = (u32)(a.N * sizeof(T) / 512);
+	const u32 slabs = (u32)(a.N * sizeof(T) / 1024);
 	const T *A = reinterpret_cast<const T *>(a.binsA);
 	const T *B = reinterpret_cast<const T *>(a.binsB);
 	const u64 groups = (a.n_pairs + 31) / 32;
-	// the streamed side is the one that is not broadcast; the broadcast row stays hot in L1
+	// the streamed side is the one that is not broadcast; the broadcast row stays resident
 	const bool a_hot = a.a_bc && !a.ia;
 	const bool b_hot = a.b_bc && !a.ib;
+	constexpr bool fixed_q = ONE; // host picks ONE when slabs == 1, T = u8 and one side is a broadcast row
+	FixedQ fq;
+	if constexpr (fixed_q) { // one-vs-many: the query row and its prefix sums live in registers for the whole kernel
+		const T *qrow = a_hot ? A + a.a_begin * a.N : B + a.b_begin * a.N;
+		fixed_q_setup<NEED>(fq, qrow, lane);
+	}
 	for (u64 g = warp_id; g < groups; g += warps_total) {
 		const u64 j = g * 32 + lane;
 		const bool valid = j < a.n_pairs;
@@ -547,19 +793,30 @@ __global__ void __launch_bounds__(256) pair_fast_kernel(const __grid_constant__ 
 		mine.smin = mine.dot = mine.emd = 0;
 		mine.jeff = mine.js = 0;
 		unsigned active = __ballot_sync(0xffffffffu, go);
-		while (active) {
-			int pi = __ffs(active) - 1;
-			active &= active - 1;
-			u64 xa = __shfl_sync(0xffffffffu, ra, pi);
-			u64 xb = __shfl_sync(0xffffffffu, rb, pi);
-			RedN r;
-			if (a_hot) { // stream B, keep A
-				r = reduce_rows_fast<T, NEED>(B + xb * a.N, A + xa * a.N, slabs, lane, true);
-			} else {
-				r = reduce_rows_fast<T, NEED>(A + xa * a.N, B + xb * a.N, slabs, lane, b_hot);
-			}
-			if (lane == pi) {
-				mine = r;
+		if constexpr (fixed_q) {
+			const unsigned char *S = reinterpret_cast<const unsigned char *>(a_hot ? B : A);
+			const bool contig = a_hot ? (a.ib == nullptr) : (a.ia == nullptr);
+			const u64 first_row = (a_hot ? a.b_begin : a.a_begin) + g * 32;
+			u32 m0 = 0, m1 = 0, m2 = 0;
+			scan_group<NEED>(S, 1024, active, a_hot ? rb : ra, contig, first_row, fq, lane, m0, m1, m2);
+			mine.smin = m0;
+			mine.dot = m1;
+			mine.emd = m2;
+		} else {
+			while (active) {
+				int pi = __ffs(active) - 1;
+				active &= active - 1;
+				u64 xa = __shfl_sync(0xffffffffu, ra, pi);
+				u64 xb = __shfl_sync(0xffffffffu, rb, pi);
+				RedN r;
+				if (a_hot) { // stream B, keep A
+					r = reduce_rows_fast<T, NEED>(B + xb * a.N, A + xa * a.N, slabs, lane, true);
+				} else {
+					r = reduce_rows_fast<T, NEED>(A + xa * a.N, B + xb * a.N, slabs, lane, b_hot);
+				}
+				if (lane == pi) {
+					mine = r;
+				}
 			}
 		}
 		if (go) {
@@ -858,15 +1115,15 @@ struct SweepArgs {
 	u64 *counters; // [0] survivors, [1] scored pairs
 };
 
-template <typename T, int NEED, bool FAST>
-__global__ void __launch_bounds__(256) sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
+template <typename T, int NEED, bool FAST, bool ONE>
+__global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
 						    const __grid_constant__ SweepArgs g)
 {
 	constexpr bool WIDE = sizeof(T) > 2;
 	const int lane = threadIdx.x & 31;
 	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
 	const u64 warp_id = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	const u32 slabs = (u32)(a.N * sizeof(T) / 512);
+	const u32 slabs = (u32)(a.N * sizeof(T) / 1024);
 	const T *Dm = reinterpret_cast<const T *>(a.binsA); // database = first argument of close(pts[i], query)
 	const T *Qm = reinterpret_cast<const T *>(a.binsB);
 	const u64 cblocks = (g.d1 - g.d0 + 31) / 32;
@@ -888,16 +1145,33 @@ __global__ void __launch_bounds__(256) sweep_kernel(const __grid_constant__ DevM
 		mw = RedW();
 		unsigned active = __ballot_sync(0xffffffffu, go);
 		const unsigned scored = active;
-		while (active) {
-			int pi = __ffs(active) - 1;
-			active &= active - 1;
-			u64 xc = __shfl_sync(0xffffffffu, c, pi);
-			if constexpr (FAST) {
-				RedN rr = reduce_rows_fast<T, NEED>(Dm + xc * a.N, Qm + r * a.N, slabs, lane, true);
-				if (lane == pi) {
-					mn = rr;
-				}
+		if constexpr (FAST) {
+			if constexpr (ONE) { // slabs == 1 && T == u8, picked by the host
+				// the query row r and its prefix sums sit in registers for the whole 32-candidate group
+				FixedQ fq;
+				fixed_q_setup<NEED>(fq, Qm + r * a.N, lane);
+				u32 m0 = 0, m1 = 0, m2 = 0;
+				scan_group<NEED>(reinterpret_cast<const unsigned char *>(Dm), 1024, active, c, true,
+						 g.d0 + (grp % cblocks) * 32, fq, lane, m0, m1, m2);
+				mn.smin = m0;
+				mn.dot = m1;
+				mn.emd = m2;
 			} else {
+				while (active) {
+					int pi = __ffs(active) - 1;
+					active &= active - 1;
+					u64 xc = __shfl_sync(0xffffffffu, c, pi);
+					RedN rr = reduce_rows_fast<T, NEED>(Dm + xc * a.N, Qm + r * a.N, slabs, lane, true);
+					if (lane == pi) {
+						mn = rr;
+					}
+				}
+			}
+		} else {
+			while (active) {
+				int pi = __ffs(active) - 1;
+				active &= active - 1;
+				u64 xc = __shfl_sync(0xffffffffu, c, pi);
 				RedN rn;
 				RedW rw;
 				reduce_rows_generic<T>(Dm + xc * a.N, Qm + r * a.N, a.N, lane, dm.need, a.sbA.mag[xc], a.sbB.mag[r], rn, rw);
@@ -958,13 +1232,13 @@ static int grid_for(mc2_ctx *ctx, u64 n_pairs, int warps_per_cta, int ctas_per_s
 	return (int)(g ? g : 1);
 }
 
-template <typename T>
+template <typename T, bool ONE>
 static void launch_fast_need(int need, int grid, cudaStream_t st, const DevModel &dm, const PairArgs &a)
 {
 	switch (need & 7) {
-#define CASE(n)                                                    \
-	case n:                                                    \
-		pair_fast_kernel<T, n><<<grid, 256, 0, st>>>(dm, a); \
+#define CASE(n)                                                         \
+	case n:                                                         \
+		pair_fast_kernel<T, n, ONE><<<ONE ? grid * 2 : grid, ONE ? 128 : 256, 0, st>>>(dm, a); \
 		break;
 		CASE(0)
 		CASE(1)
@@ -984,14 +1258,17 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 		return MC2_OK;
 	}
 	const u64 row_bytes = a.N * (u64)a.eb;
-	const bool fast = a.eb <= 2 && row_bytes % 512 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 27);
+	const bool fast = a.eb <= 2 && row_bytes % 1024 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 26);
 	prof_begin(ctx, 2);
 	if (fast) {
 		int grid = grid_for(ctx, a.n_pairs, 8, 8);
-		if (a.eb == 1) {
-			launch_fast_need<uint8_t>(dm.need, grid, ctx->stream, dm, a);
+		const bool one = a.eb == 1 && row_bytes == 1024 && ((a.a_bc && !a.ia) || (a.b_bc && !a.ib));
+		if (one) {
+			launch_fast_need<uint8_t, true>(dm.need, grid, ctx->stream, dm, a);
+		} else if (a.eb == 1) {
+			launch_fast_need<uint8_t, false>(dm.need, grid, ctx->stream, dm, a);
 		} else {
-			launch_fast_need<uint16_t>(dm.need, grid, ctx->stream, dm, a);
+			launch_fast_need<uint16_t, false>(dm.need, grid, ctx->stream, dm, a);
 		}
 	} else {
 		int grid = grid_for(ctx, a.n_pairs, 8, 8);
@@ -1039,13 +1316,13 @@ int launch_distance(mc2_ctx *ctx, const PairArgs &a, u64 *d_out)
 	return MC2_OK;
 }
 
-template <typename T>
+template <typename T, bool ONE>
 static void launch_sweep_fast(int need, int grid, cudaStream_t st, const DevModel &dm, const PairArgs &a, const SweepArgs &g)
 {
 	switch (need & 7) {
-#define CASE(n)                                                          \
-	case n:                                                          \
-		sweep_kernel<T, n, true><<<grid, 256, 0, st>>>(dm, a, g); \
+#define CASE(n)                                                               \
+	case n:                                                               \
+		sweep_kernel<T, n, true, ONE><<<ONE ? grid * 2 : grid, ONE ? 128 : 256, 0, st>>>(dm, a, g); \
 		break;
 		CASE(0)
 		CASE(1)
@@ -1089,20 +1366,22 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 	u64 want = (groups + 7) / 8, cap = (u64)ctx->sm_count * 8;
 	int grid = (int)(want < cap ? want : cap);
 	const u64 row_bytes = a.N * (u64)a.eb;
-	const bool fast = a.eb <= 2 && row_bytes % 512 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 27);
+	const bool fast = a.eb <= 2 && row_bytes % 1024 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 26);
 	prof_begin(ctx, 3);
 	if (fast) {
-		if (a.eb == 1) {
-			launch_sweep_fast<uint8_t>(dm.need, grid, ctx->stream, dm, a, g);
+		if (a.eb == 1 && row_bytes == 1024) {
+			launch_sweep_fast<uint8_t, true>(dm.need, grid, ctx->stream, dm, a, g);
+		} else if (a.eb == 1) {
+			launch_sweep_fast<uint8_t, false>(dm.need, grid, ctx->stream, dm, a, g);
 		} else {
-			launch_sweep_fast<uint16_t>(dm.need, grid, ctx->stream, dm, a, g);
+			launch_sweep_fast<uint16_t, false>(dm.need, grid, ctx->stream, dm, a, g);
 		}
 	} else {
 		switch (a.eb) {
-		case 1: sweep_kernel<uint8_t, 0, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
-		case 2: sweep_kernel<uint16_t, 0, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
-		case 4: sweep_kernel<uint32_t, 0, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
-		case 8: sweep_kernel<unsigned long long, 0, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
+		case 1: sweep_kernel<uint8_t, 0, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
+		case 2: sweep_kernel<uint16_t, 0, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
+		case 4: sweep_kernel<uint32_t, 0, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
+		case 8: sweep_kernel<unsigned long long, 0, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
 		default: set_error("elem_bytes must be 1, 2, 4 or 8"); return MC2_ERR_ARG;
 		}
 	}
