@@ -40,6 +40,19 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def traffic_per_pair(key):
+    """DRAM bytes per pair of a kernel from the committed ncu --set full capture (profiles/r1_traffic.json)"""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        d = json.load(open(p))
+        for k, v in d.items():
+            if k.startswith(key):
+                return float(v["dram_bytes_per_pair"]), v["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -269,8 +282,10 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = peaks()
     local_pairs = res["local_scored"] * args.steps
     achieved = local_pairs * bytes_per_pair / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    tpp, tsrc = traffic_per_pair("sweep_kernel")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "sweep_kernel<u8,NEED_DOT|NEED_EMD>",
+                "traffic": tpp * local_pairs / max(1, sweep_n) if tpp else None, "traffic_source": tsrc,
+                "kernel": "sweep_kernel<u8,NEED_DOT|NEED_EMD>",
                 "algorithmic_bytes_per_unit": bytes_per_pair, "units_per_launch": local_pairs / max(1, sweep_n),
                 "avg_launch_ms": sweep_ms / max(1, sweep_n), "launches": sweep_n,
                 "kernel_share_of_step": sweep_ms / ms if ms > 0 else None, "peak_source": peak_src,
@@ -320,7 +335,9 @@ def candidates_roofline(ctx, capi, model, k, eb, peak, peak_src, n=1 << 20):
     hs.free()
     bpp = N * eb + 24 + 9
     ach = n * bpp / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    tpp, tsrc = traffic_per_pair("pair_fast_kernel")
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": tpp * n if tpp else None, "traffic_source": tsrc,
             "kernel": "pair_fast_kernel<u8> one query vs 2^20 candidates (1 GiB streamed, > L2)",
             "algorithmic_bytes_per_unit": bpp, "units_per_launch": n, "avg_launch_ms": ms, "pairs_per_s": n / (ms * 1e-3),
             "peak_source": peak_src}
