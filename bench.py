@@ -353,8 +353,8 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="override the number of sequences (smoke runs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--cpu-hist-sample", type=int, default=20000)
-    ap.add_argument("--cpu-pair-sample", type=int, default=3000000)
+    ap.add_argument("--cpu-hist-sample", type=int, default=100000)
+    ap.add_argument("--cpu-pair-sample", type=int, default=20000000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

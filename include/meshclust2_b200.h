@@ -178,6 +178,13 @@ int mc2_hset_set_sideband(mc2_ctx *ctx, mc2_hset *h, uint64_t count, const uint6
 /* copy row `src_row` of `src` over row `dst_row` of `dst` the way DivergencePoint::set does: bins + length, NOT mag */
 int mc2_hset_set_row(mc2_ctx *ctx, mc2_hset *dst, uint64_t dst_row, const mc2_hset *src, uint64_t src_row);
 
+/* Batched form of the two calls above, one launch: dst row dst_rows[i] receives the bins (and true sums) of src row
+ * src_rows[i]; its length becomes len[i] (NULL: the src row's length) and its pseudo-magnitude mag[i] (NULL: the dst row
+ * keeps the magnitude it had, i.e. DivergencePoint::set semantics).  Used to assemble the (possibly stale-magnitude)
+ * center rows that Trainer::filter / merge compare (src/cluster/ClusterFactory.cpp:288-335, 383-401). */
+int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t *dst_rows, const mc2_hset *src,
+			 const uint64_t *src_rows, const uint64_t *mag, const uint64_t *len);
+
 /* ---- model -------------------------------------------------------------------------------------- */
 int mc2_model_create(mc2_ctx *ctx, const mc2_model_desc *desc, mc2_model **out);
 void mc2_model_free(mc2_model *m);

@@ -1,0 +1,313 @@
+// Trainer_b200.cpp — the ONE reference file that changes for the drop-in: a replacement for
+// src/cluster/Trainer.cpp that keeps Trainer<T>'s interface (src/cluster/Trainer.h:20-45, compiled from the reference
+// header, unmodified) and sends the candidate batches of get_close / filter / merge to libmeshclust2_b200 through the C
+// ABI (include/meshclust2_b200.h).  Everything else of MeShClust2 — CLI, FASTA I/O, mutation generator, GLM fit and
+// feature selection, the mean-shift driver (ClusterFactory), bvec, CLSTR output — is the reference's own object code.
+//
+// It is built by oracle/Makefile (`make integrated`) against the reference sources where they lie, into
+// oracle/_ref/meshclust2_b200, and exists to prove the boundary end to end: tests/test_integrated_cluster.py checks that
+// this binary and the unmodified reference binary produce the same clusters from the same weights.
+//
+// Batching follows SURVEY.md section 3.1: one device call per get_close / filter / merge (the candidates of one query);
+// the histograms of all points are uploaded once, centers are addressed by the id of the point whose bins they carry plus
+// the (possibly stale, quirk Q4) pseudo-magnitude and length the host object reports.
+#include "cluster/Trainer.h"
+#include "clutil/Datatype.h"
+#include "clutil/DivergencePoint.h"
+#include "predict/Predictor.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+
+#include "meshclust2_b200.h"
+
+namespace {
+
+std::mutex g_mu; // the update stage calls filter() from an OpenMP loop; one GPU context, one caller at a time
+
+void ok(int rc)
+{
+	if (rc != MC2_OK) {
+		std::cerr << "meshclust2_b200: " << mc2_last_error() << std::endl;
+		throw std::runtime_error(mc2_last_error());
+	}
+}
+
+struct Device {
+	mc2_ctx *ctx = nullptr;
+	mc2_model *model = nullptr;
+	mc2_hset *points = nullptr;   // row = Point::get_id()
+	mc2_hset *scratch = nullptr;  // assembled center rows (filter: 1, merge: <= 1 + delta)
+	uint64_t scratch_rows = 0;
+	uint64_t n = 0;
+	int k = 0;
+};
+
+std::map<const void *, Device> g_dev;
+
+template <class T>
+const DivergencePoint<T> &dp(const Point<T> *p)
+{
+	return dynamic_cast<const DivergencePoint<T> &>(*p);
+}
+
+template <class T>
+mc2_model_desc describe(const Feature<T> &feat, const matrix::Matrix &weights)
+{
+	mc2_model_desc d = mc2_model_desc();
+	auto lookup = feat.get_lookup();
+	auto mins = feat.get_mins();
+	auto maxs = feat.get_maxs();
+	auto combos = feat.get_combos();
+	if (lookup.size() > MC2_MAX_SINGLES || combos.size() > MC2_MAX_COMBOS) {
+		throw std::runtime_error("model too large for the device descriptor");
+	}
+	d.n_singles = (int32_t)lookup.size();
+	for (size_t i = 0; i < lookup.size(); i++) {
+		d.single_flag[i] = lookup[i];
+		d.single_min[i] = mins[i];
+		d.single_max[i] = maxs[i];
+	}
+	d.n_combos = (int32_t)combos.size();
+	for (size_t c = 0; c < combos.size(); c++) {
+		switch (combos[c].first) {
+		case Combo::xy: d.combo_kind[c] = MC2_COMBO_XY; break;
+		case Combo::xy2: d.combo_kind[c] = MC2_COMBO_XY2; break;
+		case Combo::x2y: d.combo_kind[c] = MC2_COMBO_X2Y; break;
+		case Combo::x2y2: d.combo_kind[c] = MC2_COMBO_X2Y2; break;
+		}
+		d.combo_nidx[c] = (int32_t)combos[c].second.size();
+		for (size_t t = 0; t < combos[c].second.size(); t++) {
+			d.combo_idx[c][t] = combos[c].second[t];
+		}
+	}
+	for (int r = 0; r < weights.getNumRow(); r++) {
+		d.weight[r] = weights.get(r, 0);
+	}
+	d.bias = Predictor<T>::classify_sum(0) - 0.5; // classify_sum(0) = logistic(0) + _bias = 0.5 + _bias
+	return d;
+}
+
+// lazily mirror the Trainer's state on the device: the model once, the points (indexed by their final ids) once
+template <class T>
+Device &device_for(const void *key, const Feature<T> &feat, const matrix::Matrix &weights, const std::vector<Point<T> *> &points,
+		   int k)
+{
+	Device &d = g_dev[key];
+	if (d.ctx) {
+		return d;
+	}
+	const char *dev_env = std::getenv("MC2_DEVICE");
+	ok(mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &d.ctx));
+	mc2_model_desc desc = describe<T>(feat, weights);
+	ok(mc2_model_create(d.ctx, &desc, &d.model));
+	d.k = k;
+	d.n = points.size();
+	const size_t N = (size_t)1 << (2 * k);
+	std::vector<T> bins(d.n * N);
+	std::vector<uint64_t> mag(d.n), len(d.n);
+	for (Point<T> *p : points) {
+		const uint64_t id = p->get_id();
+		if (id >= d.n) {
+			throw std::runtime_error("meshclust2_b200 integration: point ids must be 0..n-1 (no --no-train-list support)");
+		}
+		const DivergencePoint<T> &q = dp<T>(p);
+		std::copy(q.points.begin(), q.points.end(), bins.begin() + id * N);
+		mag[id] = q.getPseudoMagnitude();
+		len[id] = q.get_length();
+	}
+	ok(mc2_hset_from_host(d.ctx, bins.data(), d.n, k, (int)sizeof(T), mag.data(), len.data(), &d.points));
+	d.scratch_rows = 64;
+	std::vector<T> zero(d.scratch_rows * N, 1);
+	std::vector<uint64_t> ones(d.scratch_rows, 1);
+	ok(mc2_hset_from_host(d.ctx, zero.data(), d.scratch_rows, k, (int)sizeof(T), nullptr, ones.data(), &d.scratch));
+	return d;
+}
+
+// put host center objects into scratch rows 0..m-1: bins of the point whose id they carry + their own mag / length
+template <class T>
+void stage_centers(Device &d, const std::vector<Point<T> *> &cs)
+{
+	const uint64_t m = cs.size();
+	if (m > d.scratch_rows) {
+		throw std::runtime_error("meshclust2_b200 integration: --delta too large for the scratch set");
+	}
+	std::vector<uint64_t> dst(m), src(m), mag(m), len(m);
+	for (uint64_t i = 0; i < m; i++) {
+		dst[i] = i;
+		src[i] = cs[i]->get_id();
+		mag[i] = dp<T>(cs[i]).getPseudoMagnitude();
+		len[i] = cs[i]->get_length();
+	}
+	ok(mc2_hset_assign_rows(d.ctx, d.scratch, m, dst.data(), d.points, src.data(), mag.data(), len.data()));
+}
+
+} // namespace
+
+template <class T>
+std::tuple<Point<T> *, double, size_t, size_t> Trainer<T>::get_close(Point<T> *p, bvec_iterator<T> istart, bvec_iterator<T> iend,
+									bool &is_min_r) const
+{
+	std::lock_guard<std::mutex> lock(g_mu);
+	Device &d = device_for<T>(this, *feat, weights, points, k);
+	std::vector<uint64_t> cand;
+	std::vector<bvec_iterator<T>> where;
+	for (bvec_iterator<T> i = istart; i < iend; ++i) {
+		cand.push_back((*i).first->get_id());
+		where.push_back(i);
+	}
+	std::tuple<Point<T> *, double, size_t, size_t> result(NULL, -1, 0, 0);
+	is_min_r = true;
+	if (cand.empty()) {
+		return result;
+	}
+	std::vector<Point<T> *> q{p};
+	stage_centers<T>(d, q);
+	int64_t best = -1;
+	double best_dist = -1;
+	int32_t is_min = 1;
+	std::vector<uint8_t> marks(cand.size());
+	ok(mc2_get_close(d.ctx, d.model, d.scratch, 0, d.points, cand.data(), 0, cand.size(), cutoff, &best, &best_dist, &is_min,
+			 marks.data()));
+	for (size_t j = 0; j < cand.size(); j++) {
+		if (marks[j]) {
+			bvec_iterator<T> it = where[j];
+			*it = std::make_pair((*it).first, true);
+		}
+	}
+	if (best >= 0) {
+		bvec_iterator<T> it = where[(size_t)best];
+		result = std::make_tuple((*it).first, best_dist, it.r, it.c);
+	}
+	is_min_r = is_min != 0;
+	return result;
+}
+
+template <class T>
+long Trainer<T>::merge(vector<Center<T>> &centers, long current, long begin, long last) const
+{
+	if (last < begin) {
+		return 0;
+	}
+	std::lock_guard<std::mutex> lock(g_mu);
+	Device &d = device_for<T>(this, *feat, weights, points, k);
+	std::vector<Point<T> *> cs;
+	cs.push_back(centers[current].getCenter());
+	for (long i = begin; i <= last; i++) {
+		cs.push_back(centers[i].getCenter());
+	}
+	stage_centers<T>(d, cs);
+	std::vector<uint64_t> rows(cs.size());
+	for (size_t i = 0; i < rows.size(); i++) {
+		rows[i] = i;
+	}
+	int64_t out = 0;
+	ok(mc2_merge(d.ctx, d.model, d.scratch, rows.data(), 0, 1, (int64_t)cs.size() - 1, get_id(), &out));
+	return out == 0 ? 0 : begin + (out - 1);
+}
+
+template <class T>
+double Trainer<T>::classify(Point<T> *a, Point<T> *b) const
+{
+	std::lock_guard<std::mutex> lock(g_mu);
+	Device &d = device_for<T>(this, *feat, weights, points, k);
+	std::vector<Point<T> *> two{a, b};
+	stage_centers<T>(d, two);
+	mc2_pairs pr = mc2_pairs();
+	pr.set_a = pr.set_b = d.scratch;
+	pr.n_pairs = 1;
+	uint64_t ia = 0, ib = 1;
+	pr.ia = &ia;
+	pr.ib = &ib;
+	double score = 0;
+	ok(mc2_score_pairs(d.ctx, d.model, &pr, &score, nullptr, nullptr, nullptr, nullptr, nullptr));
+	return score;
+}
+
+template <class T>
+void Trainer<T>::filter(Point<T> *p, vector<pair<Point<T> *, bool>> &vec) const
+{
+	if (vec.empty()) {
+		return;
+	}
+	std::vector<uint8_t> keep(vec.size());
+	{
+		std::lock_guard<std::mutex> lock(g_mu);
+		Device &d = device_for<T>(this, *feat, weights, points, k);
+		std::vector<uint64_t> rows(vec.size());
+		for (size_t j = 0; j < vec.size(); j++) {
+			rows[j] = vec[j].first->get_id();
+		}
+		std::vector<Point<T> *> c{p};
+		stage_centers<T>(d, c);
+		ok(mc2_filter(d.ctx, d.model, d.scratch, 0, d.points, rows.data(), rows.size(), get_id(), keep.data()));
+	}
+	size_t w = 0;
+	for (size_t j = 0; j < vec.size(); j++) {
+		if (keep[j]) {
+			vec[w] = vec[j];
+			vec[w].second = false;
+			w++;
+		}
+	}
+	vec.resize(w);
+}
+
+// unchanged host logic: arg-min of distance_d against the (double) mean — K3, the next row of SURVEY section 8f
+template <class T>
+Point<T> *Trainer<T>::closest(Point<double> *p, vector<pair<Point<T> *, bool>> &vec) const
+{
+	Point<T> *best_pt = NULL;
+	double best_dist = 0;
+	for (auto &pt : vec) {
+		double dist = pt.first->distance_d(*p);
+		if (best_pt == NULL || dist < best_dist) {
+			best_dist = dist;
+			best_pt = pt.first;
+		}
+	}
+	return best_pt;
+}
+
+// training stays on the host exactly as in the reference: Predictor builds the model, Trainer keeps a copy
+template <class T>
+void Trainer<T>::train(std::string dump_str)
+{
+	Predictor<T> *pred = new Predictor<T>(dump_str); // never destroyed: the reference's file ctor leaves members unset
+	auto pr = pred->get_class();
+	delete feat;
+	feat = pr.first;
+	feat->set_save(false);
+	weights = pr.second.get_weights();
+}
+
+template <class T>
+void Trainer<T>::train(int min_n_feat, int max_n_feat, uint64_t feat_type, int mut_type, double min_id, std::string dump_str,
+		       double acc_cutoff)
+{
+	(void)acc_cutoff;
+	std::cout << "Splitting data" << endl;
+	uintmax_t next_id = points.size();
+	Predictor<T> pred(k, cutoff, PRED_MODE_CLASS, feat_type, mut_type, min_n_feat, max_n_feat, min_id);
+	pred.train(points, next_id, n_samples, n_templates);
+	auto pr = pred.get_class();
+	delete feat;
+	feat = pr.first;
+	weights = pr.second.get_weights();
+	const bool dump_only = dump_str != "";
+	pred.save(dump_only ? dump_str : std::string("weights.txt"), Datatype::get());
+	if (dump_only) {
+		exit(0);
+	}
+}
+
+template class Trainer<uint8_t>;
+template class Trainer<uint16_t>;
+template class Trainer<uint32_t>;
+template class Trainer<uint64_t>;
+template class Trainer<int>;
+template class Trainer<double>;

@@ -37,7 +37,7 @@ SYMBOLS = [
     "mc2_ctx_launch_count", "mc2_ctx_profile", "mc2_ctx_kernel_time", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_free", "mc2_seqs_count",
     "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
     "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
-    "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
+    "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
     "mc2_score_pairs", "mc2_get_close", "mc2_filter", "mc2_merge", "mc2_all_pairs", "mc2_distance",
     "mc2_bench_score_pairs", "mc2_bench_count_kmers", "mc2_encode_dna", "mc2_encode_dna_batch",
 ]
@@ -382,6 +382,11 @@ class HistSet:
 
     def set_row(self, dst_row, src, src_row):
         _check(lib().mc2_hset_set_row(self.ctx.h, self.h, C.c_uint64(dst_row), src.h, C.c_uint64(src_row)))
+
+    def assign_rows(self, dst_rows, src, src_rows, mag=None, length=None):
+        dst_rows, src_rows = _u64(dst_rows), _u64(src_rows)
+        _check(lib().mc2_hset_assign_rows(self.ctx.h, self.h, C.c_uint64(len(dst_rows)), _p(dst_rows), src.h, _p(src_rows),
+                                          _p(_u64(mag)), _p(_u64(length))))
 
     def free(self):
         if self.h:

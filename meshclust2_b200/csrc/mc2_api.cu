@@ -292,6 +292,31 @@ static int refresh_max_sum(mc2_ctx *ctx, mc2_hset *h)
 	return MC2_OK;
 }
 
+// one warp per row: copy bins + true sums; length / magnitude from the optional override arrays
+__global__ void __launch_bounds__(256) assign_rows_kernel(char *dbins, u64 *dmag, u64 *dsum, u64 *dsumsq, u64 *dlen, const char *sbins,
+							   const u64 *ssum, const u64 *ssumsq, const u64 *slen, u64 row_bytes, u64 n,
+							   const u64 *idx /* [dst | src | mag? | len?] x n */, int has_mag, int has_len)
+{
+	const int lane = threadIdx.x & 31;
+	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
+	for (u64 i = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps_total) {
+		const u64 d = idx[i], s = idx[n + i];
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(sbins + s * row_bytes);
+		uint32_t *dst = reinterpret_cast<uint32_t *>(dbins + d * row_bytes);
+		for (u64 w = lane; w < row_bytes / 4; w += 32) {
+			dst[w] = src[w];
+		}
+		if (lane == 0) {
+			dsum[d] = ssum[s];
+			dsumsq[d] = ssumsq[s];
+			dlen[d] = has_len ? idx[(2 + has_mag) * n + i] : slen[s];
+			if (has_mag) {
+				dmag[d] = idx[2 * n + i];
+			}
+		}
+	}
+}
+
 } // namespace mc2
 
 using namespace mc2;
@@ -834,6 +859,42 @@ int mc2_hset_set_row(mc2_ctx *ctx, mc2_hset *dst, uint64_t dst_row, const mc2_hs
 	MC2_CUDA(cudaMemcpyAsync(dst->sum + dst_row, src->sum + src_row, 8, cudaMemcpyDeviceToDevice, st));
 	MC2_CUDA(cudaMemcpyAsync(dst->sumsq + dst_row, src->sumsq + src_row, 8, cudaMemcpyDeviceToDevice, st));
 	MC2_CUDA(cudaStreamSynchronize(st));
+	if (src->max_sum > dst->max_sum) {
+		dst->max_sum = src->max_sum;
+	}
+	return MC2_OK;
+}
+
+int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t *dst_rows, const mc2_hset *src,
+			 const uint64_t *src_rows, const uint64_t *mag, const uint64_t *len)
+{
+	MC2_REQUIRE(ctx && dst && src && (n == 0 || (dst_rows && src_rows)), "mc2_hset_assign_rows: NULL argument");
+	MC2_REQUIRE(dst->k == src->k && dst->eb == src->eb, "mc2_hset_assign_rows: sets differ in k or width");
+	if (n == 0) {
+		return MC2_OK;
+	}
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	const int parts = 2 + (mag ? 1 : 0) + (len ? 1 : 0);
+	std::vector<u64> idx((size_t)parts * n);
+	for (u64 i = 0; i < n; i++) {
+		MC2_REQUIRE(dst_rows[i] < dst->n && src_rows[i] < src->n, "mc2_hset_assign_rows: row out of range");
+		idx[i] = dst_rows[i];
+		idx[n + i] = src_rows[i];
+		if (mag) idx[2 * n + i] = mag[i];
+		if (len) idx[(size_t)(2 + (mag ? 1 : 0)) * n + i] = len[i];
+	}
+	CtxExtra *x = extra(ctx);
+	int rc = ensure(x->d[B_IA], idx.size() * 8, false);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaMemcpyAsync(x->d[B_IA].p, idx.data(), idx.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+	u64 want = (n + 7) / 8, cap = (u64)ctx->sm_count * 8;
+	int grid = (int)(want < cap ? want : cap);
+	assign_rows_kernel<<<grid, 256, 0, ctx->stream>>>((char *)dst->bins, dst->mag, dst->sum, dst->sumsq, dst->len,
+							   (const char *)src->bins, src->sum, src->sumsq, src->len, dst->N * (u64)dst->eb, n,
+							   (const u64 *)x->d[B_IA].p, mag ? 1 : 0, len ? 1 : 0);
+	ctx->launches++;
+	MC2_CUDA(cudaGetLastError());
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream)); // idx is a host temporary
 	if (src->max_sum > dst->max_sum) {
 		dst->max_sum = src->max_sum;
 	}

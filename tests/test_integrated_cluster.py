@@ -1,0 +1,53 @@
+"""GPU, end to end: the reference's own meshclust2 with ONE translation unit swapped (src/cluster/Trainer.cpp ->
+integration/Trainer_b200.cpp, which calls the C ABI) must produce the same clusters as the unmodified reference binary.
+Both binaries are built in the build container by `make -C oracle ref integrated` into oracle/_ref/ (they travel to the GPU
+box; the test is skipped where they are absent).  --threads 1 and a single FASTA make the reference deterministic
+(SURVEY.md section 4), and training is the reference's own host code in both, so the weights are identical by construction."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from meshclust2_b200 import synth
+
+REF = os.path.join(ROOT, "oracle", "_ref", "meshclust2")
+OURS = os.path.join(ROOT, "oracle", "_ref", "meshclust2_b200")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(OURS)), reason="oracle/_ref binaries not built")]
+
+
+def parse_clstr(path):
+    clusters, cur = [], None
+    for line in open(path):
+        if line.startswith(">Cluster"):
+            cur = set()
+            clusters.append(cur)
+        else:
+            m = re.search(r">(\S+)", line)
+            if m:
+                cur.add(m.group(1).rstrip("."))
+    return {frozenset(c) for c in clusters if c}
+
+
+def run(binary, fasta, workdir, out):
+    os.makedirs(workdir, exist_ok=True)
+    r = subprocess.run([binary, "--id", "0.9", "--sample", "800", "--num-templates", "120", "--threads", "1", fasta,
+                        "--output", out], cwd=workdir, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return open(os.path.join(workdir, "weights.txt")).read()
+
+
+def test_same_clusters_as_the_reference(tmp_path):
+    seqs, tids = synth.make_set(800, 1000, 120, 0.08, seed=7)
+    fasta = str(tmp_path / "in.fa")
+    open(fasta, "w").write(synth.to_fasta(seqs, tids))
+    w_ref = run(REF, fasta, str(tmp_path / "ref"), str(tmp_path / "ref.clstr"))
+    w_our = run(OURS, fasta, str(tmp_path / "ours"), str(tmp_path / "ours.clstr"))
+    assert w_ref == w_our                       # same host training code, same seeds
+    c_ref, c_our = parse_clstr(str(tmp_path / "ref.clstr")), parse_clstr(str(tmp_path / "ours.clstr"))
+    assert sum(len(c) for c in c_ref) == 800 and sum(len(c) for c in c_our) == 800
+    assert c_ref == c_our, "clusters differ: %d vs %d clusters, %d in common" % (len(c_ref), len(c_our), len(c_ref & c_our))
+    assert 50 < len(c_ref) < 800
