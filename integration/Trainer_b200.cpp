@@ -156,9 +156,16 @@ std::tuple<Point<T> *, double, size_t, size_t> Trainer<T>::get_close(Point<T> *p
 	Device &d = device_for<T>(this, *feat, weights, points, k);
 	std::vector<uint64_t> cand;
 	std::vector<bvec_iterator<T>> where;
-	for (bvec_iterator<T> i = istart; i < iend; ++i) {
+	// same trip count as the reference's `omp parallel for` over the iterator range: iend - istart (bvec_iterator::operator-),
+	// which is 0 when only empty bins lie between the two positions
+	const int64_t n_iter = iend - istart;
+	bvec_iterator<T> i = istart;
+	for (int64_t t = 0; t < n_iter; t++) {
 		cand.push_back((*i).first->get_id());
 		where.push_back(i);
+		if (t + 1 < n_iter) {
+			++i;
+		}
 	}
 	std::tuple<Point<T> *, double, size_t, size_t> result(NULL, -1, 0, 0);
 	is_min_r = true;
