@@ -10,7 +10,7 @@ A step = one pass of the hot path over one batch of synthetic mutated-template D
 N > 1: one process per GPU (torchrun); sequences sharded for K1, histogram shards all-gathered over NCCL, the sweep
 split by folded query-row blocks; total work fixed ("strong" scaling).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2] [--n N_SEQ]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2] [--n-seqs N]
 """
 import argparse
 import json
@@ -62,49 +62,64 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML every 200 ms
+    (the B200_PROFILING.md clocks line without spawning nvidia-smi, whose polling loop perturbs short steps)."""
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
-
-    def start(self):
+        self.device, self.rows, self.stop_flag, self.t = device, [], False, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(device))
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        sm, smax, reasons = [], None, set()
-        for r in self.rows:
+    @staticmethod
+    def _physical_index(device):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
             try:
-                sm.append(float(r[1]))
-                smax = float(r[2])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                return int(vis.split(",")[device])
             except Exception:
                 pass
+        return device
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        if self.nv is None:
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        if self.nv is None or self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = [r[0] for r in self.rows]
+        smax = self.rows[-1][1] if self.rows else None
+        reasons = sorted(k for k, bit in names.items() if any(r[2] & bit for r in self.rows))
         busy = [x for x in sm if smax and x > 0.3 * smax] or sm
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": float(smax) if smax else None,
+                "reasons": reasons, "samples": len(sm)}
 
 
 def load_workload(name, n_override, lo, hi):
@@ -266,11 +281,13 @@ def run_ours(args, rank, world, local_rank):
     log("[bench] rank %d resident: %.1f ms/step, %d pairs scored, %d close, %d launches" % (
         rank, ms / args.steps, n_scored, res["n_close"], launches))
     # end to end from host buffers
+    log("[bench] rank %d e2e phase" % rank)
     for _ in range(min(args.warmup, 1)):
         step_e2e()
     e2e_steps = max(1, min(args.steps, 3))
     ms_e, res_e, _, _, _ = timed(step_e2e, e2e_steps)
     e2e_value = res_e["n_scored"] * e2e_steps / (ms_e * 1e-3)
+    log("[bench] rank %d e2e: %.1f ms/step" % (rank, ms_e / e2e_steps))
     h2d = host_bytes(enc)
     d2h = int(len(res_e["survivors"]) * 24 + 16 * len(res_e["blocks"]))
 
@@ -350,7 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=None, help="override the number of sequences (smoke runs)")
+    ap.add_argument("--n-seqs", dest="n", type=int, default=None, help="override the number of sequences (smoke runs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--cpu-hist-sample", type=int, default=100000)

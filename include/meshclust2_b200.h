@@ -140,6 +140,9 @@ uint64_t mc2_seqs_total_bases(const mc2_seqs *s);
  * (Loader.cpp:55-56).  elem_bytes in {1,2,4,8} = --datatype 8/16/32/64 (src/cluster/CRunner.cpp:278-291). */
 int mc2_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, mc2_hset **out);
 
+/* Same, into an existing set of the same shape (n, k, elem_bytes): no allocation in steady state (repeated batches). */
+int mc2_count_kmers_into(mc2_ctx *ctx, const mc2_seqs *seqs, mc2_hset *dst);
+
 /* KmerHashTable<unsigned long,V>(k, init).wholesaleIncrementNoOverflow(codes, first, last) on ONE sequence
  * (src/nonltr/KmerHashTable.h:20-79): values_out receives the 4^k table; *ret = 0 or -1 (saturation).
  * MC2_ERR_INPUT where the reference throws InvalidInputException. */
@@ -157,6 +160,8 @@ int mc2_hset_from_host(mc2_ctx *ctx, const void *bins, uint64_t n, int k, int el
  * ownership of its buffers. */
 int mc2_hset_from_device(mc2_ctx *ctx, const void *d_bins, uint64_t n, int k, int elem_bytes, const uint64_t *d_mag,
 			 const uint64_t *d_len, mc2_hset **out);
+/* Refill an existing set of the same shape from device memory (no allocation). */
+int mc2_hset_update_from_device(mc2_ctx *ctx, mc2_hset *h, const void *d_bins, const uint64_t *d_mag, const uint64_t *d_len);
 /* device pointer of a side-band column: which = 0 mag, 1 len, 2 sum of bins, 3 sum of squared bins (n u64 each) */
 void *mc2_hset_device_sideband(const mc2_hset *h, int which);
 void mc2_hset_free(mc2_hset *h);

@@ -35,7 +35,7 @@ SYMBOLS = [
     "mc2_abi_version", "mc2_last_error", "mc2_device_count", "mc2_ctx_create", "mc2_ctx_destroy", "mc2_ctx_sync",
     "mc2_ctx_device", "mc2_ctx_sm_count", "mc2_ctx_stream", "mc2_timer_start", "mc2_timer_stop",
     "mc2_ctx_launch_count", "mc2_ctx_profile", "mc2_ctx_kernel_time", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_free", "mc2_seqs_count",
-    "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
+    "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_count_kmers_into", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_update_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
     "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
     "mc2_score_pairs", "mc2_get_close", "mc2_filter", "mc2_merge", "mc2_all_pairs", "mc2_distance",
@@ -185,6 +185,10 @@ class Context:
         out = C.c_void_p()
         _check(lib().mc2_count_kmers(self.h, seqs.h, k, elem_bytes, C.byref(out)))
         return HistSet(self, out)
+
+    def count_kmers_into(self, seqs, hset):
+        _check(lib().mc2_count_kmers_into(self.h, seqs.h, hset.h))
+        return hset
 
     def kmer_table_increment(self, codes, first, last, k, elem_bytes, init=1):
         codes = np.ascontiguousarray(codes).view(np.int8)
@@ -349,6 +353,10 @@ class HistSet:
 
     def device_bins(self):
         return lib().mc2_hset_device_bins(self.h)
+
+    def update_from_device(self, d_bins, d_len, d_mag=None):
+        _check(lib().mc2_hset_update_from_device(self.ctx.h, self.h, C.c_void_p(d_bins), C.c_void_p(d_mag) if d_mag else None,
+                                                 C.c_void_p(d_len)))
 
     def device_sideband(self, which):
         """0 mag, 1 len, 2 sum, 3 sumsq -> raw device pointer"""

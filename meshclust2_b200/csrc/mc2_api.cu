@@ -648,6 +648,16 @@ int mc2_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, m
 	return MC2_OK;
 }
 
+int mc2_count_kmers_into(mc2_ctx *ctx, const mc2_seqs *seqs, mc2_hset *dst)
+{
+	MC2_REQUIRE(ctx && seqs && dst, "mc2_count_kmers_into: NULL argument");
+	MC2_REQUIRE(dst->n == seqs->n, "mc2_count_kmers_into: the set holds a different number of rows");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	int rc = count_into(ctx, seqs, dst->k, dst->eb, 1, dst);
+	if (rc == MC2_OK) rc = refresh_max_sum(ctx, dst);
+	return rc;
+}
+
 int mc2_kmer_table_increment(mc2_ctx *ctx, const char *codes, int32_t first, int32_t last, int k, int elem_bytes,
 			     uint64_t init_value, void *values_out, int32_t *ret)
 {
@@ -742,6 +752,22 @@ int mc2_hset_from_device(mc2_ctx *ctx, const void *d_bins, uint64_t n, int k, in
 	}
 	*out = h;
 	return MC2_OK;
+}
+
+int mc2_hset_update_from_device(mc2_ctx *ctx, mc2_hset *h, const void *d_bins, const uint64_t *d_mag, const uint64_t *d_len)
+{
+	MC2_REQUIRE(ctx && h && d_bins && d_len, "mc2_hset_update_from_device: NULL argument");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	const u64 n = h->n;
+	if (n == 0) {
+		return MC2_OK;
+	}
+	MC2_CUDA(cudaMemcpyAsync(h->bins, d_bins, n * h->N * (u64)h->eb, cudaMemcpyDeviceToDevice, ctx->stream));
+	MC2_CUDA(cudaMemcpyAsync(h->len, d_len, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	if (d_mag) MC2_CUDA(cudaMemcpyAsync(h->mag, d_mag, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	int rc = launch_sideband(ctx, h, d_mag == nullptr);
+	if (rc == MC2_OK) rc = refresh_max_sum(ctx, h);
+	return rc;
 }
 
 void *mc2_hset_device_sideband(const mc2_hset *h, int which)

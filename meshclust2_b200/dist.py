@@ -133,9 +133,14 @@ class GpuEngine:
         return self.seqs
 
     def count(self):
-        if getattr(self, "local_hset", None) is not None and self.local_hset is not self.full:
-            self.local_hset.free()
-        self.local_hset = self.ctx.count_kmers(self.seqs, self.k, self.eb)
+        # steady state: recount into the same device allocation (cudaMalloc / cudaFree stall the device)
+        hs = getattr(self, "local_hset", None)
+        if hs is not None and len(hs) == len(self.seqs):
+            self.ctx.count_kmers_into(self.seqs, hs)
+        else:
+            if hs is not None and hs is not self.full:
+                hs.free()
+            self.local_hset = self.ctx.count_kmers(self.seqs, self.k, self.eb)
 
     def use_local_as_full(self):
         if self.full is not None and self.full is not self.local_hset:
@@ -145,9 +150,11 @@ class GpuEngine:
     def export_local(self):
         torch = self.torch
         hs = self.local_hset
-        bins = torch.ones((self.per, self.N), dtype=self._dt, device=self.device)
-        length = torch.zeros((self.per,), dtype=torch.int64, device=self.device)
-        mag = torch.zeros((self.per,), dtype=torch.int64, device=self.device)
+        if getattr(self, "_exp", None) is None:
+            self._exp = (torch.ones((self.per, self.N), dtype=self._dt, device=self.device),
+                         torch.zeros((self.per,), dtype=torch.int64, device=self.device),
+                         torch.zeros((self.per,), dtype=torch.int64, device=self.device))
+        bins, length, mag = self._exp           # padding rows (if any) keep their initial all-ones / zero contents
         torch.cuda.synchronize(self.device)     # the fills above run on torch's stream
         if self.n_local:
             hs.copy_to_device(bins.data_ptr(), mag.data_ptr(), length.data_ptr(), 0, self.n_local)
@@ -155,6 +162,9 @@ class GpuEngine:
 
     def install_full(self, bins, length, mag, n_total):
         self.torch.cuda.synchronize(self.device)
+        if self.full is not None and self.full is not self.local_hset and len(self.full) == n_total:
+            self.full.update_from_device(bins.data_ptr(), length.data_ptr(), mag.data_ptr())
+            return
         if self.full is not None and self.full is not self.local_hset:
             self.full.free()
         self.full = self.ctx.hset_from_device(bins.data_ptr(), n_total, self.k, self.eb, length.data_ptr(),
