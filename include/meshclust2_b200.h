@@ -259,6 +259,19 @@ int mc2_all_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
 /* DivergencePoint<T>::distance (src/clutil/DivergencePoint.cpp:70-82) for pairs of rows */
 int mc2_distance(mc2_ctx *ctx, const mc2_pairs *pairs, uint64_t *out);
 
+/* K3 — cluster mean + closest member: get_mean (src/cluster/ClusterFactory.cpp:338-380) and the mean of mean_shift_update
+ * (:288-335) followed by Trainer<T>::closest (src/cluster/Trainer.cpp:144-157).  mean = per-bin average (double) of rows
+ * members[0..n) of `set`; *best = position in members of the FIRST member minimising DivergencePoint<T>::distance_d to that
+ * mean (src/clutil/DivergencePoint.cpp:55-66, with its per-bin u64 truncation), *best_dist its distance.
+ * mean_out (4^k doubles) and dist_out (n doubles) may be NULL. */
+int mc2_mean_closest(mc2_ctx *ctx, const mc2_hset *set, const uint64_t *members, uint64_t n, int64_t *best, double *best_dist,
+		     double *mean_out, double *dist_out);
+
+/* Trainer<T>::closest (src/cluster/Trainer.cpp:144-157) alone: the mean is supplied by the caller (the Point<double> that
+ * mean_shift_update built on the host); returns the first member minimising distance_d to it. */
+int mc2_closest(mc2_ctx *ctx, const mc2_hset *set, const uint64_t *members, uint64_t n, const double *mean, int64_t *best,
+		double *best_dist, double *dist_out);
+
 /* Device-timed variants used by bench.py: run the scoring kernel `iters` times on inputs already resident
  * (pair lists uploaded once), return the average milliseconds per launch measured with CUDA events on the ctx stream. */
 int mc2_bench_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs, int iters, int flush_l2,

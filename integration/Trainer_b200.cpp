@@ -264,20 +264,24 @@ void Trainer<T>::filter(Point<T> *p, vector<pair<Point<T> *, bool>> &vec) const
 	vec.resize(w);
 }
 
-// unchanged host logic: arg-min of distance_d against the (double) mean — K3, the next row of SURVEY section 8f
+// Trainer<T>::closest: the mean was built on the host by mean_shift_update; the distance_d arg-min runs on the device (K3)
 template <class T>
 Point<T> *Trainer<T>::closest(Point<double> *p, vector<pair<Point<T> *, bool>> &vec) const
 {
-	Point<T> *best_pt = NULL;
-	double best_dist = 0;
-	for (auto &pt : vec) {
-		double dist = pt.first->distance_d(*p);
-		if (best_pt == NULL || dist < best_dist) {
-			best_dist = dist;
-			best_pt = pt.first;
-		}
+	if (vec.empty()) {
+		return NULL;
 	}
-	return best_pt;
+	std::lock_guard<std::mutex> lock(g_mu);
+	Device &d = device_for<T>(this, *feat, weights, points, k);
+	std::vector<uint64_t> rows(vec.size());
+	for (size_t j = 0; j < vec.size(); j++) {
+		rows[j] = vec[j].first->get_id();
+	}
+	const std::vector<double> &mean = p->get_data();
+	int64_t best = -1;
+	double bd = 0;
+	ok(mc2_closest(d.ctx, d.points, rows.data(), rows.size(), mean.data(), &best, &bd, nullptr));
+	return best < 0 ? NULL : vec[(size_t)best].first;
 }
 
 // training stays on the host exactly as in the reference: Predictor builds the model, Trainer keeps a copy

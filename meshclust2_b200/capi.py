@@ -38,7 +38,7 @@ SYMBOLS = [
     "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_count_kmers_into", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_update_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
     "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
-    "mc2_score_pairs", "mc2_get_close", "mc2_filter", "mc2_merge", "mc2_all_pairs", "mc2_distance",
+    "mc2_score_pairs", "mc2_get_close", "mc2_filter", "mc2_merge", "mc2_all_pairs", "mc2_distance", "mc2_mean_closest", "mc2_closest",
     "mc2_bench_score_pairs", "mc2_bench_count_kmers", "mc2_encode_dna", "mc2_encode_dna_batch",
 ]
 
@@ -298,6 +298,26 @@ class Context:
         out = np.zeros(len(ia), dtype=np.uint64)
         _check(lib().mc2_distance(self.h, C.byref(p), _p(out)))
         return out
+
+    def mean_closest(self, hset, members):
+        """K3: (best position in members, its distance_d, mean[4^k], dist[n])"""
+        members = _u64(members)
+        best, bd = C.c_int64(), C.c_double()
+        mean = np.zeros(4 ** hset.k)
+        dist = np.zeros(len(members))
+        _check(lib().mc2_mean_closest(self.h, hset.h, _p(members), C.c_uint64(len(members)), C.byref(best), C.byref(bd),
+                                      _p(mean), _p(dist)))
+        return best.value, bd.value, mean, dist
+
+    def closest(self, hset, members, mean):
+        """Trainer::closest: (best position, distance, dist[n]) against a caller-supplied double mean"""
+        members = _u64(members)
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        best, bd = C.c_int64(), C.c_double()
+        dist = np.zeros(len(members))
+        _check(lib().mc2_closest(self.h, hset.h, _p(members), C.c_uint64(len(members)), _p(mean), C.byref(best), C.byref(bd),
+                                 _p(dist)))
+        return best.value, bd.value, dist
 
     def bench_score_pairs(self, model, set_a, set_b, ia=None, ib=None, n_pairs=None, iters=10, flush_l2=True, **kw):
         if n_pairs is None:

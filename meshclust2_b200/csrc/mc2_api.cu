@@ -1347,6 +1347,52 @@ int mc2_distance(mc2_ctx *ctx, const mc2_pairs *pairs, uint64_t *out)
 	return MC2_OK;
 }
 
+static int mean_closest_impl(mc2_ctx *ctx, const mc2_hset *set, const uint64_t *members, uint64_t n, const double *mean_in,
+			     int64_t *best, double *best_dist, double *mean_out, double *dist_out);
+
+int mc2_mean_closest(mc2_ctx *ctx, const mc2_hset *set, const uint64_t *members, uint64_t n, int64_t *best, double *best_dist,
+		     double *mean_out, double *dist_out)
+{
+	return mean_closest_impl(ctx, set, members, n, nullptr, best, best_dist, mean_out, dist_out);
+}
+
+int mc2_closest(mc2_ctx *ctx, const mc2_hset *set, const uint64_t *members, uint64_t n, const double *mean, int64_t *best,
+		double *best_dist, double *dist_out)
+{
+	MC2_REQUIRE(mean != nullptr, "mc2_closest: mean is NULL");
+	return mean_closest_impl(ctx, set, members, n, mean, best, best_dist, nullptr, dist_out);
+}
+
+static int mean_closest_impl(mc2_ctx *ctx, const mc2_hset *set, const uint64_t *members, uint64_t n, const double *mean_in,
+			     int64_t *best, double *best_dist, double *mean_out, double *dist_out)
+{
+	MC2_REQUIRE(ctx && set && members && best && best_dist, "mc2_mean_closest: NULL argument");
+	MC2_REQUIRE(n > 0, "mc2_mean_closest: empty member list (the reference throws \"N cannot be 0\")");
+	for (u64 j = 0; j < n; j++) {
+		MC2_REQUIRE(members[j] < set->n, "mc2_mean_closest: member row out of range");
+	}
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	CtxExtra *x = extra(ctx);
+	const u64 N = set->N;
+	int rc = ensure(x->d[B_IA], n * 8, false); if (rc) return rc;
+	rc = ensure(x->d[B_SCORE], N * 8, false); if (rc) return rc;   // column sums
+	rc = ensure(x->d[B_CACHE], N * 8, false); if (rc) return rc;   // mean
+	rc = ensure(x->d[B_DIST], n * 8, false); if (rc) return rc;    // distances
+	cudaStream_t st = ctx->stream;
+	MC2_CUDA(cudaMemcpyAsync(x->d[B_IA].p, members, n * 8, cudaMemcpyHostToDevice, st));
+	if (mean_in) MC2_CUDA(cudaMemcpyAsync(x->d[B_CACHE].p, mean_in, N * 8, cudaMemcpyHostToDevice, st));
+	rc = launch_mean_closest(ctx, set, (const u64 *)x->d[B_IA].p, n, (u64 *)x->d[B_SCORE].p, (double *)x->d[B_CACHE].p,
+				 (double *)x->d[B_DIST].p, ctx->d_slot, mean_in != nullptr);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaMemcpyAsync(ctx->h_slot, ctx->d_slot, 16, cudaMemcpyDeviceToHost, st));
+	if (mean_out) MC2_CUDA(cudaMemcpyAsync(mean_out, x->d[B_CACHE].p, N * 8, cudaMemcpyDeviceToHost, st));
+	if (dist_out) MC2_CUDA(cudaMemcpyAsync(dist_out, x->d[B_DIST].p, n * 8, cudaMemcpyDeviceToHost, st));
+	MC2_CUDA(cudaStreamSynchronize(st));
+	*best = ((long long *)ctx->h_slot)[0];
+	*best_dist = ((double *)ctx->h_slot)[1];
+	return MC2_OK;
+}
+
 /* ---- device-timed bench helpers ---------------------------------------------------------------- */
 int mc2_bench_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs, int iters, int flush_l2,
 			  float *avg_ms, uint64_t *n_close)

@@ -170,5 +170,7 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 		     int upper_only, double cutoff, u64 max_out, u64 *d_out_q, u64 *d_out_d, double *d_out_score,
 		     u64 *d_counters);
 int launch_distance(mc2_ctx *ctx, const PairArgs &a, u64 *d_out);
+int launch_mean_closest(mc2_ctx *ctx, const mc2_hset *h, const u64 *d_members, u64 n, u64 *d_sums, double *d_mean, double *d_dist,
+			void *d_out, bool have_mean);
 
 } // namespace mc2

@@ -786,6 +786,55 @@ int mc2o_merge(const mc2o_model *m, int eb, uint64_t N, const void *H, const uin
 }
 
 /* ------------------------------------------------------------------------------------------
+ * K3: cluster mean + closest member.  get_mean (src/cluster/ClusterFactory.cpp:338-380) and the mean of
+ * mean_shift_update (:288-335) followed by Trainer::closest (src/cluster/Trainer.cpp:144-157):
+ *   top = sum over members of the bins as doubles (operator+=), top /= count (operator/=, per-bin division),
+ *   best = first member minimising distance_d(member, top) (strict <).
+ * ------------------------------------------------------------------------------------------ */
+int mc2o_mean_closest(int eb, uint64_t N, const void *H, const uint64_t *members, uint64_t n, int64_t *best, double *best_dist,
+		      double *mean_out, double *dist_out)
+{
+	double *top = (double *)calloc(N, sizeof(double));
+	uint64_t i, j;
+	int64_t b = -1;
+	double bd = 0;
+	if (!top || n == 0) {
+		free(top);
+		return -1;
+	}
+	for (j = 0; j < n; j++) {
+		const char *row = (const char *)H + members[j] * N * (uint64_t)eb;
+		for (i = 0; i < N; i++) {
+			double v = eb == 1 ? (double)((const uint8_t *)row)[i]
+				 : eb == 2 ? (double)((const uint16_t *)row)[i]
+				 : eb == 4 ? (double)((const uint32_t *)row)[i] : (double)((const uint64_t *)row)[i];
+			top[i] += v;
+		}
+	}
+	for (i = 0; i < N; i++) {
+		top[i] /= (double)n;
+	}
+	for (j = 0; j < n; j++) {
+		const char *row = (const char *)H + members[j] * N * (uint64_t)eb;
+		double d = mc2o_distance_d(eb, N, row, top);
+		if (dist_out) {
+			dist_out[j] = d;
+		}
+		if (b < 0 || d < bd) {
+			bd = d;
+			b = (int64_t)j;
+		}
+	}
+	if (mean_out) {
+		memcpy(mean_out, top, N * sizeof(double));
+	}
+	*best = b;
+	*best_dist = bd;
+	free(top);
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * timing helpers (cpu_baseline "port")
  * ------------------------------------------------------------------------------------------ */
 static double now_s(void)

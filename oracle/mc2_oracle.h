@@ -100,6 +100,11 @@ int mc2o_merge(const mc2o_model *m, int elem_bytes, uint64_t N, const void *H, c
 uint64_t mc2o_distance(int elem_bytes, uint64_t N, const mc2o_point *p, const mc2o_point *q);
 double mc2o_distance_d(int elem_bytes, uint64_t N, const void *bins, const double *center);
 
+/* K3: mean of member histograms (double) + first member minimising distance_d to it
+ * (get_mean, src/cluster/ClusterFactory.cpp:338-380; Trainer::closest, src/cluster/Trainer.cpp:144-157) */
+int mc2o_mean_closest(int elem_bytes, uint64_t N, const void *H, const uint64_t *members, uint64_t n, int64_t *best,
+		      double *best_dist, double *mean_out, double *dist_out);
+
 /* timing helpers for bench.py's cpu_baseline "port" leg (OpenMP over units) */
 int mc2o_count_batch(const char *codes, const uint64_t *seq_off, const int *segs, const uint64_t *seg_off,
 		     uint64_t n, int k, int elem_bytes, void *hist, int threads, double *seconds);

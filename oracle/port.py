@@ -308,6 +308,21 @@ def distance_d(p, center):
     return lib().mc2o_distance_d(p.dtype.itemsize, C.c_uint64(p.size), _p(p), _p(center))
 
 
+def mean_closest(H, members):
+    """K3: (best position in members, its distance_d, mean[N], dist[n])"""
+    H = np.ascontiguousarray(H)
+    n, N = H.shape
+    members = np.ascontiguousarray(members, dtype=np.uint64)
+    best, bd = C.c_int64(), C.c_double()
+    mean = np.zeros(N)
+    dist = np.zeros(members.size)
+    rc = lib().mc2o_mean_closest(H.dtype.itemsize, C.c_uint64(N), _p(H), _p(members), C.c_uint64(members.size), C.byref(best),
+                                 C.byref(bd), _p(mean), _p(dist))
+    if rc != 0:
+        raise ValueError("mc2o_mean_closest rc=%d" % rc)
+    return best.value, bd.value, mean, dist
+
+
 def count_batch(codes, seq_off, segs, seg_off, k, elem_bytes, threads=1):
     """codes: int8 concatenated; seq_off uint64[n+1]; segs int32[total,2] (sequence-relative); seg_off uint64[n+1]"""
     n = len(seq_off) - 1

@@ -187,6 +187,20 @@ class RefModel:
         return out.value
 
 
+def mean_closest(H, members):
+    H = np.ascontiguousarray(H)
+    n, N = H.shape
+    members = np.ascontiguousarray(members, dtype=np.uint64)
+    best, bd = C.c_int64(), C.c_double()
+    mean = np.zeros(N)
+    dist = np.zeros(members.size)
+    rc = lib().ref_mean_closest(H.dtype.itemsize, C.c_uint64(N), _p(H), _p(members), C.c_uint64(members.size), C.byref(best),
+                                C.byref(bd), _p(mean), _p(dist))
+    if rc != 0:
+        raise ValueError("ref_mean_closest rc=%d" % rc)
+    return best.value, bd.value, mean, dist
+
+
 def count_batch(texts, k, elem_bytes, threads=1, want_hist=True):
     """Loader<T>::get_point over raw sequences (list of bytes), omp over sequences -> (hist or None, seconds)"""
     n = len(texts)

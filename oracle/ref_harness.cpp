@@ -352,6 +352,47 @@ int merge_impl(ModelBase* mb, uint64_t N, const void* H, const uint64_t* mag, co
 	return 0;
 }
 
+// get_mean's own sequence of calls (src/cluster/ClusterFactory.cpp:338-380) on the reference's objects; the arg-min is
+// the sequential (--threads 1) order of its reduction, identical to Trainer::closest (Trainer.cpp:144-157)
+template <class T>
+int mean_closest_impl(uint64_t N, const void *H, const uint64_t *members, uint64_t n, int64_t *best, double *best_dist,
+		      double *mean_out, double *dist_out)
+{
+	const T *h = (const T *)H;
+	std::vector<DivergencePoint<T> *> pts(n);
+	for (uint64_t j = 0; j < n; j++) {
+		pts[j] = make_point<T>(h + members[j] * N, N, 0, 1, j);
+	}
+	Point<double> *top = pts[0]->create_double();
+	top->zero();
+	Point<double> *temp = top->clone();
+	for (uint64_t j = 0; j < n; j++) {
+		pts[j]->set_arg_to_this_d(*temp);
+		*top += *temp;
+	}
+	*top /= (double)n;
+	int64_t b = -1;
+	double bd = std::numeric_limits<double>::max();
+	for (uint64_t j = 0; j < n; j++) {
+		double d = pts[j]->distance_d(*top);
+		if (dist_out) dist_out[j] = d;
+		if (d < bd) {
+			bd = d;
+			b = (int64_t)j;
+		}
+	}
+	if (mean_out) {
+		const std::vector<double> &m = top->get_data();
+		for (uint64_t i = 0; i < N; i++) mean_out[i] = m[i];
+	}
+	*best = b;
+	*best_dist = bd;
+	delete top;
+	delete temp;
+	for (auto p : pts) delete p;
+	return 0;
+}
+
 template <class T>
 int count_batch_impl(const char* text, const uint64_t* off, uint64_t n, int k, void* hist_out, int threads,
 		     double* seconds)
@@ -561,6 +602,17 @@ int ref_count_batch(const char* text, const uint64_t* off, uint64_t n, int k, in
 {
 	try {
 		DISPATCH(elem_bytes, count_batch_impl, text, off, n, k, hist_out, threads, seconds);
+	} catch (...) {
+		return -1;
+	}
+}
+
+// get_mean / mean_shift_update mean + closest member over rows members[0..n) of H
+int ref_mean_closest(int elem_bytes, uint64_t N, const void *H, const uint64_t *members, uint64_t n, int64_t *best,
+		     double *best_dist, double *mean_out, double *dist_out)
+{
+	try {
+		DISPATCH(elem_bytes, mean_closest_impl, N, H, members, n, best, best_dist, mean_out, dist_out);
 	} catch (...) {
 		return -1;
 	}

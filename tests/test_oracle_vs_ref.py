@@ -86,3 +86,18 @@ def test_trainer_callers(wname):
         assert np.array_equal(port.filter_members(m, H, mag, ln, q, cand, 0.9), rm.filter_members(H, None, ln, q, cand))
         rows = np.arange(q, min(q + 8, 120))
         assert port.merge(m, H, mag, ln, rows, 0, 1, len(rows) - 1, 0.9) == rm.merge(H, None, ln, rows, 0, 1, len(rows) - 1)
+
+
+@pytest.mark.parametrize("eb", [1, 2, 4, 8])
+def test_k3_mean_closest(eb):
+    """get_mean / mean_shift_update mean + Trainer::closest: same arg-min and bit-identical mean; distances within an ulp
+    (the reference build fuses 1 - frac*frac)"""
+    rng = np.random.default_rng(40 + eb)
+    for trial in range(15):
+        N = 4 ** int(rng.integers(1, 6))
+        hi = {1: 255, 2: 3000, 4: 100000, 8: 100000}[eb]
+        H = rng.integers(1, hi + 1, size=(50, N)).astype(port.DTYPES[eb])
+        mem = rng.integers(0, 50, int(rng.integers(1, 40)))
+        a, b = port.mean_closest(H, mem), ref.mean_closest(H, mem)
+        assert a[0] == b[0] and np.array_equal(a[2], b[2])
+        assert np.abs(a[3] - b[3]).max() <= 1e-12 * max(1.0, np.abs(b[3]).max())
