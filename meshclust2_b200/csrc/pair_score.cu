@@ -15,6 +15,7 @@
 #include "mc2_internal.cuh"
 #include <math_constants.h>
 #include <cstring>
+#include <cstdlib>
 
 namespace mc2 {
 
@@ -835,6 +836,184 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) pair_fast_kernel
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA-fed candidate scan (1 KiB uint8 rows against a fixed row): every warp owns a ring of RING 1-KiB slots in shared
+// memory.  One elected lane keeps the ring full with cp.async.bulk (the TMA engine's 1-D bulk copy, completion counted on
+// one mbarrier per slot), RING-2 rows ahead of the two rows being reduced, across group boundaries — so the number of
+// bytes in flight is set by shared memory (RING KiB per warp), not by registers.
+// ------------------------------------------------------------------------------------------------
+#define MC2_RING 8
+
+__device__ __forceinline__ u32 smem_u32(const void *p)
+{
+	return (u32)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\t"
+		     "bra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+		     "r"(parity)
+		     : "memory");
+}
+__device__ __forceinline__ void bulk_load_1k(u32 dst, const void *src, u32 bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 1024, [%2];" ::"r"(dst), "l"(src),
+		     "r"(bar)
+		     : "memory");
+}
+__device__ __forceinline__ Row8 lds_row(u32 slot, int lane)
+{
+	Row8 r;
+	u32 a = slot + lane * 32;
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "r"(a));
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "r"(a + 16));
+	return r;
+}
+
+template <int NEED>
+__global__ void __launch_bounds__(128, 4) pair_tma_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a)
+{
+	extern __shared__ __align__(128) unsigned char tma_smem[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
+	const u64 warp_id = (u64)blockIdx.x * (blockDim.x >> 5) + warp;
+	const unsigned char *A = reinterpret_cast<const unsigned char *>(a.binsA);
+	const unsigned char *B = reinterpret_cast<const unsigned char *>(a.binsB);
+	const u64 groups = (a.n_pairs + 31) / 32;
+	const bool a_hot = a.a_bc && !a.ia;
+	const unsigned char *S = a_hot ? B : A; // streamed side
+	// ring + barriers of this warp
+	unsigned char *ring = tma_smem + (size_t)warp * (MC2_RING * 1024);
+	unsigned long long *bars = reinterpret_cast<unsigned long long *>(tma_smem + (size_t)(blockDim.x >> 5) * (MC2_RING * 1024)) + warp * MC2_RING;
+	const u32 ring_s = smem_u32(ring), bars_s = smem_u32(bars);
+	if (lane == 0) {
+		for (int s = 0; s < MC2_RING; s++) {
+			mbar_init(bars_s + 8 * s, 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+	FixedQ fq;
+	fixed_q_setup<NEED>(fq, a_hot ? A + a.a_begin * 1024 : B + a.b_begin * 1024, lane);
+
+	// group state: current (c) and next (n)
+	auto resolve = [&](u64 g, u64 &ra, u64 &rb, bool &go, bool &valid) {
+		const u64 j = g * 32 + lane;
+		valid = g < groups && j < a.n_pairs;
+		ra = rb = 0;
+		go = valid && resolve_pair(a, j, ra, rb);
+	};
+	u64 g = warp_id, ra, rb, ra_n, rb_n;
+	bool go, valid, go_n, valid_n;
+	resolve(g, ra, rb, go, valid);
+	resolve(g + warps_total, ra_n, rb_n, go_n, valid_n);
+	unsigned act = __ballot_sync(0xffffffffu, go), act_n = __ballot_sync(0xffffffffu, go_n);
+	unsigned pmask = act, pmask_n = act_n; // rows not yet requested
+	u32 slot_p = 0, slot_c = 0, parity = 0; // producer / consumer slots, parity bit per slot
+	int in_flight = 0;
+
+	auto issue_one = [&]() { // request the next row of the stream into slot_p (warp-uniform control flow)
+		unsigned &m = pmask ? pmask : pmask_n;
+		const bool from_next = !pmask;
+		if (!m) {
+			return;
+		}
+		const int pi = __ffs(m) - 1;
+		m &= m - 1;
+		const u64 rsel = from_next ? (a_hot ? rb_n : ra_n) : (a_hot ? rb : ra);
+		const u64 row = __shfl_sync(0xffffffffu, rsel, pi);
+		if (lane == 0) {
+			const u32 bar = bars_s + 8 * slot_p;
+			mbar_expect_tx(bar, 1024);
+			bulk_load_1k(ring_s + slot_p * 1024, S + row * 1024, bar);
+		}
+		slot_p = (slot_p + 1) % MC2_RING;
+		in_flight++;
+	};
+	for (int s = 0; s < MC2_RING; s++) {
+		issue_one();
+	}
+	while (g < groups) {
+		u32 m0 = 0, m1 = 0, m2 = 0;
+		unsigned cmask = act;
+		while (cmask) {
+			const int ia_ = __ffs(cmask) - 1;
+			cmask &= cmask - 1;
+			const int ib_ = cmask ? __ffs(cmask) - 1 : -1;
+			cmask &= cmask ? cmask - 1 : 0;
+			// wait for the one or two oldest slots, pull them into registers, hand the slots back to the producer
+			const u32 sa = slot_c, sb = (slot_c + 1) % MC2_RING;
+			mbar_wait(bars_s + 8 * sa, (parity >> sa) & 1);
+			Row8 pa = lds_row(ring_s + sa * 1024, lane), pb = pa;
+			parity ^= 1u << sa;
+			int used = 1;
+			if (ib_ >= 0) {
+				mbar_wait(bars_s + 8 * sb, (parity >> sb) & 1);
+				pb = lds_row(ring_s + sb * 1024, lane);
+				parity ^= 1u << sb;
+				used = 2;
+			}
+			slot_c = (slot_c + used) % MC2_RING;
+			in_flight -= used;
+			__syncwarp();
+			if (lane == 0) { // generic-proxy reads above must be ordered before the async-proxy refills
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			}
+			issue_one();
+			if (used == 2) {
+				issue_one();
+			}
+			u32 oa[3], ob[3];
+			reduce_row2<NEED>(pa, pb, fq, oa, ob);
+			if (lane == ia_) {
+				m0 = oa[0];
+				m1 = oa[1];
+				m2 = oa[2];
+			}
+			if (lane == ib_) {
+				m0 = ob[0];
+				m1 = ob[1];
+				m2 = ob[2];
+			}
+		}
+		const u64 j = g * 32 + lane;
+		if (go) {
+			Side sa_ = load_side(a.sbA, ra), sb_ = load_side(a.sbB, rb);
+			RedN mine;
+			mine.smin = (NEED & NEED_MIN) ? (sa_.sum + sb_.sum - m0) >> 1 : 0; // u8 path accumulated sum|p-q|
+			mine.dot = m1;
+			mine.emd = m2;
+			mine.jeff = mine.js = 0;
+			finish_pair<RedN, false>(dm, a, j, a.N, mine, sa_, sb_);
+		} else if (valid) {
+			write_skipped(a, j);
+		}
+		// advance: next group becomes current
+		g += warps_total;
+		ra = ra_n;
+		rb = rb_n;
+		go = go_n;
+		valid = valid_n;
+		act = act_n;
+		pmask = pmask_n;
+		resolve(g + warps_total, ra_n, rb_n, go_n, valid_n);
+		act_n = __ballot_sync(0xffffffffu, go_n);
+		pmask_n = act_n;
+		// top the ring up with rows of the new "next" group if the current one is already fully requested
+		while (in_flight < MC2_RING && (pmask | pmask_n)) {
+			issue_one();
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic path: any width, any N, log features; lane-interleaved bins, 64-bit accumulators.
 // Reproduces the reference's type-dependent integer arithmetic for 32/64-bit bins.
 // ------------------------------------------------------------------------------------------------
@@ -1252,6 +1431,31 @@ static void launch_fast_need(int need, int grid, cudaStream_t st, const DevModel
 	}
 }
 
+static void launch_tma_need(int need, mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
+{
+	const int warps = 4;
+	const size_t smem = (size_t)warps * (MC2_RING * 1024) + (size_t)warps * MC2_RING * 8;
+	u64 groups = (a.n_pairs + 31) / 32;
+	u64 want = (groups + warps - 1) / warps, cap = (u64)ctx->sm_count * 4;
+	int grid = (int)(want < cap ? want : cap);
+	switch (need & 7) {
+#define CASE(n)                                                                                                       \
+	case n:                                                                                                       \
+		cudaFuncSetAttribute(pair_tma_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+		pair_tma_kernel<n><<<grid, warps * 32, smem, ctx->stream>>>(dm, a);                                    \
+		break;
+		CASE(0)
+		CASE(1)
+		CASE(2)
+		CASE(3)
+		CASE(4)
+		CASE(5)
+		CASE(6)
+		CASE(7)
+#undef CASE
+	}
+}
+
 int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 {
 	if (a.n_pairs == 0) {
@@ -1263,7 +1467,13 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 	if (fast) {
 		int grid = grid_for(ctx, a.n_pairs, 8, 8);
 		const bool one = a.eb == 1 && row_bytes == 1024 && ((a.a_bc && !a.ia) || (a.b_bc && !a.ib));
-		if (one) {
+		// The TMA-ring variant is kept as an opt-in experiment (MC2_USE_TMA=1): it feeds rows at 91 % of HBM peak when the
+		// per-row work is light, but the dot+EMD reduction is issue/latency bound, not feed bound, and its extra LDS +
+		// mbarrier traffic and register count make it slower there (53 % vs 65 % of peak, profiles/r1_need_sweep.txt).
+		static const bool use_tma = getenv("MC2_USE_TMA") != nullptr;
+		if (one && use_tma) {
+			launch_tma_need(dm.need, ctx, dm, a);
+		} else if (one) {
 			launch_fast_need<uint8_t, true>(dm.need, grid, ctx->stream, dm, a);
 		} else if (a.eb == 1) {
 			launch_fast_need<uint8_t, false>(dm.need, grid, ctx->stream, dm, a);
