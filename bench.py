@@ -323,6 +323,8 @@ def run_ours(args, rank, world, local_rank):
                    "achieved_gbs": (hi - lo) * args.steps * (250 + N * eb + 40) / (count_ms * 1e-3) / 1e9 if count_ms > 0 else None}}
     if world == 1 and not args.no_extras:
         line["roofline_candidates"] = candidates_roofline(ctx, capi, model, k, eb, peak, peak_src)
+        if args.workload != "cfg2":
+            line["also_cfg2"] = small_workload(ctx, capi, mdist, torch, model, cutoff)
     if rank == 0 and world == 1 and not args.no_cpu:
         t0 = time.time()
         cb = cpu_leg(seqs, k, eb, n_total, n_scored, cutoff, args.cpu_hist_sample, args.cpu_pair_sample)
@@ -333,6 +335,40 @@ def run_ours(args, rank, world, local_rank):
     ctx.close()
     if tdist is not None:
         tdist.destroy_process_group()
+
+
+def small_workload(ctx, capi, mdist, torch, model, cutoff, steps=20):
+    """The BASELINE configs[1] shape in the same run (10k x 1.5 kb 16S-like, k=5, uint8): K1 + all-pairs candidate sweep,
+    resident and end to end; the whole histogram set (10 MB) is L2-resident, steps are ~15 ms."""
+    from meshclust2_b200 import synth
+    seqs, _, k, eb = synth.make_config_range("cfg2", 0, None)
+    enc = capi.encode_batch(seqs)
+    eng = mdist.GpuEngine(capi, ctx, torch, model, k, eb, 0)
+    n = len(seqs)
+    eng.set_local_sequences(ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"]), n, n)
+    comm = mdist.Comm(None)
+    out = {}
+    for name in ("resident", "e2e"):
+        def step():
+            ctx.flush_l2(256 << 20)
+            if name == "e2e":
+                old = eng.seqs
+                eng.seqs = ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
+                old.free()
+            return mdist.all_pairs_step(eng, comm, torch, n, cutoff, upper_only=True, blocks_per_rank=1, max_out=1 << 22)
+        for _ in range(3):
+            res = step()
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(steps):
+            res = step()
+        ms = ctx.timer_stop() / steps
+        out[name] = {"value": res["n_scored"] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms}
+    out["workload"] = WORKLOADS["cfg2"]["desc"]
+    out["pairs_scored_per_step"] = res["n_scored"]
+    out["pairs_close_per_step"] = res["n_close"]
+    out["hist_per_step"] = n
+    return out
 
 
 def candidates_roofline(ctx, capi, model, k, eb, peak, peak_src, n=1 << 20):

@@ -332,3 +332,32 @@ def test_full_size_properties_100k_one_vs_many(built_lib, ctx):
     assert_flags_match(full["close"][idx], o["close"], o["score"])
     best = ctx.get_close(gm, hs, 7, hs, cand_begin=0, n_cand=n, cutoff=0.9)
     assert best[3][7] == 1            # the query itself is in the candidate range and is close to itself
+
+
+def test_cfg4_shape_single_file_k8_u16(built_lib, ctx):
+    """BASELINE configs[3] shape: records of 5 contigs x 10 kb joined by 50 N (--single-file), k=8, uint16 histograms
+    (65,536 bins = 128 KiB rows): K1 through the multi-segment path, K2 through the multi-slab fast path, both vs the oracle."""
+    from meshclust2_b200 import synth
+    seqs = synth.make_single_file(10, 5, 10000, seed=11, n_templates=3)
+    enc = built_lib.encode_batch(seqs, threads=4)
+    assert (np.diff(enc["seg_off"].astype(np.int64)) == 5).all()          # the 50-N gaps split every record into 5 segments
+    hs = ctx.count_kmers(ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"]), 8, 2)
+    got = hs.download()
+    want = [port.get_point(s, 8, 2) for s in seqs]
+    H = np.stack([w["hist"] for w in want])
+    assert np.array_equal(got["hist"], H)
+    assert np.array_equal(got["len"], np.array([w["len"] for w in want], dtype=np.uint64))
+    assert np.array_equal(got["mag"], np.array([w["mag"] for w in want], dtype=np.uint64))
+    rng = np.random.default_rng(5)
+    mag, ln = got["mag"], got["len"]
+    model = all_singles_model(FAST, H, mag, ln, rng)
+    gm = ctx.model(to_desc(built_lib, model))
+    ia, ib = np.repeat(np.arange(10), 10), np.tile(np.arange(10), 10)
+    g = ctx.score_pairs(gm, hs, hs, ia, ib)
+    o = port.score_pairs(model, H, mag, ln, ia, ib)
+    assert_close_rel(g["cache"], o["cache"], 1e-8, "cfg4 cache")
+    assert np.abs(g["score"] - o["score"]).max() <= 1e-8
+    assert_flags_match(g["close"], o["close"], o["score"], tol=1e-8)
+    # one-vs-many form (query broadcast) over 128 KiB rows
+    r = ctx.score_pairs(gm, hs, hs, a_begin=0, n_pairs=10, b_begin=2, b_bc=1, want=("score",))
+    assert np.abs(r["score"] - o["score"][ib == 2]).max() <= 1e-8
