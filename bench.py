@@ -241,14 +241,16 @@ def run_ours(args, rank, world, local_rank):
 
     def step_resident():
         ctx.flush_l2(256 << 20)
-        return mdist.all_pairs_step(eng, comm, torch, n_total, cutoff, upper_only=True, max_out=max_out)
+        return mdist.all_pairs_step(eng, comm, torch, n_total, cutoff, upper_only=True, blocks_per_rank=args.blocks_per_rank,
+                                    max_out=max_out)
 
     def step_e2e():
         ctx.flush_l2(256 << 20)
         old = eng.seqs
         eng.seqs = ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])   # H2D + pack, timed
         old.free()
-        return mdist.all_pairs_step(eng, comm, torch, n_total, cutoff, upper_only=True, max_out=max_out)
+        return mdist.all_pairs_step(eng, comm, torch, n_total, cutoff, upper_only=True, blocks_per_rank=args.blocks_per_rank,
+                                    max_out=max_out)
 
     def timed(fn, steps, sample_clocks=False):
         comm.barrier()
@@ -404,6 +406,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--n-seqs", dest="n", type=int, default=None, help="override the number of sequences (smoke runs)")
+    ap.add_argument("--blocks-per-rank", type=int, default=2, help="folded query-row block pairs per rank and step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--cpu-hist-sample", type=int, default=100000)

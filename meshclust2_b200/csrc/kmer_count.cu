@@ -179,56 +179,77 @@ __device__ __forceinline__ u32 group_max(u32 v, u64 *sh)
 	return t;
 }
 
-// count one sequence's k-mers into `hist` (shared or global u32 counters) and its 1-mers; returns per-thread partials
+// count one sequence's k-mers into `hist` (shared or global u32 counters) and its 1-mers; returns per-thread partials.
+// All position arithmetic is 32-bit (the reference's positions are int).  Words whose 16 k-mer starts are all inside the
+// segment take a branch-free 16-way unrolled path (2 shifts + 1 atomic per k-mer); only the (at most two) edge words of a
+// segment loop over their valid positions.  Per-increment overflow tracking (the atomic's return value) is needed only
+// for multi-segment sequences with a narrow T: with one segment "some increment met a saturated bin" is exactly
+// "some final count exceeds max(T)", which the narrowing pass sees anyway.
 template <bool WARP, bool GLOBAL>
-__device__ __forceinline__ void count_sequence(const CountArgs &a, u64 seq, u32 *hist, int gt, int gs, u64 tmax,
-					       u64 (&m1)[4], u64 &eff_len, int &novf)
+__device__ __forceinline__ void count_sequence(const CountArgs &a, u64 seq, u32 *hist, int gt, int gs, u64 tmax, u32 (&m1)[4],
+					       u64 &eff_len, int &novf, bool &ovf_from_bins)
 {
 	const u64 w0 = a.word_off[seq];
-	const u64 nw = a.word_off[seq + 1] - w0;
+	const int nw = (int)(a.word_off[seq + 1] - w0);
 	const u32 *pk = a.packed + w0;
 	const int k = a.k;
 	const int sh_r = 32 - 2 * k;
+	const u64 sg0 = a.seg_off[seq], sg1 = a.seg_off[seq + 1];
+	const bool track = (sg1 - sg0 > 1) && tmax < 0xFFFFFFFFull; // per-segment overflow counts need the atomics' old values
+	const u32 ovf_at = tmax < 0xFFFFFFFFull && tmax >= a.init ? (u32)(tmax - a.init) : 0xFFFFFFFFu; // old >= ovf_at <=> saturated
 	m1[0] = m1[1] = m1[2] = m1[3] = 0;
 	eff_len = 0;
 	novf = 0;
-	for (u64 sg = a.seg_off[seq]; sg < a.seg_off[seq + 1]; sg++) {
-		const long long s0 = a.segs[2 * sg], e0 = a.segs[2 * sg + 1];
+	ovf_from_bins = !track;
+	for (u64 sg = sg0; sg < sg1; sg++) {
+		const int s0 = a.segs[2 * sg], e0 = a.segs[2 * sg + 1];
 		eff_len += (u64)(e0 - s0 + 1);
-		const long long last = e0 - k + 1; // last k-mer start; k-mers counted only if the segment holds >= k bases
+		const int last = e0 - k + 1; // last k-mer start; k-mers counted only if the segment holds >= k bases
 		const bool do_k = (e0 - s0 + 1 >= k);
 		int ovf = 0;
-		for (long long w = s0 / 16 + gt; w <= e0 / 16; w += gs) {
+		for (int w = (s0 >> 4) + gt; w <= (e0 >> 4); w += gs) {
 			const u32 cur = pk[w];
-			const u32 nxt = ((u64)(w + 1) < nw) ? pk[w + 1] : 0u;
-			const long long j0 = w * 16;
-			// 1-mers over [s0, e0] (the k=1 table, Loader.cpp:144,150)
+			const u32 nxt = (w + 1 < nw) ? pk[w + 1] : 0u;
+			const int j0 = w << 4;
+			// 1-mers over [s0, e0] (the k=1 table, Loader.cpp:144,150): 3 popcounts, A by difference
 			{
-				int lo_t = (int)max(0LL, s0 - j0), hi_t = (int)min(15LL, e0 - j0);
+				const int lo_t = max(0, s0 - j0), hi_t = min(15, e0 - j0);
 				// valid fields mask on the low bit of each 2-bit field; field t sits at bits (31-2t, 30-2t)
-				u32 vm = 0x55555555u;
-				vm &= 0xFFFFFFFFu >> (2 * lo_t);
+				u32 vm = 0x55555555u & (0xFFFFFFFFu >> (2 * lo_t));
 				vm &= hi_t >= 15 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> (2 * (hi_t + 1)));
-				u32 lo = cur & 0x55555555u, hi = (cur >> 1) & 0x55555555u;
-				m1[0] += __popc(~hi & ~lo & vm);
-				m1[1] += __popc(~hi & lo & vm);
-				m1[2] += __popc(hi & ~lo & vm);
-				m1[3] += __popc(hi & lo & vm);
+				const u32 lo = cur & vm, hi = (cur >> 1) & vm;
+				const u32 nT = __popc(hi & lo), nCT = __popc(lo), nGT = __popc(hi);
+				m1[3] += nT;
+				m1[1] += nCT - nT;
+				m1[2] += nGT - nT;
+				m1[0] += (u32)(hi_t - lo_t + 1) - nCT - nGT + nT;
 			}
-			if (do_k && j0 <= last) {
+			if (!do_k) {
+				continue;
+			}
+			const int t0 = max(0, s0 - j0), t1 = min(15, last - j0);
+			if (t0 == 0 && t1 == 15) {
+				if (track) {
 #pragma unroll
-				for (int t = 0; t < 16; t++) {
-					const long long j = j0 + t;
-					if (j >= s0 && j <= last) {
-						u32 idx = __funnelshift_l(nxt, cur, 2 * t) >> sh_r;
-						u32 old = atomicAdd(&hist[idx], 1u);
-						ovf |= (a.init + (u64)old >= tmax);
+					for (int t = 0; t < 16; t++) {
+						u32 old = atomicAdd(&hist[__funnelshift_l(nxt, cur, 2 * t) >> sh_r], 1u);
+						ovf |= old >= ovf_at;
 					}
+				} else {
+#pragma unroll
+					for (int t = 0; t < 16; t++) {
+						atomicAdd(&hist[__funnelshift_l(nxt, cur, 2 * t) >> sh_r], 1u);
+					}
+				}
+			} else {
+				for (int t = t0; t <= t1; t++) {
+					u32 old = atomicAdd(&hist[__funnelshift_l(nxt, cur, 2 * t) >> sh_r], 1u);
+					ovf |= old >= ovf_at;
 				}
 			}
 		}
 		// one -1 return per overflowing segment (Loader.cpp:54-56); needs every increment of the segment done
-		if (group_or<WARP>(ovf)) {
+		if (track && group_or<WARP>(ovf)) {
 			novf++;
 		}
 	}
@@ -261,6 +282,17 @@ __device__ __forceinline__ void emit4(const u32 *cnt4, u64 init, u64 tmax, T *ds
 	}
 }
 
+// 8-bit fast narrowing: everything in 32 bits (init <= 255, at most 4096 bins per group in shared memory)
+__device__ __forceinline__ void emit4_u8(const uint4 &c, u32 init, uint8_t *dst, u32 &sum, u32 &sumsq, u32 &mx)
+{
+	const u32 v0 = min(c.x + init, 255u), v1 = min(c.y + init, 255u), v2 = min(c.z + init, 255u), v3 = min(c.w + init, 255u);
+	const u32 packed = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+	*reinterpret_cast<u32 *>(dst) = packed;
+	sum = __dp4a(packed, 0x01010101u, sum);
+	sumsq = __dp4a(packed, packed, sumsq);
+	mx = max(mx, max(max(c.x, c.y), max(c.z, c.w)));
+}
+
 template <typename T, bool WARP, bool GLOBAL>
 __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ CountArgs a)
 {
@@ -284,9 +316,11 @@ __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ Coun
 			}
 			group_sync<WARP>();
 		}
-		u64 m1[4], eff_len;
+		u32 m1[4];
+		u64 eff_len;
 		int novf;
-		count_sequence<WARP, GLOBAL>(a, seq, hist, gt, gs, tmax, m1, eff_len, novf);
+		bool ovf_from_bins;
+		count_sequence<WARP, GLOBAL>(a, seq, hist, gt, gs, tmax, m1, eff_len, novf, ovf_from_bins);
 		if (GLOBAL) {
 			__threadfence();
 		}
@@ -295,16 +329,38 @@ __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ Coun
 		u64 sum = 0, sumsq = 0;
 		u32 mx = 0;
 		T *dst = reinterpret_cast<T *>(a.bins) + seq * N;
-		for (u64 b = (u64)gt * 4; b < N; b += (u64)gs * 4) {
-			uint4 c = GLOBAL ? __ldcg(reinterpret_cast<const uint4 *>(hist + b)) : *reinterpret_cast<const uint4 *>(hist + b);
-			u32 c4[4] = {c.x, c.y, c.z, c.w};
-			emit4<T>(c4, a.init, tmax, dst + b, sum, sumsq, mx);
+		u64 t0, t1, t2, t3;
+		if (WARP && sizeof(T) == 1 && a.init <= 255) {
+			// warp-private shared histogram of <= 4096 bins: all partial sums fit 32 bits, one REDUX each
+			u32 s32 = 0, q32 = 0;
+			const u32 init32 = (u32)a.init;
+			for (u32 b = (u32)gt * 4; b < (u32)N; b += 128) {
+				emit4_u8(*reinterpret_cast<const uint4 *>(hist + b), init32, reinterpret_cast<uint8_t *>(dst) + b, s32, q32, mx);
+			}
+			sum = __reduce_add_sync(0xffffffffu, s32);
+			sumsq = __reduce_add_sync(0xffffffffu, q32);
+			mx = __reduce_max_sync(0xffffffffu, mx);
+			t0 = __reduce_add_sync(0xffffffffu, m1[0]);
+			t1 = __reduce_add_sync(0xffffffffu, m1[1]);
+			t2 = __reduce_add_sync(0xffffffffu, m1[2]);
+			t3 = __reduce_add_sync(0xffffffffu, m1[3]);
+		} else {
+			for (u64 b = (u64)gt * 4; b < N; b += (u64)gs * 4) {
+				uint4 c = GLOBAL ? __ldcg(reinterpret_cast<const uint4 *>(hist + b)) : *reinterpret_cast<const uint4 *>(hist + b);
+				u32 c4[4] = {c.x, c.y, c.z, c.w};
+				emit4<T>(c4, a.init, tmax, dst + b, sum, sumsq, mx);
+			}
+			sum = group_sum<WARP>(sum, sh_red);
+			sumsq = group_sum<WARP>(sumsq, sh_red);
+			mx = group_max<WARP>(mx, sh_red);
+			t0 = group_sum<WARP>(m1[0], sh_red);
+			t1 = group_sum<WARP>(m1[1], sh_red);
+			t2 = group_sum<WARP>(m1[2], sh_red);
+			t3 = group_sum<WARP>(m1[3], sh_red);
 		}
-		sum = group_sum<WARP>(sum, sh_red);
-		sumsq = group_sum<WARP>(sumsq, sh_red);
-		mx = group_max<WARP>(mx, sh_red);
-		u64 t0 = group_sum<WARP>(m1[0], sh_red), t1 = group_sum<WARP>(m1[1], sh_red);
-		u64 t2 = group_sum<WARP>(m1[2], sh_red), t3 = group_sum<WARP>(m1[3], sh_red);
+		if (ovf_from_bins && eff_len > 0) { // single segment: it overflowed iff some final count exceeds max(T)
+			novf = (tmax < 0xFFFFFFFFull && a.init + (u64)mx > tmax) ? 1 : 0;
+		}
 		if (gt == 0) {
 			a.mag[seq] = sum;
 			a.sum[seq] = sum;

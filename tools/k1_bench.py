@@ -1,0 +1,24 @@
+"""K1 timings (development aid): cfg3-shaped short reads and cfg4-shaped long multi-segment records."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from meshclust2_b200 import capi, synth
+ctx = capi.Context(0)
+def run(name, seqs, k, eb, iters=10):
+    enc = capi.encode_batch(seqs)
+    sq = ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
+    L = sum(len(s) for s in seqs) / len(seqs)
+    ms = ctx.bench_count_kmers(sq, k, eb, iters=iters, flush_l2=True)
+    ms = ctx.bench_count_kmers(sq, k, eb, iters=iters, flush_l2=True)
+    byts = len(seqs) * (L / 4 + 4 ** k * eb + 40)
+    print("%-28s n=%d L=%.0f k=%d eb=%d: %.3f ms  %.3e hist/s  %.3e kmers/s  %.0f GB/s (%.1f%% of 6540)" % (
+        name, len(seqs), L, k, eb, ms, len(seqs) / ms * 1e3, len(seqs) * L / ms * 1e3, byts / ms / 1e6, byts / ms / 1e6 / 65.4))
+seqs, _, k, eb = synth.make_config_range("cfg3", 0, int(os.environ.get("K1_N", 100000)))
+run("cfg3 short reads", seqs, 5, 1)
+run("cfg3 short reads u16", seqs, 5, 2)
+run("cfg3 short reads k=6", seqs, 6, 1)
+if not os.environ.get("K1_SHORT"):
+    long_ = synth.make_single_file(500, 5, 10000, seed=4)
+    run("cfg4 long records", long_, 8, 2, iters=3)
+    run("long records k=7", long_, 7, 2, iters=3)
+    run("long records k=5", long_, 5, 1, iters=3)
