@@ -65,8 +65,8 @@ class ClockSampler:
     """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML every 200 ms
     (the B200_PROFILING.md clocks line without spawning nvidia-smi, whose polling loop perturbs short steps)."""
 
-    def __init__(self, device):
-        self.device, self.rows, self.stop_flag, self.t = device, [], False, None
+    def __init__(self, device, interval=0.5):
+        self.device, self.rows, self.stop_flag, self.t, self.interval = device, [], False, None, interval
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -87,16 +87,21 @@ class ClockSampler:
 
     def _loop(self):
         nv = self.nv
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
         while not self.stop_flag:
             try:
-                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
-                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.rows.append((sm, mx, rs))
+                # two light NVML reads per sample; NVML queries serialise with CUDA calls in the driver, so keep them sparse
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), mx, reasons(self.h)))
             except Exception:
                 pass
-            time.sleep(0.2)
+            for _ in range(int(self.interval / 0.05)):
+                if self.stop_flag:
+                    break
+                time.sleep(0.05)
 
     def start(self):
         if self.nv is None:
@@ -211,7 +216,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": leg["cores"], "kind": leg["kind"], "sample": leg["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -333,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
         log("[bench] cpu baseline leg %.1fs" % (time.time() - t0))
         line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if tdist is not None:
         tdist.destroy_process_group()
@@ -398,7 +403,25 @@ def candidates_roofline(ctx, capi, model, k, eb, peak, peak_src, n=1 << 20):
             "peak_source": peak_src}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else libraries print to fd 1 (e.g. NCCL's version banner)
+    has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
