@@ -258,13 +258,12 @@ def run_ours(args, rank, world, local_rank):
                                     max_out=max_out)
 
     def timed(fn, steps, sample_clocks=False):
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()          # before the barrier: rank 0 must not enter the timed region later than the others
         comm.barrier()
         torch.cuda.synchronize()
         ctx.sync()
-        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
-        if sampler:
-            sampler.start()
-            time.sleep(0.3)
         l0 = ctx.launches
         ctx.profile(True)
         ctx.timer_start()
