@@ -653,6 +653,7 @@ int mc2_count_kmers_into(mc2_ctx *ctx, const mc2_seqs *seqs, mc2_hset *dst)
 	MC2_REQUIRE(ctx && seqs && dst, "mc2_count_kmers_into: NULL argument");
 	MC2_REQUIRE(dst->n == seqs->n, "mc2_count_kmers_into: the set holds a different number of rows");
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	dst->lane_off_valid = 0;
 	int rc = count_into(ctx, seqs, dst->k, dst->eb, 1, dst);
 	if (rc == MC2_OK) rc = refresh_max_sum(ctx, dst);
 	return rc;
@@ -762,6 +763,7 @@ int mc2_hset_update_from_device(mc2_ctx *ctx, mc2_hset *h, const void *d_bins, c
 	if (n == 0) {
 		return MC2_OK;
 	}
+	h->lane_off_valid = 0;
 	MC2_CUDA(cudaMemcpyAsync(h->bins, d_bins, n * h->N * (u64)h->eb, cudaMemcpyDeviceToDevice, ctx->stream));
 	MC2_CUDA(cudaMemcpyAsync(h->len, d_len, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 	if (d_mag) MC2_CUDA(cudaMemcpyAsync(h->mag, d_mag, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -798,6 +800,7 @@ void mc2_hset_free(mc2_hset *h)
 	cudaFree(h->stddev);
 	cudaFree(h->novf);
 	cudaFree(h->maxc);
+	cudaFree(h->lane_off);
 	delete h;
 }
 
@@ -877,6 +880,7 @@ int mc2_hset_set_row(mc2_ctx *ctx, mc2_hset *dst, uint64_t dst_row, const mc2_hs
 	MC2_REQUIRE(ctx && dst && src, "mc2_hset_set_row: NULL argument");
 	MC2_REQUIRE(dst->k == src->k && dst->eb == src->eb, "mc2_hset_set_row: sets differ in k or width");
 	MC2_REQUIRE(dst_row < dst->n && src_row < src->n, "mc2_hset_set_row: row out of range");
+	dst->lane_off_valid = 0;
 	cudaStream_t st = ctx->stream;
 	const u64 rb = dst->N * (u64)dst->eb;
 	// DivergencePoint::set (src/clutil/DivergencePoint.cpp:182-190): points + length (+header/id), NOT mag
@@ -900,6 +904,7 @@ int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t
 		return MC2_OK;
 	}
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	dst->lane_off_valid = 0;
 	const int parts = 2 + (mag ? 1 : 0) + (len ? 1 : 0);
 	std::vector<u64> idx((size_t)parts * n);
 	for (u64 i = 0; i < n; i++) {
@@ -1093,6 +1098,11 @@ static int fill_pair_args(mc2_ctx *ctx, const mc2_pairs *p, PairArgs &a, CtxExtr
 	a.cutoff = p->cutoff;
 	a.err = ctx->d_err;
 	a.max_sum = A->max_sum > B->max_sum ? A->max_sum : B->max_sum;
+	a.loffA = a.loffB = nullptr;
+	if (ensure_lane_off(ctx, A) == MC2_OK && ensure_lane_off(ctx, B) == MC2_OK && A->lane_off_valid && B->lane_off_valid) {
+		a.loffA = A->lane_off;
+		a.loffB = B->lane_off;
+	}
 	const u64 m = p->n_pairs;
 	if (p->ia) {
 		for (u64 j = 0; j < m; j++) {

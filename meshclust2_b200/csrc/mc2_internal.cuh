@@ -125,6 +125,11 @@ struct mc2_hset {
 	int *novf;        // n
 	u32 *maxc;        // n : largest unsaturated count+1
 	u64 max_sum;      // host-known upper bound of sum[] (selects fast paths)
+	// 1 KiB uint8 rows only: exclusive prefix of the bin sums at the 32 lane boundaries (bins [32l, 32l+32) belong to lane
+	// l), u16, n x 32.  Lets the EMD reduction start each lane's prefix chain without a per-pair warp scan.  Built lazily,
+	// dropped whenever bins change.
+	unsigned short *lane_off;
+	int lane_off_valid;
 };
 
 struct mc2_model {
@@ -158,6 +163,7 @@ struct PairArgs {
 	u64 *n_close;  // optional device counter
 	int *err;      // device error word
 	u64 max_sum;   // bound on bin sums of both sets
+	const unsigned short *loffA, *loffB; // lane-boundary prefix sums (see mc2_hset::lane_off) or NULL
 };
 
 int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a);
@@ -170,6 +176,7 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 		     int upper_only, double cutoff, u64 max_out, u64 *d_out_q, u64 *d_out_d, double *d_out_score,
 		     u64 *d_counters);
 int launch_distance(mc2_ctx *ctx, const PairArgs &a, u64 *d_out);
+int ensure_lane_off(mc2_ctx *ctx, const mc2_hset *h); // builds h->lane_off if the shape allows; no-op otherwise
 int launch_mean_closest(mc2_ctx *ctx, const mc2_hset *h, const u64 *d_members, u64 n, u64 *d_sums, double *d_mean, double *d_dist,
 			void *d_out, bool have_mean);
 

@@ -560,6 +560,7 @@ struct FixedQ {
 	Row8 q;
 	int bq[32];
 	int qsum;
+	int qoff; // sum of the fixed row's bins below this lane's chunk (from lane_off), used when LOFF
 };
 
 template <int NEED>
@@ -578,6 +579,7 @@ __device__ __forceinline__ void fixed_q_setup(FixedQ &f, const void *row, int la
 		}
 	}
 	f.qsum = base;
+	f.qoff = 0;
 }
 
 template <int NEED>
@@ -631,8 +633,9 @@ __device__ __forceinline__ void reduce_row1(const Row8 &p, const FixedQ &f, u32 
 
 // two streamed rows against the same fixed row, written side by side so the two dependency chains (lane totals ->
 // warp scan -> prefix chain -> |.| accumulation -> REDUX) interleave and hide each other's latencies
-template <int NEED>
-__device__ __forceinline__ void reduce_row2(const Row8 &pa, const Row8 &pb, const FixedQ &f, u32 (&oa)[3], u32 (&ob)[3])
+template <int NEED, bool LOFF>
+__device__ __forceinline__ void reduce_row2(const Row8 &pa, const Row8 &pb, int offa, int offb, const FixedQ &f, u32 (&oa)[3],
+					    u32 (&ob)[3])
 {
 	u32 mina = 0, minb = 0, dota = 0, dotb = 0, ea = 0, eb = 0;
 	if (NEED & NEED_MIN) {
@@ -650,20 +653,28 @@ __device__ __forceinline__ void reduce_row2(const Row8 &pa, const Row8 &pb, cons
 		}
 	}
 	if (NEED & NEED_EMD) {
-		u32 ta = 0, tb = 0;
+		int basea, baseb;
+		if (LOFF) {
+			// cumP - cumQ at the lane boundary comes from the precomputed lane offsets: no lane totals, no warp scan
+			basea = offa - f.qoff;
+			baseb = offb - f.qoff;
+		} else {
+			u32 ta = 0, tb = 0;
 #pragma unroll
-		for (int w = 0; w < 8; w++) {
-			ta = __dp4a(pa.w[w], 0x01010101u, ta);
-			tb = __dp4a(pb.w[w], 0x01010101u, tb);
-		}
-		int xa = (int)ta - f.qsum, xb = (int)tb - f.qsum;
-		const int ta0 = xa, tb0 = xb;
+			for (int w = 0; w < 8; w++) {
+				ta = __dp4a(pa.w[w], 0x01010101u, ta);
+				tb = __dp4a(pb.w[w], 0x01010101u, tb);
+			}
+			int xa = (int)ta - f.qsum, xb = (int)tb - f.qsum;
+			const int ta0 = xa, tb0 = xb;
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			scan_step(xa, d);
-			scan_step(xb, d);
+			for (int d = 1; d < 32; d <<= 1) {
+				scan_step(xa, d);
+				scan_step(xb, d);
+			}
+			basea = xa - ta0;
+			baseb = xb - tb0;
 		}
-		int basea = xa - ta0, baseb = xb - tb0;
 #pragma unroll
 		for (int w = 0; w < 8; w++) {
 			int a0 = (int)__dp4a(pa.w[w], 0x00000001u, (u32)basea);
@@ -704,26 +715,37 @@ __device__ __forceinline__ void ld_row_stream_if(Row8 &r, const void *p, int pre
 		     : "l"(p), "r"(pred));
 }
 
+__device__ __forceinline__ void ld_u16_if(int &v, const unsigned short *p, int pred)
+{
+	asm volatile("{\n\t.reg .pred q;\n\t.reg .u16 t;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.nc.u16 t, [%1];\n\t@q cvt.u32.u16 %0, t;\n\t}"
+		     : "+r"(v)
+		     : "l"(p), "r"(pred));
+}
+
 // stream the rows of up to 32 pairs (bit mask `active`, row index of pair i held by lane i in `rs`, or consecutive rows
 // first_row + i when contig) against the fixed row, two rows per step.  Two buffer pairs alternate by loop unrolling
 // (no register copies): while one pair of rows is reduced the next pair is in flight.
-template <int NEED>
-__device__ __forceinline__ void scan_group(const unsigned char *S, u64 row_bytes, unsigned active, u64 rs, bool contig,
-					   u64 first_row, const FixedQ &f, int lane, u32 &my_min, u32 &my_dot, u32 &my_emd)
+template <int NEED, bool LOFF>
+__device__ __forceinline__ void scan_group(const unsigned char *S, const unsigned short *loff, u64 row_bytes, unsigned active,
+					   u64 rs, bool contig, u64 first_row, const FixedQ &f, int lane, u32 &my_min, u32 &my_dot,
+					   u32 &my_emd)
 {
 	auto next_idx = [&]() -> int {
 		int pi = active ? __ffs(active) - 1 : -1;
 		active &= active ? active - 1 : 0;
 		return pi;
 	};
-	auto fetch = [&](Row8 &r, int pi) {
+	auto fetch = [&](Row8 &r, int &off, int pi) {
 		// the shuffle must be executed by the whole warp: clamp the source lane instead of predicating it
 		u64 x = contig ? first_row + (u64)(pi < 0 ? 0 : pi) : __shfl_sync(0xffffffffu, rs, pi < 0 ? 0 : pi);
 		ld_row_stream_if(r, S + x * row_bytes + lane * 32, pi >= 0);
+		if (LOFF && (NEED & NEED_EMD)) {
+			ld_u16_if(off, loff + x * 32 + lane, pi >= 0);
+		}
 	};
-	auto reduce = [&](const Row8 &ra, int ia, const Row8 &rb, int ib) {
+	auto reduce = [&](const Row8 &ra, int oa_, int ia, const Row8 &rb, int ob_, int ib) {
 		u32 oa[3], ob[3];
-		reduce_row2<NEED>(ra, rb, f, oa, ob); // an absent second row (ib < 0) reduces stale data that nobody keeps
+		reduce_row2<NEED, LOFF>(ra, rb, oa_, ob_, f, oa, ob); // an absent second row (ib < 0) reduces stale data that nobody keeps
 		if (lane == ia) {
 			my_min = oa[0];
 			my_dot = oa[1];
@@ -736,37 +758,38 @@ __device__ __forceinline__ void scan_group(const unsigned char *S, u64 row_bytes
 		}
 	};
 	Row8 a0 = {}, b0 = {}, a1 = {}, b1 = {};
+	int fa0 = 0, fb0 = 0, fa1 = 0, fb1 = 0; // lane offsets of the four buffered rows
 	int ia0 = next_idx();
 	if (ia0 < 0) {
 		return;
 	}
 	int ib0 = next_idx();
-	fetch(a0, ia0);
-	fetch(b0, ib0);
+	fetch(a0, fa0, ia0);
+	fetch(b0, fb0, ib0);
 	int ia1 = next_idx(), ib1 = next_idx();
-	fetch(a1, ia1);
-	fetch(b1, ib1);
+	fetch(a1, fa1, ia1);
+	fetch(b1, fb1, ib1);
 	while (true) {
-		reduce(a0, ia0, b0, ib0);
+		reduce(a0, fa0, ia0, b0, fb0, ib0);
 		if (ia1 < 0) {
 			break;
 		}
 		ia0 = next_idx();
 		ib0 = next_idx();
-		fetch(a0, ia0);
-		fetch(b0, ib0);
-		reduce(a1, ia1, b1, ib1);
+		fetch(a0, fa0, ia0);
+		fetch(b0, fb0, ib0);
+		reduce(a1, fa1, ia1, b1, fb1, ib1);
 		if (ia0 < 0) {
 			break;
 		}
 		ia1 = next_idx();
 		ib1 = next_idx();
-		fetch(a1, ia1);
-		fetch(b1, ib1);
+		fetch(a1, fa1, ia1);
+		fetch(b1, fb1, ib1);
 	}
 }
 
-template <typename T, int NEED, bool ONE>
+template <typename T, int NEED, bool ONE, bool LOFF>
 __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) pair_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a)
 {
 	const int lane = threadIdx.x & 31;
@@ -784,6 +807,9 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) pair_fast_kernel
 	if constexpr (fixed_q) { // one-vs-many: the query row and its prefix sums live in registers for the whole kernel
 		const T *qrow = a_hot ? A + a.a_begin * a.N : B + a.b_begin * a.N;
 		fixed_q_setup<NEED>(fq, qrow, lane);
+		if (LOFF) {
+			fq.qoff = a_hot ? a.loffA[a.a_begin * 32 + lane] : a.loffB[a.b_begin * 32 + lane];
+		}
 	}
 	for (u64 g = warp_id; g < groups; g += warps_total) {
 		const u64 j = g * 32 + lane;
@@ -799,7 +825,8 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) pair_fast_kernel
 			const bool contig = a_hot ? (a.ib == nullptr) : (a.ia == nullptr);
 			const u64 first_row = (a_hot ? a.b_begin : a.a_begin) + g * 32;
 			u32 m0 = 0, m1 = 0, m2 = 0;
-			scan_group<NEED>(S, 1024, active, a_hot ? rb : ra, contig, first_row, fq, lane, m0, m1, m2);
+			scan_group<NEED, LOFF>(S, a_hot ? a.loffB : a.loffA, 1024, active, a_hot ? rb : ra, contig, first_row, fq, lane, m0, m1,
+					       m2);
 			mine.smin = m0;
 			mine.dot = m1;
 			mine.emd = m2;
@@ -971,7 +998,7 @@ __global__ void __launch_bounds__(128, 4) pair_tma_kernel(const __grid_constant_
 				issue_one();
 			}
 			u32 oa[3], ob[3];
-			reduce_row2<NEED>(pa, pb, fq, oa, ob);
+			reduce_row2<NEED, false>(pa, pb, 0, 0, fq, oa, ob);
 			if (lane == ia_) {
 				m0 = oa[0];
 				m1 = oa[1];
@@ -1294,7 +1321,7 @@ struct SweepArgs {
 	u64 *counters; // [0] survivors, [1] scored pairs
 };
 
-template <typename T, int NEED, bool FAST, bool ONE>
+template <typename T, int NEED, bool FAST, bool ONE, bool LOFF>
 __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
 						    const __grid_constant__ SweepArgs g)
 {
@@ -1329,9 +1356,12 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(con
 				// the query row r and its prefix sums sit in registers for the whole 32-candidate group
 				FixedQ fq;
 				fixed_q_setup<NEED>(fq, Qm + r * a.N, lane);
+				if (LOFF) {
+					fq.qoff = a.loffB[r * 32 + lane];
+				}
 				u32 m0 = 0, m1 = 0, m2 = 0;
-				scan_group<NEED>(reinterpret_cast<const unsigned char *>(Dm), 1024, active, c, true,
-						 g.d0 + (grp % cblocks) * 32, fq, lane, m0, m1, m2);
+				scan_group<NEED, LOFF>(reinterpret_cast<const unsigned char *>(Dm), a.loffA, 1024, active, c, true,
+						       g.d0 + (grp % cblocks) * 32, fq, lane, m0, m1, m2);
 				mn.smin = m0;
 				mn.dot = m1;
 				mn.emd = m2;
@@ -1411,13 +1441,13 @@ static int grid_for(mc2_ctx *ctx, u64 n_pairs, int warps_per_cta, int ctas_per_s
 	return (int)(g ? g : 1);
 }
 
-template <typename T, bool ONE>
+template <typename T, bool ONE, bool LOFF = false>
 static void launch_fast_need(int need, int grid, cudaStream_t st, const DevModel &dm, const PairArgs &a)
 {
 	switch (need & 7) {
 #define CASE(n)                                                         \
 	case n:                                                         \
-		pair_fast_kernel<T, n, ONE><<<ONE ? grid * 2 : grid, ONE ? 128 : 256, 0, st>>>(dm, a); \
+		pair_fast_kernel<T, n, ONE, LOFF><<<ONE ? grid * 2 : grid, ONE ? 128 : 256, 0, st>>>(dm, a); \
 		break;
 		CASE(0)
 		CASE(1)
@@ -1473,6 +1503,8 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 		static const bool use_tma = getenv("MC2_USE_TMA") != nullptr;
 		if (one && use_tma) {
 			launch_tma_need(dm.need, ctx, dm, a);
+		} else if (one && a.loffA && a.loffB && (dm.need & NEED_EMD)) {
+			launch_fast_need<uint8_t, true, true>(dm.need, grid, ctx->stream, dm, a);
 		} else if (one) {
 			launch_fast_need<uint8_t, true>(dm.need, grid, ctx->stream, dm, a);
 		} else if (a.eb == 1) {
@@ -1526,13 +1558,13 @@ int launch_distance(mc2_ctx *ctx, const PairArgs &a, u64 *d_out)
 	return MC2_OK;
 }
 
-template <typename T, bool ONE>
+template <typename T, bool ONE, bool LOFF = false>
 static void launch_sweep_fast(int need, int grid, cudaStream_t st, const DevModel &dm, const PairArgs &a, const SweepArgs &g)
 {
 	switch (need & 7) {
 #define CASE(n)                                                               \
 	case n:                                                               \
-		sweep_kernel<T, n, true, ONE><<<ONE ? grid * 2 : grid, ONE ? 128 : 256, 0, st>>>(dm, a, g); \
+		sweep_kernel<T, n, true, ONE, LOFF><<<ONE ? grid * 2 : grid, ONE ? 128 : 256, 0, st>>>(dm, a, g); \
 		break;
 		CASE(0)
 		CASE(1)
@@ -1560,6 +1592,10 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 	a.eb = q->eb;
 	a.err = ctx->d_err;
 	a.max_sum = q->max_sum > d->max_sum ? q->max_sum : d->max_sum;
+	if ((dm.need & NEED_EMD) && ensure_lane_off(ctx, d) == MC2_OK && ensure_lane_off(ctx, q) == MC2_OK) {
+		a.loffA = d->lane_off_valid ? d->lane_off : nullptr;
+		a.loffB = q->lane_off_valid ? q->lane_off : nullptr;
+	}
 	SweepArgs g;
 	g.q0 = q0;
 	g.q1 = q1;
@@ -1579,7 +1615,9 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 	const bool fast = a.eb <= 2 && row_bytes % 1024 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 26);
 	prof_begin(ctx, 3);
 	if (fast) {
-		if (a.eb == 1 && row_bytes == 1024) {
+		if (a.eb == 1 && row_bytes == 1024 && a.loffA && a.loffB && (dm.need & NEED_EMD)) {
+			launch_sweep_fast<uint8_t, true, true>(dm.need, grid, ctx->stream, dm, a, g);
+		} else if (a.eb == 1 && row_bytes == 1024) {
 			launch_sweep_fast<uint8_t, true>(dm.need, grid, ctx->stream, dm, a, g);
 		} else if (a.eb == 1) {
 			launch_sweep_fast<uint8_t, false>(dm.need, grid, ctx->stream, dm, a, g);
@@ -1588,16 +1626,53 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 		}
 	} else {
 		switch (a.eb) {
-		case 1: sweep_kernel<uint8_t, 0, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
-		case 2: sweep_kernel<uint16_t, 0, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
-		case 4: sweep_kernel<uint32_t, 0, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
-		case 8: sweep_kernel<unsigned long long, 0, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
+		case 1: sweep_kernel<uint8_t, 0, false, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
+		case 2: sweep_kernel<uint16_t, 0, false, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
+		case 4: sweep_kernel<uint32_t, 0, false, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
+		case 8: sweep_kernel<unsigned long long, 0, false, false, false><<<grid, 256, 0, ctx->stream>>>(dm, a, g); break;
 		default: set_error("elem_bytes must be 1, 2, 4 or 8"); return MC2_ERR_ARG;
 		}
 	}
 	prof_end(ctx);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
+	return MC2_OK;
+}
+
+// exclusive prefix of the bin sums at the 32 lane boundaries of every 1 KiB uint8 row (see mc2_hset::lane_off)
+__global__ void __launch_bounds__(256) lane_off_kernel(const unsigned char *__restrict__ bins, u64 n, unsigned short *__restrict__ out)
+{
+	const int lane = threadIdx.x & 31;
+	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
+	for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps_total) {
+		Row8 p = ld_row_keep(bins + r * 1024 + lane * 32);
+		int tot = lane_sum<uint8_t>(p), wt;
+		int off = warp_excl_scan(tot, wt);
+		out[r * 32 + lane] = (unsigned short)off;
+	}
+}
+
+int ensure_lane_off(mc2_ctx *ctx, const mc2_hset *hc)
+{
+	mc2_hset *h = const_cast<mc2_hset *>(hc);
+	if (h->eb != 1 || h->N != 1024 || h->max_sum >= 65536 || h->n == 0) {
+		h->lane_off_valid = 0;
+		return MC2_OK;
+	}
+	if (h->lane_off_valid) {
+		return MC2_OK;
+	}
+	if (!h->lane_off) {
+		MC2_CUDA(cudaMalloc((void **)&h->lane_off, h->n * 64));
+	}
+	u64 want = (h->n + 7) / 8, cap = (u64)ctx->sm_count * 8;
+	int grid = (int)(want < cap ? want : cap);
+	prof_begin(ctx, 5);
+	lane_off_kernel<<<grid, 256, 0, ctx->stream>>>((const unsigned char *)h->bins, h->n, h->lane_off);
+	prof_end(ctx);
+	ctx->launches++;
+	MC2_CUDA(cudaGetLastError());
+	h->lane_off_valid = 1;
 	return MC2_OK;
 }
 

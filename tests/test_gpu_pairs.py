@@ -361,3 +361,36 @@ def test_cfg4_shape_single_file_k8_u16(built_lib, ctx):
     # one-vs-many form (query broadcast) over 128 KiB rows
     r = ctx.score_pairs(gm, hs, hs, a_begin=0, n_pairs=10, b_begin=2, b_bc=1, want=("score",))
     assert np.abs(r["score"] - o["score"][ib == 2]).max() <= 1e-8
+
+
+def test_assign_rows_and_in_place_refill(built_lib, ctx, golden):
+    """mc2_hset_assign_rows (batched DivergencePoint::set / clone with explicit magnitude), mc2_count_kmers_into and
+    mc2_hset_update_from_device keep the side-band consistent with the bins they carry."""
+    H, ln, mag = golden["hist_k5_eb1"][:12], golden["len_k5_eb1"][:12], golden["mag_k5_eb1"][:12]
+    src = ctx.hset_from_host(H, 5, length=ln)
+    dst = ctx.hset_from_host(np.ones((4, 1024), dtype=np.uint8), 5, length=np.ones(4, dtype=np.uint64))
+    # rows 0,2 <- src 7,3 keeping dst's magnitude (set semantics); then with explicit magnitudes and lengths
+    dst.assign_rows([0, 2], src, [7, 3])
+    got = dst.download()
+    assert np.array_equal(got["hist"][0], H[7]) and np.array_equal(got["hist"][2], H[3])
+    assert got["mag"][0] == 1024 and got["len"][0] == ln[7]          # magnitude of the old all-ones row is kept
+    dst.assign_rows([1, 3], src, [5, 9], mag=[111, 222], length=[1001, 1002])
+    got = dst.download()
+    assert list(got["mag"][[1, 3]]) == [111, 222] and list(got["len"][[1, 3]]) == [1001, 1002]
+    # scoring through the assigned rows uses the carried side-band (true sums from the source rows)
+    m = port.Model.from_text(weights_text("weights_appendixD_id90"))
+    gm = ctx.model_from_file(weights_path("weights_appendixD_id90"))
+    g = ctx.score_pairs(gm, dst, src, [1], [2], want=("score",))
+    o = port.score_pairs(m, np.stack([H[5], H[2]]), np.array([111, mag[2]], dtype=np.uint64), np.array([1001, ln[2]]), [0], [1])
+    assert abs(g["score"][0] - o["score"][0]) <= 1e-9
+    # in-place recount equals a fresh count
+    from meshclust2_b200 import synth
+    seqs, _ = synth.make_set(20, 500, 3, 0.1, seed=2)
+    enc = built_lib.encode_batch(seqs)
+    sq = ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
+    a = ctx.count_kmers(sq, 5, 1)
+    b = ctx.hset_from_host(np.ones((20, 1024), dtype=np.uint8), 5)
+    ctx.count_kmers_into(sq, b)
+    da, db = a.download(), b.download()
+    for key in ("hist", "mag", "len", "mers1", "n_overflow"):
+        assert np.array_equal(da[key], db[key]), key
