@@ -1303,6 +1303,8 @@ int mc2_all_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
 	MC2_REQUIRE(q_begin <= q_end && q_end <= set_q->n && d_begin <= d_end && d_end <= set_d->n, "mc2_all_pairs: row range out of bounds");
 	MC2_REQUIRE(set_q->k == set_d->k && set_q->eb == set_d->eb, "mc2_all_pairs: the two sets differ in k or histogram width");
 	MC2_REQUIRE(cutoff > 0, "mc2_all_pairs: cutoff must be > 0");
+	MC2_REQUIRE((q_end - q_begin) * ((d_end - d_begin + 31) / 32) < (1ULL << 32),
+		    "mc2_all_pairs: more than 2^32 (query row, 32-column block) groups in one call; split the query range");
 	MC2_REQUIRE(!model->dm.regression, "mc2_all_pairs: needs a classifier model");
 	MC2_CUDA(cudaSetDevice(ctx->device));
 	*n_out = 0;

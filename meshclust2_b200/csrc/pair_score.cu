@@ -759,6 +759,35 @@ __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigne
 	};
 	Row8 a0 = {}, b0 = {}, a1 = {}, b1 = {};
 	int fa0 = 0, fb0 = 0, fa1 = 0, fb1 = 0; // lane offsets of the four buffered rows
+	if (contig && active == 0xffffffffu) {
+		// the common case — 32 consecutive rows, none filtered: plain counted loop, no mask / ffs / predicate traffic
+		const unsigned char *rp = S + first_row * row_bytes + lane * 32;
+		const unsigned short *op = loff + first_row * 32 + lane;
+		auto get = [&](Row8 &r, int &off, int pi) {
+			r = ld_row_stream(rp + (size_t)pi * row_bytes);
+			if (LOFF && (NEED & NEED_EMD)) {
+				off = (int)__ldg(op + pi * 32);
+			}
+		};
+		get(a0, fa0, 0);
+		get(b0, fb0, 1);
+		get(a1, fa1, 2);
+		get(b1, fb1, 3);
+#pragma unroll 1
+		for (int pi = 0; pi < 32; pi += 4) {
+			reduce(a0, fa0, pi, b0, fb0, pi + 1);
+			if (pi + 4 < 32) {
+				get(a0, fa0, pi + 4);
+				get(b0, fb0, pi + 5);
+			}
+			reduce(a1, fa1, pi + 2, b1, fb1, pi + 3);
+			if (pi + 4 < 32) {
+				get(a1, fa1, pi + 6);
+				get(b1, fb1, pi + 7);
+			}
+		}
+		return;
+	}
 	int ia0 = next_idx();
 	if (ia0 < 0) {
 		return;
@@ -1333,10 +1362,16 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(con
 	const T *Dm = reinterpret_cast<const T *>(a.binsA); // database = first argument of close(pts[i], query)
 	const T *Qm = reinterpret_cast<const T *>(a.binsB);
 	const u64 cblocks = (g.d1 - g.d0 + 31) / 32;
-	const u64 groups = (g.q1 - g.q0) * cblocks;
+	const u64 groups = (g.q1 - g.q0) * cblocks; // host guarantees groups < 2^32 per launch
+	const u32 cblocks32 = (u32)cblocks;
 	for (u64 grp = warp_id; grp < groups; grp += warps_total) {
-		const u64 r = g.q0 + grp / cblocks;
-		const u64 c = g.d0 + (grp % cblocks) * 32 + lane;
+		const u32 gr = (u32)grp / cblocks32, gc = (u32)grp - gr * cblocks32;
+		const u64 r = g.q0 + gr;
+		const u64 cfirst = g.d0 + (u64)gc * 32;
+		if (g.upper_only && cfirst + 31 <= r) {
+			continue; // whole block at or below the diagonal
+		}
+		const u64 c = cfirst + lane;
 		bool go = c < g.d1 && (!g.upper_only || c > r);
 		if (go) { // FC_Runner.cpp:435-444: size_t truncation, window on the database length
 			u64 lq = a.sbB.len[r], lc = a.sbA.len[c];
@@ -1360,8 +1395,8 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(con
 					fq.qoff = a.loffB[r * 32 + lane];
 				}
 				u32 m0 = 0, m1 = 0, m2 = 0;
-				scan_group<NEED, LOFF>(reinterpret_cast<const unsigned char *>(Dm), a.loffA, 1024, active, c, true,
-						       g.d0 + (grp % cblocks) * 32, fq, lane, m0, m1, m2);
+				scan_group<NEED, LOFF>(reinterpret_cast<const unsigned char *>(Dm), a.loffA, 1024, active, c, true, cfirst, fq,
+						       lane, m0, m1, m2);
 				mn.smin = m0;
 				mn.dot = m1;
 				mn.emd = m2;
