@@ -725,7 +725,7 @@ __device__ __forceinline__ void ld_u16_if(int &v, const unsigned short *p, int p
 // stream the rows of up to 32 pairs (bit mask `active`, row index of pair i held by lane i in `rs`, or consecutive rows
 // first_row + i when contig) against the fixed row, two rows per step.  Two buffer pairs alternate by loop unrolling
 // (no register copies): while one pair of rows is reduced the next pair is in flight.
-template <int NEED, bool LOFF>
+template <int NEED, bool LOFF, bool RING = true>
 __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigned short *loff, u64 row_bytes, unsigned active,
 					   u64 rs, bool contig, u64 first_row, const FixedQ &f, int lane, u32 &my_min, u32 &my_dot,
 					   u32 &my_emd)
@@ -769,6 +769,16 @@ __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigne
 				off = (int)__ldg(op + pi * 32);
 			}
 		};
+		if (!RING) {
+			// L2-resident rows (the sweep): no register ring, the extra resident warps hide the load latency instead
+#pragma unroll 1
+			for (int pi = 0; pi < 32; pi += 2) {
+				get(a0, fa0, pi);
+				get(b0, fb0, pi + 1);
+				reduce(a0, fa0, pi, b0, fb0, pi + 1);
+			}
+			return;
+		}
 		get(a0, fa0, 0);
 		get(b0, fb0, 1);
 		get(a1, fa1, 2);
@@ -793,6 +803,16 @@ __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigne
 		return;
 	}
 	int ib0 = next_idx();
+	if (!RING) {
+		while (ia0 >= 0) {
+			fetch(a0, fa0, ia0);
+			fetch(b0, fb0, ib0);
+			reduce(a0, fa0, ia0, b0, fb0, ib0);
+			ia0 = next_idx();
+			ib0 = next_idx();
+		}
+		return;
+	}
 	fetch(a0, fa0, ia0);
 	fetch(b0, fb0, ib0);
 	int ia1 = next_idx(), ib1 = next_idx();
@@ -1351,7 +1371,7 @@ struct SweepArgs {
 };
 
 template <typename T, int NEED, bool FAST, bool ONE, bool LOFF>
-__global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
+__global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 5 : 2) sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
 						    const __grid_constant__ SweepArgs g)
 {
 	constexpr bool WIDE = sizeof(T) > 2;
@@ -1395,8 +1415,8 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(con
 					fq.qoff = a.loffB[r * 32 + lane];
 				}
 				u32 m0 = 0, m1 = 0, m2 = 0;
-				scan_group<NEED, LOFF>(reinterpret_cast<const unsigned char *>(Dm), a.loffA, 1024, active, c, true, cfirst, fq,
-						       lane, m0, m1, m2);
+				scan_group<NEED, LOFF, false>(reinterpret_cast<const unsigned char *>(Dm), a.loffA, 1024, active, c, true, cfirst,
+							      fq, lane, m0, m1, m2);
 				mn.smin = m0;
 				mn.dot = m1;
 				mn.emd = m2;
