@@ -111,6 +111,42 @@ def all_pairs_step(engine, comm, torch, n_total, cutoff, upper_only=True, blocks
                 survivors=np.concatenate(surv) if surv else np.zeros((0, 2), dtype=np.uint64), blocks=blocks)
 
 
+def candidate_scan(engine, comm, torch, q_global, n_total, cutoff):
+    """Trainer<T>::get_close with the candidate set RANGE-PARTITIONED over ranks (SURVEY.md section 8e, third bullet;
+    BASELINE configs[4] shape): the histograms stay sharded where K1 produced them, only the query row (1 KiB + side-band) is
+    broadcast from its owner, every rank scans its own shard, and the (max dist, first index) pair is combined from an
+    all-gather of one (dist, index, any-close) triple per rank.  Marks stay on the rank that owns the candidate.
+
+    engine.local_query(row_local)      -> (bins[1,N], length[1], mag[1]) tensors of a local row
+    engine.scan_local(bins, length, mag, cutoff) -> (best_local_pos or -1, best_dist, is_min, marks[local_n])
+    Returns dict(best=global row or -1, best_dist, is_min, marks_local, shard=(lo, hi))."""
+    per, bounds = shard_bounds(n_total, comm.world)
+    owner = min(q_global // per, comm.world - 1) if per else 0
+    lo, hi = bounds[comm.rank]
+    if comm.rank == owner:
+        bins, length, mag = engine.local_query(q_global - bounds[owner][0])
+    else:
+        bins, length, mag = engine.empty_query()
+    if comm.dist is not None:
+        for t in (bins, length, mag):
+            comm.dist.broadcast(t, src=owner)
+    best, bd, is_min, marks = engine.scan_local(bins, length, mag, cutoff)
+    # combine: larger dist wins, ties go to the smaller global index (the sequential first maximum)
+    mine = torch.tensor([bd if best >= 0 else -1.0, float(lo + best if best >= 0 else -1), 0.0 if is_min else 1.0],
+                        dtype=torch.float64, device=engine.device)
+    if comm.dist is not None:
+        allv = torch.empty((comm.world * 3,), dtype=torch.float64, device=engine.device)
+        comm.dist.all_gather_into_tensor(allv, mine)
+        allv = allv.cpu().numpy().reshape(comm.world, 3)
+    else:
+        allv = mine.cpu().numpy().reshape(1, 3)
+    gbest, gdist = -1, -1.0
+    for dist_r, idx_r, _ in allv:
+        if idx_r >= 0 and (gbest < 0 or dist_r > gdist or (dist_r == gdist and idx_r < gbest)):
+            gbest, gdist = int(idx_r), float(dist_r)
+    return dict(best=gbest, best_dist=gdist, is_min=not bool(allv[:, 2].any()), marks_local=marks, shard=(lo, hi))
+
+
 class GpuEngine:
     """The product engine: K1 / K2 through the C ABI on this rank's GPU; torch only carries device memory for NCCL."""
 
@@ -169,6 +205,29 @@ class GpuEngine:
             self.full.free()
         self.full = self.ctx.hset_from_device(bins.data_ptr(), n_total, self.k, self.eb, length.data_ptr(),
                                               mag.data_ptr())
+
+    # ---- sharded candidate scan (candidate_scan) ----
+    def empty_query(self):
+        torch = self.torch
+        return (torch.ones((1, self.N), dtype=self._dt, device=self.device),
+                torch.zeros((1,), dtype=torch.int64, device=self.device), torch.zeros((1,), dtype=torch.int64, device=self.device))
+
+    def local_query(self, row_local):
+        bins, length, mag = self.empty_query()
+        self.torch.cuda.synchronize(self.device)
+        self.local_hset.copy_to_device(bins.data_ptr(), mag.data_ptr(), length.data_ptr(), row_local, 1)
+        return bins, length, mag
+
+    def scan_local(self, bins, length, mag, cutoff):
+        self.torch.cuda.synchronize(self.device)
+        if getattr(self, "_qset", None) is None:
+            self._qset = self.ctx.hset_from_device(bins.data_ptr(), 1, self.k, self.eb, length.data_ptr(), mag.data_ptr())
+        else:
+            self._qset.update_from_device(bins.data_ptr(), length.data_ptr(), mag.data_ptr())
+        n = len(self.local_hset)
+        if n == 0:
+            return -1, -1.0, True, np.zeros(0, dtype=np.uint8)
+        return self.ctx.get_close(self.model, self._qset, 0, self.local_hset, cand_begin=0, n_cand=n, cutoff=cutoff)
 
     def sweep(self, q0, q1, upper_only, cutoff, max_out):
         r = self.ctx.all_pairs(self.model, self.full, self.full, cutoff, q_range=(q0, q1), upper_only=upper_only,

@@ -68,6 +68,23 @@ class OracleEngine:
         assert bins.shape[0] == n_total
         self.full = (bins.numpy(), length.numpy(), mag.numpy())
 
+    def empty_query(self):
+        return (torch.ones((1, self.N), dtype=torch.uint8), torch.zeros((1,), dtype=torch.int64),
+                torch.zeros((1,), dtype=torch.int64))
+
+    def local_query(self, row_local):
+        return (torch.from_numpy(self.H[row_local:row_local + 1].copy()), torch.from_numpy(self.ln[row_local:row_local + 1].copy()),
+                torch.from_numpy(self.mag[row_local:row_local + 1].copy()))
+
+    def scan_local(self, bins, length, mag, cutoff):
+        n = self.H.shape[0]
+        if n == 0:
+            return -1, -1.0, True, np.zeros(0, dtype=np.uint8)
+        H = np.concatenate([self.H, bins.numpy()])
+        ln = np.concatenate([self.ln, length.numpy()]).astype(np.uint64)
+        mg = np.concatenate([self.mag, mag.numpy()]).astype(np.uint64)
+        return port.get_close(self.model, H, mg, ln, n, np.arange(n), cutoff)
+
     def sweep(self, q0, q1, upper_only, cutoff, max_out):
         H, ln, mag = self.full
         n = H.shape[0]
@@ -83,6 +100,30 @@ class OracleEngine:
         cl = o["close"].astype(bool)
         pairs = np.stack([np.array(ib)[cl], np.array(ia)[cl]], axis=1).astype(np.uint64)
         return int(cl.sum()), len(ia), pairs
+
+
+def _scan_worker(rank, world, port_no, n_total, queries, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = port.Model.from_text(weights_text("weights_cfg1_id90"))
+        per, bounds = mdist.shard_bounds(n_total, world)
+        lo, hi = bounds[rank]
+        seqs, _ = synth.make_range(n_total, 1000, 6, 0.1, seed=77, lo=lo, hi=hi)
+        eng = OracleEngine(seqs, 5, 1, model, per)
+        eng.count()
+        comm = mdist.Comm(tdist)
+        res = []
+        for q in queries:
+            r = mdist.candidate_scan(eng, comm, torch, q, n_total, 0.9)
+            marks = [None] * world
+            tdist.all_gather_object(marks, r["marks_local"].tolist())
+            res.append((r["best"], round(r["best_dist"], 12), r["is_min"], sum(marks, [])))
+        if rank == 0:
+            out.put(res)
+    finally:
+        tdist.destroy_process_group()
 
 
 def _worker(rank, world, port_no, n_total, out):
@@ -141,3 +182,28 @@ def _free_port_cached():
     if not _PORT:
         _PORT.append(_free_port())
     return _PORT[0]
+
+
+@pytest.mark.timeout(300)
+def test_sharded_candidate_scan_equals_single_process():
+    """get_close with the candidates range-partitioned over 2 ranks == the oracle's get_close over the whole set"""
+    n_total, queries = 37, [0, 5, 18, 19, 36]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    pno = _free_port()
+    procs = [ctx.Process(target=_scan_worker, args=(r, 2, pno, n_total, queries, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    model = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    seqs, _ = synth.make_range(n_total, 1000, 6, 0.1, seed=77)
+    pts = [port.get_point(s, 5, 1) for s in seqs]
+    H = np.stack([p["hist"] for p in pts])
+    mag = np.array([p["mag"] for p in pts], dtype=np.uint64)
+    ln = np.array([p["len"] for p in pts], dtype=np.uint64)
+    for (best, bd, ismin, marks), qq in zip(got, queries):
+        ob = port.get_close(model, H, mag, ln, qq, np.arange(n_total), 0.9)
+        assert best == ob[0] and abs(bd - ob[1]) <= 1e-9 and ismin == ob[2] and marks == ob[3].tolist()
