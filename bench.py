@@ -238,6 +238,7 @@ def run_ours(args, rank, world, local_rank):
     enc = capi.encode_batch(seqs)
     log("[bench] rank %d host encode %.2fs" % (rank, time.time() - t0))
     ctx = capi.Context(local_rank)
+    pin_inputs(capi, enc)
     model = ctx.model_from_file(WEIGHTS)
     cutoff = model.meta["id"]
     eng = mdist.GpuEngine(capi, ctx, torch, model, k, eb, local_rank)
@@ -251,9 +252,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step_e2e():
         ctx.flush_l2(256 << 20)
-        old = eng.seqs
-        eng.seqs = ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])   # H2D + pack, timed
-        old.free()
+        ctx.upload_seqs_into(eng.seqs, enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])   # H2D + pack, timed
         return mdist.all_pairs_step(eng, comm, torch, n_total, cutoff, upper_only=True, blocks_per_rank=args.blocks_per_rank,
                                     max_out=max_out)
 
@@ -288,7 +287,7 @@ def run_ours(args, rank, world, local_rank):
         rank, ms / args.steps, n_scored, res["n_close"], launches))
     # end to end from host buffers
     log("[bench] rank %d e2e phase" % rank)
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(min(args.warmup, 3)):
         step_e2e()
     e2e_steps = max(1, min(args.steps, 3))
     ms_e, res_e, _, _, _ = timed(step_e2e, e2e_steps)
@@ -343,12 +342,21 @@ def run_ours(args, rank, world, local_rank):
         tdist.destroy_process_group()
 
 
+def pin_inputs(capi, enc):
+    """page-lock the step's host inputs (the encoded batch) so the timed H2D copies are DMA transfers from pinned memory"""
+    for key in ("codes", "seq_off", "segs", "seg_off"):
+        enc[key] = np.ascontiguousarray(enc[key])
+        if enc[key].nbytes:
+            capi.host_register(enc[key])
+
+
 def small_workload(ctx, capi, mdist, torch, model, cutoff, steps=20):
     """The BASELINE configs[1] shape in the same run (10k x 1.5 kb 16S-like, k=5, uint8): K1 + all-pairs candidate sweep,
     resident and end to end; the whole histogram set (10 MB) is L2-resident, steps are ~15 ms."""
     from meshclust2_b200 import synth
     seqs, _, k, eb = synth.make_config_range("cfg2", 0, None)
     enc = capi.encode_batch(seqs)
+    pin_inputs(capi, enc)
     eng = mdist.GpuEngine(capi, ctx, torch, model, k, eb, 0)
     n = len(seqs)
     eng.set_local_sequences(ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"]), n, n)
@@ -358,9 +366,7 @@ def small_workload(ctx, capi, mdist, torch, model, cutoff, steps=20):
         def step():
             ctx.flush_l2(256 << 20)
             if name == "e2e":
-                old = eng.seqs
-                eng.seqs = ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
-                old.free()
+                ctx.upload_seqs_into(eng.seqs, enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
             return mdist.all_pairs_step(eng, comm, torch, n, cutoff, upper_only=True, blocks_per_rank=1, max_out=1 << 22)
         for _ in range(3):
             res = step()

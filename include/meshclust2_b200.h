@@ -128,6 +128,14 @@ int mc2_encode_dna_batch(const char *text, const uint64_t *off, uint64_t n, char
  * that Loader<T>::fill_table reads (src/clutil/Loader.cpp:42-49). Copies host->device and packs to 2 bits/base. */
 int mc2_seqs_upload(mc2_ctx *ctx, const char *codes, const uint64_t *seq_off, uint64_t n, const int32_t *segs,
 		    const uint64_t *seg_off, mc2_seqs **out);
+/* Refill an existing set with another batch: device arrays are reused (grow-only), so a steady stream of batches of similar
+ * size never calls cudaMalloc / cudaFree.  On error the set is left empty (still to be freed by the caller). */
+int mc2_seqs_upload_into(mc2_ctx *ctx, mc2_seqs *dst, const char *codes, const uint64_t *seq_off, uint64_t n,
+			 const int32_t *segs, const uint64_t *seg_off);
+/* Page-lock / unlock a caller-owned host range (cudaHostRegister) so that uploads from it are asynchronous DMA copies.
+ * Optional: every entry point also accepts pageable memory. */
+int mc2_host_register(void *ptr, uint64_t bytes);
+int mc2_host_unregister(void *ptr);
 void mc2_seqs_free(mc2_seqs *s);
 uint64_t mc2_seqs_count(const mc2_seqs *s);
 uint64_t mc2_seqs_total_bases(const mc2_seqs *s);
@@ -139,6 +147,23 @@ uint64_t mc2_seqs_total_bases(const mc2_seqs *s);
  * (Chromosome::getEffectiveSize), stddev (Loader.cpp:162-171) and the number of overflowing segments
  * (Loader.cpp:55-56).  elem_bytes in {1,2,4,8} = --datatype 8/16/32/64 (src/cluster/CRunner.cpp:278-291). */
 int mc2_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, mc2_hset **out);
+
+/* Histogram-width detection fused with counting (Runner::run, src/cluster/CRunner.cpp:57-127; the free fill_table<V>,
+ * src/cluster/ClusterFactory.h:40-54).  The reference first counts every sequence into a u64 table just to find
+ * "Largest count" = 1 + the largest k-mer multiplicity, picks the narrowest of 8/16/32/64 bits that holds it
+ * (CRunner.cpp:108-126) and then counts everything again at that width.  K1 counts in 32-bit shared-memory bins
+ * whatever the output width, so the multiplicities come for free: mc2_count_kmers_auto counts once at 8 bits, and only
+ * when the largest count exceeds 255 counts again at the detected width.  *largest_count / *elem_bytes (may be NULL)
+ * receive what the reference prints as "Largest count" and the chosen width in bytes.
+ * MC2_ERR_INPUT if a segment is shorter than k: the reference's detection pass (unlike Loader::fill_table) has no length
+ * guard and hashes k characters from the segment start, reading past it (quirk Q6) - there is no result to reproduce. */
+int mc2_count_kmers_auto(mc2_ctx *ctx, const mc2_seqs *seqs, int k, uint64_t *largest_count, int *elem_bytes,
+			 mc2_hset **out);
+/* "Largest count" of a set produced by mc2_count_kmers(_into/_auto); MC2_ERR_UNSUPPORTED for sets built from
+ * histograms (their multiplicities before saturation are unknown). */
+int mc2_hset_largest_count(const mc2_hset *h, uint64_t *largest_count);
+/* CRunner.cpp:108-126: bytes per bin for a largest count: 1, 2, 4 or 8 */
+int mc2_width_for_count(uint64_t largest_count);
 
 /* Same, into an existing set of the same shape (n, k, elem_bytes): no allocation in steady state (repeated batches). */
 int mc2_count_kmers_into(mc2_ctx *ctx, const mc2_seqs *seqs, mc2_hset *dst);

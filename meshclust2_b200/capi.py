@@ -34,8 +34,8 @@ PRED_FEAT_DIV = FEAT_JEFFEREY_DIV | FEAT_JENSEN_SHANNON
 SYMBOLS = [
     "mc2_abi_version", "mc2_last_error", "mc2_device_count", "mc2_ctx_create", "mc2_ctx_destroy", "mc2_ctx_sync",
     "mc2_ctx_device", "mc2_ctx_sm_count", "mc2_ctx_stream", "mc2_timer_start", "mc2_timer_stop",
-    "mc2_ctx_launch_count", "mc2_ctx_profile", "mc2_ctx_kernel_time", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_free", "mc2_seqs_count",
-    "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_count_kmers_into", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_update_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
+    "mc2_ctx_launch_count", "mc2_ctx_profile", "mc2_ctx_kernel_time", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_upload_into", "mc2_host_register", "mc2_host_unregister", "mc2_seqs_free", "mc2_seqs_count",
+    "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_count_kmers_into", "mc2_count_kmers_auto", "mc2_hset_largest_count", "mc2_width_for_count", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_update_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
     "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
     "mc2_score_pairs", "mc2_get_close", "mc2_filter", "mc2_merge", "mc2_all_pairs", "mc2_distance", "mc2_mean_closest", "mc2_closest",
@@ -180,6 +180,23 @@ class Context:
         _check(lib().mc2_seqs_upload(self.h, _p(codes), _p(seq_off), C.c_uint64(len(seq_off) - 1), _p(segs),
                                      _p(seg_off), C.byref(out)))
         return Seqs(self, out)
+
+    def upload_seqs_into(self, dst, codes, seq_off, segs, seg_off):
+        """refill `dst` (a Seqs of this context) with another batch, reusing its device arrays"""
+        codes = np.ascontiguousarray(codes).view(np.int8)
+        seq_off = _u64(seq_off)
+        seg_off = _u64(seg_off)
+        segs = np.ascontiguousarray(segs, dtype=np.int32)
+        _check(lib().mc2_seqs_upload_into(self.h, dst.h, _p(codes), _p(seq_off), C.c_uint64(len(seq_off) - 1), _p(segs),
+                                          _p(seg_off)))
+        return dst
+
+    def count_kmers_auto(self, seqs, k):
+        """width detection fused with counting -> (HistSet, largest_count, elem_bytes)"""
+        out = C.c_void_p()
+        largest, eb = C.c_uint64(), C.c_int()
+        _check(lib().mc2_count_kmers_auto(self.h, seqs.h, k, C.byref(largest), C.byref(eb), C.byref(out)))
+        return HistSet(self, out), largest.value, eb.value
 
     def count_kmers(self, seqs, k, elem_bytes):
         out = C.c_void_p()
@@ -333,6 +350,20 @@ class Context:
         return ms.value
 
 
+def host_register(arr):
+    """page-lock a numpy array's memory so uploads from it are asynchronous DMA copies; returns the array"""
+    _check(lib().mc2_host_register(_p(arr), C.c_uint64(arr.nbytes)))
+    return arr
+
+
+def host_unregister(arr):
+    _check(lib().mc2_host_unregister(_p(arr)))
+
+
+def width_for_count(largest):
+    return lib().mc2_width_for_count(C.c_uint64(largest))
+
+
 class Seqs:
     def __init__(self, ctx, h):
         self.ctx, self.h = ctx, h
@@ -370,6 +401,12 @@ class HistSet:
     @property
     def elem_bytes(self):
         return lib().mc2_hset_elem_bytes(self.h)
+
+    def largest_count(self):
+        """Runner::run's "Largest count" (1 + largest k-mer multiplicity); only for sets produced by count_kmers*"""
+        out = C.c_uint64()
+        _check(lib().mc2_hset_largest_count(self.h, C.byref(out)))
+        return out.value
 
     def device_bins(self):
         return lib().mc2_hset_device_bins(self.h)

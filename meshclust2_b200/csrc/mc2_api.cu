@@ -72,7 +72,7 @@ static void release(Buf &b)
 	b.cap = 0;
 }
 
-enum { B_IA = 0, B_IB, B_SCORE, B_DIST, B_CLOSE, B_SKIP, B_CACHE, B_RAW, B_MISC, B_OUTQ, B_OUTD, B_OUTS, B_COUNT };
+enum { B_IA = 0, B_IB, B_SCORE, B_DIST, B_CLOSE, B_SKIP, B_CACHE, B_RAW, B_MISC, B_OUTQ, B_OUTD, B_OUTS, B_STAGE_CODES, B_STAGE_BOFF, B_ROWMAX, B_ROWMAX_H, B_COUNT };
 
 struct ProfRec {
 	int kind;
@@ -276,19 +276,49 @@ static int alloc_hset(mc2_ctx *ctx, u64 n, int k, int eb, mc2_hset **out)
 	return MC2_OK;
 }
 
+// max over rows of the bin sums and of the raw k-mer multiplicities: out[0], out[1] (zeroed by the caller)
+__global__ void __launch_bounds__(256) row_max_kernel(const u64 *sum, const u32 *maxc, u64 n, unsigned long long *out)
+{
+	u64 ms = 0;
+	u32 mc = 0;
+	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+		ms = sum[i] > ms ? sum[i] : ms;
+		mc = maxc[i] > mc ? maxc[i] : mc;
+	}
+	for (int o = 16; o; o >>= 1) {
+		u64 t = __shfl_xor_sync(0xffffffffu, ms, o);
+		ms = t > ms ? t : ms;
+	}
+	mc = __reduce_max_sync(0xffffffffu, mc);
+	if ((threadIdx.x & 31) == 0) {
+		atomicMax(out, (unsigned long long)ms);
+		atomicMax(out + 1, (unsigned long long)mc);
+	}
+}
+
 static int refresh_max_sum(mc2_ctx *ctx, mc2_hset *h)
 {
-	// host-side bound used to pick the 32-bit fast paths; one small D2H per set creation
-	std::vector<u64> s(h->n);
-	if (h->n) {
-		MC2_CUDA(cudaMemcpyAsync(s.data(), h->sum, h->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-		MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	// host-side bounds used to pick the 32-bit fast paths and the histogram width: one 16-byte D2H per set (re)fill
+	h->max_sum = 0;
+	h->max_count = 0;
+	if (h->n == 0) {
+		return MC2_OK;
 	}
-	u64 m = 0;
-	for (u64 v : s) {
-		m = v > m ? v : m;
-	}
-	h->max_sum = m;
+	CtxExtra *x = reinterpret_cast<CtxExtra *>(ctx->extra);
+	int rc = ensure(x->d[B_ROWMAX], 16, false);
+	if (rc != MC2_OK) return rc;
+	rc = ensure(x->d[B_ROWMAX_H], 16, true);
+	if (rc != MC2_OK) return rc;
+	unsigned long long *dv = (unsigned long long *)x->d[B_ROWMAX].p, *hv = (unsigned long long *)x->d[B_ROWMAX_H].p;
+	MC2_CUDA(cudaMemsetAsync(dv, 0, 16, ctx->stream));
+	u64 want = (h->n + 255) / 256, cap = (u64)ctx->sm_count * 4;
+	row_max_kernel<<<(int)(want < cap ? want : cap), 256, 0, ctx->stream>>>(h->sum, h->maxc, h->n, dv);
+	ctx->launches++;
+	MC2_CUDA(cudaGetLastError());
+	MC2_CUDA(cudaMemcpyAsync(hv, dv, 16, cudaMemcpyDeviceToHost, ctx->stream));
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	h->max_sum = hv[0];
+	h->max_count = hv[1];
 	return MC2_OK;
 }
 
@@ -504,19 +534,36 @@ int mc2_ctx_flush_l2(mc2_ctx *ctx, size_t bytes)
 }
 
 /* ---- sequences -------------------------------------------------------------------------------- */
-int mc2_seqs_upload(mc2_ctx *ctx, const char *codes, const uint64_t *seq_off, uint64_t n, const int32_t *segs,
-		    const uint64_t *seg_off, mc2_seqs **out)
+// grow-only device array of a sequence set: reallocates only when the capacity is too small, so a set that is refilled
+// with batches of similar size (mc2_seqs_upload_into) never touches cudaMalloc / cudaFree (both stall the device)
+extern "C++" {
+template <typename P>
+static int seq_reserve(P *&p, u64 &cap_bytes, u64 bytes)
 {
-	MC2_REQUIRE(ctx && seq_off && seg_off && out, "mc2_seqs_upload: NULL argument");
-	MC2_REQUIRE(n == 0 || codes != nullptr, "mc2_seqs_upload: codes is NULL");
-	*out = nullptr;
-	MC2_CUDA(cudaSetDevice(ctx->device));
+	if (p != nullptr && cap_bytes >= bytes) {
+		return MC2_OK;
+	}
+	if (p) {
+		cudaFree(p);
+		p = nullptr;
+		cap_bytes = 0;
+	}
+	u64 want = bytes + bytes / 8 + 256;
+	MC2_CUDA(cudaMalloc((void **)&p, want));
+	cap_bytes = want;
+	return MC2_OK;
+}
+} // extern "C++"
+
+static int seqs_fill(mc2_ctx *ctx, mc2_seqs *s, const char *codes, const uint64_t *seq_off, uint64_t n, const int32_t *segs,
+		     const uint64_t *seg_off)
+{
 	const u64 total_bases = seq_off[n] - seq_off[0];
 	const u64 total_segs = seg_off[n] - seg_off[0];
 	MC2_REQUIRE(total_segs == 0 || segs != nullptr, "mc2_seqs_upload: segs is NULL");
 	// host-side shape checks only (no per-base work on the host)
 	std::vector<u64> word_off(n + 1), len(n), soff(n + 1), boff(n + 1);
-	u64 w = 0, max_len = 0;
+	u64 w = 0, max_len = 0, min_seg = ~0ULL;
 	for (u64 i = 0; i < n; i++) {
 		MC2_REQUIRE(seq_off[i + 1] >= seq_off[i] && seg_off[i + 1] >= seg_off[i], "mc2_seqs_upload: offsets must be non-decreasing");
 		u64 L = seq_off[i + 1] - seq_off[i];
@@ -528,63 +575,96 @@ int mc2_seqs_upload(mc2_ctx *ctx, const char *codes, const uint64_t *seq_off, ui
 		soff[i] = seg_off[i] - seg_off[0];
 		u64 nw = (L + 15) / 16 + 1; // one spare word so the k-mer window may read past the end
 		w += (nw + 3) & ~3ULL;
-		for (u64 s = seg_off[i]; s < seg_off[i + 1]; s++) {
-			long long s0 = segs[2 * s], e0 = segs[2 * s + 1];
+		for (u64 sg = seg_off[i]; sg < seg_off[i + 1]; sg++) {
+			long long s0 = segs[2 * sg], e0 = segs[2 * sg + 1];
 			MC2_REQUIRE(s0 >= 0 && e0 >= s0 && (u64)e0 < L, "mc2_seqs_upload: segment outside its sequence");
-			MC2_REQUIRE(s == seg_off[i] || s0 > segs[2 * s - 1], "mc2_seqs_upload: segments must be sorted and disjoint");
+			MC2_REQUIRE(sg == seg_off[i] || s0 > segs[2 * sg - 1], "mc2_seqs_upload: segments must be sorted and disjoint");
+			min_seg = (u64)(e0 - s0 + 1) < min_seg ? (u64)(e0 - s0 + 1) : min_seg;
 		}
 	}
 	word_off[n] = w;
 	boff[n] = total_bases;
 	soff[n] = total_segs;
-	mc2_seqs *s = new (std::nothrow) mc2_seqs();
-	MC2_REQUIRE(s != nullptr, "out of host memory");
-	memset(s, 0, sizeof *s);
-	s->ctx = ctx;
 	s->n = n;
 	s->total_bases = total_bases;
 	s->max_len = max_len;
 	s->total_segs = total_segs;
 	s->total_words = w;
-	char *d_codes = nullptr;
-	u64 *d_boff = nullptr;
-	cudaError_t e = cudaSuccess;
-	auto fail = [&](const char *what) {
-		int rc = cuda_fail(e, what, __FILE__, __LINE__);
-		if (d_codes) cudaFree(d_codes);
-		if (d_boff) cudaFree(d_boff);
-		mc2_seqs_free(s);
-		return rc;
-	};
-	if ((e = cudaMalloc((void **)&s->packed, (w ? w : 1) * 4)) != cudaSuccess) return fail("cudaMalloc packed");
-	if ((e = cudaMalloc((void **)&s->word_off, (n + 1) * 8)) != cudaSuccess) return fail("cudaMalloc word_off");
-	if ((e = cudaMalloc((void **)&s->len, (n ? n : 1) * 8)) != cudaSuccess) return fail("cudaMalloc len");
-	if ((e = cudaMalloc((void **)&s->segs, (total_segs ? total_segs : 1) * 8)) != cudaSuccess) return fail("cudaMalloc segs");
-	if ((e = cudaMalloc((void **)&s->seg_off, (n + 1) * 8)) != cudaSuccess) return fail("cudaMalloc seg_off");
-	if ((e = cudaMalloc((void **)&d_codes, total_bases ? total_bases : 1)) != cudaSuccess) return fail("cudaMalloc codes");
-	if ((e = cudaMalloc((void **)&d_boff, (n + 1) * 8)) != cudaSuccess) return fail("cudaMalloc boff");
+	s->min_seg_len = min_seg;
+	CtxExtra *x = reinterpret_cast<CtxExtra *>(ctx->extra);
+	int rc;
+	if ((rc = seq_reserve(s->packed, s->cap_packed, (w ? w : 1) * 4)) != MC2_OK) return rc;
+	if ((rc = seq_reserve(s->word_off, s->cap_word_off, (n + 1) * 8)) != MC2_OK) return rc;
+	if ((rc = seq_reserve(s->len, s->cap_len, (n ? n : 1) * 8)) != MC2_OK) return rc;
+	if ((rc = seq_reserve(s->segs, s->cap_segs, (total_segs ? total_segs : 1) * 8)) != MC2_OK) return rc;
+	if ((rc = seq_reserve(s->seg_off, s->cap_seg_off, (n + 1) * 8)) != MC2_OK) return rc;
+	// staging for the byte-per-base codes: owned by the context, reused by every upload
+	if ((rc = ensure(x->d[B_STAGE_CODES], total_bases ? total_bases : 1, false)) != MC2_OK) return rc;
+	if ((rc = ensure(x->d[B_STAGE_BOFF], (n + 1) * 8, false)) != MC2_OK) return rc;
+	char *d_codes = (char *)x->d[B_STAGE_CODES].p;
+	u64 *d_boff = (u64 *)x->d[B_STAGE_BOFF].p;
 	cudaStream_t st = ctx->stream;
-	if ((e = cudaMemcpyAsync(s->word_off, word_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D word_off");
-	if (n && (e = cudaMemcpyAsync(s->len, len.data(), n * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D len");
-	if (total_segs && (e = cudaMemcpyAsync(s->segs, segs + 2 * seg_off[0], total_segs * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D segs");
-	if ((e = cudaMemcpyAsync(s->seg_off, soff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D seg_off");
-	if (total_bases && (e = cudaMemcpyAsync(d_codes, codes + seq_off[0], total_bases, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D codes");
-	if ((e = cudaMemcpyAsync(d_boff, boff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D boff");
-	int rc = reset_err(ctx);
+	MC2_CUDA(cudaMemcpyAsync(s->word_off, word_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	if (n) MC2_CUDA(cudaMemcpyAsync(s->len, len.data(), n * 8, cudaMemcpyHostToDevice, st));
+	if (total_segs) MC2_CUDA(cudaMemcpyAsync(s->segs, segs + 2 * seg_off[0], total_segs * 8, cudaMemcpyHostToDevice, st));
+	MC2_CUDA(cudaMemcpyAsync(s->seg_off, soff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	if (total_bases) MC2_CUDA(cudaMemcpyAsync(d_codes, codes + seq_off[0], total_bases, cudaMemcpyHostToDevice, st));
+	MC2_CUDA(cudaMemcpyAsync(d_boff, boff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	rc = reset_err(ctx);
 	if (rc == MC2_OK) rc = launch_pack(ctx, d_codes, d_boff, s);
 	if (rc == MC2_OK) rc = fetch_err(ctx);
-	e = cudaStreamSynchronize(st);
-	cudaFree(d_codes);
-	cudaFree(d_boff);
-	d_codes = nullptr;
-	d_boff = nullptr;
-	if (rc == MC2_OK && e != cudaSuccess) return fail("pack");
+	cudaError_t e = cudaStreamSynchronize(st); // the host vectors above go out of scope; the error word is read below
+	if (rc == MC2_OK && e != cudaSuccess) rc = cuda_fail(e, "pack", __FILE__, __LINE__);
 	if (rc == MC2_OK) rc = check_err(ctx);
+	return rc;
+}
+
+int mc2_seqs_upload(mc2_ctx *ctx, const char *codes, const uint64_t *seq_off, uint64_t n, const int32_t *segs,
+		    const uint64_t *seg_off, mc2_seqs **out)
+{
+	MC2_REQUIRE(ctx && seq_off && seg_off && out, "mc2_seqs_upload: NULL argument");
+	MC2_REQUIRE(n == 0 || codes != nullptr, "mc2_seqs_upload: codes is NULL");
+	*out = nullptr;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	mc2_seqs *s = new (std::nothrow) mc2_seqs();
+	MC2_REQUIRE(s != nullptr, "out of host memory");
+	memset(s, 0, sizeof *s);
+	s->ctx = ctx;
+	int rc = seqs_fill(ctx, s, codes, seq_off, n, segs, seg_off);
 	if (rc != MC2_OK) {
 		mc2_seqs_free(s);
 		return rc;
 	}
 	*out = s;
+	return MC2_OK;
+}
+
+int mc2_seqs_upload_into(mc2_ctx *ctx, mc2_seqs *dst, const char *codes, const uint64_t *seq_off, uint64_t n,
+			 const int32_t *segs, const uint64_t *seg_off)
+{
+	MC2_REQUIRE(ctx && dst && seq_off && seg_off, "mc2_seqs_upload_into: NULL argument");
+	MC2_REQUIRE(n == 0 || codes != nullptr, "mc2_seqs_upload_into: codes is NULL");
+	MC2_REQUIRE(dst->ctx == ctx, "mc2_seqs_upload_into: the set belongs to another context");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	int rc = seqs_fill(ctx, dst, codes, seq_off, n, segs, seg_off);
+	if (rc != MC2_OK) {
+		dst->n = 0; // contents undefined after a failed refill: leave an empty, still freeable set
+		dst->total_bases = dst->total_segs = dst->total_words = dst->max_len = 0;
+	}
+	return rc;
+}
+
+int mc2_host_register(void *ptr, uint64_t bytes)
+{
+	MC2_REQUIRE(ptr != nullptr && bytes > 0, "mc2_host_register: NULL or empty range");
+	MC2_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+	return MC2_OK;
+}
+
+int mc2_host_unregister(void *ptr)
+{
+	MC2_REQUIRE(ptr != nullptr, "mc2_host_unregister: NULL");
+	MC2_CUDA(cudaHostUnregister(ptr));
 	return MC2_OK;
 }
 
@@ -644,6 +724,56 @@ int mc2_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, m
 		mc2_hset_free(h);
 		return rc;
 	}
+	h->counted = 1;
+	*out = h;
+	return MC2_OK;
+}
+
+int mc2_hset_largest_count(const mc2_hset *h, uint64_t *largest_count)
+{
+	MC2_REQUIRE(h && largest_count, "mc2_hset_largest_count: NULL argument");
+	if (!h->counted) {
+		set_error("mc2_hset_largest_count: the set was not produced by mc2_count_kmers (or its rows were overwritten)");
+		return MC2_ERR_UNSUPPORTED;
+	}
+	// u64 table initialised to 1 plus the multiplicity (CRunner.cpp:69-74); an empty input leaves largest_count at 0 (:57)
+	*largest_count = h->n ? 1 + h->max_count : 0;
+	return MC2_OK;
+}
+
+int mc2_width_for_count(uint64_t largest_count)
+{
+	// CRunner.cpp:108-126
+	if (largest_count <= 0xFFull) return 1;
+	if (largest_count <= 0xFFFFull) return 2;
+	if (largest_count <= 0xFFFFFFFFull) return 4;
+	return 8;
+}
+
+int mc2_count_kmers_auto(mc2_ctx *ctx, const mc2_seqs *seqs, int k, uint64_t *largest_count, int *elem_bytes, mc2_hset **out)
+{
+	MC2_REQUIRE(ctx && seqs && out, "mc2_count_kmers_auto: NULL argument");
+	*out = nullptr;
+	if (seqs->total_segs && seqs->min_seg_len < (u64)k) {
+		// quirk Q6: the reference's detection pass has no `length >= k` guard and hashes k characters from the start of
+		// a shorter segment, reading past it (it throws or reads foreign memory); there is no result to reproduce
+		set_error("mc2_count_kmers_auto: a segment is shorter than k (the reference's width detection reads past it)");
+		return MC2_ERR_INPUT;
+	}
+	mc2_hset *h = nullptr;
+	int rc = mc2_count_kmers(ctx, seqs, k, 1, &h); // multiplicities are exact at any width; 8-bit output is the cheapest
+	if (rc != MC2_OK) return rc;
+	uint64_t largest = 0;
+	mc2_hset_largest_count(h, &largest);
+	const int eb = mc2_width_for_count(largest);
+	if (eb != 1) {
+		mc2_hset_free(h);
+		h = nullptr;
+		rc = mc2_count_kmers(ctx, seqs, k, eb, &h);
+		if (rc != MC2_OK) return rc;
+	}
+	if (largest_count) *largest_count = largest;
+	if (elem_bytes) *elem_bytes = eb;
 	*out = h;
 	return MC2_OK;
 }
@@ -656,6 +786,7 @@ int mc2_count_kmers_into(mc2_ctx *ctx, const mc2_seqs *seqs, mc2_hset *dst)
 	dst->lane_off_valid = 0;
 	int rc = count_into(ctx, seqs, dst->k, dst->eb, 1, dst);
 	if (rc == MC2_OK) rc = refresh_max_sum(ctx, dst);
+	dst->counted = rc == MC2_OK;
 	return rc;
 }
 
@@ -764,6 +895,7 @@ int mc2_hset_update_from_device(mc2_ctx *ctx, mc2_hset *h, const void *d_bins, c
 		return MC2_OK;
 	}
 	h->lane_off_valid = 0;
+	h->counted = 0;
 	MC2_CUDA(cudaMemcpyAsync(h->bins, d_bins, n * h->N * (u64)h->eb, cudaMemcpyDeviceToDevice, ctx->stream));
 	MC2_CUDA(cudaMemcpyAsync(h->len, d_len, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 	if (d_mag) MC2_CUDA(cudaMemcpyAsync(h->mag, d_mag, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -881,6 +1013,7 @@ int mc2_hset_set_row(mc2_ctx *ctx, mc2_hset *dst, uint64_t dst_row, const mc2_hs
 	MC2_REQUIRE(dst->k == src->k && dst->eb == src->eb, "mc2_hset_set_row: sets differ in k or width");
 	MC2_REQUIRE(dst_row < dst->n && src_row < src->n, "mc2_hset_set_row: row out of range");
 	dst->lane_off_valid = 0;
+	dst->counted = 0;
 	cudaStream_t st = ctx->stream;
 	const u64 rb = dst->N * (u64)dst->eb;
 	// DivergencePoint::set (src/clutil/DivergencePoint.cpp:182-190): points + length (+header/id), NOT mag
@@ -905,6 +1038,7 @@ int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t
 	}
 	MC2_CUDA(cudaSetDevice(ctx->device));
 	dst->lane_off_valid = 0;
+	dst->counted = 0;
 	const int parts = 2 + (mag ? 1 : 0) + (len ? 1 : 0);
 	std::vector<u64> idx((size_t)parts * n);
 	for (u64 i = 0; i < n; i++) {

@@ -110,6 +110,8 @@ struct mc2_seqs {
 	u64 *seg_off;     // [n+1]
 	u64 total_segs;
 	u64 total_words;
+	u64 min_seg_len;  // shortest segment (bases); ~0 when there is none
+	u64 cap_packed, cap_word_off, cap_len, cap_segs, cap_seg_off; // bytes allocated (grow-only, mc2_seqs_upload_into)
 };
 
 struct mc2_hset {
@@ -125,6 +127,8 @@ struct mc2_hset {
 	int *novf;        // n
 	u32 *maxc;        // n : largest unsaturated count+1
 	u64 max_sum;      // host-known upper bound of sum[] (selects fast paths)
+	u64 max_count;    // host-known max of maxc[] (raw multiplicity; valid while `counted`)
+	int counted;      // rows came from mc2_count_kmers(_into) with init 1 and were not overwritten since
 	// 1 KiB uint8 rows only: exclusive prefix of the bin sums at the 32 lane boundaries (bins [32l, 32l+32) belong to lane
 	// l), u16, n x 32.  Lets the EMD reduction start each lane's prefix chain without a per-pair warp scan.  Built lazily,
 	// dropped whenever bins change.

@@ -286,6 +286,54 @@ int mc2o_count(const char *codes, const int *segs, int nseg, int k, int elem_byt
 	return rc;
 }
 
+/* Histogram-width detection, Runner::run (src/cluster/CRunner.cpp:57-93): a u64 table (init 1) per sequence filled by
+ * the free fill_table<V> (src/cluster/ClusterFactory.h:40-54) -> wholesaleIncrement(start, end-k+1) for EVERY segment
+ * (quirk Q6: no `length >= k` guard), then max_element.  u64 never saturates here, so the result is
+ * 1 + the largest k-mer multiplicity of the sequence.  A segment shorter than k makes the reference hash k characters
+ * starting at `start`, i.e. read past the segment (and possibly the string); that is not restated: returns -1. */
+int mc2o_largest_count(const char *codes, const int *segs, int nseg, int k, uint64_t *largest)
+{
+	const uint64_t N = 1ULL << (2 * k);
+	uint64_t *values = (uint64_t *)malloc(N * sizeof(uint64_t));
+	uint64_t i, best = 0;
+	int s, novf = 0, rc;
+	if (!values) {
+		return -2;
+	}
+	for (s = 0; s < nseg; s++) {
+		if (segs[2 * s + 1] - segs[2 * s] + 1 < k) {
+			free(values);
+			return -1;
+		}
+	}
+	rc = count_u64(codes, segs, nseg, k, values, &novf); /* same increments: no guard needed, nothing saturates */
+	if (rc == 0) {
+		for (i = 0; i < N; i++) { /* std::max_element, CRunner.cpp:74 */
+			if (values[i] > best) {
+				best = values[i];
+			}
+		}
+		*largest = best;
+	}
+	free(values);
+	return rc;
+}
+
+/* Width choice from the largest count, CRunner.cpp:108-126: smallest of 8/16/32/64 bits whose max holds it. */
+int mc2o_width_for(uint64_t largest_count)
+{
+	if (largest_count <= UINT8_MAX) {
+		return 1;
+	}
+	if (largest_count <= UINT16_MAX) {
+		return 2;
+	}
+	if (largest_count <= UINT32_MAX) {
+		return 4;
+	}
+	return 8;
+}
+
 /* mag: DivergencePoint ctor, src/clutil/DivergencePoint.cpp:99-110; stddev: Loader.cpp:162-171 */
 void mc2o_point_stats(const void *hist, uint64_t N, int elem_bytes, uint64_t *mag, double *stddev)
 {

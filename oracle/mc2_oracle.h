@@ -71,6 +71,10 @@ int mc2o_encode(const char *text, long len, char *base_out, int *segs_out, int m
  * n_overflow_segs: number of segments whose wholesaleIncrementNoOverflow returned -1. */
 int mc2o_count(const char *codes, const int *segs, int nseg, int k, int elem_bytes, void *hist, uint64_t *mers1,
 	       int *n_overflow_segs);
+/* f2: Runner::run's width detection (CRunner.cpp:57-93, ClusterFactory.h:40-54): 1 + largest k-mer multiplicity;
+ * -1 where the reference would read past a segment shorter than k (quirk Q6). mc2o_width_for: CRunner.cpp:108-126. */
+int mc2o_largest_count(const char *codes, const int *segs, int nseg, int k, uint64_t *largest);
+int mc2o_width_for(uint64_t largest_count);
 /* a4: mag = sum(bins); stddev as in Loader::get_point */
 void mc2o_point_stats(const void *hist, uint64_t N, int elem_bytes, uint64_t *mag, double *stddev);
 /* Loader<T>::get_point(header, ACGT-string) front half: strip everything but A,C,G,T (Loader.cpp:112-134) */

@@ -186,6 +186,21 @@ def count(codes, segs, k, elem_bytes):
     return hist, m1, novf.value
 
 
+def largest_count(codes, segs, k):
+    """Runner::run's width detection for one sequence: 1 + largest k-mer multiplicity (u64 table, init 1)"""
+    out = C.c_uint64()
+    segs = np.ascontiguousarray(segs, dtype=np.int32)
+    codes = np.ascontiguousarray(codes, dtype=np.int8)
+    rc = lib().mc2o_largest_count(_p(codes), _p(segs), len(segs), k, C.byref(out))
+    if rc != 0:
+        raise ValueError("mc2o_largest_count rc=%d" % rc)
+    return out.value
+
+
+def width_for(largest):
+    return lib().mc2o_width_for(C.c_uint64(largest))
+
+
 def point_stats(hist):
     mag, sd = C.c_uint64(), C.c_double()
     lib().mc2o_point_stats(_p(hist), C.c_uint64(hist.size), hist.dtype.itemsize, C.byref(mag), C.byref(sd))

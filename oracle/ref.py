@@ -201,6 +201,18 @@ def mean_closest(H, members):
     return best.value, bd.value, mean, dist
 
 
+def largest_count(texts, k):
+    """Runner::run's width detection over raw sequences (list of bytes) -> Largest count"""
+    n = len(texts)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(t) for t in texts])
+    out = C.c_uint64()
+    rc = lib().ref_largest_count(b"".join(texts), _p(off), C.c_uint64(n), k, C.byref(out))
+    if rc != 0:
+        raise ValueError("ref_largest_count rc=%d" % rc)
+    return out.value
+
+
 def count_batch(texts, k, elem_bytes, threads=1, want_hist=True):
     """Loader<T>::get_point over raw sequences (list of bytes), omp over sequences -> (hist or None, seconds)"""
     n = len(texts)

@@ -56,6 +56,7 @@
 #include "predict/Predictor.h"
 #include "cluster/Trainer.h"
 #undef private
+#include "cluster/ClusterFactory.h"
 #include "Loader.h"
 #include "DivergencePoint.h"
 #include "../predict/Feature.h"
@@ -613,6 +614,32 @@ int ref_mean_closest(int elem_bytes, uint64_t N, const void *H, const uint64_t *
 {
 	try {
 		DISPATCH(elem_bytes, mean_closest_impl, N, H, members, n, best, best_dist, mean_out, dist_out);
+	} catch (...) {
+		return -1;
+	}
+}
+
+// Runner::run's histogram-width detection (src/cluster/CRunner.cpp:57-93): per sequence a u64 table (init 1) filled by
+// the free fill_table<V> of src/cluster/ClusterFactory.h:40-54 (wholesaleIncrement, no length guard), max over everything.
+int ref_largest_count(const char* text, const uint64_t* off, uint64_t n, int k, uint64_t* largest)
+{
+	try {
+		uint64_t best = 0;
+		for (uint64_t i = 0; i < n; i++) {
+			ChromosomeOneDigitDna chrom;
+			std::string header(">s");
+			std::string s(text + off[i], (size_t)(off[i + 1] - off[i]));
+			chrom.setHeader(header);
+			chrom.appendToSequence(s);
+			chrom.finalize();
+			std::vector<uint64_t> values;
+			KmerHashTable<unsigned long, uint64_t> table(k, 1);
+			fill_table<uint64_t>(table, &chrom, values);
+			uint64_t l_count = *std::max_element(values.begin(), values.end());
+			if (l_count > best) { best = l_count; }
+		}
+		*largest = best;
+		return 0;
 	} catch (...) {
 		return -1;
 	}

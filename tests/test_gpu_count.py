@@ -125,3 +125,63 @@ def test_full_size_property_cfg2_shape(built_lib, ctx):
     assert np.array_equal(got["mers1"].sum(axis=1), lens + 4)
     for i in range(0, 10000, 397):
         assert np.array_equal(got["hist"][i], port.get_point(seqs[i], 5, 1)["hist"])
+
+
+def test_auto_width_detection(built_lib, ctx):
+    """mc2_count_kmers_auto = Runner::run's width detection + counting (CRunner.cpp:57-127): Largest count, chosen width and
+    histograms equal the oracle's; an 8-bit result needs a single counting pass."""
+    seqs, _ = synth.make_range(60, 1000, 5, 0.1, seed=11)
+    cases = {"u8": (seqs, 5), "u8-edge": (seqs + [b"A" * 258], 5), "u16": (seqs + [b"A" * 700, b"ACGT" * 50 + b"N" * 40 + b"GGGTC" * 30], 5),
+             "u16-k8": (seqs + [b"AC" * 40000], 8), "u32": ([b"A" * 70000, b"ACGTTGCA" * 10], 3)}
+    for name, (ss, k) in cases.items():
+        want = 0
+        for s in ss:
+            c, sg, _ = port.encode(s)
+            want = max(want, port.largest_count(c, sg, k))
+        l0 = ctx.launches
+        hs, largest, eb = ctx.count_kmers_auto(_upload(built_lib, ctx, ss), k)
+        passes = ctx.launches - l0
+        assert largest == want and eb == port.width_for(want) == hs.elem_bytes, name
+        assert hs.largest_count() == want
+        _check_against_oracle(hs.download(), ss, k, eb)
+        if eb == 1:
+            assert passes <= 3, (name, passes)      # count + side-band max, no second counting pass
+    assert [built_lib.width_for_count(v) for v in (0, 255, 256, 65535, 65536, 2 ** 32 - 1, 2 ** 32)] == [1, 1, 2, 2, 4, 4, 8]
+    # edge: "A"*258 at k=5 -> 254 repeats + 1 = 255 still fits 8 bits
+    # sets built from histograms have no multiplicities
+    hs2 = ctx.hset_from_host(np.ones((2, 16), dtype=np.uint8), 2)
+    with pytest.raises(built_lib.Mc2Error):
+        hs2.largest_count()
+    # a segment shorter than k: the reference's detection pass reads past it
+    with pytest.raises(built_lib.Mc2Error):
+        ctx.count_kmers_auto(_upload(built_lib, ctx, [b"ACGTAC"]), 8)
+    # empty input: Largest count stays 0 -> 8 bit
+    hs3, largest, eb = ctx.count_kmers_auto(_upload(built_lib, ctx, []), 5)
+    assert largest == 0 and eb == 1 and len(hs3) == 0
+
+
+def test_upload_into_reuses_the_set(built_lib, ctx):
+    """mc2_seqs_upload_into: refilling with smaller / larger / different batches gives the same histograms as fresh uploads"""
+    rng = np.random.default_rng(5)
+    first, _ = synth.make_range(50, 800, 5, 0.1, seed=1)
+    s = _upload(built_lib, ctx, first)
+    for trial in range(4):
+        n = int(rng.integers(1, 120))
+        batch, _ = synth.make_range(n, int(rng.integers(30, 3000)), 3, 0.2, seed=100 + trial)
+        if trial == 2:
+            batch = batch + [b"ACGT" * 30 + b"N" * 25 + b"TTGCA" * 20]
+        enc = built_lib.encode_batch(batch, threads=2)
+        codes = built_lib.host_register(np.ascontiguousarray(enc["codes"])) if trial % 2 else enc["codes"]
+        ctx.upload_seqs_into(s, codes, enc["seq_off"], enc["segs"], enc["seg_off"])
+        if trial % 2:
+            built_lib.host_unregister(codes)
+        assert len(s) == len(batch)
+        _check_against_oracle(ctx.count_kmers(s, 5, 1).download(), batch, 5, 1)
+    # a failed refill (code outside 0..3 inside a segment) leaves an empty set that can be refilled again
+    bad = np.array([0, 1, 2, 9, 1, 2, 3, 0] * 4, dtype=np.int8)
+    with pytest.raises(built_lib.Mc2Error):
+        ctx.upload_seqs_into(s, bad, np.array([0, 32], dtype=np.uint64), np.array([[0, 31]], dtype=np.int32), np.array([0, 1], dtype=np.uint64))
+    assert len(s) == 0
+    enc = built_lib.encode_batch(first, threads=2)
+    ctx.upload_seqs_into(s, enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
+    _check_against_oracle(ctx.count_kmers(s, 5, 1).download(), first, 5, 1)

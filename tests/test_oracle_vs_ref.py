@@ -101,3 +101,24 @@ def test_k3_mean_closest(eb):
         a, b = port.mean_closest(H, mem), ref.mean_closest(H, mem)
         assert a[0] == b[0] and np.array_equal(a[2], b[2])
         assert np.abs(a[3] - b[3]).max() <= 1e-12 * max(1.0, np.abs(b[3]).max())
+
+
+def test_width_detection_largest_count():
+    """Runner::run's "Largest count" (CRunner.cpp:57-93) and the width rule (CRunner.cpp:108-126)"""
+    from meshclust2_b200 import synth
+    seqs, _ = synth.make_range(40, 1000, 5, 0.1, seed=3)
+    sets = {"plain": seqs, "homopolymer": seqs + [b"A" * 700], "segments": seqs + [b"ACGT" * 100 + b"N" * 30 + b"ACGT" * 90],
+            "u16": seqs + [b"AC" * 40000], "one": [b"ACGTTGCAAGGCTTAACCGGTTAAC"]}
+    for name, ss in sets.items():
+        for k in (2, 5, 8):
+            want = ref.largest_count(ss, k)
+            got = 0
+            for s in ss:
+                c, sg, _ = port.encode(s)
+                got = max(got, port.largest_count(c, sg, k))
+            assert got == want, (name, k)
+    assert [port.width_for(v) for v in (0, 255, 256, 65535, 65536, 2 ** 32 - 1, 2 ** 32)] == [1, 1, 2, 2, 4, 4, 8]
+    # a segment shorter than k: not restated (the reference reads past the segment)
+    c, sg, _ = port.encode(b"ACGTAC")
+    with pytest.raises(ValueError):
+        port.largest_count(c, sg, 8)

@@ -1,0 +1,106 @@
+#!/usr/bin/env python3
+"""Multi-rank parity check on real GPUs: the row-block sharded all-pairs sweep and the range-partitioned candidate scan
+(meshclust2_b200/dist.py) against the CPU oracle, one process per GPU over NCCL.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+      tools/multi_gpu_check.py [--n-seqs 3000]
+  python tools/multi_gpu_check.py            # world size 1, same code path without a process group
+
+Every rank checks its own shard of the result; exit status 0 only if all ranks agree with the oracle.
+(The oracle is test infrastructure: this script is a test, not a product path.)"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-seqs", type=int, default=3000)
+    ap.add_argument("--queries", type=int, default=12)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    import torch
+    from meshclust2_b200 import capi, dist as mdist, synth
+    from oracle import port
+    tdist = None
+    if world > 1:
+        import torch.distributed as td
+        torch.cuda.set_device(local_rank)
+        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        tdist = td
+    comm = mdist.Comm(tdist)
+    n_total = args.n_seqs
+    weights = os.path.join(ROOT, "tests", "golden", "weights_cfg1_id90.txt")
+    k, eb, cutoff = 5, 1, 0.9
+    per, bounds = mdist.shard_bounds(n_total, world)
+    lo, hi = bounds[rank]
+    seqs, _ = synth.make_range(n_total, 1000, 40, 0.1, seed=4242, lo=lo, hi=hi)
+    ctx = capi.Context(local_rank)
+    model = ctx.model_from_file(weights)
+    eng = mdist.GpuEngine(capi, ctx, torch, model, k, eb, local_rank)
+    enc = capi.encode_batch(seqs)
+    eng.set_local_sequences(ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"]), hi - lo, per)
+
+    # oracle view of the whole set (every rank builds it: small)
+    all_seqs, _ = synth.make_range(n_total, 1000, 40, 0.1, seed=4242)
+    omodel = port.Model.from_text(open(weights).read())
+    pts = [port.get_point(s, k, eb) for s in all_seqs]
+    H = np.stack([p["hist"] for p in pts])
+    mag = np.array([p["mag"] for p in pts], dtype=np.uint64)
+    ln = np.array([p["len"] for p in pts], dtype=np.uint64)
+
+    bad = 0
+    # --- sweep, twice (second pass exercises the in-place buffer reuse) ---
+    for rep in range(2):
+        res = mdist.all_pairs_step(eng, comm, torch, n_total, cutoff, upper_only=True, blocks_per_rank=2)
+        mine = sorted(map(tuple, res["survivors"].tolist()))
+        want = []
+        scored = 0
+        for q0, q1 in res["blocks"]:
+            for q in range(q0, q1):
+                cand = np.arange(q + 1, n_total)
+                if cand.size == 0:
+                    continue
+                wlo, whi = int(float(ln[q]) * cutoff), int(float(ln[q]) / cutoff)   # fastcar window, FC_Runner.cpp:427-470
+                cand = cand[(ln[cand] >= wlo) & (ln[cand] <= whi)]
+                if cand.size == 0:
+                    continue
+                r = port.score_pairs(omodel, H, mag, ln, cand.astype(np.uint64), np.full(cand.size, q, dtype=np.uint64))
+                scored += int(cand.size)
+                want += [(int(q), int(c)) for c in cand[r["close"].astype(bool)]]
+        want.sort()
+        if mine != want or res["local_scored"] != scored:
+            print("[rank %d] sweep pass %d MISMATCH: %d vs %d survivors, %d vs %d scored" % (
+                rank, rep, len(mine), len(want), res["local_scored"], scored), flush=True)
+            bad += 1
+    # --- candidate scan ---
+    rng = np.random.default_rng(9)
+    queries = [0, n_total - 1, per - 1 if per else 0, min(per, n_total - 1)] + rng.integers(0, n_total, args.queries).tolist()
+    n_close = 0
+    for q in queries:
+        r = mdist.candidate_scan(eng, comm, torch, int(q), n_total, cutoff)
+        ob, obd, omin, omarks = port.get_close(omodel, H, mag, ln, int(q), np.arange(n_total), cutoff)
+        n_close += int(omarks.sum())
+        if r["best"] != ob or (ob >= 0 and abs(r["best_dist"] - obd) > 1e-9) or r["is_min"] != omin \
+                or not np.array_equal(np.asarray(r["marks_local"], dtype=np.uint8), omarks[lo:hi]):
+            print("[rank %d] scan q=%d MISMATCH: best %d vs %d, dist %r vs %r, is_min %r vs %r" % (
+                rank, q, r["best"], ob, r["best_dist"], obd, r["is_min"], omin), flush=True)
+            bad += 1
+    tot_bad = comm.all_reduce_sum([bad], torch, eng.device)[0]
+    if rank == 0:
+        print("multi_gpu_check world=%d n=%d: %s (sweep scored %d close %d; %d scan queries, %d marks)" % (
+            world, n_total, "OK" if tot_bad == 0 else "FAILED", res["n_scored"], res["n_close"], len(queries), n_close), flush=True)
+    if tdist is not None:
+        tdist.destroy_process_group()
+    sys.exit(0 if tot_bad == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
