@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmeshclust2_b200.so")
+LIB_PATH = os.environ.get("MC2_LIB") or os.path.join(_HERE, "lib", "libmeshclust2_b200.so")   # MC2_LIB: tuning variants
 
 MAX_SINGLES, MAX_COMBOS, MAX_COMBO_IDX = 16, 16, 4
 DTYPES = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}

@@ -203,6 +203,24 @@ static int model_need(const mc2_model_desc &d, DevModel &dm)
 	dm.bias = d.bias;
 	dm.regression = d.regression;
 	dm.need = need;
+	dm.fast_epi = 1;
+	for (int c = 0; c < SC_COUNT; c++) {
+		dm.slot[c] = -1;
+	}
+	for (int i = 0; i < d.n_singles; i++) {
+		const int c = dm.code[i];
+		if (dm.slot[c] >= 0) {
+			dm.fast_epi = 0; // the same single twice (never produced by the reference's selector)
+			continue;
+		}
+		dm.slot[c] = i;
+		dm.csim[c] = dm.is_sim[i];
+		dm.cmin[c] = dm.smin[i];
+		dm.crange[c] = dm.smax[i] - dm.smin[i];
+		dm.crcp[c] = 1.0 / dm.crange[c];
+		const double ar = fabs(dm.crange[c]);
+		dm.crcp_ok[c] = std::isfinite(dm.crcp[c]) && ar > 1e-100 && ar < 1e100;
+	}
 	return MC2_OK;
 }
 

@@ -63,6 +63,15 @@ struct DevModel {
 	double bias;
 	int regression;
 	int need;
+	// straight-line epilogue (eval_pair_fast): constants indexed by single CODE instead of by position, so the kernel
+	// reads them at fixed constant-bank offsets.  slot = position of the code in the model's cache order, -1 = absent.
+	int fast_epi;                 // 0: a single appears twice -> interpretive epilogue only
+	int slot[SC_COUNT];
+	int csim[SC_COUNT];
+	int crcp_ok[SC_COUNT];        // crcp usable (finite, normal range): division by crange = two fused multiply-adds
+	double cmin[SC_COUNT];
+	double crange[SC_COUNT];      // max - min, the divisor of Feature::normalize_cache (Feature.cpp:136-154)
+	double crcp[SC_COUNT];        // correctly rounded 1 / crange
 };
 
 // side-band SoA of a histogram set (device pointers)

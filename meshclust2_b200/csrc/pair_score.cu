@@ -249,12 +249,148 @@ __device__ int raw_single_wide(int code, u64 N, const RedW &r, const Side &p, co
 	return 2;
 }
 
+// a / b for a model constant b whose correctly rounded reciprocal y = RN(1/b) was computed on the host (Markstein):
+// q0 = RN(a*y) is within one ulp of a/b, r = a - b*q0 is exact in one fused multiply-add, RN(q0 + r*y) is the correctly
+// rounded quotient, i.e. bit-identical to a / b.  Anything outside the comfortable range (infinities, NaN, values near
+// under/overflow, unusable reciprocal) takes the real division.
+__device__ __forceinline__ double div_const(double a, double b, double y, int ok)
+{
+	if (ok) {
+		const double q0 = __dmul_rn(a, y);
+		const double r = __fma_rn(-b, q0, a);
+		const double q = __fma_rn(r, y, q0);
+		if ((fabs(q0) < 1e200 && fabs(a) > 1e-200) || a == 0.0) {
+			return q;
+		}
+	}
+	return a / b;
+}
+
+// pearson_exact in 64-bit integers when every term provably fits (always, for the 1 KiB / 128 KiB histograms of real
+// data); identical value: the same integer converted to double once
+__device__ __forceinline__ double pearson_fast(u64 N, u64 dot, const Side &p, const Side &q)
+{
+	if ((p.mag | q.mag | p.sum | q.sum) < (1ULL << 30) && N <= (1ULL << 20) && dot < (1ULL << 40) &&
+	    (p.sumsq | q.sumsq) < (1ULL << 40)) {
+		const long long n = (long long)N, pm = (long long)p.mag, qm = (long long)q.mag;
+		const long long ndot = n * (long long)dot - pm * (long long)q.sum - qm * (long long)p.sum + pm * qm;
+		const long long nnp = n * (long long)p.sumsq - 2 * pm * (long long)p.sum + pm * pm;
+		const long long nnq = n * (long long)q.sumsq - 2 * qm * (long long)q.sum + qm * qm;
+		return (double)ndot / sqrt((double)nnp * (double)nnq);
+	}
+	return pearson_exact(N, dot, p, q);
+}
+
+// eval_pair for 8/16-bit histograms without the interpreter: one guarded straight-line block per single code (uniform
+// branches on the model), normalisation through div_const, the logistic only where the decision or the score needs it.
+// Same operations in the same order as eval_pair, so the values are the same bits.
+// lazy: the caller keeps `score` only for close pairs; with bias 0, sum < -1e-6 means logistic(sum) < 0.5 - 2e-7, the
+// pair is not close whatever the last-bit rounding of exp, and exp + division are skipped.
+__device__ __forceinline__ int eval_pair_fast(const DevModel &dm, u64 N, const RedN &r, const Side &p, const Side &q, bool lazy,
+					      double &score, double &d0, int &close)
+{
+	double cache[MC2_MAX_SINGLES];
+	int bad = 0;
+#define MC2_PUT(CODE, RAW)                                                                                         \
+	{                                                                                                          \
+		const double nv_ = div_const((RAW) - dm.cmin[CODE], dm.crange[CODE], dm.crcp[CODE], dm.crcp_ok[CODE]); \
+		if (isnan(nv_)) {                                                                                  \
+			bad |= 1;                                                                                  \
+		}                                                                                                  \
+		cache[dm.slot[CODE]] = dm.csim[CODE] ? nv_ : 1 - nv_;                                              \
+	}
+	if (dm.slot[SC_MANHATTAN] >= 0) { // Feature.cpp:858-871 (int accumulator)
+		MC2_PUT(SC_MANHATTAN, (double)(int)(p.sum + q.sum - 2 * r.smin));
+	}
+	if (dm.slot[SC_EUCLIDEAN] >= 0 || dm.slot[SC_SIMRATIO] >= 0) {
+		const double rn2 = sqrt((double)(p.sumsq + q.sumsq - 2 * r.dot));
+		if (dm.slot[SC_EUCLIDEAN] >= 0) { // Feature.cpp:1112-1124
+			MC2_PUT(SC_EUCLIDEAN, rn2);
+		}
+		if (dm.slot[SC_SIMRATIO] >= 0) { // Feature.cpp:828-841
+			const double dot = (double)r.dot;
+			MC2_PUT(SC_SIMRATIO, dot / (dot + rn2));
+		}
+	}
+	if (dm.slot[SC_NORMALIZED_VECTORS] >= 0) { // Feature.cpp:1170-1184 (u64 product, wraps like the reference)
+		MC2_PUT(SC_NORMALIZED_VECTORS, (double)r.dot / sqrt((double)(p.sumsq * q.sumsq)));
+	}
+	if (dm.slot[SC_PEARSON] >= 0) {
+		MC2_PUT(SC_PEARSON, pearson_fast(N, r.dot, p, q));
+	}
+	if (dm.slot[SC_INTERSECTION] >= 0) { // Feature.cpp:763-777
+		MC2_PUT(SC_INTERSECTION, (double)(2 * r.smin) / (double)(p.mag + q.mag));
+	}
+	if (dm.slot[SC_EMD] >= 0) { // Feature.cpp:1504-1518
+		MC2_PUT(SC_EMD, (double)r.emd);
+	}
+	if (dm.slot[SC_LENGTHD] >= 0) { // Feature.cpp:873-887 (throws 123 on a zero length)
+		if (p.len == 0 || q.len == 0) {
+			bad |= 1;
+		}
+		MC2_PUT(SC_LENGTHD, (double)(p.len > q.len ? p.len - q.len : q.len - p.len));
+	}
+	if (dm.slot[SC_KULCZYNSKI2] >= 0) { // Feature.cpp:681-695
+		const double ap = (double)p.mag / (double)N;
+		const double aq = (double)q.mag / (double)N;
+		const double coeff = (double)N * (ap + aq) / (2 * ap * aq);
+		MC2_PUT(SC_KULCZYNSKI2, coeff * (double)r.smin);
+	}
+	if (dm.slot[SC_JEFFEREY] >= 0) { // Feature.cpp:1230-1263
+		MC2_PUT(SC_JEFFEREY, r.jeff);
+	}
+	if (dm.slot[SC_JENSEN_SHANNON] >= 0) { // Feature.cpp:983-1009
+		MC2_PUT(SC_JENSEN_SHANNON, r.js / 2);
+	}
+#undef MC2_PUT
+	double sum = dm.weight[0];
+	d0 = 0;
+#pragma unroll 1
+	for (int c = 0; c < dm.n_combos; c++) {
+		const int *ix = dm.idx[c];
+		const int kind = dm.kind[c];
+		double d;
+		if (kind == MC2_COMBO_XY || kind == MC2_COMBO_X2Y2) {
+			double prod = 1;
+			for (int t = 0; t < dm.nidx[c]; t++) {
+				const double x = cache[ix[t]];
+				prod *= kind == MC2_COMBO_XY ? x : x * x;
+			}
+			d = prod;
+		} else if (kind == MC2_COMBO_XY2) {
+			d = cache[ix[0]] * cache[ix[1]] * cache[ix[1]];
+		} else {
+			d = cache[ix[0]] * cache[ix[0]] * cache[ix[1]];
+		}
+		if (c == 0) {
+			d0 = d;
+		}
+		sum += dm.weight[c + 1] * d;
+	}
+	if (dm.regression) { // Predictor::p_predict, Predictor.cpp:284-300
+		score = sum < 0 ? 0 : (sum > 1 ? 1 : sum);
+		close = 0;
+	} else if (lazy && dm.bias == 0.0 && sum < -1e-6) {
+		score = 0;
+		close = 0;
+	} else {
+		score = 1.0 / (1 + exp(-sum)) + dm.bias;
+		close = round(score) > 0;
+	}
+	return bad;
+}
+
 // normalise (Feature.cpp:136-154), combos (Feature.h:205-239), GLM sum, logistic + bias (Predictor.cpp:316-320)
 // returns a bit mask: 1 = the reference would throw, 2 = internal (unknown single code)
 template <typename RED, bool WIDE>
 __device__ int eval_pair(const DevModel &dm, u64 N, const RED &r, const Side &first, const Side &second, double *raw_out,
-			 double *cache_out, double &score, double &d0, int &close)
+			 double *cache_out, double &score, double &d0, int &close, bool lazy = false)
 {
+	if constexpr (!WIDE) {
+		if (dm.fast_epi && raw_out == nullptr && cache_out == nullptr) {
+			return eval_pair_fast(dm, N, r, first, second, lazy, score, d0, close);
+		}
+	}
 	double cache[MC2_MAX_SINGLES];
 	int bad = 0;
 #pragma unroll 1
@@ -332,7 +468,7 @@ __device__ void finish_pair(const DevModel &dm, const PairArgs &a, u64 j, u64 N,
 	int close;
 	const u64 S = (u64)dm.n_singles;
 	int bad = eval_pair<RED, WIDE>(dm, N, r, first, second, a.raw ? a.raw + j * S : nullptr,
-				       a.cache ? a.cache + j * S : nullptr, score, d0, close);
+				       a.cache ? a.cache + j * S : nullptr, score, d0, close, a.score == nullptr);
 	if (bad) {
 		atomicOr(a.err, bad & 1 ? 1 : 2);
 	}
@@ -783,19 +919,19 @@ __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigne
 		get(b0, fb0, 1);
 		get(a1, fa1, 2);
 		get(b1, fb1, 3);
+		// the last four rows are peeled off so that the loop body prefetches unconditionally (a predicated prefetch
+		// costs ~6 predicated register moves per pair)
 #pragma unroll 1
-		for (int pi = 0; pi < 32; pi += 4) {
+		for (int pi = 0; pi < 28; pi += 4) {
 			reduce(a0, fa0, pi, b0, fb0, pi + 1);
-			if (pi + 4 < 32) {
-				get(a0, fa0, pi + 4);
-				get(b0, fb0, pi + 5);
-			}
+			get(a0, fa0, pi + 4);
+			get(b0, fb0, pi + 5);
 			reduce(a1, fa1, pi + 2, b1, fb1, pi + 3);
-			if (pi + 4 < 32) {
-				get(a1, fa1, pi + 6);
-				get(b1, fb1, pi + 7);
-			}
+			get(a1, fa1, pi + 6);
+			get(b1, fb1, pi + 7);
 		}
+		reduce(a0, fa0, 28, b0, fb0, 29);
+		reduce(a1, fa1, 30, b1, fb1, 31);
 		return;
 	}
 	int ia0 = next_idx();
@@ -1370,8 +1506,11 @@ struct SweepArgs {
 	u64 *counters; // [0] survivors, [1] scored pairs
 };
 
+#ifndef MC2_SWEEP_CTAS_PER_SM
+#define MC2_SWEEP_CTAS_PER_SM 4 // resident 128-thread CTAs of the 1 KiB-row sweep (register budget 65536 / (128 * n))
+#endif
 template <typename T, int NEED, bool FAST, bool ONE, bool LOFF>
-__global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
+__global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_SWEEP_CTAS_PER_SM : 2) sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
 						    const __grid_constant__ SweepArgs g)
 {
 	constexpr bool WIDE = sizeof(T) > 2;
@@ -1458,7 +1597,7 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(con
 				if (FAST && sizeof(T) == 1 && (NEED & NEED_MIN)) {
 					mn.smin = (sd.sum + sq.sum - mn.smin) >> 1;
 				}
-				bad = eval_pair<RedN, false>(dm, a.N, mn, sd, sq, nullptr, nullptr, score, d0, close);
+				bad = eval_pair<RedN, false>(dm, a.N, mn, sd, sq, nullptr, nullptr, score, d0, close, true);
 			}
 			if (bad) {
 				atomicOr(a.err, bad & 1 ? 1 : 2);
@@ -1481,6 +1620,243 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) sweep_kernel(con
 				g.out_q[idx] = r;
 				g.out_d[idx] = c;
 				g.out_score[idx] = score;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two query rows per warp (1 KiB uint8 rows with lane offsets, EMD models).  The prefix-sum chain of a streamed row
+// (32 IDP) does not depend on the query it is compared with, so a warp that keeps TWO query rows and their prefix sums
+// in registers (80 registers) pays for it once per two pairs: per pair 16 + 8 IDP and 32 VABSDIFF instead of 32 + 8 and
+// 32, one row load and one lane-offset load per two pairs, half the L2 traffic.  The query's own lane offset is folded
+// into its register prefixes (bq' = bq + qoff), so the streamed chain starts from the row's lane offset alone.
+// ------------------------------------------------------------------------------------------------
+struct FixedQE {
+	Row8 q;
+	int bq[32];
+};
+
+__device__ __forceinline__ void fixed_qe_setup(FixedQE &f, const unsigned char *row, int qoff, int lane)
+{
+	f.q = ld_row_keep(row + lane * 32);
+	int base = qoff;
+#pragma unroll
+	for (int w = 0; w < 8; w++) {
+		f.bq[4 * w + 0] = (int)__dp4a(f.q.w[w], 0x00000001u, (u32)base);
+		f.bq[4 * w + 1] = (int)__dp4a(f.q.w[w], 0x00000101u, (u32)base);
+		f.bq[4 * w + 2] = (int)__dp4a(f.q.w[w], 0x00010101u, (u32)base);
+		f.bq[4 * w + 3] = (int)__dp4a(f.q.w[w], 0x01010101u, (u32)base);
+		base = f.bq[4 * w + 3];
+	}
+}
+
+// one streamed row against both fixed rows; o0 / o1 = {sum|p-q|, dot, emd} for query 0 / 1
+template <int NEED>
+__device__ __forceinline__ void reduce_row_q2(const Row8 &p, int off, const FixedQE &f0, const FixedQE &f1, u32 (&o0)[3], u32 (&o1)[3])
+{
+	u32 min0 = 0, min1 = 0, dot0 = 0, dot1 = 0;
+	if (NEED & NEED_MIN) {
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			min0 = vabsdiff4_acc(p.w[w], f0.q.w[w], min0);
+			min1 = vabsdiff4_acc(p.w[w], f1.q.w[w], min1);
+		}
+	}
+	if (NEED & NEED_DOT) {
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			dot0 = __dp4a(p.w[w], f0.q.w[w], dot0);
+			dot1 = __dp4a(p.w[w], f1.q.w[w], dot1);
+		}
+	}
+	u32 e0a = 0, e0b = 0, e1a = 0, e1b = 0; // two accumulation chains per query
+	int base = off;
+#pragma unroll
+	for (int w = 0; w < 8; w++) {
+		int a0 = (int)__dp4a(p.w[w], 0x00000001u, (u32)base);
+		int a1 = (int)__dp4a(p.w[w], 0x00000101u, (u32)base);
+		int a2 = (int)__dp4a(p.w[w], 0x00010101u, (u32)base);
+		int a3 = (int)__dp4a(p.w[w], 0x01010101u, (u32)base);
+		base = a3;
+		e0a = __sad(a0, f0.bq[4 * w + 0], e0a);
+		e1a = __sad(a0, f1.bq[4 * w + 0], e1a);
+		e0b = __sad(a1, f0.bq[4 * w + 1], e0b);
+		e1b = __sad(a1, f1.bq[4 * w + 1], e1b);
+		e0a = __sad(a2, f0.bq[4 * w + 2], e0a);
+		e1a = __sad(a2, f1.bq[4 * w + 2], e1a);
+		e0b = __sad(a3, f0.bq[4 * w + 3], e0b);
+		e1b = __sad(a3, f1.bq[4 * w + 3], e1b);
+	}
+	o0[0] = (NEED & NEED_MIN) ? __reduce_add_sync(0xffffffffu, min0) : 0;
+	o1[0] = (NEED & NEED_MIN) ? __reduce_add_sync(0xffffffffu, min1) : 0;
+	o0[1] = (NEED & NEED_DOT) ? __reduce_add_sync(0xffffffffu, dot0) : 0;
+	o1[1] = (NEED & NEED_DOT) ? __reduce_add_sync(0xffffffffu, dot1) : 0;
+	o0[2] = __reduce_add_sync(0xffffffffu, e0a + e0b);
+	o1[2] = __reduce_add_sync(0xffffffffu, e1a + e1b);
+}
+
+template <int NEED>
+__global__ void __launch_bounds__(128, 3) sweep_q2_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
+							  const __grid_constant__ SweepArgs g)
+{
+	const int lane = threadIdx.x & 31;
+	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
+	const u64 warp_id = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const unsigned char *Dm = reinterpret_cast<const unsigned char *>(a.binsA);
+	const unsigned char *Qm = reinterpret_cast<const unsigned char *>(a.binsB);
+	const u64 cblocks = (g.d1 - g.d0 + 31) / 32;
+	const u64 qpairs = (g.q1 - g.q0 + 1) / 2;
+	const u64 groups = qpairs * cblocks; // host guarantees groups < 2^32 per launch
+	const u32 cblocks32 = (u32)cblocks;
+	for (u64 grp = warp_id; grp < groups; grp += warps_total) {
+		const u32 gp = (u32)grp / cblocks32, gc = (u32)grp - gp * cblocks32;
+		const u64 r0 = g.q0 + 2 * (u64)gp;
+		const bool have1 = r0 + 1 < g.q1;
+		const u64 r1 = have1 ? r0 + 1 : r0;
+		const u64 cfirst = g.d0 + (u64)gc * 32;
+		if (g.upper_only && cfirst + 31 <= r0) {
+			continue; // whole block at or below the diagonal for both queries
+		}
+		const u64 c = cfirst + lane;
+		bool go0 = c < g.d1 && (!g.upper_only || c > r0);
+		bool go1 = have1 && c < g.d1 && (!g.upper_only || c > r1);
+		if (go0 || go1) { // FC_Runner.cpp:435-444: size_t truncation, window on the database length
+			const u64 lc = a.sbA.len[c];
+			const u64 lq0 = a.sbB.len[r0], lq1 = a.sbB.len[r1];
+			go0 = go0 && lc >= (u64)((double)lq0 * g.cutoff) && lc <= (u64)((double)lq0 / g.cutoff);
+			go1 = go1 && lc >= (u64)((double)lq1 * g.cutoff) && lc <= (u64)((double)lq1 / g.cutoff);
+		}
+		const unsigned act0 = __ballot_sync(0xffffffffu, go0), act1 = __ballot_sync(0xffffffffu, go1);
+		unsigned active = act0 | act1;
+		u32 m0[3] = {0, 0, 0}, m1[3] = {0, 0, 0};
+		if (active) {
+			FixedQE f0, f1;
+			fixed_qe_setup(f0, Qm + r0 * 1024, (int)a.loffB[r0 * 32 + lane], lane);
+			fixed_qe_setup(f1, Qm + r1 * 1024, (int)a.loffB[r1 * 32 + lane], lane);
+			const unsigned char *rp = Dm + cfirst * 1024 + lane * 32;
+			const unsigned short *op = a.loffA + cfirst * 32 + lane;
+			Row8 p0 = {}, p1 = {}, p2 = {}, p3 = {};
+			int f_0 = 0, f_1 = 0, f_2 = 0, f_3 = 0;
+			auto reduce = [&](const Row8 &p, int off, int pi) {
+				u32 o0[3], o1[3];
+				reduce_row_q2<NEED>(p, off, f0, f1, o0, o1);
+				if (lane == pi) {
+					m0[0] = o0[0];
+					m0[1] = o0[1];
+					m0[2] = o0[2];
+					m1[0] = o1[0];
+					m1[1] = o1[1];
+					m1[2] = o1[2];
+				}
+			};
+			if (active == 0xffffffffu) {
+				// 32 consecutive rows wanted by at least one of the two queries: counted loop over a four-row register ring
+				auto get = [&](Row8 &p, int &off, int pi) {
+					p = ld_row_stream(rp + (size_t)pi * 1024);
+					off = (int)__ldg(op + pi * 32);
+				};
+				get(p0, f_0, 0);
+				get(p1, f_1, 1);
+				get(p2, f_2, 2);
+				get(p3, f_3, 3);
+#pragma unroll 1
+				for (int pi = 0; pi < 32; pi += 4) {
+					reduce(p0, f_0, pi);
+					if (pi + 4 < 32) {
+						get(p0, f_0, pi + 4);
+					}
+					reduce(p1, f_1, pi + 1);
+					if (pi + 4 < 32) {
+						get(p1, f_1, pi + 5);
+					}
+					reduce(p2, f_2, pi + 2);
+					if (pi + 4 < 32) {
+						get(p2, f_2, pi + 6);
+					}
+					reduce(p3, f_3, pi + 3);
+					if (pi + 4 < 32) {
+						get(p3, f_3, pi + 7);
+					}
+				}
+			} else {
+				auto next_idx = [&]() -> int {
+					int pi = active ? __ffs(active) - 1 : -1;
+					active &= active ? active - 1 : 0;
+					return pi;
+				};
+				auto fetch = [&](Row8 &p, int &off, int pi) {
+					const int x = pi < 0 ? 0 : pi;
+					ld_row_stream_if(p, rp + (size_t)x * 1024, pi >= 0);
+					ld_u16_if(off, op + x * 32, pi >= 0);
+				};
+				int i0 = next_idx(), i1 = next_idx(), i2 = next_idx(), i3 = next_idx();
+				fetch(p0, f_0, i0);
+				fetch(p1, f_1, i1);
+				fetch(p2, f_2, i2);
+				fetch(p3, f_3, i3);
+				while (true) { // indices are handed out in order: the first absent one ends the group
+					if (i0 < 0) break;
+					reduce(p0, f_0, i0);
+					i0 = next_idx();
+					fetch(p0, f_0, i0);
+					if (i1 < 0) break;
+					reduce(p1, f_1, i1);
+					i1 = next_idx();
+					fetch(p1, f_1, i1);
+					if (i2 < 0) break;
+					reduce(p2, f_2, i2);
+					i2 = next_idx();
+					fetch(p2, f_2, i2);
+					if (i3 < 0) break;
+					reduce(p3, f_3, i3);
+					i3 = next_idx();
+					fetch(p3, f_3, i3);
+				}
+			}
+		}
+		// epilogue: one pair per lane and query, fp64, fused cutoff + survivor compaction
+#pragma unroll 1
+		for (int t = 0; t < 2; t++) {
+			const bool go = t ? go1 : go0;
+			const unsigned scored = t ? act1 : act0;
+			if (!scored) {
+				continue;
+			}
+			const u64 r = t ? r1 : r0;
+			int close = 0;
+			double score = 0, d0;
+			if (go) {
+				RedN mn;
+				mn.smin = t ? m1[0] : m0[0];
+				mn.dot = t ? m1[1] : m0[1];
+				mn.emd = t ? m1[2] : m0[2];
+				mn.jeff = mn.js = 0;
+				Side sd = load_side(a.sbA, c), sq = load_side(a.sbB, r);
+				if (NEED & NEED_MIN) {
+					mn.smin = (sd.sum + sq.sum - mn.smin) >> 1;
+				}
+				int bad = eval_pair<RedN, false>(dm, a.N, mn, sd, sq, nullptr, nullptr, score, d0, close, true);
+				if (bad) {
+					atomicOr(a.err, bad & 1 ? 1 : 2);
+				}
+			}
+			const unsigned cm = __ballot_sync(0xffffffffu, close);
+			u64 base = 0;
+			if (lane == 0) {
+				if (cm) {
+					base = atomicAdd(g.counters, (u64)__popc(cm));
+				}
+				atomicAdd(g.counters + 1, (u64)__popc(scored));
+			}
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (close) {
+				u64 idx = base + __popc(cm & ((1u << lane) - 1));
+				if (idx < g.max_out) {
+					g.out_q[idx] = r;
+					g.out_d[idx] = c;
+					g.out_score[idx] = score;
+				}
 			}
 		}
 	}
@@ -1621,7 +1997,7 @@ static void launch_sweep_fast(int need, int grid, cudaStream_t st, const DevMode
 	switch (need & 7) {
 #define CASE(n)                                                               \
 	case n:                                                               \
-		sweep_kernel<T, n, true, ONE, LOFF><<<ONE ? grid * 2 : grid, ONE ? 128 : 256, 0, st>>>(dm, a, g); \
+		sweep_kernel<T, n, true, ONE, LOFF><<<grid, ONE ? 128 : 256, 0, st>>>(dm, a, g); \
 		break;
 		CASE(0)
 		CASE(1)
@@ -1668,14 +2044,30 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 	const u64 groups = (q1 - q0) * ((d1 - d0 + 31) / 32);
 	u64 want = (groups + 7) / 8, cap = (u64)ctx->sm_count * 8;
 	int grid = (int)(want < cap ? want : cap);
+	// 1 KiB rows: 128-thread CTAs, four waves of the resident set (groups differ in cost: diagonal, length window)
+	const u64 want_one = (groups + 3) / 4, cap_one = (u64)ctx->sm_count * MC2_SWEEP_CTAS_PER_SM * 4;
+	const int grid_one = (int)(want_one < cap_one ? want_one : cap_one);
 	const u64 row_bytes = a.N * (u64)a.eb;
 	const bool fast = a.eb <= 2 && row_bytes % 1024 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 26);
 	prof_begin(ctx, 3);
+	// The two-queries-per-warp kernel (sweep_q2_kernel) executes 18 % fewer instructions per pair but runs at 12 warps / SM
+	// and is latency bound there: 38.9 ms vs 35.3 ms for the one-query kernel on the 20k x 20k triangle.  Opt-in only.
+	static const bool one_query = getenv("MC2_SWEEP_TWO_QUERY") == nullptr;
 	if (fast) {
-		if (a.eb == 1 && row_bytes == 1024 && a.loffA && a.loffB && (dm.need & NEED_EMD)) {
-			launch_sweep_fast<uint8_t, true, true>(dm.need, grid, ctx->stream, dm, a, g);
+		if (a.eb == 1 && row_bytes == 1024 && a.loffA && a.loffB && (dm.need & NEED_EMD) && !one_query) {
+			const u64 groups2 = ((q1 - q0 + 1) / 2) * ((d1 - d0 + 31) / 32);
+			u64 want2 = (groups2 + 3) / 4, cap2 = (u64)ctx->sm_count * 3;
+			int grid2 = (int)(want2 < cap2 ? want2 : cap2);
+			switch (dm.need & 3) {
+			case 0: sweep_q2_kernel<NEED_EMD><<<grid2, 128, 0, ctx->stream>>>(dm, a, g); break;
+			case 1: sweep_q2_kernel<NEED_EMD | 1><<<grid2, 128, 0, ctx->stream>>>(dm, a, g); break;
+			case 2: sweep_q2_kernel<NEED_EMD | 2><<<grid2, 128, 0, ctx->stream>>>(dm, a, g); break;
+			case 3: sweep_q2_kernel<NEED_EMD | 3><<<grid2, 128, 0, ctx->stream>>>(dm, a, g); break;
+			}
+		} else if (a.eb == 1 && row_bytes == 1024 && a.loffA && a.loffB && (dm.need & NEED_EMD)) {
+			launch_sweep_fast<uint8_t, true, true>(dm.need, grid_one, ctx->stream, dm, a, g);
 		} else if (a.eb == 1 && row_bytes == 1024) {
-			launch_sweep_fast<uint8_t, true>(dm.need, grid, ctx->stream, dm, a, g);
+			launch_sweep_fast<uint8_t, true>(dm.need, grid_one, ctx->stream, dm, a, g);
 		} else if (a.eb == 1) {
 			launch_sweep_fast<uint8_t, false>(dm.need, grid, ctx->stream, dm, a, g);
 		} else {
