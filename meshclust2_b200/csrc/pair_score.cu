@@ -974,8 +974,11 @@ __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigne
 	}
 }
 
+#ifndef MC2_PAIR_CTAS_PER_SM
+#define MC2_PAIR_CTAS_PER_SM 4 // resident 128-thread CTAs of the one-vs-many (1 KiB rows) form
+#endif
 template <typename T, int NEED, bool ONE, bool LOFF>
-__global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? 4 : 2) pair_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a)
+__global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_PAIR_CTAS_PER_SM : 2) pair_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a)
 {
 	const int lane = threadIdx.x & 31;
 	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
@@ -1507,7 +1510,7 @@ struct SweepArgs {
 };
 
 #ifndef MC2_SWEEP_CTAS_PER_SM
-#define MC2_SWEEP_CTAS_PER_SM 4 // resident 128-thread CTAs of the 1 KiB-row sweep (register budget 65536 / (128 * n))
+#define MC2_SWEEP_CTAS_PER_SM 5 // resident 128-thread CTAs of the 1 KiB-row sweep: 96 registers; measured 4: 922 ms, 5: 898 ms, 6: slower (spills)
 #endif
 template <typename T, int NEED, bool FAST, bool ONE, bool LOFF>
 __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_SWEEP_CTAS_PER_SM : 2) sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
@@ -1880,7 +1883,7 @@ static void launch_fast_need(int need, int grid, cudaStream_t st, const DevModel
 	switch (need & 7) {
 #define CASE(n)                                                         \
 	case n:                                                         \
-		pair_fast_kernel<T, n, ONE, LOFF><<<ONE ? grid * 2 : grid, ONE ? 128 : 256, 0, st>>>(dm, a); \
+		pair_fast_kernel<T, n, ONE, LOFF><<<grid, ONE ? 128 : 256, 0, st>>>(dm, a); \
 		break;
 		CASE(0)
 		CASE(1)
@@ -1929,6 +1932,7 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 	prof_begin(ctx, 2);
 	if (fast) {
 		int grid = grid_for(ctx, a.n_pairs, 8, 8);
+		const int grid_one = grid_for(ctx, a.n_pairs, 4, MC2_PAIR_CTAS_PER_SM * 4); // 128-thread CTAs, four waves
 		const bool one = a.eb == 1 && row_bytes == 1024 && ((a.a_bc && !a.ia) || (a.b_bc && !a.ib));
 		// The TMA-ring variant is kept as an opt-in experiment (MC2_USE_TMA=1): it feeds rows at 91 % of HBM peak when the
 		// per-row work is light, but the dot+EMD reduction is issue/latency bound, not feed bound, and its extra LDS +
@@ -1937,9 +1941,9 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 		if (one && use_tma) {
 			launch_tma_need(dm.need, ctx, dm, a);
 		} else if (one && a.loffA && a.loffB && (dm.need & NEED_EMD)) {
-			launch_fast_need<uint8_t, true, true>(dm.need, grid, ctx->stream, dm, a);
+			launch_fast_need<uint8_t, true, true>(dm.need, grid_one, ctx->stream, dm, a);
 		} else if (one) {
-			launch_fast_need<uint8_t, true>(dm.need, grid, ctx->stream, dm, a);
+			launch_fast_need<uint8_t, true>(dm.need, grid_one, ctx->stream, dm, a);
 		} else if (a.eb == 1) {
 			launch_fast_need<uint8_t, false>(dm.need, grid, ctx->stream, dm, a);
 		} else {
