@@ -919,19 +919,18 @@ __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigne
 		get(b0, fb0, 1);
 		get(a1, fa1, 2);
 		get(b1, fb1, 3);
-		// the last four rows are peeled off so that the loop body prefetches unconditionally (a predicated prefetch
-		// costs ~6 predicated register moves per pair)
+		// the prefetch is unconditional: the last trip re-reads rows 0..3 of the group (L2 hits, results unused) instead
+		// of predicating the loads (~6 predicated register moves per pair) or peeling a second copy of the body (the
+		// kernel is instruction-cache sensitive: stall_no_instruction grew from 0.4 to 1.0 per issue with the copy)
 #pragma unroll 1
-		for (int pi = 0; pi < 28; pi += 4) {
+		for (int pi = 0; pi < 32; pi += 4) {
 			reduce(a0, fa0, pi, b0, fb0, pi + 1);
-			get(a0, fa0, pi + 4);
-			get(b0, fb0, pi + 5);
+			get(a0, fa0, (pi + 4) & 31);
+			get(b0, fb0, (pi + 5) & 31);
 			reduce(a1, fa1, pi + 2, b1, fb1, pi + 3);
-			get(a1, fa1, pi + 6);
-			get(b1, fb1, pi + 7);
+			get(a1, fa1, (pi + 6) & 31);
+			get(b1, fb1, (pi + 7) & 31);
 		}
-		reduce(a0, fa0, 28, b0, fb0, 29);
-		reduce(a1, fa1, 30, b1, fb1, 31);
 		return;
 	}
 	int ia0 = next_idx();
@@ -1600,7 +1599,8 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_SWEEP_CTAS_PER_SM :
 				if (FAST && sizeof(T) == 1 && (NEED & NEED_MIN)) {
 					mn.smin = (sd.sum + sq.sum - mn.smin) >> 1;
 				}
-				bad = eval_pair<RedN, false>(dm, a.N, mn, sd, sq, nullptr, nullptr, score, d0, close, true);
+				bad = FAST ? eval_pair_fast(dm, a.N, mn, sd, sq, true, score, d0, close) // host routes !fast_epi models to FAST=false
+					   : eval_pair<RedN, false>(dm, a.N, mn, sd, sq, nullptr, nullptr, score, d0, close, true);
 			}
 			if (bad) {
 				atomicOr(a.err, bad & 1 ? 1 : 2);
@@ -1839,7 +1839,7 @@ __global__ void __launch_bounds__(128, 3) sweep_q2_kernel(const __grid_constant_
 				if (NEED & NEED_MIN) {
 					mn.smin = (sd.sum + sq.sum - mn.smin) >> 1;
 				}
-				int bad = eval_pair<RedN, false>(dm, a.N, mn, sd, sq, nullptr, nullptr, score, d0, close, true);
+				int bad = eval_pair_fast(dm, a.N, mn, sd, sq, true, score, d0, close);
 				if (bad) {
 					atomicOr(a.err, bad & 1 ? 1 : 2);
 				}
@@ -2052,7 +2052,7 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 	const u64 want_one = (groups + 3) / 4, cap_one = (u64)ctx->sm_count * MC2_SWEEP_CTAS_PER_SM * 4;
 	const int grid_one = (int)(want_one < cap_one ? want_one : cap_one);
 	const u64 row_bytes = a.N * (u64)a.eb;
-	const bool fast = a.eb <= 2 && row_bytes % 1024 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 26);
+	const bool fast = a.eb <= 2 && row_bytes % 1024 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 26) && dm.fast_epi;
 	prof_begin(ctx, 3);
 	// The two-queries-per-warp kernel (sweep_q2_kernel) executes 18 % fewer instructions per pair but runs at 12 warps / SM
 	// and is latency bound there: 38.9 ms vs 35.3 ms for the one-query kernel on the 20k x 20k triangle.  Opt-in only.
