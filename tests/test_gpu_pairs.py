@@ -120,6 +120,14 @@ def test_random_models_vs_oracle(built_lib, ctx, k, eb, flags):
     assert np.abs(g["score"] - o["score"]).max() <= 1e-8, what
     assert_flags_match(g["close"], o["close"], o["score"], tol=1e-8, what=what)
     assert not g["skipped"].any()
+    # the straight-line epilogue (taken when neither cache nor raw is requested; constant divisions through a reciprocal
+    # with an exact correction step, 64-bit Pearson) must give the very same bits as the interpretive one above
+    f = ctx.score_pairs(gm, hs, hs, ia, ib, want=("score", "dist", "close"))
+    assert np.array_equal(f["score"], g["score"]) and np.array_equal(f["dist"], g["dist"]), what
+    assert np.array_equal(f["close"], g["close"]), what
+    # lazy form (no score requested: the logistic is evaluated only where the decision needs it)
+    z = ctx.score_pairs(gm, hs, hs, ia, ib, want=("dist", "close"))
+    assert np.array_equal(z["close"], g["close"]) and np.array_equal(z["dist"], g["dist"]), what
 
 
 @pytest.mark.parametrize("eb", [1, 2])
