@@ -185,7 +185,19 @@ __device__ __forceinline__ u32 group_max(u32 v, u64 *sh)
 // segment loop over their valid positions.  Per-increment overflow tracking (the atomic's return value) is needed only
 // for multi-segment sequences with a narrow T: with one segment "some increment met a saturated bin" is exactly
 // "some final count exceeds max(T)", which the narrowing pass sees anyway.
-template <bool WARP, bool GLOBAL>
+// one k-mer occurrence; returns the bin's previous count.  P16: two 16-bit bins per 32-bit shared word (k = 8 in 128 KB);
+// the host only picks it when no sequence has 65 536 or more k-mers, so a half can never carry into its neighbour.
+template <bool P16>
+__device__ __forceinline__ u32 hist_add(u32 *hist, u32 idx)
+{
+	if (P16) {
+		const u32 sh = (idx & 1u) * 16u;
+		return (atomicAdd(&hist[idx >> 1], 1u << sh) >> sh) & 0xFFFFu;
+	}
+	return atomicAdd(&hist[idx], 1u);
+}
+
+template <bool WARP, bool GLOBAL, bool P16 = false>
 __device__ __forceinline__ void count_sequence(const CountArgs &a, u64 seq, u32 *hist, int gt, int gs, u64 tmax, u32 (&m1)[4],
 					       u64 &eff_len, int &novf, bool &ovf_from_bins)
 {
@@ -232,18 +244,18 @@ __device__ __forceinline__ void count_sequence(const CountArgs &a, u64 seq, u32 
 				if (track) {
 #pragma unroll
 					for (int t = 0; t < 16; t++) {
-						u32 old = atomicAdd(&hist[__funnelshift_l(nxt, cur, 2 * t) >> sh_r], 1u);
+						u32 old = hist_add<P16>(hist, __funnelshift_l(nxt, cur, 2 * t) >> sh_r);
 						ovf |= old >= ovf_at;
 					}
 				} else {
 #pragma unroll
 					for (int t = 0; t < 16; t++) {
-						atomicAdd(&hist[__funnelshift_l(nxt, cur, 2 * t) >> sh_r], 1u);
+						hist_add<P16>(hist, __funnelshift_l(nxt, cur, 2 * t) >> sh_r);
 					}
 				}
 			} else {
 				for (int t = t0; t <= t1; t++) {
-					u32 old = atomicAdd(&hist[__funnelshift_l(nxt, cur, 2 * t) >> sh_r], 1u);
+					u32 old = hist_add<P16>(hist, __funnelshift_l(nxt, cur, 2 * t) >> sh_r);
 					ovf |= old >= ovf_at;
 				}
 			}
@@ -293,8 +305,8 @@ __device__ __forceinline__ void emit4_u8(const uint4 &c, u32 init, uint8_t *dst,
 	mx = max(mx, max(max(c.x, c.y), max(c.z, c.w)));
 }
 
-template <typename T, bool WARP, bool GLOBAL>
-__global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ CountArgs a)
+template <typename T, bool WARP, bool GLOBAL, bool P16 = false>
+__global__ void __launch_bounds__(P16 ? 1024 : 256) count_kernel(const __grid_constant__ CountArgs a)
 {
 	extern __shared__ __align__(16) u32 sh_hist[];
 	__shared__ u64 sh_red[32];
@@ -311,7 +323,7 @@ __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ Coun
 		if (GLOBAL) {
 			hist = a.gscratch + (seq - a.seq_begin) * N; // zeroed by the host before the launch
 		} else {
-			for (u64 b = gt * 4; b < N; b += (u64)gs * 4) {
+			for (u64 b = gt * 4; b < (P16 ? N / 2 : N); b += (u64)gs * 4) {
 				*reinterpret_cast<uint4 *>(hist + b) = make_uint4(0, 0, 0, 0);
 			}
 			group_sync<WARP>();
@@ -320,7 +332,7 @@ __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ Coun
 		u64 eff_len;
 		int novf;
 		bool ovf_from_bins;
-		count_sequence<WARP, GLOBAL>(a, seq, hist, gt, gs, tmax, m1, eff_len, novf, ovf_from_bins);
+		count_sequence<WARP, GLOBAL, P16>(a, seq, hist, gt, gs, tmax, m1, eff_len, novf, ovf_from_bins);
 		if (GLOBAL) {
 			__threadfence();
 		}
@@ -345,10 +357,20 @@ __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ Coun
 			t2 = __reduce_add_sync(0xffffffffu, m1[2]);
 			t3 = __reduce_add_sync(0xffffffffu, m1[3]);
 		} else {
-			for (u64 b = (u64)gt * 4; b < N; b += (u64)gs * 4) {
-				uint4 c = GLOBAL ? __ldcg(reinterpret_cast<const uint4 *>(hist + b)) : *reinterpret_cast<const uint4 *>(hist + b);
-				u32 c4[4] = {c.x, c.y, c.z, c.w};
-				emit4<T>(c4, a.init, tmax, dst + b, sum, sumsq, mx);
+			if constexpr (P16) { // 4 shared words = 8 bins per thread and step
+				for (u64 b = (u64)gt * 8; b < N; b += (u64)gs * 8) {
+					const uint4 c = *reinterpret_cast<const uint4 *>(hist + (b >> 1));
+					u32 lo4[4] = {c.x & 0xFFFFu, c.x >> 16, c.y & 0xFFFFu, c.y >> 16};
+					u32 hi4[4] = {c.z & 0xFFFFu, c.z >> 16, c.w & 0xFFFFu, c.w >> 16};
+					emit4<T>(lo4, a.init, tmax, dst + b, sum, sumsq, mx);
+					emit4<T>(hi4, a.init, tmax, dst + b + 4, sum, sumsq, mx);
+				}
+			} else {
+				for (u64 b = (u64)gt * 4; b < N; b += (u64)gs * 4) {
+					uint4 c = GLOBAL ? __ldcg(reinterpret_cast<const uint4 *>(hist + b)) : *reinterpret_cast<const uint4 *>(hist + b);
+					u32 c4[4] = {c.x, c.y, c.z, c.w};
+					emit4<T>(c4, a.init, tmax, dst + b, sum, sumsq, mx);
+				}
 			}
 			sum = group_sum<WARP>(sum, sh_red);
 			sumsq = group_sum<WARP>(sumsq, sh_red);
@@ -456,6 +478,19 @@ static int launch_count_t(mc2_ctx *ctx, const mc2_seqs *s, CountArgs &a)
 			count_kernel<T, false, false><<<grid, 256, hist_bytes, ctx->stream>>>(a);
 			prof_end(ctx);
 		}
+		ctx->launches++;
+		MC2_CUDA(cudaGetLastError());
+		return MC2_OK;
+	}
+	if (N * 2 <= 200 * 1024 && s->max_len < 65536) {
+		// 16-bit packed shared histogram, one 1024-thread CTA per sequence (k = 8: 128 KB of the SM's 227 KB): no bin can
+		// reach 65 536 occurrences, so halves never carry; counting, narrowing and the side-band stay on chip
+		const size_t smem = (size_t)N * 2;
+		int grid = (int)(s->n < (u64)ctx->sm_count ? s->n : (u64)ctx->sm_count);
+		MC2_CUDA(cudaFuncSetAttribute(count_kernel<T, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		prof_begin(ctx, 1);
+		count_kernel<T, false, false, true><<<grid, 1024, smem, ctx->stream>>>(a);
+		prof_end(ctx);
 		ctx->launches++;
 		MC2_CUDA(cudaGetLastError());
 		return MC2_OK;

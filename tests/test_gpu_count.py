@@ -13,14 +13,14 @@ def _upload(capi, ctx, seqs):
     return ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
 
 
-def _check_against_oracle(got, seqs, k, eb):
+def _check_against_oracle(got, seqs, k, eb, sd_tol=1e-12):
     for i, s in enumerate(seqs):
         w = port.get_point(s, k, eb)
         assert np.array_equal(got["hist"][i], w["hist"]), (k, eb, i)
         assert np.array_equal(got["mers1"][i], w["mers1"]), (k, eb, i)
         assert got["mag"][i] == w["mag"] and got["len"][i] == w["len"], (k, eb, i)
         assert got["n_overflow"][i] == w["n_overflow"], (k, eb, i)
-        assert abs(got["stddev"][i] - w["stddev"]) <= 1e-12 * max(1.0, w["stddev"]), (k, eb, i)
+        assert abs(got["stddev"][i] - w["stddev"]) <= sd_tol * max(1.0, w["stddev"]), (k, eb, i)
 
 
 @pytest.mark.parametrize("k,eb", [(5, 1), (3, 2), (2, 4), (4, 8), (6, 1), (3, 1)])
@@ -185,3 +185,21 @@ def test_upload_into_reuses_the_set(built_lib, ctx):
     enc = built_lib.encode_batch(first, threads=2)
     ctx.upload_seqs_into(s, enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
     _check_against_oracle(ctx.count_kmers(s, 5, 1).download(), first, 5, 1)
+
+
+def test_k8_packed_shared_and_global_paths(built_lib, ctx):
+    """k = 8: sequences shorter than 65 536 bases count in 16-bit packed shared memory, longer ones in global counters;
+    both against the oracle, including a poly-A that saturates uint16 and the 65 535-base boundary."""
+    rng = np.random.default_rng(8)
+    def rnd(n):
+        return bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n))
+    short = [rnd(3000), b"A" * 65535, rnd(65535), b"ACGTTGCA" * 100 + b"N" * 40 + rnd(500) + b"N" * 12 + b"GT" * 300, rnd(7)]
+    long_ = short + [b"A" * 70000, rnd(66000)]
+    for seqs in (short, long_):
+        for eb in (1, 2, 4):
+            hs = ctx.count_kmers(_upload(built_lib, ctx, seqs), 8, eb)
+            # stddev: the device uses the exact integer identity; the reference's two-pass fp64 sum over 65 536 bins with one
+            # bin at 69 994 loses ~1e-12 relative to cancellation, so this extreme case is held to 1e-9
+            _check_against_oracle(hs.download(), seqs, 8, eb, sd_tol=1e-9)
+    hs, largest, eb = ctx.count_kmers_auto(_upload(built_lib, ctx, [s for s in long_ if len(s) >= 8]), 8)
+    assert largest == 69994 and eb == 4
