@@ -177,6 +177,7 @@ struct PairArgs {
 	int *err;      // device error word
 	u64 max_sum;   // bound on bin sums of both sets
 	const unsigned short *loffA, *loffB; // lane-boundary prefix sums (see mc2_hset::lane_off) or NULL
+	int group;     // pairs per warp group (1..32, power of two; 0 = 32): small batches of wide rows spread over more warps
 };
 
 int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a);

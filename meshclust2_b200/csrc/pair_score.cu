@@ -985,7 +985,10 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_PAIR_CTAS_PER_SM : 
 	const u32 slabs = (u32)(a.N * sizeof(T) / 1024);
 	const T *A = reinterpret_cast<const T *>(a.binsA);
 	const T *B = reinterpret_cast<const T *>(a.binsB);
-	const u64 groups = (a.n_pairs + 31) / 32;
+	// pairs per warp group: 32 (one epilogue lane each) unless the batch is too small to occupy the GPU that way; the
+	// fixed-row (ONE) form always takes 32 consecutive rows
+	const u32 G = (ONE || a.group <= 0) ? 32u : (u32)a.group;
+	const u64 groups = (a.n_pairs + G - 1) / G;
 	// the streamed side is the one that is not broadcast; the broadcast row stays resident
 	const bool a_hot = a.a_bc && !a.ia;
 	const bool b_hot = a.b_bc && !a.ib;
@@ -999,8 +1002,8 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_PAIR_CTAS_PER_SM : 
 		}
 	}
 	for (u64 g = warp_id; g < groups; g += warps_total) {
-		const u64 j = g * 32 + lane;
-		const bool valid = j < a.n_pairs;
+		const u64 j = g * G + lane;
+		const bool valid = (u32)lane < G && j < a.n_pairs;
 		u64 ra = 0, rb = 0;
 		bool go = valid && resolve_pair(a, j, ra, rb);
 		RedN mine;
@@ -1321,10 +1324,11 @@ __global__ void __launch_bounds__(256) pair_generic_kernel(const __grid_constant
 	const u64 warp_id = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	const T *A = reinterpret_cast<const T *>(a.binsA);
 	const T *B = reinterpret_cast<const T *>(a.binsB);
-	const u64 groups = (a.n_pairs + 31) / 32;
+	const u32 G = a.group <= 0 ? 32u : (u32)a.group;
+	const u64 groups = (a.n_pairs + G - 1) / G;
 	for (u64 g = warp_id; g < groups; g += warps_total) {
-		const u64 j = g * 32 + lane;
-		const bool valid = j < a.n_pairs;
+		const u64 j = g * G + lane;
+		const bool valid = (u32)lane < G && j < a.n_pairs;
 		u64 ra = 0, rb = 0;
 		bool go = valid && resolve_pair(a, j, ra, rb);
 		RedN mn;
@@ -1868,9 +1872,9 @@ __global__ void __launch_bounds__(128, 3) sweep_q2_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-static int grid_for(mc2_ctx *ctx, u64 n_pairs, int warps_per_cta, int ctas_per_sm)
+static int grid_for(mc2_ctx *ctx, u64 n_pairs, int warps_per_cta, int ctas_per_sm, int group = 32)
 {
-	u64 groups = (n_pairs + 31) / 32;
+	u64 groups = (n_pairs + group - 1) / group;
 	u64 want = (groups + warps_per_cta - 1) / warps_per_cta;
 	u64 cap = (u64)ctx->sm_count * ctas_per_sm;
 	u64 g = want < cap ? want : cap;
@@ -1922,16 +1926,28 @@ static void launch_tma_need(int need, mc2_ctx *ctx, const DevModel &dm, const Pa
 	}
 }
 
-int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
+int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a_in)
 {
-	if (a.n_pairs == 0) {
+	if (a_in.n_pairs == 0) {
 		return MC2_OK;
 	}
+	PairArgs a = a_in;
 	const u64 row_bytes = a.N * (u64)a.eb;
+	// a warp handles `group` pairs one after the other; when rows are wide (many 1 KiB slabs each) and the batch is small,
+	// 32 pairs per warp leaves most of the GPU idle (5 000 pairs of 128 KiB rows = 157 busy warps): shrink the group until
+	// there are about two warps' worth of groups per resident warp slot
+	{
+		const u64 slots = (u64)ctx->sm_count * 16;
+		int group = 32;
+		while (group > 1 && row_bytes > 1024 && (a.n_pairs + group - 1) / group < 2 * slots) {
+			group >>= 1;
+		}
+		a.group = group;
+	}
 	const bool fast = a.eb <= 2 && row_bytes % 1024 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 26);
 	prof_begin(ctx, 2);
 	if (fast) {
-		int grid = grid_for(ctx, a.n_pairs, 8, 8);
+		int grid = grid_for(ctx, a.n_pairs, 8, 8, a.group);
 		const int grid_one = grid_for(ctx, a.n_pairs, 4, MC2_PAIR_CTAS_PER_SM * 4); // 128-thread CTAs, four waves
 		const bool one = a.eb == 1 && row_bytes == 1024 && ((a.a_bc && !a.ia) || (a.b_bc && !a.ib));
 		// The TMA-ring variant is kept as an opt-in experiment (MC2_USE_TMA=1): it feeds rows at 91 % of HBM peak when the
@@ -1950,7 +1966,7 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a)
 			launch_fast_need<uint16_t, false>(dm.need, grid, ctx->stream, dm, a);
 		}
 	} else {
-		int grid = grid_for(ctx, a.n_pairs, 8, 8);
+		int grid = grid_for(ctx, a.n_pairs, 8, 8, a.group);
 		switch (a.eb) {
 		case 1: pair_generic_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(dm, a); break;
 		case 2: pair_generic_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(dm, a); break;
