@@ -132,6 +132,19 @@ int mc2_seqs_upload(mc2_ctx *ctx, const char *codes, const uint64_t *seq_off, ui
  * size never calls cudaMalloc / cudaFree.  On error the set is left empty (still to be freed by the caller). */
 int mc2_seqs_upload_into(mc2_ctx *ctx, mc2_seqs *dst, const char *codes, const uint64_t *seq_off, uint64_t n,
 			 const int32_t *segs, const uint64_t *seg_off);
+/* The input contract itself on the device: raw nucleotide text of n sequences (concatenated, no headers, no
+ * line breaks; seq_off[n+1] byte offsets) -> segments + 2-bit packed bases, following Chromosome::help
+ * (src/nonltr/Chromosome.cpp:130-154: upper-case; removeAmbiguous :263-291; mergeSegments :298-353; makeSegmentList
+ * :355-385) and ChromosomeOneDigit::encode with the DNA code map (src/nonltr/ChromosomeOneDigit.cpp:79-133,
+ * src/nonltr/ChromosomeOneDigitDna.cpp:48-68).  Same result as mc2_encode_dna_batch + mc2_seqs_upload, without the host
+ * pass.  MC2_ERR_INPUT for a byte that is not a nucleotide letter in a sequence that has at least one segment
+ * (InvalidInputException, ChromosomeOneDigit.cpp:86-95). */
+int mc2_seqs_from_text(mc2_ctx *ctx, const char *text, const uint64_t *seq_off, uint64_t n, mc2_seqs **out);
+/* segments of a sequence set back on the host (inclusive, sequence-relative pairs; seg_off[n+1]; lengths[n] = bases per
+ * sequence); any pointer may be NULL.  mc2_seqs_total_segments sizes segs_out. */
+int mc2_seqs_download_segments(mc2_ctx *ctx, const mc2_seqs *s, int32_t *segs_out, uint64_t *seg_off_out,
+			       uint64_t *lengths_out);
+uint64_t mc2_seqs_total_segments(const mc2_seqs *s);
 /* Page-lock / unlock a caller-owned host range (cudaHostRegister) so that uploads from it are asynchronous DMA copies.
  * Optional: every entry point also accepts pageable memory. */
 int mc2_host_register(void *ptr, uint64_t bytes);

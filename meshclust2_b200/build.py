@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("mc2_api.cu", "kmer_count.cu", "pair_score.cu", "mean_shift.cu", "host_encode.cpp")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("mc2_api.cu", "kmer_count.cu", "pair_score.cu", "mean_shift.cu", "text_ingest.cu", "host_encode.cpp")]
 HDR = [os.path.join(HERE, "csrc", "mc2_internal.cuh"), os.path.join(HERE, "..", "include", "meshclust2_b200.h")]
 OUT = os.path.join(HERE, "lib", "libmeshclust2_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

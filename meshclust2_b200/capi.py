@@ -34,7 +34,7 @@ PRED_FEAT_DIV = FEAT_JEFFEREY_DIV | FEAT_JENSEN_SHANNON
 SYMBOLS = [
     "mc2_abi_version", "mc2_last_error", "mc2_device_count", "mc2_ctx_create", "mc2_ctx_destroy", "mc2_ctx_sync",
     "mc2_ctx_device", "mc2_ctx_sm_count", "mc2_ctx_stream", "mc2_timer_start", "mc2_timer_stop",
-    "mc2_ctx_launch_count", "mc2_ctx_profile", "mc2_ctx_kernel_time", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_upload_into", "mc2_host_register", "mc2_host_unregister", "mc2_seqs_free", "mc2_seqs_count",
+    "mc2_ctx_launch_count", "mc2_ctx_profile", "mc2_ctx_kernel_time", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_upload_into", "mc2_seqs_from_text", "mc2_seqs_download_segments", "mc2_seqs_total_segments", "mc2_host_register", "mc2_host_unregister", "mc2_seqs_free", "mc2_seqs_count",
     "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_count_kmers_into", "mc2_count_kmers_auto", "mc2_hset_largest_count", "mc2_width_for_count", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_update_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
     "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
@@ -93,6 +93,7 @@ def lib():
         L.mc2_ctx_launch_count.restype = C.c_uint64
         L.mc2_seqs_count.restype = C.c_uint64
         L.mc2_seqs_total_bases.restype = C.c_uint64
+        L.mc2_seqs_total_segments.restype = C.c_uint64
         L.mc2_hset_count.restype = C.c_uint64
         L.mc2_hset_device_bins.restype = C.c_void_p
         L.mc2_hset_device_sideband.restype = C.c_void_p
@@ -179,6 +180,20 @@ class Context:
         out = C.c_void_p()
         _check(lib().mc2_seqs_upload(self.h, _p(codes), _p(seq_off), C.c_uint64(len(seq_off) - 1), _p(segs),
                                      _p(seg_off), C.byref(out)))
+        return Seqs(self, out)
+
+    def seqs_from_text(self, seqs):
+        """raw nucleotide text (list of bytes, or (blob, offsets)) -> Seqs, segmentation + encoding + packing on the device"""
+        if isinstance(seqs, tuple):
+            blob, off = seqs
+            off = _u64(off)
+        else:
+            off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+            off[1:] = np.cumsum([len(s) for s in seqs])
+            blob = b"".join(seqs)
+        buf = np.frombuffer(blob, dtype=np.uint8) if len(blob) else np.zeros(1, dtype=np.uint8)
+        out = C.c_void_p()
+        _check(lib().mc2_seqs_from_text(self.h, _p(buf), _p(off), C.c_uint64(len(off) - 1), C.byref(out)))
         return Seqs(self, out)
 
     def upload_seqs_into(self, dst, codes, seq_off, segs, seg_off):
@@ -374,6 +389,16 @@ class Seqs:
     @property
     def total_bases(self):
         return lib().mc2_seqs_total_bases(self.h)
+
+    def segments(self):
+        """(segs int32[total,2], seg_off uint64[n+1], lengths uint64[n]) as held on the device"""
+        n = len(self)
+        tot = lib().mc2_seqs_total_segments(self.h)
+        segs = np.zeros((tot, 2), dtype=np.int32)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        ln = np.zeros(n, dtype=np.uint64)
+        _check(lib().mc2_seqs_download_segments(self.ctx.h, self.h, _p(segs) if tot else None, _p(off), _p(ln) if n else None))
+        return segs, off, ln
 
     def free(self):
         if self.h:

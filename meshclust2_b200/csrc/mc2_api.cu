@@ -72,7 +72,7 @@ static void release(Buf &b)
 	b.cap = 0;
 }
 
-enum { B_IA = 0, B_IB, B_SCORE, B_DIST, B_CLOSE, B_SKIP, B_CACHE, B_RAW, B_MISC, B_OUTQ, B_OUTD, B_OUTS, B_STAGE_CODES, B_STAGE_BOFF, B_ROWMAX, B_ROWMAX_H, B_COUNT };
+enum { B_IA = 0, B_IB, B_SCORE, B_DIST, B_CLOSE, B_SKIP, B_CACHE, B_RAW, B_MISC, B_OUTQ, B_OUTD, B_OUTS, B_STAGE_CODES, B_STAGE_BOFF, B_ROWMAX, B_ROWMAX_H, B_SEGCOUNT, B_COUNT };
 
 struct ProfRec {
 	int kind;
@@ -670,6 +670,105 @@ int mc2_seqs_upload_into(mc2_ctx *ctx, mc2_seqs *dst, const char *codes, const u
 		dst->total_bases = dst->total_segs = dst->total_words = dst->max_len = 0;
 	}
 	return rc;
+}
+
+int mc2_seqs_from_text(mc2_ctx *ctx, const char *text, const uint64_t *seq_off, uint64_t n, mc2_seqs **out)
+{
+	MC2_REQUIRE(ctx && seq_off && out, "mc2_seqs_from_text: NULL argument");
+	MC2_REQUIRE(n == 0 || text != nullptr, "mc2_seqs_from_text: text is NULL");
+	*out = nullptr;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	const u64 total_bases = seq_off[n] - seq_off[0];
+	std::vector<u64> word_off(n + 1), len(n), boff(n + 1);
+	u64 w = 0, max_len = 0;
+	for (u64 i = 0; i < n; i++) {
+		MC2_REQUIRE(seq_off[i + 1] >= seq_off[i], "mc2_seqs_from_text: offsets must be non-decreasing");
+		const u64 L = seq_off[i + 1] - seq_off[i];
+		MC2_REQUIRE(L < (1ULL << 31), "mc2_seqs_from_text: a sequence is longer than 2^31-1 bases (reference positions are int)");
+		len[i] = L;
+		max_len = L > max_len ? L : max_len;
+		word_off[i] = w;
+		boff[i] = seq_off[i] - seq_off[0];
+		const u64 nw = (L + 15) / 16 + 1;
+		w += (nw + 3) & ~3ULL;
+	}
+	word_off[n] = w;
+	boff[n] = total_bases;
+	mc2_seqs *s = new (std::nothrow) mc2_seqs();
+	MC2_REQUIRE(s != nullptr, "out of host memory");
+	memset(s, 0, sizeof *s);
+	s->ctx = ctx;
+	s->n = n;
+	s->total_bases = total_bases;
+	s->max_len = max_len;
+	s->total_words = w;
+	s->min_seg_len = ~0ULL;
+	CtxExtra *x = extra(ctx);
+	cudaStream_t st = ctx->stream;
+	int rc = MC2_OK;
+	auto fail = [&](int code) {
+		mc2_seqs_free(s);
+		return code;
+	};
+	if ((rc = seq_reserve(s->packed, s->cap_packed, (w ? w : 1) * 4)) != MC2_OK) return fail(rc);
+	if ((rc = seq_reserve(s->word_off, s->cap_word_off, (n + 1) * 8)) != MC2_OK) return fail(rc);
+	if ((rc = seq_reserve(s->len, s->cap_len, (n ? n : 1) * 8)) != MC2_OK) return fail(rc);
+	if ((rc = seq_reserve(s->seg_off, s->cap_seg_off, (n + 1) * 8)) != MC2_OK) return fail(rc);
+	if ((rc = ensure(x->d[B_STAGE_CODES], total_bases ? total_bases : 1, false)) != MC2_OK) return fail(rc);
+	if ((rc = ensure(x->d[B_STAGE_BOFF], (n + 1) * 8, false)) != MC2_OK) return fail(rc);
+	if ((rc = ensure(x->d[B_SEGCOUNT], (n ? n : 1) * 4, false)) != MC2_OK) return fail(rc);
+	if ((rc = ensure(x->d[B_ROWMAX], 16, false)) != MC2_OK) return fail(rc);
+	if ((rc = ensure(x->d[B_ROWMAX_H], 16, true)) != MC2_OK) return fail(rc);
+	char *d_text = (char *)x->d[B_STAGE_CODES].p;
+	u64 *d_boff = (u64 *)x->d[B_STAGE_BOFF].p;
+	u32 *d_count = (u32 *)x->d[B_SEGCOUNT].p;
+	unsigned long long *d_word = (unsigned long long *)x->d[B_ROWMAX].p, *h_word = (unsigned long long *)x->d[B_ROWMAX_H].p;
+	cudaError_t e = cudaSuccess;
+#define MC2_TRY(call)                                                  \
+	if ((e = (call)) != cudaSuccess) {                             \
+		return fail(cuda_fail(e, #call, __FILE__, __LINE__)); \
+	}
+	MC2_TRY(cudaMemcpyAsync(s->word_off, word_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	if (n) MC2_TRY(cudaMemcpyAsync(s->len, len.data(), n * 8, cudaMemcpyHostToDevice, st));
+	if (total_bases) MC2_TRY(cudaMemcpyAsync(d_text, text + seq_off[0], total_bases, cudaMemcpyHostToDevice, st));
+	MC2_TRY(cudaMemcpyAsync(d_boff, boff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	// pass 1: segments per sequence -> exclusive scan -> total
+	if ((rc = launch_segment(ctx, false, d_text, d_boff, n, d_count, nullptr, nullptr, nullptr)) != MC2_OK) return fail(rc);
+	if ((rc = launch_seg_scan(ctx, d_count, n, s->seg_off)) != MC2_OK) return fail(rc);
+	MC2_TRY(cudaMemcpyAsync(h_word, s->seg_off + n, 8, cudaMemcpyDeviceToHost, st));
+	MC2_TRY(cudaStreamSynchronize(st));
+	s->total_segs = h_word[0];
+	if ((rc = seq_reserve(s->segs, s->cap_segs, (s->total_segs ? s->total_segs : 1) * 8)) != MC2_OK) return fail(rc);
+	// pass 2: write the segments, then letters -> 2-bit words
+	MC2_TRY(cudaMemsetAsync(d_word, 0xff, 8, st));
+	if ((rc = launch_segment(ctx, true, d_text, d_boff, n, d_count, s->seg_off, s->segs, d_word)) != MC2_OK) return fail(rc);
+	if ((rc = reset_err(ctx)) != MC2_OK) return fail(rc);
+	if ((rc = launch_pack_text(ctx, d_text, d_boff, s)) != MC2_OK) return fail(rc);
+	if ((rc = fetch_err(ctx)) != MC2_OK) return fail(rc);
+	MC2_TRY(cudaMemcpyAsync(h_word, d_word, 8, cudaMemcpyDeviceToHost, st));
+	MC2_TRY(cudaStreamSynchronize(st));
+#undef MC2_TRY
+	s->min_seg_len = h_word[0];
+	if ((rc = check_err(ctx)) != MC2_OK) return fail(rc);
+	*out = s;
+	return MC2_OK;
+}
+
+int mc2_seqs_download_segments(mc2_ctx *ctx, const mc2_seqs *s, int32_t *segs_out, uint64_t *seg_off_out, uint64_t *lengths_out)
+{
+	MC2_REQUIRE(ctx && s, "mc2_seqs_download_segments: NULL argument");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	if (segs_out && s->total_segs) MC2_CUDA(cudaMemcpyAsync(segs_out, s->segs, s->total_segs * 8, cudaMemcpyDeviceToHost, st));
+	if (seg_off_out) MC2_CUDA(cudaMemcpyAsync(seg_off_out, s->seg_off, (s->n + 1) * 8, cudaMemcpyDeviceToHost, st));
+	if (lengths_out && s->n) MC2_CUDA(cudaMemcpyAsync(lengths_out, s->len, s->n * 8, cudaMemcpyDeviceToHost, st));
+	MC2_CUDA(cudaStreamSynchronize(st));
+	return MC2_OK;
+}
+
+uint64_t mc2_seqs_total_segments(const mc2_seqs *s)
+{
+	return s ? s->total_segs : 0;
 }
 
 int mc2_host_register(void *ptr, uint64_t bytes)

@@ -181,6 +181,11 @@ struct PairArgs {
 };
 
 int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a);
+// text_ingest.cu
+int launch_segment(mc2_ctx *ctx, bool write, const char *d_text, const u64 *d_seq_off, u64 n, u32 *d_count, const u64 *d_seg_off,
+		   int *d_segs, unsigned long long *d_min_seg);
+int launch_seg_scan(mc2_ctx *ctx, const u32 *d_count, u64 n, u64 *d_seg_off);
+int launch_pack_text(mc2_ctx *ctx, const char *d_text, const u64 *d_seq_off, mc2_seqs *s);
 int launch_argmax(mc2_ctx *ctx, const double *dist, const uint8_t *skipped, const uint8_t *close, u64 n, int mode,
 		  void *d_out);
 int launch_count(mc2_ctx *ctx, const mc2_seqs *s, int k, int eb, mc2_hset *h, u64 init_value);

@@ -22,3 +22,17 @@ if not os.environ.get("K1_SHORT"):
     run("cfg4 long records", long_, 8, 2, iters=3)
     run("long records k=7", long_, 7, 2, iters=3)
     run("long records k=5", long_, 5, 1, iters=3)
+# input contract on the device (mc2_seqs_from_text) vs host encode + upload, cfg3 shape
+import time
+blob = b"".join(seqs)
+off = np.zeros(len(seqs) + 1, dtype=np.uint64); off[1:] = np.cumsum([len(s) for s in seqs])
+buf = capi.host_register(np.frombuffer(bytearray(blob), dtype=np.uint8))
+for name, fn in (("device ingest (text -> packed + segments)", lambda: ctx.seqs_from_text((buf, off)).free()),
+                 ("host encode (16 threads) + upload", lambda: (lambda e: ctx.upload_seqs(e["codes"], e["seq_off"], e["segs"], e["seg_off"]).free())(capi.encode_batch(seqs, threads=16)))):
+    fn(); fn()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        fn()
+    ctx.sync()
+    dt = (time.perf_counter() - t0) / 5
+    print("%-45s %.2f ms for %d sequences, %.1f Mbases -> %.2f Gbases/s" % (name, dt * 1e3, len(seqs), len(blob) / 1e6, len(blob) / dt / 1e9))
