@@ -79,8 +79,20 @@ struct ProfRec {
 	cudaEvent_t e0, e1;
 };
 
+struct Deferred {
+	void *dst;
+	const void *src;
+	size_t bytes;
+};
+
 struct CtxExtra {
 	Buf d[B_COUNT];
+	// page-locked staging for the small copies of the one-query entry points (index lists in, flags / results out): a
+	// copy from or to pageable memory costs ~10 us of driver staging each, the same copy through pinned memory ~2 us.
+	// Bump-allocated; reset at the synchronisation that ends the call.
+	char *stage = nullptr;
+	size_t stage_cap = 0, stage_used = 0;
+	std::vector<Deferred> deferred; // device -> pinned copies in flight, to be handed to the caller after the sync
 	std::vector<ProfRec> pending;
 	std::vector<cudaEvent_t> pool;
 	double prof_ms[MC2_KERNEL_KINDS] = {0};
@@ -135,6 +147,81 @@ static void prof_drain(mc2_ctx *ctx)
 		x->pool.push_back(r.e1);
 	}
 	x->pending.clear();
+}
+
+static CtxExtra *extra_of(mc2_ctx *ctx)
+{
+	return reinterpret_cast<CtxExtra *>(ctx->extra);
+}
+
+// end-of-call synchronisation: waits for the stream, delivers the staged device->host results, recycles the staging area
+static int sync_stage(mc2_ctx *ctx)
+{
+	CtxExtra *x = extra_of(ctx);
+	cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess) {
+		for (const Deferred &c : x->deferred) {
+			memcpy(c.dst, c.src, c.bytes);
+		}
+	}
+	x->deferred.clear();
+	x->stage_used = 0;
+	MC2_CUDA(e);
+	return MC2_OK;
+}
+
+static const size_t kStageBytes = 4u << 20, kStageMaxCopy = 1u << 20;
+
+static char *stage_take(mc2_ctx *ctx, size_t bytes)
+{
+	CtxExtra *x = extra_of(ctx);
+	if (bytes > kStageMaxCopy) {
+		return nullptr;
+	}
+	if (!x->stage) {
+		if (cudaHostAlloc((void **)&x->stage, kStageBytes, cudaHostAllocDefault) != cudaSuccess) {
+			cudaGetLastError();
+			x->stage = nullptr;
+			return nullptr;
+		}
+		x->stage_cap = kStageBytes;
+	}
+	const size_t need = (bytes + 63) & ~(size_t)63;
+	if (x->stage_used + need > x->stage_cap) {
+		if (sync_stage(ctx) != MC2_OK) { // everything staged so far has been consumed once the stream is idle
+			return nullptr;
+		}
+	}
+	char *p = x->stage + x->stage_used;
+	x->stage_used += need;
+	return p;
+}
+
+// host -> device on the context's stream; src may be released as soon as this returns when the copy was staged, so callers
+// that pass temporaries must still synchronise if it reports "not staged"
+static int h2d(mc2_ctx *ctx, void *dst, const void *src, size_t bytes, bool *staged = nullptr)
+{
+	char *p = stage_take(ctx, bytes);
+	if (staged) *staged = p != nullptr;
+	if (p) {
+		memcpy(p, src, bytes);
+		src = p;
+	}
+	MC2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	return MC2_OK;
+}
+
+// device -> host, delivered by the next sync_stage()
+static int d2h(mc2_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+	char *p = stage_take(ctx, bytes);
+	if (p) {
+		MC2_CUDA(cudaMemcpyAsync(p, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		extra_of(ctx)->deferred.push_back(Deferred{dst, p, bytes});
+		return MC2_OK;
+	}
+	MC2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	return MC2_OK;
 }
 
 static int model_need(const mc2_model_desc &d, DevModel &dm)
@@ -448,6 +535,9 @@ void mc2_ctx_destroy(mc2_ctx *ctx)
 		}
 		for (auto &b : x->d) {
 			release(b);
+		}
+		if (x->stage) {
+			cudaFreeHost(x->stage);
 		}
 		delete x;
 	}
@@ -1168,7 +1258,9 @@ int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t
 	CtxExtra *x = extra(ctx);
 	int rc = ensure(x->d[B_IA], idx.size() * 8, false);
 	if (rc != MC2_OK) return rc;
-	MC2_CUDA(cudaMemcpyAsync(x->d[B_IA].p, idx.data(), idx.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+	bool staged = false;
+	rc = h2d(ctx, x->d[B_IA].p, idx.data(), idx.size() * 8, &staged);
+	if (rc != MC2_OK) return rc;
 	u64 want = (n + 7) / 8, cap = (u64)ctx->sm_count * 8;
 	int grid = (int)(want < cap ? want : cap);
 	assign_rows_kernel<<<grid, 256, 0, ctx->stream>>>((char *)dst->bins, dst->mag, dst->sum, dst->sumsq, dst->len,
@@ -1176,7 +1268,9 @@ int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t
 							   (const u64 *)x->d[B_IA].p, mag ? 1 : 0, len ? 1 : 0);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
-	MC2_CUDA(cudaStreamSynchronize(ctx->stream)); // idx is a host temporary
+	if (!staged) {
+		MC2_CUDA(cudaStreamSynchronize(ctx->stream)); // idx is a host temporary; a staged copy is stream-ordered instead
+	}
 	if (src->max_sum > dst->max_sum) {
 		dst->max_sum = src->max_sum;
 	}
@@ -1361,7 +1455,8 @@ static int fill_pair_args(mc2_ctx *ctx, const mc2_pairs *p, PairArgs &a, CtxExtr
 		}
 		int rc = ensure(x->d[B_IA], m * 8, false);
 		if (rc != MC2_OK) return rc;
-		MC2_CUDA(cudaMemcpyAsync(x->d[B_IA].p, p->ia, m * 8, cudaMemcpyHostToDevice, ctx->stream));
+		rc = h2d(ctx, x->d[B_IA].p, p->ia, m * 8);
+		if (rc != MC2_OK) return rc;
 		a.ia = (const u64 *)x->d[B_IA].p;
 	} else {
 		MC2_REQUIRE(m == 0 || (p->a_broadcast ? p->a_begin < A->n : (p->a_begin <= A->n && m <= A->n - p->a_begin)), "pairs: a range out of bounds");
@@ -1372,7 +1467,8 @@ static int fill_pair_args(mc2_ctx *ctx, const mc2_pairs *p, PairArgs &a, CtxExtr
 		}
 		int rc = ensure(x->d[B_IB], m * 8, false);
 		if (rc != MC2_OK) return rc;
-		MC2_CUDA(cudaMemcpyAsync(x->d[B_IB].p, p->ib, m * 8, cudaMemcpyHostToDevice, ctx->stream));
+		rc = h2d(ctx, x->d[B_IB].p, p->ib, m * 8);
+		if (rc != MC2_OK) return rc;
 		a.ib = (const u64 *)x->d[B_IB].p;
 	} else {
 		MC2_REQUIRE(m == 0 || (p->b_broadcast ? p->b_begin < B->n : (p->b_begin <= B->n && m <= B->n - p->b_begin)), "pairs: b range out of bounds");
@@ -1405,14 +1501,13 @@ int mc2_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs
 	if (rc == MC2_OK) rc = launch_pair_score(ctx, model->dm, a);
 	if (rc == MC2_OK) rc = fetch_err(ctx);
 	if (rc != MC2_OK) return rc;
-	cudaStream_t st = ctx->stream;
-	if (score) MC2_CUDA(cudaMemcpyAsync(score, a.score, m * 8, cudaMemcpyDeviceToHost, st));
-	if (dist) MC2_CUDA(cudaMemcpyAsync(dist, a.dist, m * 8, cudaMemcpyDeviceToHost, st));
-	if (close) MC2_CUDA(cudaMemcpyAsync(close, a.close, m, cudaMemcpyDeviceToHost, st));
-	if (skipped) MC2_CUDA(cudaMemcpyAsync(skipped, a.skipped, m, cudaMemcpyDeviceToHost, st));
-	if (cache) MC2_CUDA(cudaMemcpyAsync(cache, a.cache, m * S * 8, cudaMemcpyDeviceToHost, st));
-	if (raw) MC2_CUDA(cudaMemcpyAsync(raw, a.raw, m * S * 8, cudaMemcpyDeviceToHost, st));
-	MC2_CUDA(cudaStreamSynchronize(st));
+	if (score && (rc = d2h(ctx, score, a.score, m * 8)) != MC2_OK) return rc;
+	if (dist && (rc = d2h(ctx, dist, a.dist, m * 8)) != MC2_OK) return rc;
+	if (close && (rc = d2h(ctx, close, a.close, m)) != MC2_OK) return rc;
+	if (skipped && (rc = d2h(ctx, skipped, a.skipped, m)) != MC2_OK) return rc;
+	if (cache && (rc = d2h(ctx, cache, a.cache, m * S * 8)) != MC2_OK) return rc;
+	if (raw && (rc = d2h(ctx, raw, a.raw, m * S * 8)) != MC2_OK) return rc;
+	if ((rc = sync_stage(ctx)) != MC2_OK) return rc;
 	return check_err(ctx);
 }
 
@@ -1445,9 +1540,10 @@ static int score_and_reduce(mc2_ctx *ctx, const mc2_model *model, const mc2_pair
 	if (rc != MC2_OK) return rc;
 	cudaStream_t st = ctx->stream;
 	if (reduce_mode >= 0) MC2_CUDA(cudaMemcpyAsync(ctx->h_slot, ctx->d_slot, sizeof(ArgOutHost), cudaMemcpyDeviceToHost, st));
-	if (close_out) MC2_CUDA(cudaMemcpyAsync(close_out, a.close, m, cudaMemcpyDeviceToHost, st));
-	if (skipped_out) MC2_CUDA(cudaMemcpyAsync(skipped_out, a.skipped, m, cudaMemcpyDeviceToHost, st));
-	MC2_CUDA(cudaStreamSynchronize(st));
+	if (close_out && (rc = d2h(ctx, close_out, a.close, m)) != MC2_OK) return rc;
+	if (skipped_out && (rc = d2h(ctx, skipped_out, a.skipped, m)) != MC2_OK) return rc;
+	rc = sync_stage(ctx);
+	if (rc != MC2_OK) return rc;
 	if (reduce_mode >= 0) *red = *reinterpret_cast<ArgOutHost *>(ctx->h_slot);
 	return check_err(ctx);
 }
@@ -1642,15 +1738,15 @@ static int mean_closest_impl(mc2_ctx *ctx, const mc2_hset *set, const uint64_t *
 	rc = ensure(x->d[B_CACHE], N * 8, false); if (rc) return rc;   // mean
 	rc = ensure(x->d[B_DIST], n * 8, false); if (rc) return rc;    // distances
 	cudaStream_t st = ctx->stream;
-	MC2_CUDA(cudaMemcpyAsync(x->d[B_IA].p, members, n * 8, cudaMemcpyHostToDevice, st));
-	if (mean_in) MC2_CUDA(cudaMemcpyAsync(x->d[B_CACHE].p, mean_in, N * 8, cudaMemcpyHostToDevice, st));
+	if ((rc = h2d(ctx, x->d[B_IA].p, members, n * 8)) != MC2_OK) return rc;
+	if (mean_in && (rc = h2d(ctx, x->d[B_CACHE].p, mean_in, N * 8)) != MC2_OK) return rc;
 	rc = launch_mean_closest(ctx, set, (const u64 *)x->d[B_IA].p, n, (u64 *)x->d[B_SCORE].p, (double *)x->d[B_CACHE].p,
 				 (double *)x->d[B_DIST].p, ctx->d_slot, mean_in != nullptr);
 	if (rc != MC2_OK) return rc;
 	MC2_CUDA(cudaMemcpyAsync(ctx->h_slot, ctx->d_slot, 16, cudaMemcpyDeviceToHost, st));
-	if (mean_out) MC2_CUDA(cudaMemcpyAsync(mean_out, x->d[B_CACHE].p, N * 8, cudaMemcpyDeviceToHost, st));
-	if (dist_out) MC2_CUDA(cudaMemcpyAsync(dist_out, x->d[B_DIST].p, n * 8, cudaMemcpyDeviceToHost, st));
-	MC2_CUDA(cudaStreamSynchronize(st));
+	if (mean_out && (rc = d2h(ctx, mean_out, x->d[B_CACHE].p, N * 8)) != MC2_OK) return rc;
+	if (dist_out && (rc = d2h(ctx, dist_out, x->d[B_DIST].p, n * 8)) != MC2_OK) return rc;
+	if ((rc = sync_stage(ctx)) != MC2_OK) return rc;
 	*best = ((long long *)ctx->h_slot)[0];
 	*best_dist = ((double *)ctx->h_slot)[1];
 	return MC2_OK;
