@@ -1512,6 +1512,9 @@ struct SweepArgs {
 	u64 *counters; // [0] survivors, [1] scored pairs
 };
 
+#ifndef MC2_SWEEP_SPAN
+#define MC2_SWEEP_SPAN 4 // 32-column blocks per (query row) group in the 1 KiB-row sweep
+#endif
 #ifndef MC2_SWEEP_CTAS_PER_SM
 #define MC2_SWEEP_CTAS_PER_SM 5 // resident 128-thread CTAs of the 1 KiB-row sweep: 96 registers; measured 4: 922 ms, 5: 898 ms, 6: slower (spills)
 #endif
@@ -1526,13 +1529,24 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_SWEEP_CTAS_PER_SM :
 	const u32 slabs = (u32)(a.N * sizeof(T) / 1024);
 	const T *Dm = reinterpret_cast<const T *>(a.binsA); // database = first argument of close(pts[i], query)
 	const T *Qm = reinterpret_cast<const T *>(a.binsB);
+	// a group = one query row x SPAN consecutive 32-column blocks: the 1 KiB form keeps the query row and its 32 prefix
+	// sums in registers across the span, so their set-up (one row load + 32 IDP) is paid once per 128 pairs
+	constexpr u32 SPAN = ONE ? MC2_SWEEP_SPAN : 1;
 	const u64 cblocks = (g.d1 - g.d0 + 31) / 32;
-	const u64 groups = (g.q1 - g.q0) * cblocks; // host guarantees groups < 2^32 per launch
-	const u32 cblocks32 = (u32)cblocks;
+	const u32 cspans32 = (u32)((cblocks + SPAN - 1) / SPAN);
+	const u64 groups = (g.q1 - g.q0) * (u64)cspans32; // host guarantees groups < 2^32 per launch
 	for (u64 grp = warp_id; grp < groups; grp += warps_total) {
-		const u32 gr = (u32)grp / cblocks32, gc = (u32)grp - gr * cblocks32;
+		const u32 gr = (u32)grp / cspans32, gs = (u32)grp - gr * cspans32;
 		const u64 r = g.q0 + gr;
-		const u64 cfirst = g.d0 + (u64)gc * 32;
+		FixedQ fq;
+		bool fq_ready = false;
+#pragma unroll 1
+		for (u32 h = 0; h < SPAN; h++) {
+		const u64 gc = (u64)gs * SPAN + h;
+		if (gc >= cblocks) {
+			break;
+		}
+		const u64 cfirst = g.d0 + gc * 32;
 		if (g.upper_only && cfirst + 31 <= r) {
 			continue; // whole block at or below the diagonal
 		}
@@ -1554,10 +1568,12 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_SWEEP_CTAS_PER_SM :
 		if constexpr (FAST) {
 			if constexpr (ONE) { // slabs == 1 && T == u8, picked by the host
 				// the query row r and its prefix sums sit in registers for the whole 32-candidate group
-				FixedQ fq;
-				fixed_q_setup<NEED>(fq, Qm + r * a.N, lane);
-				if (LOFF) {
-					fq.qoff = a.loffB[r * 32 + lane];
+				if (!fq_ready) {
+					fixed_q_setup<NEED>(fq, Qm + r * a.N, lane);
+					if (LOFF) {
+						fq.qoff = a.loffB[r * 32 + lane];
+					}
+					fq_ready = true;
 				}
 				u32 m0 = 0, m1 = 0, m2 = 0;
 				// RING = true: at the bench size (100 MB set, ~90 % L2 hits) the prefetch ring beats the ringless / 5-CTA
@@ -1629,6 +1645,7 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_SWEEP_CTAS_PER_SM :
 				g.out_score[idx] = score;
 			}
 		}
+		} // span
 	}
 }
 
@@ -2065,7 +2082,8 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 	u64 want = (groups + 7) / 8, cap = (u64)ctx->sm_count * 8;
 	int grid = (int)(want < cap ? want : cap);
 	// 1 KiB rows: 128-thread CTAs, four waves of the resident set (groups differ in cost: diagonal, length window)
-	const u64 want_one = (groups + 3) / 4, cap_one = (u64)ctx->sm_count * MC2_SWEEP_CTAS_PER_SM * 4;
+	const u64 groups_one = (q1 - q0) * ((((d1 - d0 + 31) / 32) + MC2_SWEEP_SPAN - 1) / MC2_SWEEP_SPAN);
+	const u64 want_one = (groups_one + 3) / 4, cap_one = (u64)ctx->sm_count * MC2_SWEEP_CTAS_PER_SM * 4;
 	const int grid_one = (int)(want_one < cap_one ? want_one : cap_one);
 	const u64 row_bytes = a.N * (u64)a.eb;
 	const bool fast = a.eb <= 2 && row_bytes % 1024 == 0 && !(dm.need & NEED_LOG) && a.max_sum < (1ULL << 26) && dm.fast_epi;
