@@ -1,7 +1,7 @@
 """End-to-end meshclust2 on the BASELINE configs[0] / configs[1] shapes: the unmodified reference binary (oracle/_ref/
 meshclust2) next to the same binary with src/cluster/Trainer.cpp swapped for integration/Trainer_b200.cpp (GPU through the C
 ABI).  Prints wall-clock, the reference's own stage timestamps and whether the two CLSTR outputs hold the same clusters.
-usage: python tools/e2e_cluster.py [cfg1|cfg2] [threads]"""
+usage: python tests/e2e_cluster.py [cfg1|cfg2] [threads]"""
 import os, re, subprocess, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

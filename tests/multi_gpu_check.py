@@ -3,8 +3,8 @@
 (meshclust2_b200/dist.py) against the CPU oracle, one process per GPU over NCCL.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      tools/multi_gpu_check.py [--n-seqs 3000]
-  python tools/multi_gpu_check.py            # world size 1, same code path without a process group
+      tests/multi_gpu_check.py [--n-seqs 3000]
+  python tests/multi_gpu_check.py            # world size 1, same code path without a process group
 
 Every rank checks its own shard of the result; exit status 0 only if all ranks agree with the oracle.
 (The oracle is test infrastructure: this script is a test, not a product path.)"""

@@ -1,5 +1,5 @@
 """GPU: the rank-sharded forms (meshclust2_b200/dist.py) through the C ABI against the oracle.  World size 1 always; world
-size 2 over NCCL when the box has two GPUs (tools/multi_gpu_check.py under torch.distributed.run)."""
+size 2 over NCCL when the box has two GPUs (tests/multi_gpu_check.py under torch.distributed.run)."""
 import os
 import socket
 import subprocess
@@ -17,7 +17,7 @@ def _run(cmd):
 
 
 def test_sharded_forms_world1(built_lib):
-    _run([sys.executable, "tools/multi_gpu_check.py", "--n-seqs", "1500"])
+    _run([sys.executable, "tests/multi_gpu_check.py", "--n-seqs", "1500"])
 
 
 def test_sharded_forms_world2_nccl(built_lib):
@@ -28,4 +28,4 @@ def test_sharded_forms_world2_nccl(built_lib):
     port_no = s.getsockname()[1]
     s.close()
     _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-          "--master-port", str(port_no), "tools/multi_gpu_check.py", "--n-seqs", "1501"])
+          "--master-port", str(port_no), "tests/multi_gpu_check.py", "--n-seqs", "1501"])
