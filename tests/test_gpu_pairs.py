@@ -342,6 +342,37 @@ def test_full_size_properties_100k_one_vs_many(built_lib, ctx):
     assert best[3][7] == 1            # the query itself is in the candidate range and is close to itself
 
 
+def test_full_size_sweep_rows_vs_oracle(built_lib, ctx):
+    """BASELINE configs[2] size (100 k x 1 kb, k=5, u8, real K1 histograms): scattered query rows of the upper-triangular sweep
+    against the oracle (survivors, scores and the number of in-window pairs), and the row blocks add up to the whole sweep."""
+    from meshclust2_b200 import synth
+    n = 100000
+    seqs, _, k, eb = synth.make_config_range("cfg3", 0, n)
+    hs = ctx.count_kmers(ctx.seqs_from_text(seqs), k, eb)
+    got = hs.download()
+    H, mag, ln = got["hist"], got["mag"], got["len"]
+    m = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    gm = ctx.model_from_file(weights_path("weights_cfg1_id90"))
+    for q in (0, 1, 31, 4095, 50000, 50001, 99870, 99998):
+        r = ctx.all_pairs(gm, hs, hs, 0.9, q_range=(q, q + 1), upper_only=True, max_out=1 << 20)
+        cand = np.arange(q + 1, n)
+        lo, hi = int(float(ln[q]) * 0.9), int(float(ln[q]) / 0.9)
+        cand = cand[(ln[cand] >= lo) & (ln[cand] <= hi)]
+        o = port.score_pairs(m, H, mag, ln, cand, np.full(len(cand), q), threads=8, want_cache=False)
+        assert r["n_scored"] == len(cand), q
+        want = cand[o["close"].astype(bool)]
+        order = np.argsort(r["d"])
+        assert np.array_equal(r["d"][order], want), q
+        assert (r["q"] == q).all()
+        assert np.abs(r["score"][order] - o["score"][o["close"].astype(bool)]).max(initial=0) <= 1e-9, q
+    # additivity over row blocks (what the multi-GPU split relies on)
+    whole = ctx.all_pairs(gm, hs, hs, 0.9, q_range=(99000, n), upper_only=True, max_out=1 << 22)
+    parts = [ctx.all_pairs(gm, hs, hs, 0.9, q_range=(a, b), upper_only=True, max_out=1 << 22) for a, b in ((99000, 99333), (99333, 99334), (99334, n))]
+    assert whole["n_scored"] == sum(p["n_scored"] for p in parts) and whole["n_out"] == sum(p["n_out"] for p in parts)
+    key = lambda r: sorted(zip(r["q"].tolist(), r["d"].tolist(), r["score"].tolist()))
+    assert key(whole) == sorted(sum((key(p) for p in parts), []))
+
+
 def test_cfg4_shape_single_file_k8_u16(built_lib, ctx):
     """BASELINE configs[3] shape: records of 5 contigs x 10 kb joined by 50 N (--single-file), k=8, uint16 histograms
     (65,536 bins = 128 KiB rows): K1 through the multi-segment path, K2 through the multi-slab fast path, both vs the oracle."""
