@@ -861,10 +861,13 @@ __device__ __forceinline__ void ld_u16_if(int &v, const unsigned short *p, int p
 // stream the rows of up to 32 pairs (bit mask `active`, row index of pair i held by lane i in `rs`, or consecutive rows
 // first_row + i when contig) against the fixed row, two rows per step.  Two buffer pairs alternate by loop unrolling
 // (no register copies): while one pair of rows is reduced the next pair is in flight.
-template <int NEED, bool LOFF, bool RING = true>
+// PF > 0 (HBM-streaming callers): while rows pi..pi+3 are reduced, the rows PF ahead are pulled into L2 with
+// prefetch.global.L2 — of this group, or past its end of the group this warp takes next (pf_next) — so the register ring's
+// loads find them on chip; one instruction per row and lane, no registers held.
+template <int NEED, bool LOFF, bool RING = true, int PF = 0>
 __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigned short *loff, u64 row_bytes, unsigned active,
 					   u64 rs, bool contig, u64 first_row, const FixedQ &f, int lane, u32 &my_min, u32 &my_dot,
-					   u32 &my_emd)
+					   u32 &my_emd, const unsigned char *pf_next = nullptr)
 {
 	auto next_idx = [&]() -> int {
 		int pi = active ? __ffs(active) - 1 : -1;
@@ -924,6 +927,14 @@ __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigne
 		// kernel is instruction-cache sensitive: stall_no_instruction grew from 0.4 to 1.0 per issue with the copy)
 #pragma unroll 1
 		for (int pi = 0; pi < 32; pi += 4) {
+			if (PF > 0) {
+				const int t = pi + PF;
+				const unsigned char *p = t < 32 ? rp + (size_t)t * row_bytes : pf_next + (size_t)(t - 32) * row_bytes;
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)u * row_bytes));
+				}
+			}
 			reduce(a0, fa0, pi, b0, fb0, pi + 1);
 			get(a0, fa0, (pi + 4) & 31);
 			get(b0, fb0, (pi + 5) & 31);
@@ -973,6 +984,9 @@ __device__ __forceinline__ void scan_group(const unsigned char *S, const unsigne
 	}
 }
 
+#ifndef MC2_PAIR_PREFETCH_ROWS
+#define MC2_PAIR_PREFETCH_ROWS 8 // one-vs-many: L2 prefetch distance in rows (0 = off)
+#endif
 #ifndef MC2_PAIR_CTAS_PER_SM
 #define MC2_PAIR_CTAS_PER_SM 4 // resident 128-thread CTAs of the one-vs-many (1 KiB rows) form
 #endif
@@ -1015,8 +1029,11 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_PAIR_CTAS_PER_SM : 
 			const bool contig = a_hot ? (a.ib == nullptr) : (a.ia == nullptr);
 			const u64 first_row = (a_hot ? a.b_begin : a.a_begin) + g * 32;
 			u32 m0 = 0, m1 = 0, m2 = 0;
-			scan_group<NEED, LOFF>(S, a_hot ? a.loffB : a.loffA, 1024, active, a_hot ? rb : ra, contig, first_row, fq, lane, m0, m1,
-					       m2);
+			// rows to prefetch past this group's end: the group this warp takes next (or this one again at the very end)
+			const u64 g_next = g + warps_total < groups ? g + warps_total : g;
+			const unsigned char *pf_next = S + ((a_hot ? a.b_begin : a.a_begin) + g_next * 32) * 1024 + lane * 32;
+			scan_group<NEED, LOFF, true, MC2_PAIR_PREFETCH_ROWS>(S, a_hot ? a.loffB : a.loffA, 1024, active, a_hot ? rb : ra, contig,
+									      first_row, fq, lane, m0, m1, m2, pf_next);
 			mine.smin = m0;
 			mine.dot = m1;
 			mine.emd = m2;
