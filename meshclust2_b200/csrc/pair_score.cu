@@ -649,6 +649,9 @@ __device__ __forceinline__ void slab_reduce(const Row8 &p, const Row8 &q, int qs
 	}
 }
 
+#ifndef MC2_SLAB_PREFETCH
+#define MC2_SLAB_PREFETCH 8 // multi-slab rows: L2 prefetch distance in 1 KiB slabs
+#endif
 // whole row pair, any number of slabs; q rows come through L1 (hot when q is the broadcast side)
 template <typename T, int NEED>
 __device__ __forceinline__ RedN reduce_rows_fast(const T *__restrict__ P, const T *__restrict__ Q, u32 slabs, int lane,
@@ -666,6 +669,12 @@ __device__ __forceinline__ RedN reduce_rows_fast(const T *__restrict__ P, const 
 		if (s + 1 < slabs) { // next slab in flight during this slab's ALU work
 			pn = ld_row_stream(pp + (size_t)(s + 1) * 1024);
 			qn = q_hot ? ld_row_keep(qq + (size_t)(s + 1) * 1024) : ld_row_stream(qq + (size_t)(s + 1) * 1024);
+		}
+		if (s + MC2_SLAB_PREFETCH < slabs) { // and the slabs further ahead on their way from HBM into L2
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (size_t)(s + MC2_SLAB_PREFETCH) * 1024));
+			if (!q_hot) {
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(qq + (size_t)(s + MC2_SLAB_PREFETCH) * 1024));
+			}
 		}
 		u32 a_min = 0, lo = 0, hi = 0, e = 0;
 		slab_reduce<T, NEED>(pv, qv, (NEED & NEED_EMD) ? lane_sum<T>(qv) : 0, carry, a_min, lo, hi, e);
@@ -1667,6 +1676,109 @@ __global__ void __launch_bounds__(ONE ? 128 : 256, ONE ? MC2_SWEEP_CTAS_PER_SM :
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wide rows (several 1 KiB slabs, e.g. k = 8 uint16 = 128 KiB): the sweep with the QUERY ROW IN SHARED MEMORY.
+// In sweep_kernel every (query, candidate) pair pulls both rows through L2 -> SM: 2 x 128 KiB per pair although only the
+// candidate row comes from HBM.  Here a CTA owns one query row, copies it once into its shared memory (128 KB of the SM's
+// 227 KB) and its 16 warps stream candidate rows against it: L2 -> SM traffic halves, HBM traffic is unchanged (one
+// candidate row per pair), slabs further ahead are prefetched into L2.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NEED>
+__device__ __forceinline__ RedN reduce_rows_smemq(const T *__restrict__ P, const unsigned char *qs, u32 slabs, int lane)
+{
+	u64 t_min = 0, t_dot = 0, t_emd = 0;
+	int carry = 0;
+	const char *pp = reinterpret_cast<const char *>(P) + lane * 32;
+	const unsigned char *qq = qs + lane * 32;
+	Row8 pv = ld_row_stream(pp);
+#pragma unroll 1
+	for (u32 s = 0; s < slabs; s++) {
+		Row8 pn = pv;
+		if (s + 1 < slabs) {
+			pn = ld_row_stream(pp + (size_t)(s + 1) * 1024);
+		}
+		if (s + MC2_SLAB_PREFETCH < slabs) {
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (size_t)(s + MC2_SLAB_PREFETCH) * 1024));
+		}
+		Row8 qv;
+		const uint4 q0 = *reinterpret_cast<const uint4 *>(qq + (size_t)s * 1024);
+		const uint4 q1 = *reinterpret_cast<const uint4 *>(qq + (size_t)s * 1024 + 16);
+		qv.w[0] = q0.x; qv.w[1] = q0.y; qv.w[2] = q0.z; qv.w[3] = q0.w;
+		qv.w[4] = q1.x; qv.w[5] = q1.y; qv.w[6] = q1.z; qv.w[7] = q1.w;
+		u32 a_min = 0, lo = 0, hi = 0, e = 0;
+		slab_reduce<T, NEED>(pv, qv, (NEED & NEED_EMD) ? lane_sum<T>(qv) : 0, carry, a_min, lo, hi, e);
+		t_min += a_min;
+		t_dot += (u64)lo + ((u64)hi << 8);
+		t_emd += e;
+		pv = pn;
+	}
+	RedN r;
+	r.smin = (NEED & NEED_MIN) ? warp_sum_u64(t_min) : 0;
+	r.dot = (NEED & NEED_DOT) ? warp_sum_u64(t_dot) : 0;
+	r.emd = (NEED & NEED_EMD) ? warp_sum_u64(t_emd) : 0;
+	r.jeff = r.js = 0;
+	return r;
+}
+
+template <typename T, int NEED>
+__global__ void __launch_bounds__(512, 1) sweep_wide_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ PairArgs a,
+							    const __grid_constant__ SweepArgs g)
+{
+	extern __shared__ __align__(16) unsigned char qs[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const u64 row_bytes = a.N * sizeof(T);
+	const u32 slabs = (u32)(row_bytes / 1024);
+	const T *Dm = reinterpret_cast<const T *>(a.binsA); // database = first argument of close(pts[i], query)
+	const T *Qm = reinterpret_cast<const T *>(a.binsB);
+	u64 scored = 0;
+	for (u64 r = g.q0 + blockIdx.x; r < g.q1; r += gridDim.x) {
+		__syncthreads(); // the previous query row is no longer being read
+		const uint4 *src = reinterpret_cast<const uint4 *>(Qm + r * a.N);
+		for (u32 i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) {
+			reinterpret_cast<uint4 *>(qs)[i] = __ldg(src + i);
+		}
+		__syncthreads();
+		const Side sq = load_side(a.sbB, r);
+		// FC_Runner.cpp:435-444: size_t truncation, window on the database length
+		const u64 begin_length = (u64)((double)sq.len * g.cutoff), end_length = (u64)((double)sq.len / g.cutoff);
+		u64 c0 = g.d0;
+		if (g.upper_only && r + 1 > c0) {
+			c0 = r + 1;
+		}
+		for (u64 c = c0 + warp; c < g.d1; c += nwarps) {
+			const u64 lc = a.sbA.len[c];
+			if (lc < begin_length || lc > end_length) {
+				continue; // warp-uniform
+			}
+			scored++;
+			RedN mn = reduce_rows_smemq<T, NEED>(Dm + c * a.N, qs, slabs, lane);
+			if (lane == 0) {
+				const Side sd = load_side(a.sbA, c);
+				if (sizeof(T) == 1 && (NEED & NEED_MIN)) {
+					mn.smin = (sd.sum + sq.sum - mn.smin) >> 1;
+				}
+				double score = 0, d0v;
+				int close = 0;
+				const int bad = eval_pair_fast(dm, a.N, mn, sd, sq, true, score, d0v, close);
+				if (bad) {
+					atomicOr(a.err, bad & 1 ? 1 : 2);
+				}
+				if (close) {
+					const u64 idx = atomicAdd(g.counters, 1ULL);
+					if (idx < g.max_out) {
+						g.out_q[idx] = r;
+						g.out_d[idx] = c;
+						g.out_score[idx] = score;
+					}
+				}
+			}
+		}
+	}
+	if (lane == 0 && scored) {
+		atomicAdd(g.counters + 1, scored);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // Two query rows per warp (1 KiB uint8 rows with lane offsets, EMD models).  The prefix-sum chain of a streamed row
 // (32 IDP) does not depend on the query it is compared with, so a warp that keeps TWO query rows and their prefix sums
 // in registers (80 registers) pays for it once per two pairs: per pair 16 + 8 IDP and 32 VABSDIFF instead of 32 + 8 and
@@ -2065,6 +2177,27 @@ static void launch_sweep_fast(int need, int grid, cudaStream_t st, const DevMode
 	}
 }
 
+template <typename T>
+static void launch_sweep_wide(int need, int grid, size_t smem, cudaStream_t st, const DevModel &dm, const PairArgs &a, const SweepArgs &g)
+{
+	switch (need & 7) {
+#define CASE(n)                                                                                                  \
+	case n:                                                                                                  \
+		cudaFuncSetAttribute(sweep_wide_kernel<T, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+		sweep_wide_kernel<T, n><<<grid, 512, smem, st>>>(dm, a, g);                                       \
+		break;
+		CASE(0)
+		CASE(1)
+		CASE(2)
+		CASE(3)
+		CASE(4)
+		CASE(5)
+		CASE(6)
+		CASE(7)
+#undef CASE
+	}
+}
+
 int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0, u64 q1, const mc2_hset *d, u64 d0, u64 d1,
 		     int upper_only, double cutoff, u64 max_out, u64 *d_out_q, u64 *d_out_d, double *d_out_score,
 		     u64 *d_counters)
@@ -2108,6 +2241,7 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 	// The two-queries-per-warp kernel (sweep_q2_kernel) executes 18 % fewer instructions per pair but runs at 12 warps / SM
 	// and is latency bound there: 38.9 ms vs 35.3 ms for the one-query kernel on the 20k x 20k triangle.  Opt-in only.
 	static const bool one_query = getenv("MC2_SWEEP_TWO_QUERY") == nullptr;
+	static const bool no_wide = getenv("MC2_SWEEP_NO_WIDE") != nullptr; // A/B switch: wide rows through sweep_kernel
 	if (fast) {
 		if (a.eb == 1 && row_bytes == 1024 && a.loffA && a.loffB && (dm.need & NEED_EMD) && !one_query) {
 			const u64 groups2 = ((q1 - q0 + 1) / 2) * ((d1 - d0 + 31) / 32);
@@ -2123,6 +2257,15 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 			launch_sweep_fast<uint8_t, true, true>(dm.need, grid_one, ctx->stream, dm, a, g);
 		} else if (a.eb == 1 && row_bytes == 1024) {
 			launch_sweep_fast<uint8_t, true>(dm.need, grid_one, ctx->stream, dm, a, g);
+		} else if (row_bytes <= 200 * 1024 && !no_wide) {
+			// wide rows that fit shared memory: one CTA per query row, query row on chip (see sweep_wide_kernel)
+			const u64 nq = q1 - q0, capw = (u64)ctx->sm_count * 8;
+			const int gridw = (int)(nq < capw ? nq : capw);
+			if (a.eb == 1) {
+				launch_sweep_wide<uint8_t>(dm.need, gridw, (size_t)row_bytes, ctx->stream, dm, a, g);
+			} else {
+				launch_sweep_wide<uint16_t>(dm.need, gridw, (size_t)row_bytes, ctx->stream, dm, a, g);
+			}
 		} else if (a.eb == 1) {
 			launch_sweep_fast<uint8_t, false>(dm.need, grid, ctx->stream, dm, a, g);
 		} else {

@@ -402,6 +402,36 @@ def test_cfg4_shape_single_file_k8_u16(built_lib, ctx):
     assert np.abs(r["score"] - o["score"][ib == 2]).max() <= 1e-8
 
 
+@pytest.mark.parametrize("k,eb", [(6, 1), (7, 2), (8, 2), (5, 2), (3, 4), (5, 1)])
+def test_sweep_wide_rows_vs_oracle(built_lib, ctx, k, eb):
+    """all-pairs sweep over multi-slab rows (4 KiB ... 128 KiB: query row staged in shared memory), the generic wide-type
+    form and, as a control, 1 KiB rows: survivors, scores and in-window counts against the oracle; rectangular and upper."""
+    rng = np.random.default_rng(50 * k + eb)
+    n = 70
+    hi = {1: 40, 2: 3000, 4: 100000}[eb]
+    H = synth_hist(rng, n, k, eb, hi=hi)
+    mag, ln = _side(H, rng, stale=True)
+    ln = (ln % 200 + 900).astype(np.uint64)                       # lengths spread enough for the window to cut some pairs
+    model = all_singles_model(FAST, H, mag, ln, rng)
+    hs = ctx.hset_from_host(H, k, mag=mag, length=ln)
+    gm = ctx.model(to_desc(built_lib, model))
+    for upper, (q0, q1) in ((True, (0, n)), (False, (3, 41))):
+        r = ctx.all_pairs(gm, hs, hs, 0.93, q_range=(q0, q1), upper_only=upper, max_out=n * n)
+        ia, ib = [], []
+        for q in range(q0, q1):
+            lo, hi_ = int(float(ln[q]) * 0.93), int(float(ln[q]) / 0.93)
+            for c in range(q + 1 if upper else 0, n):
+                if lo <= ln[c] <= hi_:
+                    ia.append(c), ib.append(q)
+        o = port.score_pairs(model, H, mag, ln, ia, ib)
+        assert r["n_scored"] == len(ia), (k, eb, upper)
+        want = {(b, a): s for a, b, cl, s in zip(ia, ib, o["close"], o["score"]) if cl}
+        got = {(q, c): s for q, c, s in zip(r["q"].tolist(), r["d"].tolist(), r["score"].tolist())}
+        near = {key for key, s in zip(zip(ib, ia), o["score"]) if abs(s - 0.5) < 1e-8}
+        assert set(got) - near == set(want) - near, (k, eb, upper, len(got), len(want))
+        assert max([abs(got[key] - want[key]) for key in set(got) & set(want)] + [0.0]) <= 1e-8
+
+
 def test_assign_rows_and_in_place_refill(built_lib, ctx, golden):
     """mc2_hset_assign_rows (batched DivergencePoint::set / clone with explicit magnitude), mc2_count_kmers_into and
     mc2_hset_update_from_device keep the side-band consistent with the bins they carry."""

@@ -21,7 +21,7 @@ print("auto width: largest count %d -> %d bytes" % (largest, eb))
 if eb != 2:
     hs = ctx.count_kmers(sq, 8, 2)
 gm = ctx.model_from_file(os.path.join("tests", "golden", os.environ.get("PT_W", "weights_cfg1_id90") + ".txt"))
-for rep in range(2):
+for rep in range(int(os.environ.get('CFG4_REPS', 2))):
     ctx.timer_start(); r = ctx.all_pairs(gm, hs, hs, 0.9, upper_only=True, max_out=1 << 22); ms = ctx.timer_stop()
     print("sweep %d x %d upper: %.1f ms scored %d -> %.3e pairs/s = %.0f GB/s at 131105 B/pair (%.1f%% of 6540), survivors %d" % (
         n, n, ms, r["n_scored"], r["n_scored"] / ms * 1e3, r["n_scored"] * 131105 / ms / 1e6, r["n_scored"] * 131105 / ms / 1e6 / 65.4, r["n_out"]))
