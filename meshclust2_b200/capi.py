@@ -312,12 +312,18 @@ class Context:
                                C.c_double(ident), C.byref(out)))
         return out.value
 
-    def all_pairs(self, model, set_q, set_d, cutoff, q_range=None, d_range=None, upper_only=False, max_out=1 << 20):
+    def all_pairs(self, model, set_q, set_d, cutoff, q_range=None, d_range=None, upper_only=False, max_out=1 << 20, out=None):
+        """out: optional (q uint64[max_out], d uint64[max_out], score float64[max_out]) buffers to fill (e.g. page-locked and
+        reused across calls); the returned arrays are then views of them"""
         q0, q1 = q_range if q_range else (0, len(set_q))
         d0, d1 = d_range if d_range else (0, len(set_d))
-        oq = np.zeros(max_out, dtype=np.uint64)
-        od = np.zeros(max_out, dtype=np.uint64)
-        osc = np.zeros(max_out)
+        if out is not None:
+            oq, od, osc = out
+            assert len(oq) >= max_out and len(od) >= max_out and len(osc) >= max_out
+        else:
+            oq = np.empty(max_out, dtype=np.uint64)
+            od = np.empty(max_out, dtype=np.uint64)
+            osc = np.empty(max_out)
         n_out, n_scored = C.c_uint64(), C.c_uint64()
         _check(lib().mc2_all_pairs(self.h, model.h, set_q.h, C.c_uint64(q0), C.c_uint64(q1), set_d.h, C.c_uint64(d0),
                                    C.c_uint64(d1), int(upper_only), C.c_double(cutoff), C.c_uint64(max_out), _p(oq),

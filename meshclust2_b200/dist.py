@@ -230,6 +230,14 @@ class GpuEngine:
         return self.ctx.get_close(self.model, self._qset, 0, self.local_hset, cand_begin=0, n_cand=n, cutoff=cutoff)
 
     def sweep(self, q0, q1, upper_only, cutoff, max_out):
+        # survivor buffers: allocated once, page-locked, reused by every sweep of this engine (fresh pageable arrays cost
+        # page faults + a staged copy per call)
+        if getattr(self, "_surv", None) is None or len(self._surv[0]) < max_out:
+            for old in getattr(self, "_surv", None) or ():
+                self.capi.host_unregister(old)
+            self._surv = (self.capi.host_register(np.zeros(max_out, dtype=np.uint64)),
+                          self.capi.host_register(np.zeros(max_out, dtype=np.uint64)),
+                          self.capi.host_register(np.zeros(max_out, dtype=np.float64)))
         r = self.ctx.all_pairs(self.model, self.full, self.full, cutoff, q_range=(q0, q1), upper_only=upper_only,
-                               max_out=max_out)
+                               max_out=max_out, out=self._surv)
         return r["n_out"], r["n_scored"], np.stack([r["q"], r["d"]], axis=1)
