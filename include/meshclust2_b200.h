@@ -253,6 +253,12 @@ typedef struct {
 	int32_t len_filter;
 	int32_t anchor_is_b;
 	double cutoff;
+	/* optional (bc_override != 0): the broadcast row reports this pseudo-magnitude and length instead of its set's own.
+	 * A cluster center carries the bins of the point it was last set() to but keeps its own magnitude (quirk Q4,
+	 * ClusterFactory.cpp:328); this scores it straight from the point set without staging a copy of the row. */
+	int32_t bc_override;
+	int32_t reserved_;
+	uint64_t bc_mag, bc_len;
 } mc2_pairs;
 
 /* Feature<T>::compute + operator() + Trainer<T>::classify / Predictor<T>::p_close / p_predict
@@ -275,6 +281,13 @@ int mc2_get_close(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
 
 /* Trainer<T>::filter (src/cluster/Trainer.cpp:123-141): keep[j] = 1 iff member j survives (in window and
  * round(classify(center, member)) != 0). Feature order compute(center, member). */
+/* mc2_get_close / mc2_filter for a query (center) that is row `q` of set_q as far as bins and true sums go, but reports
+ * q_mag / q_len as its pseudo-magnitude and length (mc2_pairs.bc_override): one call, no staging of the row. */
+int mc2_get_close_as(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, uint64_t q, uint64_t q_mag, uint64_t q_len,
+		     const mc2_hset *set_c, const uint64_t *cand, uint64_t cand_begin, uint64_t n_cand, double cutoff,
+		     int64_t *best, double *best_dist, int32_t *is_min, uint8_t *marks);
+int mc2_filter_as(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint64_t center, uint64_t c_mag, uint64_t c_len,
+		  const mc2_hset *set_m, const uint64_t *members, uint64_t n_members, double id, uint8_t *keep);
 int mc2_filter(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint64_t center, const mc2_hset *set_m,
 	       const uint64_t *members, uint64_t n_members, double id, uint8_t *keep);
 

@@ -172,14 +172,13 @@ std::tuple<Point<T> *, double, size_t, size_t> Trainer<T>::get_close(Point<T> *p
 	if (cand.empty()) {
 		return result;
 	}
-	std::vector<Point<T> *> q{p};
-	stage_centers<T>(d, q);
 	int64_t best = -1;
 	double best_dist = -1;
 	int32_t is_min = 1;
 	std::vector<uint8_t> marks(cand.size());
-	ok(mc2_get_close(d.ctx, d.model, d.scratch, 0, d.points, cand.data(), 0, cand.size(), cutoff, &best, &best_dist, &is_min,
-			 marks.data()));
+	// the query is the row of the point whose bins it carries, with its own (possibly stale) magnitude and length
+	ok(mc2_get_close_as(d.ctx, d.model, d.points, p->get_id(), dp<T>(p).getPseudoMagnitude(), p->get_length(), d.points,
+			    cand.data(), 0, cand.size(), cutoff, &best, &best_dist, &is_min, marks.data()));
 	for (size_t j = 0; j < cand.size(); j++) {
 		if (marks[j]) {
 			bvec_iterator<T> it = where[j];
@@ -249,9 +248,8 @@ void Trainer<T>::filter(Point<T> *p, vector<pair<Point<T> *, bool>> &vec) const
 		for (size_t j = 0; j < vec.size(); j++) {
 			rows[j] = vec[j].first->get_id();
 		}
-		std::vector<Point<T> *> c{p};
-		stage_centers<T>(d, c);
-		ok(mc2_filter(d.ctx, d.model, d.scratch, 0, d.points, rows.data(), rows.size(), get_id(), keep.data()));
+		ok(mc2_filter_as(d.ctx, d.model, d.points, p->get_id(), dp<T>(p).getPseudoMagnitude(), p->get_length(), d.points,
+				 rows.data(), rows.size(), get_id(), keep.data()));
 	}
 	size_t w = 0;
 	for (size_t j = 0; j < vec.size(); j++) {

@@ -38,7 +38,7 @@ SYMBOLS = [
     "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_count_kmers_into", "mc2_count_kmers_auto", "mc2_hset_largest_count", "mc2_width_for_count", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_update_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
     "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
-    "mc2_score_pairs", "mc2_get_close", "mc2_filter", "mc2_merge", "mc2_all_pairs", "mc2_distance", "mc2_mean_closest", "mc2_closest",
+    "mc2_score_pairs", "mc2_get_close", "mc2_get_close_as", "mc2_filter", "mc2_filter_as", "mc2_merge", "mc2_all_pairs", "mc2_distance", "mc2_mean_closest", "mc2_closest",
     "mc2_bench_score_pairs", "mc2_bench_count_kmers", "mc2_encode_dna", "mc2_encode_dna_batch",
 ]
 
@@ -73,6 +73,7 @@ class Pairs(C.Structure):
         ("a_broadcast", C.c_int32), ("b_broadcast", C.c_int32),
         ("len_filter", C.c_int32), ("anchor_is_b", C.c_int32),
         ("cutoff", C.c_double),
+        ("bc_override", C.c_int32), ("reserved_", C.c_int32), ("bc_mag", C.c_uint64), ("bc_len", C.c_uint64),
     ]
 
 
@@ -297,6 +298,25 @@ class Context:
                                    C.c_uint64(n_cand), C.c_double(cutoff), C.byref(best), C.byref(bd), C.byref(ismin),
                                    _p(marks)))
         return best.value, bd.value, bool(ismin.value), marks
+
+    def get_close_as(self, model, set_q, q, q_mag, q_len, set_c, cand=None, cand_begin=0, n_cand=None, cutoff=0.9):
+        """get_close for a center = row q of set_q reporting (q_mag, q_len) as its side-band"""
+        cand = _u64(cand)
+        if n_cand is None:
+            n_cand = len(cand)
+        best, bd, ismin = C.c_int64(), C.c_double(), C.c_int32()
+        marks = np.zeros(n_cand, dtype=np.uint8)
+        _check(lib().mc2_get_close_as(self.h, model.h, set_q.h, C.c_uint64(q), C.c_uint64(q_mag), C.c_uint64(q_len), set_c.h,
+                                      _p(cand), C.c_uint64(cand_begin), C.c_uint64(n_cand), C.c_double(cutoff), C.byref(best),
+                                      C.byref(bd), C.byref(ismin), _p(marks)))
+        return best.value, bd.value, bool(ismin.value), marks
+
+    def filter_as(self, model, set_c, center, c_mag, c_len, set_m, members, ident):
+        members = _u64(members)
+        keep = np.zeros(len(members), dtype=np.uint8)
+        _check(lib().mc2_filter_as(self.h, model.h, set_c.h, C.c_uint64(center), C.c_uint64(c_mag), C.c_uint64(c_len), set_m.h,
+                                   _p(members), C.c_uint64(len(members)), C.c_double(ident), _p(keep)))
+        return keep
 
     def filter(self, model, set_c, center, set_m, members, ident):
         members = _u64(members)

@@ -72,7 +72,7 @@ static void release(Buf &b)
 	b.cap = 0;
 }
 
-enum { B_IA = 0, B_IB, B_SCORE, B_DIST, B_CLOSE, B_SKIP, B_CACHE, B_RAW, B_MISC, B_OUTQ, B_OUTD, B_OUTS, B_STAGE_CODES, B_STAGE_BOFF, B_ROWMAX, B_ROWMAX_H, B_SEGCOUNT, B_COUNT };
+enum { B_IA = 0, B_IB, B_SCORE, B_DIST, B_CLOSE, B_SKIP, B_CACHE, B_RAW, B_MISC, B_OUTQ, B_OUTD, B_OUTS, B_STAGE_CODES, B_STAGE_BOFF, B_ROWMAX, B_ROWMAX_H, B_SEGCOUNT, B_OVERRIDE, B_COUNT };
 
 struct ProfRec {
 	int kind;
@@ -320,6 +320,7 @@ static int check_err(mc2_ctx *ctx)
 {
 	int e = *ctx->h_err;
 	if (e == 0) {
+		ctx->err_dirty = 0; // the device word is known to be zero: the next call need not clear it
 		return MC2_OK;
 	}
 	if (e & 4) {
@@ -336,7 +337,10 @@ static int check_err(mc2_ctx *ctx)
 
 static int reset_err(mc2_ctx *ctx)
 {
-	MC2_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+	if (ctx->err_dirty) {
+		MC2_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+	}
+	ctx->err_dirty = 1; // until a check_err() has seen it clean
 	return MC2_OK;
 }
 
@@ -430,7 +434,8 @@ static int refresh_max_sum(mc2_ctx *ctx, mc2_hset *h)
 // one warp per row: copy bins + true sums; length / magnitude from the optional override arrays
 __global__ void __launch_bounds__(256) assign_rows_kernel(char *dbins, u64 *dmag, u64 *dsum, u64 *dsumsq, u64 *dlen, const char *sbins,
 							   const u64 *ssum, const u64 *ssumsq, const u64 *slen, u64 row_bytes, u64 n,
-							   const u64 *idx /* [dst | src | mag? | len?] x n */, int has_mag, int has_len)
+							   const u64 *idx /* [dst | src | mag? | len?] x n */, int has_mag, int has_len,
+							   unsigned short *dloff, const unsigned short *sloff)
 {
 	const int lane = threadIdx.x & 31;
 	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
@@ -440,6 +445,9 @@ __global__ void __launch_bounds__(256) assign_rows_kernel(char *dbins, u64 *dmag
 		uint32_t *dst = reinterpret_cast<uint32_t *>(dbins + d * row_bytes);
 		for (u64 w = lane; w < row_bytes / 4; w += 32) {
 			dst[w] = src[w];
+		}
+		if (dloff) { // lane offsets depend on the bins only: they travel with the row
+			dloff[d * 32 + lane] = sloff[s * 32 + lane];
 		}
 		if (lane == 0) {
 			dsum[d] = ssum[s];
@@ -508,12 +516,15 @@ int mc2_ctx_create(int device, mc2_ctx **out)
 	MC2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	MC2_CUDA(cudaEventCreate(&c->ev0));
 	MC2_CUDA(cudaEventCreate(&c->ev1));
-	MC2_CUDA(cudaMalloc((void **)&c->d_err, 64));
-	MC2_CUDA(cudaMallocHost((void **)&c->h_err, 64));
+	// result slot: [0,64) reduction result, [64,128) the sticky error word, [128,4096) close flags of small batches, so that
+	// one device->host copy ends a one-query call
 	MC2_CUDA(cudaMallocHost(&c->h_slot, 4096));
 	MC2_CUDA(cudaMalloc(&c->d_slot, 4096));
+	MC2_CUDA(cudaMemset(c->d_slot, 0, 4096));
 	memset(c->h_slot, 0, 4096);
-	*c->h_err = 0;
+	c->d_err = reinterpret_cast<int *>(reinterpret_cast<char *>(c->d_slot) + 64);
+	c->h_err = reinterpret_cast<int *>(reinterpret_cast<char *>(c->h_slot) + 64);
+	c->err_dirty = 1;
 	CtxExtra *x = new (std::nothrow) CtxExtra();
 	c->extra = x;
 	*out = c;
@@ -544,8 +555,6 @@ void mc2_ctx_destroy(mc2_ctx *ctx)
 	if (ctx->flush_buf) {
 		cudaFree(ctx->flush_buf);
 	}
-	cudaFree(ctx->d_err);
-	cudaFreeHost(ctx->h_err);
 	cudaFreeHost(ctx->h_slot);
 	cudaFree(ctx->d_slot);
 	cudaEventDestroy(ctx->ev0);
@@ -1244,7 +1253,9 @@ int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t
 		return MC2_OK;
 	}
 	MC2_CUDA(cudaSetDevice(ctx->device));
-	dst->lane_off_valid = 0;
+	// the destination's lane offsets stay valid when both sides have them (they are copied with the rows)
+	const bool keep_loff = dst->lane_off_valid && src->lane_off_valid && dst->lane_off && src->lane_off;
+	dst->lane_off_valid = keep_loff ? 1 : 0;
 	dst->counted = 0;
 	const int parts = 2 + (mag ? 1 : 0) + (len ? 1 : 0);
 	std::vector<u64> idx((size_t)parts * n);
@@ -1265,7 +1276,8 @@ int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t
 	int grid = (int)(want < cap ? want : cap);
 	assign_rows_kernel<<<grid, 256, 0, ctx->stream>>>((char *)dst->bins, dst->mag, dst->sum, dst->sumsq, dst->len,
 							   (const char *)src->bins, src->sum, src->sumsq, src->len, dst->N * (u64)dst->eb, n,
-							   (const u64 *)x->d[B_IA].p, mag ? 1 : 0, len ? 1 : 0);
+							   (const u64 *)x->d[B_IA].p, mag ? 1 : 0, len ? 1 : 0,
+							   keep_loff ? dst->lane_off : nullptr, keep_loff ? src->lane_off : nullptr);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
 	if (!staged) {
@@ -1476,6 +1488,24 @@ static int fill_pair_args(mc2_ctx *ctx, const mc2_pairs *p, PairArgs &a, CtxExtr
 	if (p->len_filter) {
 		MC2_REQUIRE(p->cutoff > 0, "pairs: cutoff must be > 0 when len_filter is set");
 	}
+	if (p->bc_override) {
+		// the broadcast row's mag / len come from the caller: a two-word device array addressed so that index `row` hits it
+		const bool on_a = p->a_broadcast && !p->ia, on_b = p->b_broadcast && !p->ib;
+		MC2_REQUIRE(on_a != on_b, "pairs: bc_override needs exactly one broadcast side without an index list");
+		int rc = ensure(x->d[B_OVERRIDE], 16, false);
+		if (rc != MC2_OK) return rc;
+		const u64 two[2] = {p->bc_mag, p->bc_len};
+		rc = h2d(ctx, x->d[B_OVERRIDE].p, two, 16);
+		if (rc != MC2_OK) return rc;
+		const u64 *dv = (const u64 *)x->d[B_OVERRIDE].p;
+		if (on_a) {
+			a.sbA.mag = dv - p->a_begin;
+			a.sbA.len = dv + 1 - p->a_begin;
+		} else {
+			a.sbB.mag = dv - p->b_begin;
+			a.sbB.len = dv + 1 - p->b_begin;
+		}
+	}
 	return MC2_OK;
 }
 
@@ -1533,24 +1563,53 @@ static int score_and_reduce(mc2_ctx *ctx, const mc2_model *model, const mc2_pair
 	a.dist = (double *)x->d[B_DIST].p;
 	a.close = (uint8_t *)x->d[B_CLOSE].p;
 	a.skipped = (uint8_t *)x->d[B_SKIP].p;
+	// small batches with a reduction: the arg-max kernel also drops the close flags into the result slot, and ONE copy of
+	// [result | error word | flags] ends the call
+	const bool flags_in_slot = reduce_mode >= 0 && close_out && m <= 4096 - 128;
+	uint8_t *d_flags = flags_in_slot ? reinterpret_cast<uint8_t *>(ctx->d_slot) + 128 : nullptr;
 	rc = reset_err(ctx);
 	if (rc == MC2_OK) rc = launch_pair_score(ctx, model->dm, a);
-	if (rc == MC2_OK && reduce_mode >= 0) rc = launch_argmax(ctx, a.dist, a.skipped, a.close, m, reduce_mode, ctx->d_slot);
-	if (rc == MC2_OK) rc = fetch_err(ctx);
+	if (rc == MC2_OK && reduce_mode >= 0) rc = launch_argmax(ctx, a.dist, a.skipped, a.close, m, reduce_mode, ctx->d_slot, d_flags);
 	if (rc != MC2_OK) return rc;
 	cudaStream_t st = ctx->stream;
-	if (reduce_mode >= 0) MC2_CUDA(cudaMemcpyAsync(ctx->h_slot, ctx->d_slot, sizeof(ArgOutHost), cudaMemcpyDeviceToHost, st));
-	if (close_out && (rc = d2h(ctx, close_out, a.close, m)) != MC2_OK) return rc;
+	if (reduce_mode >= 0) {
+		const size_t bytes = flags_in_slot ? 128 + (size_t)m : 128;
+		MC2_CUDA(cudaMemcpyAsync(ctx->h_slot, ctx->d_slot, bytes, cudaMemcpyDeviceToHost, st)); // covers the error word
+	} else {
+		rc = fetch_err(ctx);
+		if (rc != MC2_OK) return rc;
+	}
+	if (close_out && !flags_in_slot && (rc = d2h(ctx, close_out, a.close, m)) != MC2_OK) return rc;
 	if (skipped_out && (rc = d2h(ctx, skipped_out, a.skipped, m)) != MC2_OK) return rc;
 	rc = sync_stage(ctx);
 	if (rc != MC2_OK) return rc;
+	if (flags_in_slot) memcpy(close_out, reinterpret_cast<const char *>(ctx->h_slot) + 128, m);
 	if (reduce_mode >= 0) *red = *reinterpret_cast<ArgOutHost *>(ctx->h_slot);
 	return check_err(ctx);
 }
 
+static int get_close_impl(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, uint64_t q, int ovr, uint64_t q_mag,
+			  uint64_t q_len, const mc2_hset *set_c, const uint64_t *cand, uint64_t cand_begin, uint64_t n_cand,
+			  double cutoff, int64_t *best, double *best_dist, int32_t *is_min, uint8_t *marks);
+
 int mc2_get_close(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, uint64_t q, const mc2_hset *set_c,
 		  const uint64_t *cand, uint64_t cand_begin, uint64_t n_cand, double cutoff, int64_t *best,
 		  double *best_dist, int32_t *is_min, uint8_t *marks)
+{
+	return get_close_impl(ctx, model, set_q, q, 0, 0, 0, set_c, cand, cand_begin, n_cand, cutoff, best, best_dist, is_min, marks);
+}
+
+int mc2_get_close_as(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, uint64_t q, uint64_t q_mag, uint64_t q_len,
+		     const mc2_hset *set_c, const uint64_t *cand, uint64_t cand_begin, uint64_t n_cand, double cutoff,
+		     int64_t *best, double *best_dist, int32_t *is_min, uint8_t *marks)
+{
+	return get_close_impl(ctx, model, set_q, q, 1, q_mag, q_len, set_c, cand, cand_begin, n_cand, cutoff, best, best_dist, is_min,
+			      marks);
+}
+
+static int get_close_impl(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, uint64_t q, int ovr, uint64_t q_mag,
+			  uint64_t q_len, const mc2_hset *set_c, const uint64_t *cand, uint64_t cand_begin, uint64_t n_cand,
+			  double cutoff, int64_t *best, double *best_dist, int32_t *is_min, uint8_t *marks)
 {
 	MC2_REQUIRE(ctx && model && set_q && set_c && best && best_dist && is_min, "mc2_get_close: NULL argument");
 	MC2_REQUIRE(q < set_q->n, "mc2_get_close: query row out of range");
@@ -1571,6 +1630,9 @@ int mc2_get_close(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
 	p.len_filter = 1;
 	p.anchor_is_b = 1;
 	p.cutoff = cutoff;
+	p.bc_override = ovr;
+	p.bc_mag = q_mag;
+	p.bc_len = q_len;
 	ArgOutHost r;
 	int rc = score_and_reduce(ctx, model, &p, 0, &r, marks, nullptr);
 	if (rc != MC2_OK) return rc;
@@ -1580,8 +1642,23 @@ int mc2_get_close(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
 	return MC2_OK;
 }
 
+static int filter_impl(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint64_t center, int ovr, uint64_t c_mag,
+		       uint64_t c_len, const mc2_hset *set_m, const uint64_t *members, uint64_t n_members, double id, uint8_t *keep);
+
 int mc2_filter(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint64_t center, const mc2_hset *set_m,
 	       const uint64_t *members, uint64_t n_members, double id, uint8_t *keep)
+{
+	return filter_impl(ctx, model, set_c, center, 0, 0, 0, set_m, members, n_members, id, keep);
+}
+
+int mc2_filter_as(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint64_t center, uint64_t c_mag, uint64_t c_len,
+		  const mc2_hset *set_m, const uint64_t *members, uint64_t n_members, double id, uint8_t *keep)
+{
+	return filter_impl(ctx, model, set_c, center, 1, c_mag, c_len, set_m, members, n_members, id, keep);
+}
+
+static int filter_impl(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint64_t center, int ovr, uint64_t c_mag,
+		       uint64_t c_len, const mc2_hset *set_m, const uint64_t *members, uint64_t n_members, double id, uint8_t *keep)
 {
 	MC2_REQUIRE(ctx && model && set_c && set_m && (n_members == 0 || (members && keep)), "mc2_filter: NULL argument");
 	MC2_REQUIRE(center < set_c->n, "mc2_filter: center row out of range");
@@ -1598,6 +1675,9 @@ int mc2_filter(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint
 	p.len_filter = 1;
 	p.anchor_is_b = 0;
 	p.cutoff = id;
+	p.bc_override = ovr;
+	p.bc_mag = c_mag;
+	p.bc_len = c_len;
 	// keep <=> in window and round(score) != 0 ; the kernel's close flag is round(score) > 0 and score >= 0 always
 	// holds for logistic(sum)+bias with bias >= -0.5; for generality fetch the scores when bias is negative.
 	if (model->dm.bias < 0) {

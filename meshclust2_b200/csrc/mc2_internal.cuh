@@ -99,6 +99,7 @@ struct mc2_ctx {
 	void *d_slot;     // device result slot (4 KB)
 	void *extra;      // CtxExtra (growable scratch buffers), owned by mc2_api.cu
 	int prof_on;      // per-kernel event timing enabled
+	int err_dirty;    // the device error word may be non-zero (set by reset_err, cleared by a clean check_err)
 };
 
 namespace mc2 {
@@ -186,8 +187,8 @@ int launch_segment(mc2_ctx *ctx, bool write, const char *d_text, const u64 *d_se
 		   int *d_segs, unsigned long long *d_min_seg);
 int launch_seg_scan(mc2_ctx *ctx, const u32 *d_count, u64 n, u64 *d_seg_off);
 int launch_pack_text(mc2_ctx *ctx, const char *d_text, const u64 *d_seq_off, mc2_seqs *s);
-int launch_argmax(mc2_ctx *ctx, const double *dist, const uint8_t *skipped, const uint8_t *close, u64 n, int mode,
-		  void *d_out);
+int launch_argmax(mc2_ctx *ctx, const double *dist, const uint8_t *skipped, const uint8_t *close, u64 n, int mode, void *d_out,
+		  uint8_t *d_flags_out = nullptr);
 int launch_count(mc2_ctx *ctx, const mc2_seqs *s, int k, int eb, mc2_hset *h, u64 init_value);
 int launch_sideband(mc2_ctx *ctx, mc2_hset *h, bool set_mag);
 int launch_pack(mc2_ctx *ctx, const char *d_codes, const u64 *d_seq_off, mc2_seqs *s);

@@ -44,34 +44,66 @@ __global__ void __launch_bounds__(256) mean_kernel(const u64 *__restrict__ sums,
 	}
 }
 
-// one thread per member, the mean staged through shared memory in chunks
+// one thread per member, the mean staged through shared memory in chunks.
+// The reference's `u64 mag += p_i + c_i` truncates at every step (a sequential chain of 4^k steps per member, not
+// associative).  For 8/16-bit histograms every partial sum is below 2^53, so the chain can stay in the double domain:
+// (u64)((double)mag + x) == floor((double)mag + x) exactly, and DADD + FRND is half the latency of DADD + F2I + I2F.  The
+// rounded mean (T)round(c_i) depends only on the bin and is computed once per chunk by the staging threads.
 template <typename T>
 __global__ void __launch_bounds__(128) distance_d_kernel(const T *__restrict__ bins, u64 N, const u64 *__restrict__ members, u64 n,
 							   const double *__restrict__ mean, double *__restrict__ dist)
 {
 	__shared__ double c[512];
+	__shared__ T rc[512];
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	const bool on = j < n;
 	const T *row = on ? bins + members[j] * N : bins;
+	constexpr bool NARROW = sizeof(T) <= 2;
 	u64 d = 0, mag = 0;
+	double magd = 0;
 	for (u64 base = 0; base < N; base += 512) {
 		const u64 cnt = min((u64)512, N - base);
 		__syncthreads();
 		for (u64 t = threadIdx.x; t < cnt; t += blockDim.x) {
-			c[t] = mean[base + t];
+			const double ci = mean[base + t];
+			c[t] = ci;
+			rc[t] = (T)round(ci);
 		}
 		__syncthreads();
 		if (on) {
-			for (u64 t = 0; t < cnt; t++) {
-				const T p = row[base + t];
-				const double ci = c[t];
-				const T r = (T)round(ci);
-				d += 2 * (p < r ? p : r);
-				mag = (u64)((double)mag + ((double)p + ci)); // u64 += T + double, truncating each step
+			if (NARROW && cnt % 16 == 0) {
+				// 16 bytes of the member's row per load
+				constexpr int PER = 16 / (int)sizeof(T);
+				for (u64 t = 0; t < cnt; t += PER) {
+					const uint4 v = *reinterpret_cast<const uint4 *>(row + base + t);
+					const T *pv = reinterpret_cast<const T *>(&v);
+#pragma unroll
+					for (int u = 0; u < PER; u++) {
+						const T p = pv[u];
+						const T r = rc[t + u];
+						d += 2 * (u64)(p < r ? p : r);
+						magd = floor(magd + ((double)p + c[t + u]));
+					}
+				}
+			} else {
+				for (u64 t = 0; t < cnt; t++) {
+					const T p = row[base + t];
+					const double ci = c[t];
+					const T r = rc[t];
+					d += 2 * (p < r ? p : r);
+					if (NARROW) {
+						magd = floor(magd + ((double)p + ci));
+					} else {
+						mag = (u64)((double)mag + ((double)p + ci)); // u64 += T + double, truncating each step
+					}
+				}
 			}
 		}
 	}
 	if (on) {
+		if (NARROW) {
+			mag = (u64)magd;
+		}
 		double frac = (double)d / (double)mag;
 		dist[j] = 10000.0 * (1.0 - frac * frac);
 	}

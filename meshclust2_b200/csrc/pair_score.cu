@@ -1435,9 +1435,15 @@ struct ArgOut {
 	int has; // mode 1: a close candidate was found
 };
 
+// flags_out (may be NULL): the close flags copied next to the result so that one device->host copy returns both
 __global__ void __launch_bounds__(1024) argmax_kernel(const double *dist, const uint8_t *skipped, const uint8_t *close, u64 n,
-						      int mode, ArgOut *out)
+						      int mode, ArgOut *out, uint8_t *flags_out)
 {
+	if (flags_out) {
+		for (u64 i = threadIdx.x; i < n; i += blockDim.x) {
+			flags_out[i] = close[i];
+		}
+	}
 	__shared__ double s_d[32];
 	__shared__ long long s_i[32];
 	__shared__ int s_any[32];
@@ -2127,10 +2133,11 @@ int launch_pair_score(mc2_ctx *ctx, const DevModel &dm, const PairArgs &a_in)
 	return MC2_OK;
 }
 
-int launch_argmax(mc2_ctx *ctx, const double *dist, const uint8_t *skipped, const uint8_t *close, u64 n, int mode, void *d_out)
+int launch_argmax(mc2_ctx *ctx, const double *dist, const uint8_t *skipped, const uint8_t *close, u64 n, int mode, void *d_out,
+		  uint8_t *d_flags_out)
 {
 	prof_begin(ctx, 4);
-	argmax_kernel<<<1, 1024, 0, ctx->stream>>>(dist, skipped, close, n, mode, reinterpret_cast<ArgOut *>(d_out));
+	argmax_kernel<<<1, 1024, 0, ctx->stream>>>(dist, skipped, close, n, mode, reinterpret_cast<ArgOut *>(d_out), d_flags_out);
 	prof_end(ctx);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());

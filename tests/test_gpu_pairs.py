@@ -463,3 +463,29 @@ def test_assign_rows_and_in_place_refill(built_lib, ctx, golden):
     da, db = a.download(), b.download()
     for key in ("hist", "mag", "len", "mers1", "n_overflow"):
         assert np.array_equal(da[key], db[key]), key
+
+
+def test_get_close_as_and_filter_as_equal_staged_centers(built_lib, ctx, golden):
+    """mc2_get_close_as / mc2_filter_as (center = a point's row with its own magnitude and length) == staging that row into a
+    scratch set with mc2_hset_assign_rows and calling mc2_get_close / mc2_filter, and == the oracle."""
+    H, ln, mag = golden["hist_k5_eb1"], golden["len_k5_eb1"], golden["mag_k5_eb1"]
+    cand = golden["cand"]
+    hs = ctx.hset_from_host(H, 5, mag=mag, length=ln)
+    sc = ctx.hset_from_host(np.ones((4, 1024), dtype=np.uint8), 5, length=np.ones(4, dtype=np.uint64))
+    m = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    gm = ctx.model_from_file(weights_path("weights_cfg1_id90"))
+    for q in (int(cand[0]), int(cand[5]), int(cand[-1])):
+        for qmag, qlen in ((int(mag[q]), int(ln[q])), (int(mag[q]) + 37, int(ln[q]) - 3)):
+            sc.assign_rows([1], hs, [q], mag=[qmag], length=[qlen])
+            a = ctx.get_close(gm, sc, 1, hs, cand=cand, cutoff=0.9)
+            b = ctx.get_close_as(gm, hs, q, qmag, qlen, hs, cand=cand, cutoff=0.9)
+            assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and np.array_equal(a[3], b[3])
+            fa = ctx.filter(gm, sc, 1, hs, cand, 0.9)
+            fb = ctx.filter_as(gm, hs, q, qmag, qlen, hs, cand, 0.9)
+            assert np.array_equal(fa, fb)
+            # oracle: a center object = point q's bins with the overridden side-band appended as an extra row
+            H2 = np.vstack([H, H[q:q + 1]])
+            mag2 = np.append(mag, np.uint64(qmag)).astype(np.uint64)
+            ln2 = np.append(ln, np.uint64(qlen)).astype(np.uint64)
+            o = port.get_close(m, H2, mag2, ln2, len(H), cand, 0.9)
+            assert b[0] == o[0] and abs(b[1] - o[1]) <= 1e-9 and b[2] == o[2] and np.array_equal(b[3], o[3])
