@@ -347,7 +347,10 @@ def pin_inputs(capi, enc):
     for key in ("codes", "seq_off", "segs", "seg_off"):
         enc[key] = np.ascontiguousarray(enc[key])
         if enc[key].nbytes:
-            capi.host_register(enc[key])
+            try:
+                capi.host_register(enc[key])
+            except capi.Mc2Error as e:          # e.g. a locked-memory limit: the copies still work, just through pageable memory
+                log("[bench] could not page-lock %s: %s" % (key, e))
 
 
 def small_workload(ctx, capi, mdist, torch, model, cutoff, steps=20):

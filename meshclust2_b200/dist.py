@@ -233,11 +233,17 @@ class GpuEngine:
         # survivor buffers: allocated once, page-locked, reused by every sweep of this engine (fresh pageable arrays cost
         # page faults + a staged copy per call)
         if getattr(self, "_surv", None) is None or len(self._surv[0]) < max_out:
-            for old in getattr(self, "_surv", None) or ():
+            for old in getattr(self, "_surv_pinned", None) or ():
                 self.capi.host_unregister(old)
-            self._surv = (self.capi.host_register(np.zeros(max_out, dtype=np.uint64)),
-                          self.capi.host_register(np.zeros(max_out, dtype=np.uint64)),
-                          self.capi.host_register(np.zeros(max_out, dtype=np.float64)))
+            bufs = (np.zeros(max_out, dtype=np.uint64), np.zeros(max_out, dtype=np.uint64), np.zeros(max_out, dtype=np.float64))
+            self._surv_pinned = []
+            for b in bufs:
+                try:
+                    self.capi.host_register(b)
+                    self._surv_pinned.append(b)
+                except self.capi.Mc2Error:      # locked-memory limit: pageable buffers still work
+                    pass
+            self._surv = bufs
         r = self.ctx.all_pairs(self.model, self.full, self.full, cutoff, q_range=(q0, q1), upper_only=upper_only,
                                max_out=max_out, out=self._surv)
         return r["n_out"], r["n_scored"], np.stack([r["q"], r["d"]], axis=1)
