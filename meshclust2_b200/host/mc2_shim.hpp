@@ -228,15 +228,11 @@ public:
 		for (auto &s : seqs) {
 			blob += s;
 		}
-		std::vector<char> codes(off[n] ? off[n] : 1);
-		const uint64_t max_segs = off[n] / 20 + 2 * n + 16;
-		std::vector<int32_t> segs(2 * max_segs);
-		std::vector<uint64_t> seg_off(n + 1);
-		check(mc2_encode_dna_batch(blob.data(), off.data(), n, codes.data(), segs.data(), max_segs, seg_off.data(), nullptr,
-					   threads));
+		// segmentation, letter coding and packing happen on the device (mc2_seqs_from_text == Chromosome::help + encode)
+		(void)threads;
 		mc2_ctx *ctx = Context::instance().get();
 		mc2_seqs *sq = nullptr;
-		check(mc2_seqs_upload(ctx, codes.data(), off.data(), n, segs.data(), seg_off.data(), &sq));
+		check(mc2_seqs_from_text(ctx, blob.data(), off.data(), n, &sq));
 		mc2_hset *h = nullptr;
 		int rc = mc2_count_kmers(ctx, sq, k, (int)sizeof(T), &h);
 		mc2_seqs_free(sq);
@@ -275,6 +271,31 @@ public:
 	{
 		static uint64_t n = 0;
 		return n;
+	}
+	// Runner::run's histogram-width detection (src/cluster/CRunner.cpp:57-127): "Largest count" over raw sequences and the
+	// number of bytes per bin the reference would pick for it (1, 2, 4 or 8 = uint8_t ... uint64_t)
+	static uint64_t largest_count(const std::vector<std::string> &seqs, int k, int *elem_bytes = nullptr)
+	{
+		std::vector<uint64_t> off(seqs.size() + 1, 0);
+		std::string blob;
+		for (size_t i = 0; i < seqs.size(); i++) {
+			off[i + 1] = off[i] + seqs[i].size();
+			blob += seqs[i];
+		}
+		mc2_ctx *ctx = Context::instance().get();
+		mc2_seqs *sq = nullptr;
+		check(mc2_seqs_from_text(ctx, blob.data(), off.data(), seqs.size(), &sq));
+		mc2_hset *h = nullptr;
+		uint64_t largest = 0;
+		int eb = 1;
+		int rc = mc2_count_kmers_auto(ctx, sq, k, &largest, &eb, &h);
+		mc2_seqs_free(sq);
+		check(rc);
+		mc2_hset_free(h);
+		if (elem_bytes) {
+			*elem_bytes = eb;
+		}
+		return largest;
 	}
 };
 

@@ -1,6 +1,7 @@
 // test_shim.cpp — exercises meshclust2_b200/host/mc2_shim.hpp (the reference-named C++ classes over the C ABI) against a
 // fixture file written by tests/test_shim.py from the reference-generated golden vectors.
 //   usage: test_shim <fixture.txt> <weights.txt>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -95,6 +96,19 @@ int main(int argc, char **argv)
 		auto *p = Loader<uint8_t>::get_point(">x", "ACGTNNNNACGTACGTxxACGTACGTACGTACGTACGT", id2, 3);
 		CHECK(p->get_length() == 32 && id2 == 8 && p->get_id() == 7, "get_point(header, string) strips non-ACGT");
 		delete p;
+	}
+	// ---- width detection (Runner::run) ----
+	{
+		int eb = 0;
+		uint64_t lc = Loader<uint8_t>::largest_count(seqs, k, &eb);
+		unsigned want = 0;
+		for (size_t i = 0; i < n; i++) {
+			for (size_t b = 0; b < N; b++) want = std::max<unsigned>(want, (unsigned)hist[i][b]);
+		}
+		CHECK(lc == want && eb == 1, "largest count " << lc << " vs " << want); // no saturation in the fixture: max bin = 1 + multiplicity
+		std::vector<std::string> rep{std::string(400, 'A'), seqs[0]};
+		lc = Loader<uint8_t>::largest_count(rep, k, &eb);
+		CHECK(lc == (uint64_t)(400 - k + 1 + 1) && eb == 2, "poly-A needs 16 bits: " << lc);
 	}
 	// ---- KmerHashTable ----
 	{
