@@ -140,6 +140,8 @@ int mc2_seqs_upload_into(mc2_ctx *ctx, mc2_seqs *dst, const char *codes, const u
  * pass.  MC2_ERR_INPUT for a byte that is not a nucleotide letter in a sequence that has at least one segment
  * (InvalidInputException, ChromosomeOneDigit.cpp:86-95). */
 int mc2_seqs_from_text(mc2_ctx *ctx, const char *text, const uint64_t *seq_off, uint64_t n, mc2_seqs **out);
+/* same, refilling an existing set (device arrays reused, as mc2_seqs_upload_into) */
+int mc2_seqs_from_text_into(mc2_ctx *ctx, mc2_seqs *dst, const char *text, const uint64_t *seq_off, uint64_t n);
 /* segments of a sequence set back on the host (inclusive, sequence-relative pairs; seg_off[n+1]; lengths[n] = bases per
  * sequence); any pointer may be NULL.  mc2_seqs_total_segments sizes segs_out. */
 int mc2_seqs_download_segments(mc2_ctx *ctx, const mc2_seqs *s, int32_t *segs_out, uint64_t *seg_off_out,

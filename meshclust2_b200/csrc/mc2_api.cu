@@ -771,12 +771,8 @@ int mc2_seqs_upload_into(mc2_ctx *ctx, mc2_seqs *dst, const char *codes, const u
 	return rc;
 }
 
-int mc2_seqs_from_text(mc2_ctx *ctx, const char *text, const uint64_t *seq_off, uint64_t n, mc2_seqs **out)
+static int text_fill(mc2_ctx *ctx, mc2_seqs *s, const char *text, const uint64_t *seq_off, uint64_t n)
 {
-	MC2_REQUIRE(ctx && seq_off && out, "mc2_seqs_from_text: NULL argument");
-	MC2_REQUIRE(n == 0 || text != nullptr, "mc2_seqs_from_text: text is NULL");
-	*out = nullptr;
-	MC2_CUDA(cudaSetDevice(ctx->device));
 	const u64 total_bases = seq_off[n] - seq_off[0];
 	std::vector<u64> word_off(n + 1), len(n), boff(n + 1);
 	u64 w = 0, max_len = 0;
@@ -793,10 +789,6 @@ int mc2_seqs_from_text(mc2_ctx *ctx, const char *text, const uint64_t *seq_off, 
 	}
 	word_off[n] = w;
 	boff[n] = total_bases;
-	mc2_seqs *s = new (std::nothrow) mc2_seqs();
-	MC2_REQUIRE(s != nullptr, "out of host memory");
-	memset(s, 0, sizeof *s);
-	s->ctx = ctx;
 	s->n = n;
 	s->total_bases = total_bases;
 	s->max_len = max_len;
@@ -805,8 +797,9 @@ int mc2_seqs_from_text(mc2_ctx *ctx, const char *text, const uint64_t *seq_off, 
 	CtxExtra *x = extra(ctx);
 	cudaStream_t st = ctx->stream;
 	int rc = MC2_OK;
-	auto fail = [&](int code) {
-		mc2_seqs_free(s);
+	auto fail = [&](int code) { // contents undefined after a failed fill: leave an empty, still freeable set
+		s->n = 0;
+		s->total_bases = s->total_segs = s->total_words = s->max_len = 0;
 		return code;
 	};
 	if ((rc = seq_reserve(s->packed, s->cap_packed, (w ? w : 1) * 4)) != MC2_OK) return fail(rc);
@@ -849,8 +842,35 @@ int mc2_seqs_from_text(mc2_ctx *ctx, const char *text, const uint64_t *seq_off, 
 #undef MC2_TRY
 	s->min_seg_len = h_word[0];
 	if ((rc = check_err(ctx)) != MC2_OK) return fail(rc);
+	return MC2_OK;
+}
+
+int mc2_seqs_from_text(mc2_ctx *ctx, const char *text, const uint64_t *seq_off, uint64_t n, mc2_seqs **out)
+{
+	MC2_REQUIRE(ctx && seq_off && out, "mc2_seqs_from_text: NULL argument");
+	MC2_REQUIRE(n == 0 || text != nullptr, "mc2_seqs_from_text: text is NULL");
+	*out = nullptr;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	mc2_seqs *s = new (std::nothrow) mc2_seqs();
+	MC2_REQUIRE(s != nullptr, "out of host memory");
+	memset(s, 0, sizeof *s);
+	s->ctx = ctx;
+	int rc = text_fill(ctx, s, text, seq_off, n);
+	if (rc != MC2_OK) {
+		mc2_seqs_free(s);
+		return rc;
+	}
 	*out = s;
 	return MC2_OK;
+}
+
+int mc2_seqs_from_text_into(mc2_ctx *ctx, mc2_seqs *dst, const char *text, const uint64_t *seq_off, uint64_t n)
+{
+	MC2_REQUIRE(ctx && dst && seq_off, "mc2_seqs_from_text_into: NULL argument");
+	MC2_REQUIRE(n == 0 || text != nullptr, "mc2_seqs_from_text_into: text is NULL");
+	MC2_REQUIRE(dst->ctx == ctx, "mc2_seqs_from_text_into: the set belongs to another context");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	return text_fill(ctx, dst, text, seq_off, n);
 }
 
 int mc2_seqs_download_segments(mc2_ctx *ctx, const mc2_seqs *s, int32_t *segs_out, uint64_t *seg_off_out, uint64_t *lengths_out)
