@@ -10,6 +10,7 @@
 // of two consecutive big-endian 2-bit words, counts go to a shared-memory u32 histogram with atomics and
 // are narrowed (saturating) to T on the way out, fused with the side-band sums K2 needs.
 #include "mc2_internal.cuh"
+#include <cstdlib>
 
 namespace mc2 {
 
@@ -403,6 +404,247 @@ __global__ void __launch_bounds__(P16 ? 1024 : 256) count_kernel(const __grid_co
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// count_warp_kernel — the short-read shape (warp per sequence, u8 / u16 bins, at most 4096 bins, init <= 255), written for
+// instruction count: count_kernel above spends ~1 200 warp-instructions on a 1 kb read, most of them outside the counting
+// loop.  Here
+//   * the warp-private histogram sits on a boundary of its own size, so a bin's shared address is
+//     (funnel-shifted word & mask) | base: one 64-bit funnel shift, one LOP3 and the reduction per k-mer occurrence;
+//   * words whose 16 k-mer starts all lie in the segment take the unrolled path; the at most 30 starts in the two edge
+//     words of the segment are spread over the lanes instead of being looped over by one lane;
+//   * the narrowing pass re-zeroes the histogram it reads, all partial sums fit 32 bits (one REDUX each);
+//   * the next sequence's offsets, segment and first 64 packed words are loaded while the current one is narrowed;
+//   * the eleven side-band values leave through two lane-specialised stores.
+// Sequences with several segments (N runs) fall back to count_sequence() inside the same warp loop.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts_zero4(u32 addr)
+{
+	asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ uint4 lds4(u32 addr)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void reds_inc(u32 addr)
+{
+	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
+}
+// low 32 bits of (hi:lo) >> r, r in 0..63
+__device__ __forceinline__ u32 shr64_lo(u32 hi, u32 lo, int r)
+{
+	return (u32)((((u64)hi << 32) | lo) >> r);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) count_warp_kernel(const __grid_constant__ CountArgs a)
+{
+	static_assert(sizeof(T) <= 2, "count_warp_kernel: u8 / u16 bins only");
+	extern __shared__ __align__(16) u32 sh_hist[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
+	const u32 N = (u32)a.N, hbytes = N * 4u;
+	const u32 sh0 = (u32)__cvta_generic_to_shared(sh_hist);
+	const u32 hbase = ((sh0 + hbytes - 1u) & ~(hbytes - 1u)) + (u32)wid * hbytes; // the launch reserves one histogram of slack
+	u32 *hist = sh_hist + ((hbase - sh0) >> 2);
+	const u32 amask = hbytes - 4u; // (N - 1) << 2
+	const int k = a.k;
+	const int r0 = 62 - 2 * k; // (cur:nxt) >> (r0 - 2t) puts the k-mer starting at base t of cur on bits [2, 2k + 2)
+	const u32 init = (u32)a.init;
+	const u64 tmax = sizeof(T) == 1 ? 0xFFull : 0xFFFFull;
+	const double rcpN = 1.0 / (double)N;
+	const u64 n = a.n;
+	// lane-specialised side-band stores: lanes 0..8 one 64-bit value each, lanes 9..10 one 32-bit value each
+	u64 *p64 = lane == 0 ? a.mag : lane == 1 ? a.sum : lane == 2 ? a.sumsq : lane == 3 ? a.len
+		 : lane < 8 ? a.mers1 + (lane - 4) : reinterpret_cast<u64 *>(a.stddev);
+	const u32 stride64 = (lane >= 4 && lane < 8) ? 4u : 1u;
+	u32 *p32 = lane == 9 ? reinterpret_cast<u32 *>(a.novf) : a.maxc;
+
+	for (u32 b = (u32)lane * 16u; b < hbytes; b += 512u) {
+		sts_zero4(hbase + b);
+	}
+	__syncwarp();
+	const u64 groups = (u64)gridDim.x * warps;
+	u64 seq = (u64)blockIdx.x * warps + wid;
+	if (seq >= n) {
+		return;
+	}
+	u64 w0 = a.word_off[seq], sg0 = a.seg_off[seq];
+	u32 nw = (u32)(a.word_off[seq + 1] - w0), nseg = (u32)(a.seg_off[seq + 1] - sg0);
+	int2 se = nseg ? *reinterpret_cast<const int2 *>(a.segs + 2 * sg0) : make_int2(0, -1);
+	u32 rw0 = (u32)lane < nw ? a.packed[w0 + lane] : 0u, rw1 = (u32)lane + 32u < nw ? a.packed[w0 + 32 + lane] : 0u;
+	for (;;) {
+		const u64 nseq = seq + groups;
+		const bool more = nseq < n;
+		u64 n_w0 = 0, n_w1 = 0, n_sg0 = 0, n_sg1 = 0;
+		if (more) {
+			n_w0 = a.word_off[nseq];
+			n_w1 = a.word_off[nseq + 1];
+			n_sg0 = a.seg_off[nseq];
+			n_sg1 = a.seg_off[nseq + 1];
+		}
+		// ---- count
+		u32 cC = 0, cG = 0, cT = 0; // per-lane 1-mer partials (A follows from the effective length)
+		u64 eff_len = 0;
+		int novf = 0;
+		bool ovf_from_bins = true;
+		const u32 *pk = a.packed + w0;
+		if (nseg == 1) {
+			const int s0 = se.x, e0 = se.y;
+			eff_len = (u64)(e0 - s0 + 1);
+			const int last = e0 - k + 1;
+			const bool do_k = last >= s0;
+			const int wf = (s0 + 15) >> 4;               // first word whose 16 starts are all >= s0
+			const int wl = do_k ? (last + 1) >> 4 : 0;  // words below wl have all 16 starts <= last
+			const int wb = s0 >> 4, we = e0 >> 4;
+			u32 nCT = 0, nGT = 0, nT = 0;
+			int it = 0;
+			for (int wi = wb; wi <= we; wi += 32, it++) {
+				const int w = wi + lane;
+				u32 cur;
+				if (wb == 0 && it < 2) {
+					cur = it ? rw1 : rw0;
+				} else {
+					cur = w < (int)nw ? pk[w] : 0u;
+				}
+				u32 nxt = __shfl_down_sync(0xffffffffu, cur, 1);
+				if (lane == 31) {
+					nxt = w + 1 < (int)nw ? pk[w + 1] : 0u;
+				}
+				if (w <= we) {
+					const int j0 = w << 4;
+					u32 vm = 0x55555555u;
+					if (j0 < s0 || j0 + 15 > e0) {
+						const int lo_t = max(0, s0 - j0), hi_t = min(15, e0 - j0);
+						vm &= 0xFFFFFFFFu >> (2 * lo_t);
+						vm &= hi_t >= 15 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> (2 * (hi_t + 1)));
+					}
+					const u32 lo = cur & vm, hi = (cur >> 1) & vm;
+					nT += __popc(hi & lo);
+					nCT += __popc(lo);
+					nGT += __popc(hi);
+					if (do_k && w >= wf && w < wl) {
+#pragma unroll
+						for (int t = 0; t < 16; t++) {
+							reds_inc((shr64_lo(cur, nxt, r0 - 2 * t) & amask) | hbase);
+						}
+					}
+				}
+			}
+			if (do_k) {
+				// starts outside the full words: [s0, wf*16) in front, [max(wl, wf)*16, last] behind; < 16 each
+				int pos;
+				bool ok;
+				if (lane < 16) {
+					pos = s0 + lane;
+					ok = pos <= min(wf * 16 - 1, last);
+				} else {
+					pos = max(wl, wf) * 16 + (lane - 16);
+					ok = pos <= last;
+				}
+				if (ok) {
+					const int w = pos >> 4, t = pos & 15;
+					const u32 cur = pk[w];
+					const u32 nxt = w + 1 < (int)nw ? pk[w + 1] : 0u;
+					reds_inc((shr64_lo(cur, nxt, r0 - 2 * t) & amask) | hbase);
+				}
+			}
+			cT = nT;
+			cC = nCT - nT;
+			cG = nGT - nT;
+		} else if (nseg > 1) {
+			u32 m1[4];
+			count_sequence<true, false, false>(a, seq, hist, lane, 32, tmax, m1, eff_len, novf, ovf_from_bins);
+			cC = m1[1];
+			cG = m1[2];
+			cT = m1[3];
+		}
+		// ---- next sequence's segment and first words, in flight while this one is narrowed
+		int2 n_se = make_int2(0, -1);
+		u32 n_rw0 = 0, n_rw1 = 0;
+		const u32 n_nw = (u32)(n_w1 - n_w0), n_nseg = (u32)(n_sg1 - n_sg0);
+		if (more) {
+			if (n_nseg) {
+				n_se = *reinterpret_cast<const int2 *>(a.segs + 2 * n_sg0);
+			}
+			if ((u32)lane < n_nw) {
+				n_rw0 = a.packed[n_w0 + lane];
+			}
+			if ((u32)lane + 32u < n_nw) {
+				n_rw1 = a.packed[n_w0 + 32 + lane];
+			}
+		}
+		__syncwarp();
+		// ---- narrow (saturating) + side-band; leaves the histogram zeroed
+		T *dst = reinterpret_cast<T *>(a.bins) + seq * N;
+		u32 s32 = 0, q32 = 0, mx = 0;
+		u64 q64 = 0;
+		for (u32 b = (u32)lane * 4u; b < N; b += 128u) {
+			const uint4 c = lds4(hbase + b * 4u);
+			sts_zero4(hbase + b * 4u);
+			mx = max(mx, max(max(c.x, c.y), max(c.z, c.w)));
+			if constexpr (sizeof(T) == 1) {
+				const u32 v0 = min(c.x + init, 255u), v1 = min(c.y + init, 255u), v2 = min(c.z + init, 255u),
+					  v3 = min(c.w + init, 255u);
+				const u32 pv = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+				*reinterpret_cast<u32 *>(dst + b) = pv;
+				s32 = __dp4a(pv, 0x01010101u, s32);
+				q32 = __dp4a(pv, pv, q32);
+			} else {
+				const u32 v0 = min(c.x + init, 65535u), v1 = min(c.y + init, 65535u), v2 = min(c.z + init, 65535u),
+					  v3 = min(c.w + init, 65535u);
+				*reinterpret_cast<uint2 *>(dst + b) = make_uint2(v0 | (v1 << 16), v2 | (v3 << 16));
+				s32 += v0 + v1 + v2 + v3;
+				q64 += (u64)(v0 * v0) + (u64)(v1 * v1) + (u64)(v2 * v2) + (u64)(v3 * v3);
+			}
+		}
+		const u64 sum = __reduce_add_sync(0xffffffffu, s32);
+		u64 sumsq;
+		if constexpr (sizeof(T) == 1) {
+			sumsq = __reduce_add_sync(0xffffffffu, q32);
+		} else {
+			// per lane < 2^39: reduce in two 20-bit-split halves, each total below 2^32
+			const u32 ql = __reduce_add_sync(0xffffffffu, (u32)(q64 & 0xFFFFFu));
+			const u32 qh = __reduce_add_sync(0xffffffffu, (u32)(q64 >> 20));
+			sumsq = ((u64)qh << 20) + ql;
+		}
+		mx = __reduce_max_sync(0xffffffffu, mx);
+		const u32 tC = __reduce_add_sync(0xffffffffu, cC), tG = __reduce_add_sync(0xffffffffu, cG),
+			  tT = __reduce_add_sync(0xffffffffu, cT);
+		const u64 tA = eff_len - tC - tG - tT;
+		if (ovf_from_bins) { // single segment: it overflowed iff some final count exceeds max(T)
+			novf = (u64)init + mx > tmax ? 1 : 0;
+		}
+		// Loader.cpp:162-171: sqrt(sum((p_i - mag/N)^2)/N) == sqrt(N*sumsq - sum^2)/N; here N*sumsq < 2^57, exact in 64 bits
+		const double sd = sqrt((double)((u64)N * sumsq - sum * sum)) * rcpN;
+		u64 v64 = sum;
+		v64 = lane == 2 ? sumsq : v64;
+		v64 = lane == 3 ? eff_len : v64;
+		v64 = lane == 4 ? 1 + tA : v64;
+		v64 = lane == 5 ? 1 + (u64)tC : v64;
+		v64 = lane == 6 ? 1 + (u64)tG : v64;
+		v64 = lane == 7 ? 1 + (u64)tT : v64;
+		v64 = lane == 8 ? (u64)__double_as_longlong(sd) : v64;
+		if (lane < 9) {
+			p64[seq * stride64] = v64;
+		} else if (lane < 11) {
+			p32[seq] = lane == 9 ? (u32)novf : mx;
+		}
+		if (!more) {
+			break;
+		}
+		__syncwarp();
+		seq = nseq;
+		w0 = n_w0;
+		sg0 = n_sg0;
+		nw = n_nw;
+		nseg = n_nseg;
+		se = n_se;
+		rw0 = n_rw0;
+		rw1 = n_rw1;
+	}
+}
+
 // sums / sums of squares for a set uploaded from the host (mc2_hset_from_host)
 template <typename T>
 __global__ void __launch_bounds__(256) sideband_kernel(const T *__restrict__ bins, u64 n, u64 N, u64 *sum, u64 *sumsq,
@@ -460,6 +702,27 @@ static int launch_count_t(mc2_ctx *ctx, const mc2_seqs *s, CountArgs &a)
 	if (hist_bytes <= 64 * 1024) {
 		// shared-memory histograms
 		const bool warp_mode = hist_bytes <= 16 * 1024 && avg_len <= 4096;
+		if constexpr (sizeof(T) <= 2) {
+			const bool legacy = getenv("MC2_K1_LEGACY") != nullptr; // A/B switch for tools/k1_bench.py
+			if (warp_mode && a.init <= 255 && !legacy) {
+				int warps = (int)(32 * 1024 / hist_bytes);
+				warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
+				const size_t smem = (size_t)(warps + 1) * hist_bytes; // one histogram of slack for the alignment
+				MC2_CUDA(cudaFuncSetAttribute(count_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+				int per_sm = 0;
+				MC2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_warp_kernel<T>, warps * 32, smem));
+				per_sm = per_sm < 1 ? 1 : per_sm;
+				// one resident wave; every warp walks its sequences with the next one's loads in flight
+				const u64 want = (s->n + warps - 1) / warps, cap = (u64)ctx->sm_count * per_sm;
+				const int grid = (int)(want < cap ? want : cap);
+				prof_begin(ctx, 1);
+				count_warp_kernel<T><<<grid, warps * 32, smem, ctx->stream>>>(a);
+				prof_end(ctx);
+				ctx->launches++;
+				MC2_CUDA(cudaGetLastError());
+				return MC2_OK;
+			}
+		}
 		if (warp_mode) {
 			int warps = (int)(48 * 1024 / hist_bytes);
 			warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
