@@ -98,10 +98,11 @@ int mc2_timer_stop(mc2_ctx *ctx, float *ms);
 /* count of this library's kernel launches on this ctx since creation (bench.py's gpu_launches) */
 uint64_t mc2_ctx_launch_count(const mc2_ctx *ctx);
 /* Per-kernel device timing (CUDA events around each launch on the ctx stream), for bench.py's roofline object.
- * kinds: 0 pack, 1 k-mer count, 2 pair score (gather / one-vs-many), 3 sweep (query-vs-database), 4 argmax, 5 side-band.
+ * kinds: 0 pack, 1 k-mer count, 2 pair score (gather / one-vs-many), 3 sweep (query-vs-database), 4 argmax, 5 side-band,
+ * 6 batched update / merge stage.
  * mc2_ctx_profile(ctx, 1) starts collecting (and clears the totals), (ctx, 0) stops;
  * mc2_ctx_kernel_time synchronises the stream and returns the summed milliseconds and launch count of one kind. */
-#define MC2_KERNEL_KINDS 6
+#define MC2_KERNEL_KINDS 7
 int mc2_ctx_profile(mc2_ctx *ctx, int enable);
 int mc2_ctx_kernel_time(mc2_ctx *ctx, int kind, double *total_ms, uint64_t *launches);
 /* write `bytes` of zeros to a scratch buffer (L2 flush between timed iterations) */
@@ -297,6 +298,26 @@ int mc2_filter(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint
  * *out = chosen index in [begin,last] or 0 when none is close. */
 int mc2_merge(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *centers, const uint64_t *rows, int64_t cur,
 	      int64_t begin, int64_t last, double id, int64_t *out);
+
+/* Batched update stage ("batching independent queries (update stage: all centers are independent)").
+ * `centers` holds one staged row per center (mc2_hset_assign_rows: bins of the point whose id the center carries + the host
+ * object's own pseudo-magnitude and length); the members of center c are rows members[member_off[c] .. member_off[c+1]) of
+ * set_m.
+ *
+ * mc2_update_centers = mean_shift_update (src/cluster/ClusterFactory.cpp:288-335) for every center of one pass of the loops at
+ * :639-642 / :650-653: Trainer::filter (src/cluster/Trainer.cpp:123-141: length window, then round(classify(center, member))
+ * != 0), the per-bin mean of the survivors, Trainer::closest (:144-157: first minimum of distance_d).  next[c] = position
+ * inside center c's member list of the chosen member, -1 when no member survives; n_good[c] = number of survivors (may be
+ * NULL).  One pair-scoring launch + one launch of a CTA per center, whatever the number of centers.
+ *
+ * mc2_merge_centers = Trainer::merge (src/cluster/Trainer.cpp:74-109) for every center of one pass of merge()
+ * (src/cluster/ClusterFactory.cpp:382-401): center c against centers c+1 .. min(n_centers-1, c+delta); out[c] = the chosen
+ * center index, or 0 when none is close (the reference's return value; callers test `ret > c`).  trn.merge never looks at
+ * the lazily removed flag, so the passes of one merge() call are independent of each other. */
+int mc2_update_centers(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *centers, uint64_t n_centers, const mc2_hset *set_m,
+		       const uint64_t *member_off, const uint64_t *members, double id, int64_t *next, uint64_t *n_good);
+int mc2_merge_centers(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *centers, uint64_t n_centers, int64_t delta, double id,
+		      int64_t *out);
 
 /* All-pairs / query-vs-database sweep with the length prefilter, as fastcar's work() does
  * (src/fastcar/FC_Runner.cpp:427-470): for every query row r in [q_begin,q_end) of set_q and database row c in

@@ -11,19 +11,29 @@
 // Batching follows SURVEY.md section 3.1: one device call per get_close / filter / merge (the candidates of one query);
 // the histograms of all points are uploaded once, centers are addressed by the id of the point whose bins they carry plus
 // the (possibly stale, quirk Q4) pseudo-magnitude and length the host object reports.
+//
+// The update stage goes further (north_star: the mean-shift driver is "unchanged apart from batching candidate pairs to the
+// device"): mc2_batched_update / mc2_batched_merge below serve every center of one pass of ClusterFactory<T>::MS's two loops
+// with one device call each (mc2_update_centers, mc2_merge_centers).  They are reached through the two-hunk edit of
+// src/cluster/ClusterFactory.cpp that integration/patch_cluster_factory.py applies at build time; with
+// MC2_NO_BATCH=1 in the environment they decline and the reference's per-center loops run instead.
 #include "cluster/Trainer.h"
 #include "clutil/Datatype.h"
 #include "clutil/DivergencePoint.h"
 #include "predict/Predictor.h"
 
 #include <cfloat>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
 #include <stdexcept>
+#include <thread>
 
 #include "meshclust2_b200.h"
+#include "update_batch_b200.h"
 
 namespace {
 
@@ -43,11 +53,60 @@ struct Device {
 	mc2_hset *points = nullptr;   // row = Point::get_id()
 	mc2_hset *scratch = nullptr;  // assembled center rows (filter: 1, merge: <= 1 + delta)
 	uint64_t scratch_rows = 0;
+	mc2_hset *centers = nullptr;  // every center of an update / merge pass (batched stage)
+	uint64_t center_rows = 0;
 	uint64_t n = 0;
 	int k = 0;
 };
 
 std::map<const void *, Device> g_dev;
+
+// MC2_TIMING=1: wall-clock spent behind the boundary, printed to stderr at exit (development aid)
+struct Timing {
+	double init = 0, get_close = 0, filter = 0, closest = 0, merge = 0, update_batch = 0, merge_batch = 0;
+	unsigned long n_get_close = 0, n_filter = 0, n_closest = 0, n_merge = 0, n_update_batch = 0, n_merge_batch = 0;
+	bool on = std::getenv("MC2_TIMING") != nullptr;
+	~Timing()
+	{
+		if (on) {
+			std::fprintf(stderr,
+				     "meshclust2_b200 timing: init %.3f s | get_close %lu calls %.3f s | filter %lu %.3f s | closest %lu %.3f s | "
+				     "merge %lu %.3f s | update batches %lu %.3f s | merge batches %lu %.3f s\n",
+				     init, n_get_close, get_close, n_filter, filter, n_closest, closest, n_merge, merge, n_update_batch,
+				     update_batch, n_merge_batch, merge_batch);
+		}
+	}
+} g_time;
+
+struct Stopwatch {
+	double &acc;
+	unsigned long &n;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	Stopwatch(double &a, unsigned long &c) : acc(a), n(c) {}
+	~Stopwatch()
+	{
+		acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		n++;
+	}
+};
+
+// The CUDA context and the upload of the point histograms do not depend on the model, so Trainer::train starts them on a
+// second thread while the host fits the GLM (seconds); device_for() joins.  Rows are uploaded in the order of the Trainer's
+// point vector, which is the order CRunner.cpp:587-592 assigns the final ids in; device_for() checks that before use.
+struct Prewarm {
+	std::thread th;
+	mc2_ctx *ctx = nullptr;
+	mc2_hset *points = nullptr;
+	std::string err;
+	bool started = false;
+	~Prewarm()
+	{
+		if (th.joinable()) {
+			th.join();
+		}
+	}
+};
+std::map<const void *, Prewarm> g_pre;
 
 template <class T>
 const DivergencePoint<T> &dp(const Point<T> *p)
@@ -101,26 +160,51 @@ Device &device_for(const void *key, const Feature<T> &feat, const matrix::Matrix
 	if (d.ctx) {
 		return d;
 	}
-	const char *dev_env = std::getenv("MC2_DEVICE");
-	ok(mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &d.ctx));
-	mc2_model_desc desc = describe<T>(feat, weights);
-	ok(mc2_model_create(d.ctx, &desc, &d.model));
+	unsigned long once = 0;
+	Stopwatch sw(g_time.init, once);
 	d.k = k;
 	d.n = points.size();
 	const size_t N = (size_t)1 << (2 * k);
-	std::vector<T> bins(d.n * N);
-	std::vector<uint64_t> mag(d.n), len(d.n);
-	for (Point<T> *p : points) {
-		const uint64_t id = p->get_id();
-		if (id >= d.n) {
-			throw std::runtime_error("meshclust2_b200 integration: point ids must be 0..n-1 (no --no-train-list support)");
+	auto pre = g_pre.find(key);
+	if (pre != g_pre.end() && pre->second.started) {
+		Prewarm &w = pre->second;
+		if (w.th.joinable()) {
+			w.th.join();
 		}
-		const DivergencePoint<T> &q = dp<T>(p);
-		std::copy(q.points.begin(), q.points.end(), bins.begin() + id * N);
-		mag[id] = q.getPseudoMagnitude();
-		len[id] = q.get_length();
+		bool in_order = w.err.empty() && w.ctx && w.points;
+		for (size_t i = 0; in_order && i < points.size(); i++) {
+			in_order = points[i]->get_id() == i;
+		}
+		if (in_order) {
+			d.ctx = w.ctx;
+			d.points = w.points;
+		} else {
+			if (w.points) mc2_hset_free(w.points);
+			if (w.ctx) mc2_ctx_destroy(w.ctx);
+		}
+		w.ctx = nullptr;
+		w.points = nullptr;
+		w.started = false;
 	}
-	ok(mc2_hset_from_host(d.ctx, bins.data(), d.n, k, (int)sizeof(T), mag.data(), len.data(), &d.points));
+	if (!d.ctx) {
+		const char *dev_env = std::getenv("MC2_DEVICE");
+		ok(mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &d.ctx));
+		std::vector<T> bins(d.n * N);
+		std::vector<uint64_t> mag(d.n), len(d.n);
+		for (Point<T> *p : points) {
+			const uint64_t id = p->get_id();
+			if (id >= d.n) {
+				throw std::runtime_error("meshclust2_b200 integration: point ids must be 0..n-1 (no --no-train-list support)");
+			}
+			const DivergencePoint<T> &q = dp<T>(p);
+			std::copy(q.points.begin(), q.points.end(), bins.begin() + id * N);
+			mag[id] = q.getPseudoMagnitude();
+			len[id] = q.get_length();
+		}
+		ok(mc2_hset_from_host(d.ctx, bins.data(), d.n, k, (int)sizeof(T), mag.data(), len.data(), &d.points));
+	}
+	mc2_model_desc desc = describe<T>(feat, weights);
+	ok(mc2_model_create(d.ctx, &desc, &d.model));
 	d.scratch_rows = 64;
 	std::vector<T> zero(d.scratch_rows * N, 1);
 	std::vector<uint64_t> ones(d.scratch_rows, 1);
@@ -128,14 +212,49 @@ Device &device_for(const void *key, const Feature<T> &feat, const matrix::Matrix
 	return d;
 }
 
-// put host center objects into scratch rows 0..m-1: bins of the point whose id they carry + their own mag / length
 template <class T>
-void stage_centers(Device &d, const std::vector<Point<T> *> &cs)
+void start_prewarm(const void *key, const std::vector<Point<T> *> &points, int k)
+{
+	if (std::getenv("MC2_NO_PREWARM")) {
+		return;
+	}
+	std::lock_guard<std::mutex> lock(g_mu);
+	Prewarm &w = g_pre[key];
+	if (w.started || g_dev.count(key)) {
+		return;
+	}
+	w.started = true;
+	Prewarm *wp = &w; // std::map nodes are stable
+	const std::vector<Point<T> *> *pts = &points;
+	w.th = std::thread([wp, pts, k]() {
+		try {
+			const char *dev_env = std::getenv("MC2_DEVICE");
+			if (mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &wp->ctx) != MC2_OK) {
+				throw std::runtime_error(mc2_last_error());
+			}
+			const size_t n = pts->size(), N = (size_t)1 << (2 * k);
+			std::vector<T> bins(n * N);
+			std::vector<uint64_t> mag(n), len(n);
+			for (size_t i = 0; i < n; i++) {
+				const DivergencePoint<T> &q = dp<T>((*pts)[i]);
+				std::copy(q.points.begin(), q.points.end(), bins.begin() + i * N);
+				mag[i] = q.getPseudoMagnitude();
+				len[i] = q.get_length();
+			}
+			if (mc2_hset_from_host(wp->ctx, bins.data(), n, k, (int)sizeof(T), mag.data(), len.data(), &wp->points) != MC2_OK) {
+				throw std::runtime_error(mc2_last_error());
+			}
+		} catch (const std::exception &e) {
+			wp->err = e.what();
+		}
+	});
+}
+
+// put host center objects into rows 0..m-1 of `into`: bins of the point whose id they carry + their own mag / length
+template <class T>
+void stage_into(Device &d, mc2_hset *into, const std::vector<Point<T> *> &cs)
 {
 	const uint64_t m = cs.size();
-	if (m > d.scratch_rows) {
-		throw std::runtime_error("meshclust2_b200 integration: --delta too large for the scratch set");
-	}
 	std::vector<uint64_t> dst(m), src(m), mag(m), len(m);
 	for (uint64_t i = 0; i < m; i++) {
 		dst[i] = i;
@@ -143,7 +262,45 @@ void stage_centers(Device &d, const std::vector<Point<T> *> &cs)
 		mag[i] = dp<T>(cs[i]).getPseudoMagnitude();
 		len[i] = cs[i]->get_length();
 	}
-	ok(mc2_hset_assign_rows(d.ctx, d.scratch, m, dst.data(), d.points, src.data(), mag.data(), len.data()));
+	ok(mc2_hset_assign_rows(d.ctx, into, m, dst.data(), d.points, src.data(), mag.data(), len.data()));
+}
+
+template <class T>
+void stage_centers(Device &d, const std::vector<Point<T> *> &cs)
+{
+	if (cs.size() > d.scratch_rows) {
+		throw std::runtime_error("meshclust2_b200 integration: --delta too large for the scratch set");
+	}
+	stage_into<T>(d, d.scratch, cs);
+}
+
+// all centers of a pass, staged into a set that is sized on first use (the number of centers only shrinks afterwards)
+template <class T>
+void stage_all_centers(Device &d, std::vector<Center<T>> &part)
+{
+	const uint64_t n = part.size();
+	if (n > d.center_rows) {
+		if (d.centers) {
+			mc2_hset_free(d.centers);
+			d.centers = nullptr;
+		}
+		const size_t N = (size_t)1 << (2 * d.k);
+		std::vector<T> ones(n * N, 1);
+		std::vector<uint64_t> len1(n, 1);
+		ok(mc2_hset_from_host(d.ctx, ones.data(), n, d.k, (int)sizeof(T), nullptr, len1.data(), &d.centers));
+		d.center_rows = n;
+	}
+	std::vector<Point<T> *> cs(n);
+	for (uint64_t j = 0; j < n; j++) {
+		cs[j] = part[j].getCenter();
+	}
+	stage_into<T>(d, d.centers, cs);
+}
+
+bool batching_enabled()
+{
+	static const bool off = std::getenv("MC2_NO_BATCH") != nullptr;
+	return !off;
 }
 
 } // namespace
@@ -154,6 +311,7 @@ std::tuple<Point<T> *, double, size_t, size_t> Trainer<T>::get_close(Point<T> *p
 {
 	std::lock_guard<std::mutex> lock(g_mu);
 	Device &d = device_for<T>(this, *feat, weights, points, k);
+	Stopwatch sw(g_time.get_close, g_time.n_get_close);
 	std::vector<uint64_t> cand;
 	std::vector<bvec_iterator<T>> where;
 	// same trip count as the reference's `omp parallel for` over the iterator range: iend - istart (bvec_iterator::operator-),
@@ -201,6 +359,7 @@ long Trainer<T>::merge(vector<Center<T>> &centers, long current, long begin, lon
 	}
 	std::lock_guard<std::mutex> lock(g_mu);
 	Device &d = device_for<T>(this, *feat, weights, points, k);
+	Stopwatch sw(g_time.merge, g_time.n_merge);
 	std::vector<Point<T> *> cs;
 	cs.push_back(centers[current].getCenter());
 	for (long i = begin; i <= last; i++) {
@@ -244,6 +403,7 @@ void Trainer<T>::filter(Point<T> *p, vector<pair<Point<T> *, bool>> &vec) const
 	{
 		std::lock_guard<std::mutex> lock(g_mu);
 		Device &d = device_for<T>(this, *feat, weights, points, k);
+		Stopwatch sw(g_time.filter, g_time.n_filter);
 		std::vector<uint64_t> rows(vec.size());
 		for (size_t j = 0; j < vec.size(); j++) {
 			rows[j] = vec[j].first->get_id();
@@ -271,6 +431,7 @@ Point<T> *Trainer<T>::closest(Point<double> *p, vector<pair<Point<T> *, bool>> &
 	}
 	std::lock_guard<std::mutex> lock(g_mu);
 	Device &d = device_for<T>(this, *feat, weights, points, k);
+	Stopwatch sw(g_time.closest, g_time.n_closest);
 	std::vector<uint64_t> rows(vec.size());
 	for (size_t j = 0; j < vec.size(); j++) {
 		rows[j] = vec[j].first->get_id();
@@ -286,6 +447,7 @@ Point<T> *Trainer<T>::closest(Point<double> *p, vector<pair<Point<T> *, bool>> &
 template <class T>
 void Trainer<T>::train(std::string dump_str)
 {
+	start_prewarm<T>(this, points, k);
 	Predictor<T> *pred = new Predictor<T>(dump_str); // never destroyed: the reference's file ctor leaves members unset
 	auto pr = pred->get_class();
 	delete feat;
@@ -299,6 +461,9 @@ void Trainer<T>::train(int min_n_feat, int max_n_feat, uint64_t feat_type, int m
 		       double acc_cutoff)
 {
 	(void)acc_cutoff;
+	if (dump_str == "") {
+		start_prewarm<T>(this, points, k); // not for --dump runs, which exit right after training
+	}
 	std::cout << "Splitting data" << endl;
 	uintmax_t next_id = points.size();
 	Predictor<T> pred(k, cutoff, PRED_MODE_CLASS, feat_type, mut_type, min_n_feat, max_n_feat, min_id);
@@ -313,6 +478,95 @@ void Trainer<T>::train(int min_n_feat, int max_n_feat, uint64_t feat_type, int m
 		exit(0);
 	}
 }
+
+// ---- batched update stage -------------------------------------------------------------------------------------------
+// One pass of `for j: mean_shift_update(part, j, trn, delta)` (src/cluster/ClusterFactory.cpp:639-642 and :648-651).  The
+// iterations are independent: each reads the point lists of clusters j-delta..j+delta and its own center, and writes only
+// its own center.  Member lists are built as mean_shift_update builds `good` (:292-307), the device filters them, averages
+// the survivors and picks the closest one; the host applies center->set(*next) (:328) or, when nothing survives and
+// delta == 0, center->set(*first) (:329-332).
+template <class T>
+bool mc2_batched_update(std::vector<Center<T>> &part, const Trainer<T> &trn, int delta)
+{
+	if (!batching_enabled() || part.empty()) {
+		return false;
+	}
+	std::lock_guard<std::mutex> lock(g_mu);
+	auto it = g_dev.find(&trn);
+	if (it == g_dev.end() || !it->second.ctx) {
+		return false; // no device mirror yet: the per-center path creates it
+	}
+	Device &d = it->second;
+	Stopwatch sw(g_time.update_batch, g_time.n_update_batch);
+	const long n = (long)part.size();
+	std::vector<uint64_t> off((size_t)n + 1, 0), members;
+	std::vector<Point<T> *> who;
+	for (long j = 0; j < n; j++) {
+		const long i_begin = std::max(0L, j - delta), i_end = std::min(j + (long)delta, n - 1);
+		for (long i = i_begin; i <= i_end; i++) {
+			for (Point<T> *p : part[i].getPoints()) {
+				members.push_back(p->get_id());
+				who.push_back(p);
+			}
+		}
+		off[(size_t)j + 1] = members.size();
+	}
+	stage_all_centers<T>(d, part);
+	std::vector<int64_t> next((size_t)n);
+	ok(mc2_update_centers(d.ctx, d.model, d.centers, (uint64_t)n, d.points, off.data(), members.data(), trn.get_id(), next.data(),
+			      nullptr));
+	for (long j = 0; j < n; j++) {
+		Point<T> *center = part[j].getCenter();
+		if (next[(size_t)j] >= 0) {
+			center->set(*who[off[(size_t)j] + (uint64_t)next[(size_t)j]]);
+		} else if (delta == 0) {
+			center->set(*part[j].getPoints()[0]);
+		}
+	}
+	return true;
+}
+
+// One call of merge() (src/cluster/ClusterFactory.cpp:382-401).  Trainer::merge reads only the center points, which the
+// loop never changes, so every center's choice comes from one device call; the list splicing and the erase stay as they are.
+template <class T>
+bool mc2_batched_merge(std::vector<Center<T>> &centers, const Trainer<T> &trn, int delta)
+{
+	if (!batching_enabled() || centers.empty()) {
+		return false;
+	}
+	std::vector<int64_t> ret(centers.size());
+	{
+		std::lock_guard<std::mutex> lock(g_mu);
+		auto it = g_dev.find(&trn);
+		if (it == g_dev.end() || !it->second.ctx) {
+			return false;
+		}
+		Device &d = it->second;
+		Stopwatch sw(g_time.merge_batch, g_time.n_merge_batch);
+		stage_all_centers<T>(d, centers);
+		ok(mc2_merge_centers(d.ctx, d.model, d.centers, centers.size(), delta, trn.get_id(), ret.data()));
+	}
+	for (size_t i = 0; i < centers.size(); i++) {
+		if (ret[i] > (int64_t)i) {
+			auto &to_add = centers[(size_t)ret[i]].getPoints();
+			auto &to_del = centers[i].getPoints();
+			to_add.insert(std::end(to_add), std::begin(to_del), std::end(to_del));
+			centers[i].lazy_remove();
+		}
+	}
+	centers.erase(std::remove_if(centers.begin(), centers.end(), [](const Center<T> &c) { return c.is_delete(); }), centers.end());
+	return true;
+}
+
+#define MC2_INSTANTIATE_BATCH(T)                                                                         \
+	template bool mc2_batched_update<T>(std::vector<Center<T>> &, const Trainer<T> &, int);          \
+	template bool mc2_batched_merge<T>(std::vector<Center<T>> &, const Trainer<T> &, int);
+MC2_INSTANTIATE_BATCH(uint8_t)
+MC2_INSTANTIATE_BATCH(uint16_t)
+MC2_INSTANTIATE_BATCH(uint32_t)
+MC2_INSTANTIATE_BATCH(uint64_t)
+MC2_INSTANTIATE_BATCH(int)
+MC2_INSTANTIATE_BATCH(double)
 
 template class Trainer<uint8_t>;
 template class Trainer<uint16_t>;

@@ -39,6 +39,7 @@ SYMBOLS = [
     "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
     "mc2_score_pairs", "mc2_get_close", "mc2_get_close_as", "mc2_filter", "mc2_filter_as", "mc2_merge", "mc2_all_pairs", "mc2_distance", "mc2_mean_closest", "mc2_closest",
+    "mc2_update_centers", "mc2_merge_centers",
     "mc2_bench_score_pairs", "mc2_bench_count_kmers", "mc2_encode_dna", "mc2_encode_dna_batch",
 ]
 
@@ -372,6 +373,22 @@ class Context:
         _check(lib().mc2_mean_closest(self.h, hset.h, _p(members), C.c_uint64(len(members)), C.byref(best), C.byref(bd),
                                       _p(mean), _p(dist)))
         return best.value, bd.value, mean, dist
+
+    def update_centers(self, model, centers, n_centers, set_m, member_off, members, ident):
+        """Batched mean_shift_update: (next position per center or -1, survivors per center)"""
+        member_off, members = _u64(member_off), _u64(members)
+        nxt = np.zeros(n_centers, dtype=np.int64)
+        ng = np.zeros(n_centers, dtype=np.uint64)
+        _check(lib().mc2_update_centers(self.h, model.h, centers.h, C.c_uint64(n_centers), set_m.h, _p(member_off), _p(members),
+                                        C.c_double(ident), _p(nxt), _p(ng)))
+        return nxt, ng
+
+    def merge_centers(self, model, centers, n_centers, delta, ident):
+        """Batched Trainer::merge: chosen center index per center, 0 when none is close"""
+        out = np.zeros(n_centers, dtype=np.int64)
+        _check(lib().mc2_merge_centers(self.h, model.h, centers.h, C.c_uint64(n_centers), C.c_int64(delta), C.c_double(ident),
+                                       _p(out)))
+        return out
 
     def closest(self, hset, members, mean):
         """Trainer::closest: (best position, distance, dist[n]) against a caller-supplied double mean"""

@@ -1852,6 +1852,147 @@ static int mean_closest_impl(mc2_ctx *ctx, const mc2_hset *set, const uint64_t *
 	return MC2_OK;
 }
 
+/* ---- batched update / merge stage ---------------------------------------------------------------- */
+// scores the pair list (ia into set_a, ib into set_b) with the length window and leaves dist / close / skipped on the device
+static int score_on_device(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *p, PairArgs &a)
+{
+	CtxExtra *x = extra(ctx);
+	int rc = fill_pair_args(ctx, p, a, x);
+	if (rc != MC2_OK) return rc;
+	const u64 m = p->n_pairs;
+	rc = ensure(x->d[B_DIST], m * 8, false); if (rc) return rc;
+	rc = ensure(x->d[B_CLOSE], m, false); if (rc) return rc;
+	rc = ensure(x->d[B_SKIP], m, false); if (rc) return rc;
+	a.dist = (double *)x->d[B_DIST].p;
+	a.close = (uint8_t *)x->d[B_CLOSE].p;
+	a.skipped = (uint8_t *)x->d[B_SKIP].p;
+	rc = reset_err(ctx);
+	if (rc == MC2_OK) rc = launch_pair_score(ctx, model->dm, a);
+	return rc;
+}
+
+int mc2_update_centers(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *centers, uint64_t n_centers, const mc2_hset *set_m,
+		       const uint64_t *member_off, const uint64_t *members, double id, int64_t *next, uint64_t *n_good)
+{
+	MC2_REQUIRE(ctx && model && centers && set_m && (n_centers == 0 || (member_off && next)), "mc2_update_centers: NULL argument");
+	MC2_REQUIRE(n_centers <= centers->n, "mc2_update_centers: more centers than staged rows");
+	if (n_centers == 0) return MC2_OK;
+	// round(score) != 0 (Trainer.cpp:135) is the kernel's close flag round(score) > 0 as long as score > -0.5
+	if (model->dm.bias < -0.5 || model->dm.regression) {
+		set_error("mc2_update_centers: needs a classifier with bias >= -0.5");
+		return MC2_ERR_UNSUPPORTED;
+	}
+	MC2_REQUIRE(member_off[0] == 0, "mc2_update_centers: member_off[0] must be 0");
+	for (u64 c = 0; c < n_centers; c++) {
+		MC2_REQUIRE(member_off[c] <= member_off[c + 1], "mc2_update_centers: member_off must be non-decreasing");
+	}
+	const u64 m = member_off[n_centers];
+	MC2_REQUIRE(m == 0 || members, "mc2_update_centers: members is NULL");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	if (m == 0) {
+		for (u64 c = 0; c < n_centers; c++) {
+			next[c] = -1;
+			if (n_good) n_good[c] = 0;
+		}
+		return MC2_OK;
+	}
+	std::vector<uint64_t> ia(m);
+	for (u64 c = 0; c < n_centers; c++) {
+		for (u64 p = member_off[c]; p < member_off[c + 1]; p++) {
+			ia[p] = c;
+		}
+	}
+	mc2_pairs p;
+	memset(&p, 0, sizeof p);
+	p.set_a = centers; // classify(center, member), Trainer.cpp:133
+	p.set_b = set_m;
+	p.n_pairs = m;
+	p.ia = ia.data();
+	p.ib = members;
+	p.len_filter = 1;
+	p.anchor_is_b = 0;
+	p.cutoff = id;
+	PairArgs a;
+	int rc = score_on_device(ctx, model, &p, a);
+	if (rc != MC2_OK) return rc;
+	CtxExtra *x = extra(ctx);
+	const u64 N = set_m->N;
+	// scratch: [member_off | next | n_good] and the per-center means, chunked so the means stay below 256 MiB
+	u64 chunk = (256ull << 20) / (N * 8);
+	chunk = chunk < 1 ? 1 : (chunk > n_centers ? n_centers : chunk);
+	rc = ensure(x->d[B_MISC], (3 * n_centers + 1) * 8, false); if (rc) return rc;
+	rc = ensure(x->d[B_RAW], chunk * N * 8, false); if (rc) return rc;
+	u64 *d_off = (u64 *)x->d[B_MISC].p;
+	long long *d_next = (long long *)(d_off + n_centers + 1);
+	u64 *d_ng = (u64 *)(d_next + n_centers);
+	bool staged = false;
+	rc = h2d(ctx, d_off, member_off, (n_centers + 1) * 8, &staged);
+	if (rc != MC2_OK) return rc;
+	for (u64 c0 = 0; c0 < n_centers && rc == MC2_OK; c0 += chunk) {
+		const u64 cnt = n_centers - c0 < chunk ? n_centers - c0 : chunk;
+		rc = launch_update_batch(ctx, set_m, d_off, a.ib, a.close, a.skipped, c0, cnt, (double *)x->d[B_RAW].p, d_next, d_ng);
+	}
+	if (rc == MC2_OK) rc = fetch_err(ctx);
+	if (rc != MC2_OK) return rc;
+	static_assert(sizeof(int64_t) == sizeof(long long), "int64_t layout");
+	MC2_CUDA(cudaMemcpyAsync(next, d_next, n_centers * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if (n_good) MC2_CUDA(cudaMemcpyAsync(n_good, d_ng, n_centers * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if ((rc = sync_stage(ctx)) != MC2_OK) return rc;
+	return check_err(ctx);
+}
+
+int mc2_merge_centers(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *centers, uint64_t n_centers, int64_t delta, double id,
+		      int64_t *out)
+{
+	MC2_REQUIRE(ctx && model && centers && (n_centers == 0 || out), "mc2_merge_centers: NULL argument");
+	MC2_REQUIRE(n_centers <= centers->n && delta >= 0, "mc2_merge_centers: bad center count or delta");
+	if (n_centers == 0) return MC2_OK;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	std::vector<uint64_t> off(n_centers + 1), ia, ib;
+	for (u64 c = 0; c < n_centers; c++) {
+		off[c] = ia.size();
+		const u64 last = (u64)delta < n_centers - 1 - c ? c + (u64)delta : n_centers - 1; // min(size-1, c+delta)
+		for (u64 i = c + 1; i <= last; i++) {
+			ia.push_back(i); // compute(*cen, *p): the other center first (Trainer.cpp:93)
+			ib.push_back(c);
+		}
+	}
+	off[n_centers] = ia.size();
+	const u64 m = ia.size();
+	if (m == 0) {
+		for (u64 c = 0; c < n_centers; c++) out[c] = 0;
+		return MC2_OK;
+	}
+	mc2_pairs p;
+	memset(&p, 0, sizeof p);
+	p.set_a = centers;
+	p.set_b = centers;
+	p.n_pairs = m;
+	p.ia = ia.data();
+	p.ib = ib.data();
+	p.len_filter = 1;
+	p.anchor_is_b = 1; // the window comes from the current center's length (Trainer.cpp:82-83, 91)
+	p.cutoff = id;
+	PairArgs a;
+	int rc = score_on_device(ctx, model, &p, a);
+	if (rc != MC2_OK) return rc;
+	CtxExtra *x = extra(ctx);
+	rc = ensure(x->d[B_MISC], (2 * n_centers + 1) * 8, false); if (rc) return rc;
+	u64 *d_off = (u64 *)x->d[B_MISC].p;
+	long long *d_out = (long long *)(d_off + n_centers + 1);
+	bool staged = false;
+	rc = h2d(ctx, d_off, off.data(), (n_centers + 1) * 8, &staged);
+	if (rc == MC2_OK) rc = launch_merge_batch(ctx, a.dist, a.skipped, a.close, d_off, n_centers, d_out);
+	if (rc == MC2_OK) rc = fetch_err(ctx);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaMemcpyAsync(out, d_out, n_centers * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if ((rc = sync_stage(ctx)) != MC2_OK) return rc;
+	for (u64 c = 0; c < n_centers; c++) {
+		out[c] = out[c] < 0 ? 0 : (int64_t)(c + 1) + out[c];
+	}
+	return check_err(ctx);
+}
+
 /* ---- device-timed bench helpers ---------------------------------------------------------------- */
 int mc2_bench_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs, int iters, int flush_l2,
 			  float *avg_ms, uint64_t *n_close)

@@ -1,5 +1,7 @@
 """GPU, end to end: the reference's own meshclust2 with ONE translation unit swapped (src/cluster/Trainer.cpp ->
-integration/Trainer_b200.cpp, which calls the C ABI) must produce the same clusters as the unmodified reference binary.
+integration/Trainer_b200.cpp, which calls the C ABI) and the update stage's two loops offered to the device as one batch per
+pass (integration/patch_cluster_factory.py) must produce the same clusters as the unmodified reference binary -- with the
+batched update stage (default) and with the per-center calls (MC2_NO_BATCH=1).
 Both binaries are built in the build container by `make -C oracle ref integrated` into oracle/_ref/ (they travel to the GPU
 box; the test is skipped where they are absent).  --threads 1 and a single FASTA make the reference deterministic
 (SURVEY.md section 4), and training is the reference's own host code in both, so the weights are identical by construction."""
@@ -32,10 +34,11 @@ def parse_clstr(path):
     return {frozenset(c) for c in clusters if c}
 
 
-def run(binary, fasta, workdir, out):
+def run(binary, fasta, workdir, out, env=None):
     os.makedirs(workdir, exist_ok=True)
     r = subprocess.run([binary, "--id", "0.9", "--sample", "800", "--num-templates", "120", "--threads", "1", fasta,
-                        "--output", out], cwd=workdir, capture_output=True, text=True, timeout=900)
+                        "--output", out], cwd=workdir, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return open(os.path.join(workdir, "weights.txt")).read()
 
@@ -45,9 +48,11 @@ def test_same_clusters_as_the_reference(tmp_path):
     fasta = str(tmp_path / "in.fa")
     open(fasta, "w").write(synth.to_fasta(seqs, tids))
     w_ref = run(REF, fasta, str(tmp_path / "ref"), str(tmp_path / "ref.clstr"))
-    w_our = run(OURS, fasta, str(tmp_path / "ours"), str(tmp_path / "ours.clstr"))
-    assert w_ref == w_our                       # same host training code, same seeds
-    c_ref, c_our = parse_clstr(str(tmp_path / "ref.clstr")), parse_clstr(str(tmp_path / "ours.clstr"))
-    assert sum(len(c) for c in c_ref) == 800 and sum(len(c) for c in c_our) == 800
-    assert c_ref == c_our, "clusters differ: %d vs %d clusters, %d in common" % (len(c_ref), len(c_our), len(c_ref & c_our))
-    assert 50 < len(c_ref) < 800
+    c_ref = parse_clstr(str(tmp_path / "ref.clstr"))
+    assert sum(len(c) for c in c_ref) == 800 and 50 < len(c_ref) < 800
+    for tag, env in (("batched", {}), ("percall", {"MC2_NO_BATCH": "1"})):
+        w_our = run(OURS, fasta, str(tmp_path / tag), str(tmp_path / (tag + ".clstr")), env)
+        assert w_ref == w_our                   # same host training code, same seeds
+        c_our = parse_clstr(str(tmp_path / (tag + ".clstr")))
+        assert sum(len(c) for c in c_our) == 800
+        assert c_ref == c_our, "%s: clusters differ: %d vs %d clusters, %d in common" % (tag, len(c_ref), len(c_our), len(c_ref & c_our))
