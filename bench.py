@@ -400,11 +400,74 @@ def small_workload(ctx, capi, mdist, torch, model, cutoff, steps=20):
             res = step()
         ms = ctx.timer_stop() / steps
         out[name] = {"value": res["n_scored"] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms}
+    try:
+        out["update_stage"] = update_stage(ctx, capi, model, eng.full, cutoff)
+    except Exception as e:                              # an extra, never the reason a bench line is lost
+        log("[bench] update-stage extra failed: %r" % (e,))
     out["workload"] = WORKLOADS["cfg2"]["desc"]
     out["pairs_scored_per_step"] = res["n_scored"]
     out["pairs_close_per_step"] = res["n_close"]
     out["hist_per_step"] = n
     return out
+
+
+def update_stage(ctx, capi, model, hs, cutoff, delta=5, per_cluster=5, passes=5):
+    """One pass of the mean-shift update stage (ClusterFactory.cpp:636-653) over the configs[1]-shaped point set: clusters of
+    5 consecutive points (the synthetic set keeps a template's variants together), center = the cluster's first point,
+    members of center j = the points of clusters j-delta..j+delta, merge candidates = the next delta centers.  Batched
+    (mc2_update_centers + mc2_merge_centers: one device call each per pass) next to what the reference's per-center loops
+    issue through the same C ABI (mc2_filter_as + mc2_mean_closest + mc2_merge per center).  Host wall clock, since the
+    difference IS the per-call overhead; both forms return the same choices."""
+    n = len(hs)
+    got = hs.download()
+    mag, ln = got["mag"].astype(np.uint64), got["len"].astype(np.uint64)
+    nc = n // per_cluster
+    rows = np.arange(nc, dtype=np.uint64) * per_cluster
+    off = np.zeros(nc + 1, dtype=np.uint64)
+    mem = []
+    for j in range(nc):
+        lo, hi = max(0, j - delta) * per_cluster, min(nc, j + delta + 1) * per_cluster
+        mem.append(np.arange(lo, hi, dtype=np.uint64))
+        off[j + 1] = off[j] + np.uint64(hi - lo)
+    members = np.concatenate(mem)
+    sc = ctx.hset_from_host(np.ones((nc, 4 ** hs.k), dtype=np.uint8), hs.k, length=np.ones(nc, dtype=np.uint64))
+    idx = np.arange(nc, dtype=np.uint64)
+
+    def batched():
+        sc.assign_rows(idx, hs, rows, mag=mag[rows], length=ln[rows])
+        nxt, ng = ctx.update_centers(model, sc, nc, hs, off, members, cutoff)
+        mg = ctx.merge_centers(model, sc, nc, delta, cutoff)
+        return nxt, mg
+
+    def per_center(limit):
+        nxt = np.full(limit, -1, dtype=np.int64)
+        mg = np.zeros(limit, dtype=np.int64)
+        sc.assign_rows(idx, hs, rows, mag=mag[rows], length=ln[rows])
+        for j in range(limit):
+            keep = ctx.filter_as(model, hs, int(rows[j]), int(mag[rows[j]]), int(ln[rows[j]]), hs, mem[j], cutoff).astype(bool)
+            if keep.any():
+                nxt[j] = np.flatnonzero(keep)[ctx.mean_closest(hs, mem[j][keep])[0]]
+            mg[j] = ctx.merge(model, sc, idx, j, j + 1, min(nc - 1, j + delta), cutoff)
+        return nxt, mg
+
+    batched()
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        b = batched()
+    ctx.sync()
+    t_b = (time.perf_counter() - t0) / passes
+    limit = min(nc, 500)                                 # a bounded sample of the per-center form, scaled to the pass
+    per_center(8)
+    t0 = time.perf_counter()
+    p = per_center(limit)
+    ctx.sync()
+    t_p = (time.perf_counter() - t0) * nc / limit
+    same = bool(np.array_equal(b[0][:limit], p[0]) and np.array_equal(b[1][:limit], p[1]))
+    sc.free()
+    return {"centers": nc, "member_pairs_per_pass": int(off[-1]), "batched_ms_per_pass": t_b * 1e3,
+            "per_center_calls_ms_per_pass": t_p * 1e3, "speedup": t_p / t_b, "same_choices": same,
+            "sample": "per-center form timed on the first %d centers and scaled to %d" % (limit, nc)}
 
 
 def candidates_roofline(ctx, capi, model, k, eb, peak, peak_src, n=1 << 20):

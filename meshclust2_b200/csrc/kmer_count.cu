@@ -208,7 +208,9 @@ __device__ __forceinline__ void count_sequence(const CountArgs &a, u64 seq, u32 
 	const int k = a.k;
 	const int sh_r = 32 - 2 * k;
 	const u64 sg0 = a.seg_off[seq], sg1 = a.seg_off[seq + 1];
-	const bool track = (sg1 - sg0 > 1) && tmax < 0xFFFFFFFFull; // per-segment overflow counts need the atomics' old values
+	// per-segment overflow counts need the atomics' old values -- except in the packed 16-bit form with 16-bit (or wider)
+	// output bins, where the launcher has checked that init + the longest sequence cannot reach 65 535: nothing saturates
+	const bool track = (sg1 - sg0 > 1) && tmax < 0xFFFFFFFFull && !(P16 && tmax >= 0xFFFFull);
 	const u32 ovf_at = tmax < 0xFFFFFFFFull && tmax >= a.init ? (u32)(tmax - a.init) : 0xFFFFFFFFu; // old >= ovf_at <=> saturated
 	m1[0] = m1[1] = m1[2] = m1[3] = 0;
 	eff_len = 0;
@@ -321,6 +323,16 @@ __global__ void __launch_bounds__(P16 ? 1024 : 256) count_kernel(const __grid_co
 	u32 *hist = GLOBAL ? nullptr : (WARP ? sh_hist + (u64)(threadIdx.x >> 5) * N : sh_hist);
 	// WARP mode: every warp of the CTA iterates the same number of times (no CTA-wide barriers are used)
 	for (u64 seq = a.seq_begin + group; seq < a.n; seq += groups) {
+		if (!WARP && !GLOBAL) {
+			// pull the next sequence's packed words into L2 while this one is counted: 128 B per thread
+			const u64 nx = seq + groups;
+			if (nx < a.n) {
+				const u64 line = a.word_off[nx] + (u64)gt * 32;
+				if (line < a.word_off[nx + 1]) {
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(a.packed + line));
+				}
+			}
+		}
 		if (GLOBAL) {
 			hist = a.gscratch + (seq - a.seq_begin) * N; // zeroed by the host before the launch
 		} else {
@@ -358,7 +370,26 @@ __global__ void __launch_bounds__(P16 ? 1024 : 256) count_kernel(const __grid_co
 			t2 = __reduce_add_sync(0xffffffffu, m1[2]);
 			t3 = __reduce_add_sync(0xffffffffu, m1[3]);
 		} else {
-			if constexpr (P16) { // 4 shared words = 8 bins per thread and step
+			if constexpr (P16 && sizeof(T) == 2) {
+				// packed counts -> packed bins: no bin can saturate (see count_sequence), so count + init is one 32-bit add
+				// per two bins and 8 bins leave as one 16-byte store
+				const u32 init2 = (u32)a.init * 0x10001u;
+				u32 s32 = 0, mx2 = 0;
+				for (u32 b = (u32)gt * 8; b < (u32)N; b += (u32)gs * 8) {
+					const uint4 c = *reinterpret_cast<const uint4 *>(hist + (b >> 1));
+					const u32 v[4] = {c.x + init2, c.y + init2, c.z + init2, c.w + init2};
+					*reinterpret_cast<uint4 *>(dst + b) = make_uint4(v[0], v[1], v[2], v[3]);
+					mx2 = __vmaxu2(mx2, __vmaxu2(__vmaxu2(c.x, c.y), __vmaxu2(c.z, c.w)));
+#pragma unroll
+					for (int i = 0; i < 4; i++) {
+						const u32 lo = v[i] & 0xFFFFu, hi = v[i] >> 16;
+						s32 = __dp2a_lo(v[i], 0x0101u, s32); // both halves, one instruction; < 2^23 per thread
+						sumsq += (u64)(lo * lo) + (u64)(hi * hi);
+					}
+				}
+				sum = s32;
+				mx = max(mx2 & 0xFFFFu, mx2 >> 16);
+			} else if constexpr (P16) { // 4 shared words = 8 bins per thread and step
 				for (u64 b = (u64)gt * 8; b < N; b += (u64)gs * 8) {
 					const uint4 c = *reinterpret_cast<const uint4 *>(hist + (b >> 1));
 					u32 lo4[4] = {c.x & 0xFFFFu, c.x >> 16, c.y & 0xFFFFu, c.y >> 16};
@@ -437,8 +468,11 @@ __device__ __forceinline__ u32 shr64_lo(u32 hi, u32 lo, int r)
 	return (u32)((((u64)hi << 32) | lo) >> r);
 }
 
+#ifndef MC2_K1_MIN_CTAS
+#define MC2_K1_MIN_CTAS 4 // CTAs of 8 warps per SM the register budget must allow (4 -> 64 registers; 5 and 6 measured no faster)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(256) count_warp_kernel(const __grid_constant__ CountArgs a)
+__global__ void __launch_bounds__(256, MC2_K1_MIN_CTAS) count_warp_kernel(const __grid_constant__ CountArgs a)
 {
 	static_assert(sizeof(T) <= 2, "count_warp_kernel: u8 / u16 bins only");
 	extern __shared__ __align__(16) u32 sh_hist[];
@@ -453,7 +487,7 @@ __global__ void __launch_bounds__(256) count_warp_kernel(const __grid_constant__
 	const u32 init = (u32)a.init;
 	const u64 tmax = sizeof(T) == 1 ? 0xFFull : 0xFFFFull;
 	const double rcpN = 1.0 / (double)N;
-	const u64 n = a.n;
+	const u32 n = (u32)a.n;
 	// lane-specialised side-band stores: lanes 0..8 one 64-bit value each, lanes 9..10 one 32-bit value each
 	u64 *p64 = lane == 0 ? a.mag : lane == 1 ? a.sum : lane == 2 ? a.sumsq : lane == 3 ? a.len
 		 : lane < 8 ? a.mers1 + (lane - 4) : reinterpret_cast<u64 *>(a.stddev);
@@ -464,8 +498,8 @@ __global__ void __launch_bounds__(256) count_warp_kernel(const __grid_constant__
 		sts_zero4(hbase + b);
 	}
 	__syncwarp();
-	const u64 groups = (u64)gridDim.x * warps;
-	u64 seq = (u64)blockIdx.x * warps + wid;
+	const u32 groups = gridDim.x * (u32)warps; // the launcher keeps n below 2^32
+	u32 seq = blockIdx.x * (u32)warps + (u32)wid;
 	if (seq >= n) {
 		return;
 	}
@@ -474,8 +508,8 @@ __global__ void __launch_bounds__(256) count_warp_kernel(const __grid_constant__
 	int2 se = nseg ? *reinterpret_cast<const int2 *>(a.segs + 2 * sg0) : make_int2(0, -1);
 	u32 rw0 = (u32)lane < nw ? a.packed[w0 + lane] : 0u, rw1 = (u32)lane + 32u < nw ? a.packed[w0 + 32 + lane] : 0u;
 	for (;;) {
-		const u64 nseq = seq + groups;
-		const bool more = nseq < n;
+		const u32 nseq = seq + groups;
+		const bool more = nseq < n && nseq > seq;
 		u64 n_w0 = 0, n_w1 = 0, n_sg0 = 0, n_sg1 = 0;
 		if (more) {
 			n_w0 = a.word_off[nseq];
@@ -489,7 +523,57 @@ __global__ void __launch_bounds__(256) count_warp_kernel(const __grid_constant__
 		int novf = 0;
 		bool ovf_from_bins = true;
 		const u32 *pk = a.packed + w0;
-		if (nseg == 1) {
+		if (nseg == 1 && se.x == 0 && nw <= 64u) {
+			// the common shape: one segment from base 0, at most 64 words, i.e. exactly the two words this lane already
+			// holds (word `lane` and word `lane + 32`); neighbours come from shuffles, nothing is loaded or looped over
+			const int e0 = se.y;
+			eff_len = (u64)(e0 + 1);
+			const int last = e0 - k + 1;
+			const int wl = last >= 0 ? (last + 1) >> 4 : 0; // words below wl have all 16 starts <= last
+			const u32 first_b = __shfl_sync(0xffffffffu, rw1, 0);
+			u32 nxt0 = __shfl_down_sync(0xffffffffu, rw0, 1);
+			u32 nxt1 = __shfl_down_sync(0xffffffffu, rw1, 1);
+			nxt0 = lane == 31 ? first_b : nxt0;
+			nxt1 = lane == 31 ? 0u : nxt1;
+			// 1-mers: fields 0 .. e0 - 16w of word w (none when negative, all when >= 15)
+			u32 nCT = 0, nGT = 0, nT = 0;
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				const u32 cur = h ? rw1 : rw0;
+				const int rem = e0 - ((lane + 32 * h) << 4);
+				const int shn = min(max(2 * rem + 2, 0), 32);
+				const u32 vm = 0x55555555u & ~(u32)(0xFFFFFFFFull >> shn);
+				const u32 lo = cur & vm, hi = (cur >> 1) & vm;
+				nT += __popc(hi & lo);
+				nCT += __popc(lo);
+				nGT += __popc(hi);
+			}
+			if (lane < wl) {
+#pragma unroll
+				for (int t = 0; t < 16; t++) {
+					reds_inc((shr64_lo(rw0, nxt0, r0 - 2 * t) & amask) | hbase);
+				}
+			}
+			if (lane + 32 < wl) {
+#pragma unroll
+				for (int t = 0; t < 16; t++) {
+					reds_inc((shr64_lo(rw1, nxt1, r0 - 2 * t) & amask) | hbase);
+				}
+			}
+			// the < 16 starts of word wl, one per lane
+			{
+				const u32 src_c = wl < 32 ? rw0 : rw1, src_n = wl + 1 < 32 ? rw0 : rw1;
+				const u32 ec = __shfl_sync(0xffffffffu, src_c, wl & 31);
+				u32 en = __shfl_sync(0xffffffffu, src_n, (wl + 1) & 31);
+				en = wl + 1 < 64 ? en : 0u;
+				if (wl < 64 && (wl << 4) + lane <= last && lane < 16) {
+					reds_inc((shr64_lo(ec, en, r0 - 2 * lane) & amask) | hbase);
+				}
+			}
+			cT = nT;
+			cC = nCT - nT;
+			cG = nGT - nT;
+		} else if (nseg == 1) {
 			const int s0 = se.x, e0 = se.y;
 			eff_len = (u64)(e0 - s0 + 1);
 			const int last = e0 - k + 1;
@@ -576,17 +660,17 @@ __global__ void __launch_bounds__(256) count_warp_kernel(const __grid_constant__
 		}
 		__syncwarp();
 		// ---- narrow (saturating) + side-band; leaves the histogram zeroed
-		T *dst = reinterpret_cast<T *>(a.bins) + seq * N;
+		T *dst = reinterpret_cast<T *>(a.bins) + (u64)seq * N;
 		u32 s32 = 0, q32 = 0, mx = 0;
 		u64 q64 = 0;
 		for (u32 b = (u32)lane * 4u; b < N; b += 128u) {
 			const uint4 c = lds4(hbase + b * 4u);
 			sts_zero4(hbase + b * 4u);
-			mx = max(mx, max(max(c.x, c.y), max(c.z, c.w)));
+			mx = max(max(mx, c.x), max(max(c.y, c.z), c.w)); // two three-input maxima
 			if constexpr (sizeof(T) == 1) {
 				const u32 v0 = min(c.x + init, 255u), v1 = min(c.y + init, 255u), v2 = min(c.z + init, 255u),
 					  v3 = min(c.w + init, 255u);
-				const u32 pv = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+				const u32 pv = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
 				*reinterpret_cast<u32 *>(dst + b) = pv;
 				s32 = __dp4a(pv, 0x01010101u, s32);
 				q32 = __dp4a(pv, pv, q32);
@@ -626,7 +710,7 @@ __global__ void __launch_bounds__(256) count_warp_kernel(const __grid_constant__
 		v64 = lane == 7 ? 1 + (u64)tT : v64;
 		v64 = lane == 8 ? (u64)__double_as_longlong(sd) : v64;
 		if (lane < 9) {
-			p64[seq * stride64] = v64;
+			p64[(u64)seq * stride64] = v64;
 		} else if (lane < 11) {
 			p32[seq] = lane == 9 ? (u32)novf : mx;
 		}
@@ -704,7 +788,7 @@ static int launch_count_t(mc2_ctx *ctx, const mc2_seqs *s, CountArgs &a)
 		const bool warp_mode = hist_bytes <= 16 * 1024 && avg_len <= 4096;
 		if constexpr (sizeof(T) <= 2) {
 			const bool legacy = getenv("MC2_K1_LEGACY") != nullptr; // A/B switch for tools/k1_bench.py
-			if (warp_mode && a.init <= 255 && !legacy) {
+			if (warp_mode && a.init <= 255 && s->n < 0xFFFFFFFFull && !legacy) {
 				int warps = (int)(32 * 1024 / hist_bytes);
 				warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
 				const size_t smem = (size_t)(warps + 1) * hist_bytes; // one histogram of slack for the alignment
@@ -713,7 +797,9 @@ static int launch_count_t(mc2_ctx *ctx, const mc2_seqs *s, CountArgs &a)
 				MC2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_warp_kernel<T>, warps * 32, smem));
 				per_sm = per_sm < 1 ? 1 : per_sm;
 				// one resident wave; every warp walks its sequences with the next one's loads in flight
-				const u64 want = (s->n + warps - 1) / warps, cap = (u64)ctx->sm_count * per_sm;
+				const char *waves_env = getenv("MC2_K1_WAVES"); // tuning knob: CTAs launched per resident CTA
+				const int waves = waves_env ? (atoi(waves_env) > 0 ? atoi(waves_env) : 1) : 1;
+				const u64 want = (s->n + warps - 1) / warps, cap = (u64)ctx->sm_count * per_sm * waves;
 				const int grid = (int)(want < cap ? want : cap);
 				prof_begin(ctx, 1);
 				count_warp_kernel<T><<<grid, warps * 32, smem, ctx->stream>>>(a);
@@ -745,7 +831,7 @@ static int launch_count_t(mc2_ctx *ctx, const mc2_seqs *s, CountArgs &a)
 		MC2_CUDA(cudaGetLastError());
 		return MC2_OK;
 	}
-	if (N * 2 <= 200 * 1024 && s->max_len < 65536) {
+	if (N * 2 <= 200 * 1024 && a.init + s->max_len <= 65535) {
 		// 16-bit packed shared histogram, one 1024-thread CTA per sequence (k = 8: 128 KB of the SM's 227 KB): no bin can
 		// reach 65 536 occurrences, so halves never carry; counting, narrowing and the side-band stay on chip
 		const size_t smem = (size_t)N * 2;

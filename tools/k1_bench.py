@@ -14,7 +14,7 @@ def run(name, seqs, k, eb, iters=10):
     print("%-28s n=%d L=%.0f k=%d eb=%d: %.3f ms  %.3e hist/s  %.3e kmers/s  %.0f GB/s (%.1f%% of 6540)" % (
         name, len(seqs), L, k, eb, ms, len(seqs) / ms * 1e3, len(seqs) * L / ms * 1e3, byts / ms / 1e6, byts / ms / 1e6 / 65.4))
 seqs, _, k, eb = synth.make_config_range("cfg3", 0, int(os.environ.get("K1_N", 100000)))
-for legacy in (False, True):
+for legacy in ((False,) if os.environ.get("K1_NO_LEGACY") else (False, True)):
     if legacy:
         os.environ["MC2_K1_LEGACY"] = "1"   # count_kernel (the generic form) instead of count_warp_kernel
     else:
@@ -26,10 +26,12 @@ for legacy in (False, True):
 os.environ.pop("MC2_K1_LEGACY", None)
 if os.environ.get("K1_SHORT"):
     sys.exit(0)
-long_ = synth.make_single_file(500, 5, 10000, seed=4)
+long_ = synth.make_single_file(int(os.environ.get("K1_LONG_N", 500)), 5, 10000, seed=4)
 run("cfg4 long records", long_, 8, 2, iters=3)
 run("long records k=7", long_, 7, 2, iters=3)
 run("long records k=5", long_, 5, 1, iters=3)
+if os.environ.get("K1_NO_INGEST"):
+    sys.exit(0)
 # input contract on the device (mc2_seqs_from_text) vs host encode + upload, cfg3 shape
 import time
 blob = b"".join(seqs)
