@@ -90,9 +90,53 @@ struct Stopwatch {
 	}
 };
 
-// The CUDA context and the upload of the point histograms do not depend on the model, so Trainer::train starts them on a
-// second thread while the host fits the GLM (seconds); device_for() joins.  Rows are uploaded in the order of the Trainer's
-// point vector, which is the order CRunner.cpp:587-592 assigns the final ids in; device_for() checks that before use.
+// Start-up off the critical path.  Creating the CUDA context (driver initialisation, loading this library's kernels, the
+// page-locked staging areas) takes about a second and depends on nothing the program computes, so a thread started before
+// main() does it while the FASTA file is read; the upload of the point histograms does not depend on the model, so
+// Trainer::train starts it on a second thread while the host fits the GLM.  device_for() joins both.  Rows are uploaded in
+// the order of the Trainer's point vector, which is the order CRunner.cpp:587-592 assigns the final ids in; device_for()
+// checks that before use.  MC2_NO_PREWARM=1 turns both off.
+struct EarlyContext {
+	std::thread th;
+	mc2_ctx *ctx = nullptr;
+	std::string err;
+	bool taken = false;
+	EarlyContext()
+	{
+		if (std::getenv("MC2_NO_PREWARM")) {
+			return;
+		}
+		th = std::thread([this]() {
+			const char *dev_env = std::getenv("MC2_DEVICE");
+			if (mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &ctx) != MC2_OK) {
+				err = mc2_last_error();
+				ctx = nullptr;
+			}
+		});
+	}
+	// the context, once; nullptr when it was not started, failed, or was handed out already
+	mc2_ctx *take()
+	{
+		if (th.joinable()) {
+			th.join();
+		}
+		if (taken) {
+			return nullptr;
+		}
+		taken = true;
+		return ctx;
+	}
+	~EarlyContext()
+	{
+		if (th.joinable()) {
+			th.join();
+		}
+		if (!taken && ctx) {
+			mc2_ctx_destroy(ctx);
+		}
+	}
+} g_early;
+
 struct Prewarm {
 	std::thread th;
 	mc2_ctx *ctx = nullptr;
@@ -187,8 +231,11 @@ Device &device_for(const void *key, const Feature<T> &feat, const matrix::Matrix
 		w.started = false;
 	}
 	if (!d.ctx) {
+		d.ctx = g_early.take();
 		const char *dev_env = std::getenv("MC2_DEVICE");
-		ok(mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &d.ctx));
+		if (!d.ctx) {
+			ok(mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &d.ctx));
+		}
 		std::vector<T> bins(d.n * N);
 		std::vector<uint64_t> mag(d.n), len(d.n);
 		for (Point<T> *p : points) {
@@ -228,8 +275,9 @@ void start_prewarm(const void *key, const std::vector<Point<T> *> &points, int k
 	const std::vector<Point<T> *> *pts = &points;
 	w.th = std::thread([wp, pts, k]() {
 		try {
+			wp->ctx = g_early.take();
 			const char *dev_env = std::getenv("MC2_DEVICE");
-			if (mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &wp->ctx) != MC2_OK) {
+			if (!wp->ctx && mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &wp->ctx) != MC2_OK) {
 				throw std::runtime_error(mc2_last_error());
 			}
 			const size_t n = pts->size(), N = (size_t)1 << (2 * k);

@@ -50,3 +50,6 @@ a = res["meshclust2"]
 for name in list(res)[1:]:
     b = res[name]
     print("%s: clusters reference %d, b200 %d, identical sets: %s; weights identical: %s" % (name, len(a[0]), len(b[0]), a[0] == b[0], a[1] == b[1]))
+    if a[1] != b[1]:
+        print("    (the two runs trained different models: with --threads > 1 the reference's own OpenMP training is not "
+              "reproducible run to run, SURVEY section 4 -- compare clusters at --threads 1)")
