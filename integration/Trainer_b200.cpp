@@ -33,19 +33,13 @@
 #include <thread>
 
 #include "meshclust2_b200.h"
+#include "device_b200.h"
 #include "update_batch_b200.h"
 
 namespace {
 
-std::mutex g_mu; // the update stage calls filter() from an OpenMP loop; one GPU context, one caller at a time
-
-void ok(int rc)
-{
-	if (rc != MC2_OK) {
-		std::cerr << "meshclust2_b200: " << mc2_last_error() << std::endl;
-		throw std::runtime_error(mc2_last_error());
-	}
-}
+std::mutex &g_mu = mc2i::device_mutex(); // the update stage calls filter() from an OpenMP loop; one GPU context, one caller at a time
+using mc2i::ok;
 
 struct Device {
 	mc2_ctx *ctx = nullptr;
@@ -90,53 +84,10 @@ struct Stopwatch {
 	}
 };
 
-// Start-up off the critical path.  Creating the CUDA context (driver initialisation, loading this library's kernels, the
-// page-locked staging areas) takes about a second and depends on nothing the program computes, so a thread started before
-// main() does it while the FASTA file is read; the upload of the point histograms does not depend on the model, so
-// Trainer::train starts it on a second thread while the host fits the GLM.  device_for() joins both.  Rows are uploaded in
-// the order of the Trainer's point vector, which is the order CRunner.cpp:587-592 assigns the final ids in; device_for()
-// checks that before use.  MC2_NO_PREWARM=1 turns both off.
-struct EarlyContext {
-	std::thread th;
-	mc2_ctx *ctx = nullptr;
-	std::string err;
-	bool taken = false;
-	EarlyContext()
-	{
-		if (std::getenv("MC2_NO_PREWARM")) {
-			return;
-		}
-		th = std::thread([this]() {
-			const char *dev_env = std::getenv("MC2_DEVICE");
-			if (mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &ctx) != MC2_OK) {
-				err = mc2_last_error();
-				ctx = nullptr;
-			}
-		});
-	}
-	// the context, once; nullptr when it was not started, failed, or was handed out already
-	mc2_ctx *take()
-	{
-		if (th.joinable()) {
-			th.join();
-		}
-		if (taken) {
-			return nullptr;
-		}
-		taken = true;
-		return ctx;
-	}
-	~EarlyContext()
-	{
-		if (th.joinable()) {
-			th.join();
-		}
-		if (!taken && ctx) {
-			mc2_ctx_destroy(ctx);
-		}
-	}
-} g_early;
-
+// Start-up off the critical path: the CUDA context is created by a thread started before main() (integration/device_b200.cpp);
+// the upload of the point histograms does not depend on the model, so Trainer::train starts it on a second thread while the
+// host fits the GLM.  device_for() joins.  Rows are uploaded in the order of the Trainer's point vector, which is the order
+// CRunner.cpp:587-592 assigns the final ids in; device_for() checks that before use.  MC2_NO_PREWARM=1 turns both off.
 struct Prewarm {
 	std::thread th;
 	mc2_ctx *ctx = nullptr;
@@ -222,20 +173,15 @@ Device &device_for(const void *key, const Feature<T> &feat, const matrix::Matrix
 		if (in_order) {
 			d.ctx = w.ctx;
 			d.points = w.points;
-		} else {
-			if (w.points) mc2_hset_free(w.points);
-			if (w.ctx) mc2_ctx_destroy(w.ctx);
+		} else if (w.points) {
+			mc2_hset_free(w.points);
 		}
 		w.ctx = nullptr;
 		w.points = nullptr;
 		w.started = false;
 	}
 	if (!d.ctx) {
-		d.ctx = g_early.take();
-		const char *dev_env = std::getenv("MC2_DEVICE");
-		if (!d.ctx) {
-			ok(mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &d.ctx));
-		}
+		d.ctx = mc2i::shared_ctx();
 		std::vector<T> bins(d.n * N);
 		std::vector<uint64_t> mag(d.n), len(d.n);
 		for (Point<T> *p : points) {
@@ -275,11 +221,7 @@ void start_prewarm(const void *key, const std::vector<Point<T> *> &points, int k
 	const std::vector<Point<T> *> *pts = &points;
 	w.th = std::thread([wp, pts, k]() {
 		try {
-			wp->ctx = g_early.take();
-			const char *dev_env = std::getenv("MC2_DEVICE");
-			if (!wp->ctx && mc2_ctx_create(dev_env ? std::atoi(dev_env) : 0, &wp->ctx) != MC2_OK) {
-				throw std::runtime_error(mc2_last_error());
-			}
+			wp->ctx = mc2i::shared_ctx();
 			const size_t n = pts->size(), N = (size_t)1 << (2 * k);
 			std::vector<T> bins(n * N);
 			std::vector<uint64_t> mag(n), len(n);
@@ -345,11 +287,7 @@ void stage_all_centers(Device &d, std::vector<Center<T>> &part)
 	stage_into<T>(d, d.centers, cs);
 }
 
-bool batching_enabled()
-{
-	static const bool off = std::getenv("MC2_NO_BATCH") != nullptr;
-	return !off;
-}
+using mc2i::batching_enabled;
 
 } // namespace
 

@@ -40,18 +40,26 @@ def run(binary, fasta, workdir, out, env=None):
                         "--output", out], cwd=workdir, capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    return open(os.path.join(workdir, "weights.txt")).read()
+    # what Runner::find_k and the width detection of Runner::run print (CRunner.cpp:497-498, :93, :109-121)
+    decisions = [l for l in r.stdout.splitlines() if l.startswith(("avg length", "Recommended K", "Largest count", "Using "))]
+    return open(os.path.join(workdir, "weights.txt")).read(), decisions
 
 
 def test_same_clusters_as_the_reference(tmp_path):
     seqs, tids = synth.make_set(800, 1000, 120, 0.08, seed=7)
     fasta = str(tmp_path / "in.fa")
     open(fasta, "w").write(synth.to_fasta(seqs, tids))
-    w_ref = run(REF, fasta, str(tmp_path / "ref"), str(tmp_path / "ref.clstr"))
+    w_ref, d_ref = run(REF, fasta, str(tmp_path / "ref"), str(tmp_path / "ref.clstr"))
+    assert len(d_ref) == 4, d_ref
     c_ref = parse_clstr(str(tmp_path / "ref.clstr"))
     assert sum(len(c) for c in c_ref) == 800 and 50 < len(c_ref) < 800
-    for tag, env in (("batched", {}), ("percall", {"MC2_NO_BATCH": "1"})):
-        w_our = run(OURS, fasta, str(tmp_path / tag), str(tmp_path / (tag + ".clstr")), env)
+    # batched: update stage as one device batch per pass; ingest: also FASTA text -> segments -> k-mer histograms on the device
+    # (declined for small files by default); k1: the reference's reader, histograms through K1; percall: one device call per
+    # center, reader and histograms from the reference
+    for tag, env in (("batched", {}), ("ingest", {"MC2_K1_MIN_BASES": "0"}),
+                     ("k1", {"MC2_K1_MIN_BASES": "0", "MC2_NO_DEVICE_READER": "1"}), ("percall", {"MC2_NO_BATCH": "1"})):
+        w_our, d_our = run(OURS, fasta, str(tmp_path / tag), str(tmp_path / (tag + ".clstr")), env)
+        assert d_ref == d_our, (tag, d_ref, d_our)   # average length, k, largest count, histogram width
         assert w_ref == w_our                   # same host training code, same seeds
         c_our = parse_clstr(str(tmp_path / (tag + ".clstr")))
         assert sum(len(c) for c in c_our) == 800
