@@ -75,7 +75,7 @@ struct Phase {
 uint64_t min_bases()
 {
 	static const char *min_env = std::getenv("MC2_K1_MIN_BASES");
-	return min_env ? std::strtoull(min_env, nullptr, 10) : (64ull << 20);
+	return min_env ? std::strtoull(min_env, nullptr, 10) : (32ull << 20);
 }
 
 // the DNA code map of ChromosomeOneDigitDna::buildCodes (src/nonltr/ChromosomeOneDigitDna.cpp:48-68); -1 = not a nucleotide
@@ -125,9 +125,10 @@ bool mc2_batched_get_points(const std::vector<Chromosome *> &chroms, uintmax_t &
 		}
 		seg_off[i + 1] = segs.size() / 2;
 	}
-	// Below a few tens of megabases the host loop (~35 ns per base) finishes before the CUDA context is even up (about a
-	// second, otherwise hidden behind the FASTA parse and the GLM fit): decline, and let the device start where it pays.
-	// MC2_K1_MIN_BASES overrides the threshold (0: always on the device -- what tests/test_integrated_cluster.py runs).
+	// Below a few tens of megabases the reference's reader + host loop (~90 ns per base over its three passes) finish before
+	// the CUDA context is even up (one to two seconds, otherwise hidden behind the FASTA parse and the GLM fit): decline, and
+	// let the device start where it pays.  MC2_K1_MIN_BASES overrides the threshold (default 32 Mi; 0: always on the device
+	// -- what tests/test_integrated_cluster.py runs).
 	if (total < min_bases()) {
 		return false;
 	}

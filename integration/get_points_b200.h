@@ -1,7 +1,7 @@
 // get_points_b200.h -- the entry point the edited src/cluster/CRunner.cpp calls (integration/patch_crunner.py):
 // the k-mer histograms of every sequence of one FASTA file in one device batch instead of one Loader<T>::get_point per
 // sequence.  Returns false when it declines (MC2_NO_BATCH=1, a histogram type the device path does not serve, or a file
-// below MC2_K1_MIN_BASES bases -- default 64 Mi -- where the host loop ends before the CUDA context is up); the caller then
+// below MC2_K1_MIN_BASES bases -- default 32 Mi -- where the host loop ends before the CUDA context is up); the caller then
 // runs the reference's own loop.  Defined in integration/GetPoints_b200.cpp.
 #ifndef MC2_GET_POINTS_B200_H
 #define MC2_GET_POINTS_B200_H

@@ -12,7 +12,7 @@ seqs, tids, k, eb = synth.make_config_range("cfg3", 0, n)
 tmp = tempfile.mkdtemp()
 fasta = os.path.join(tmp, "in.fa")
 open(fasta, "w").write(synth.to_fasta(seqs, tids))
-for name in ("meshclust2", "meshclust2_b200"):  # the relinked binary takes the device reader above MC2_K1_MIN_BASES (default 64 Mi)
+for name in ("meshclust2", "meshclust2_b200"):  # the relinked binary takes the device reader above MC2_K1_MIN_BASES (default 32 Mi)
     wd = os.path.join(tmp, name); os.makedirs(wd)
     t0 = time.time()
     r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", name), "--id", "0.9", "--threads", threads, "--sample", "300",
