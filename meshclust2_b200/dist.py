@@ -147,6 +147,80 @@ def candidate_scan(engine, comm, torch, q_global, n_total, cutoff):
     return dict(best=gbest, best_dist=gdist, is_min=not bool(allv[:, 2].any()), marks_local=marks, shard=(lo, hi))
 
 
+def balanced_ranges(weights, world):
+    """Contiguous ranges of items for `world` ranks with about equal total weight (prefix-sum split); every item lands in
+    exactly one range, ranges may be empty."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = len(w)
+    if n == 0:
+        return [(0, 0)] * world
+    cum = np.concatenate([[0.0], np.cumsum(w + 1.0)])      # + 1: an item costs something even with no members
+    cuts = [int(np.searchsorted(cum, cum[-1] * r / world, side="left")) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, n
+    cuts = np.maximum.accumulate(np.minimum(cuts, n))
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
+
+
+def _gather_ranges(values, ranges, comm, torch, device, fill):
+    """values: this rank's int64 results for its range -> the full array in range order on every rank."""
+    total = ranges[-1][1]
+    if comm.dist is None:
+        return np.asarray(values, dtype=np.int64)
+    width = max(1, max(hi - lo for lo, hi in ranges))
+    mine = torch.full((width,), fill, dtype=torch.int64, device=device)
+    if len(values):
+        mine[:len(values)] = torch.as_tensor(np.asarray(values, dtype=np.int64), device=device)
+    allv = torch.empty((comm.world * width,), dtype=torch.int64, device=device)
+    comm.dist.all_gather_into_tensor(allv, mine)
+    allv = allv.cpu().numpy().reshape(comm.world, width)
+    out = np.full(total, fill, dtype=np.int64)
+    for r, (lo, hi) in enumerate(ranges):
+        out[lo:hi] = allv[r, :hi - lo]
+    return out
+
+
+def update_pass(engine, comm, torch, center_rows, center_mag, center_len, member_off, members, cutoff):
+    """One pass of the update loop (ClusterFactory.cpp:639-642: mean_shift_update for every center) over the replicated point
+    set, centers split over ranks by member count.  center_rows[c] = row of the point center c carries, center_mag / center_len
+    = what the host center object reports (quirk Q4); members[member_off[c]:member_off[c+1]] = rows of the candidate members.
+
+    engine.update_centers(rows, mag, length, off, members, cutoff) -> (next positions int64[m], survivors uint64[m])
+    Returns (next[n_centers] position in the center's member list or -1, n_good[n_centers]) on every rank."""
+    member_off = np.asarray(member_off, dtype=np.uint64)
+    nc = len(center_rows)
+    ranges = balanced_ranges(np.diff(member_off.astype(np.int64)), comm.world)
+    lo, hi = ranges[comm.rank]
+    if hi > lo:
+        off = member_off[lo:hi + 1] - member_off[lo]
+        nxt, ng = engine.update_centers(center_rows[lo:hi], center_mag[lo:hi], center_len[lo:hi], off,
+                                        members[int(member_off[lo]):int(member_off[hi])], cutoff)
+    else:
+        nxt, ng = np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    nxt = _gather_ranges(nxt, ranges, comm, torch, engine.device, -1)
+    ng = _gather_ranges(np.asarray(ng, dtype=np.int64), ranges, comm, torch, engine.device, 0)
+    assert len(nxt) == nc
+    return nxt, ng
+
+
+def merge_pass(engine, comm, torch, center_rows, center_mag, center_len, delta, cutoff):
+    """One call of merge() (ClusterFactory.cpp:382-401: Trainer::merge of center c against centers c+1 .. c+delta), centers
+    split contiguously over ranks; a rank stages its range plus the `delta` centers after it.
+
+    engine.merge_centers(rows, mag, length, delta, cutoff) -> chosen index per staged center (0 = none), staged-relative
+    Returns out[n_centers] (global center index, 0 = none) on every rank."""
+    nc = len(center_rows)
+    ranges = balanced_ranges(np.ones(nc), comm.world)
+    lo, hi = ranges[comm.rank]
+    if hi > lo:
+        end = min(nc, hi + delta)
+        rel = np.asarray(engine.merge_centers(center_rows[lo:end], center_mag[lo:end], center_len[lo:end], delta, cutoff),
+                         dtype=np.int64)[:hi - lo]
+        mine = np.where(rel > 0, rel + lo, 0)
+    else:
+        mine = np.zeros(0, dtype=np.int64)
+    return _gather_ranges(mine, ranges, comm, torch, engine.device, 0)
+
+
 class GpuEngine:
     """The product engine: K1 / K2 through the C ABI on this rank's GPU; torch only carries device memory for NCCL."""
 
@@ -228,6 +302,27 @@ class GpuEngine:
         if n == 0:
             return -1, -1.0, True, np.zeros(0, dtype=np.uint8)
         return self.ctx.get_close(self.model, self._qset, 0, self.local_hset, cand_begin=0, n_cand=n, cutoff=cutoff)
+
+    # ---- update stage (update_pass / merge_pass) over the replicated set self.full ----
+    def _stage_centers(self, rows, mag, length):
+        n = len(rows)
+        sc = getattr(self, "_centers", None)
+        if sc is None or len(sc) < n:
+            if sc is not None:
+                sc.free()
+            cap = max(n, 64)
+            sc = self._centers = self.ctx.hset_from_host(np.ones((cap, self.N), dtype=self.capi.DTYPES[self.eb]), self.k,
+                                                         length=np.ones(cap, dtype=np.uint64))
+        sc.assign_rows(np.arange(n, dtype=np.uint64), self.full, rows, mag=mag, length=length)
+        return sc
+
+    def update_centers(self, rows, mag, length, off, members, cutoff):
+        sc = self._stage_centers(rows, mag, length)
+        return self.ctx.update_centers(self.model, sc, len(rows), self.full, off, members, cutoff)
+
+    def merge_centers(self, rows, mag, length, delta, cutoff):
+        sc = self._stage_centers(rows, mag, length)
+        return self.ctx.merge_centers(self.model, sc, len(rows), delta, cutoff)
 
     def sweep(self, q0, q1, upper_only, cutoff, max_out):
         # survivor buffers: allocated once, page-locked, reused by every sweep of this engine (fresh pageable arrays cost

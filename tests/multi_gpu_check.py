@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Multi-rank parity check on real GPUs: the row-block sharded all-pairs sweep and the range-partitioned candidate scan
-(meshclust2_b200/dist.py) against the CPU oracle, one process per GPU over NCCL.
+"""Multi-rank parity check on real GPUs: the row-block sharded all-pairs sweep, the range-partitioned candidate scan and the
+center-sharded update stage (meshclust2_b200/dist.py) against the CPU oracle, one process per GPU over NCCL.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
       tests/multi_gpu_check.py [--n-seqs 3000]
@@ -93,6 +93,46 @@ def main():
             print("[rank %d] scan q=%d MISMATCH: best %d vs %d, dist %r vs %r, is_min %r vs %r" % (
                 rank, q, r["best"], ob, r["best_dist"], obd, r["is_min"], omin), flush=True)
             bad += 1
+    # --- update stage: one pass of mean_shift_update + merge over every center, centers split over ranks ---
+    rng = np.random.default_rng(21)
+    nc = min(400, n_total // 3)
+    rows = (np.arange(nc, dtype=np.uint64) * 3) % n_total
+    rows[6:9] = rows[5]
+    cmag, clen = mag[rows].copy(), ln[rows].copy()
+    cmag[::2] += np.uint64(23)                                   # stale magnitudes (quirk Q4)
+    off, mem = [0], []
+    for j, r in enumerate(rows):
+        m_lo, m_hi = max(0, int(r) - 9), min(n_total, int(r) + 10 + (j % 5) * 7)
+        if j % 37 == 2:
+            m_hi = m_lo
+        mem.append(np.arange(m_lo, m_hi, dtype=np.uint64))
+        off.append(off[-1] + m_hi - m_lo)
+    off, members, delta = np.array(off, dtype=np.uint64), np.concatenate(mem), 4
+    nxt, ng = mdist.update_pass(eng, comm, torch, rows, cmag, clen, off, members, cutoff)
+    mg = mdist.merge_pass(eng, comm, torch, rows, cmag, clen, delta, cutoff)
+    H2 = np.vstack([H, H[rows.astype(np.int64)]])
+    mag2, ln2 = np.concatenate([mag, cmag]).astype(np.uint64), np.concatenate([ln, clen]).astype(np.uint64)
+    Hc, idx = H[rows.astype(np.int64)], np.arange(nc)
+    n_moved = n_merged = 0
+    for c in range(rank, nc, world):                             # every rank checks a stride of the (replicated) result
+        memc = members[int(off[c]):int(off[c + 1])]
+        want_next, want_good = -1, 0
+        if len(memc):
+            keep = port.filter_members(omodel, H2, mag2, ln2, n_total + c, memc, cutoff).astype(bool)
+            want_good = int(keep.sum())
+            if want_good:
+                want_next = int(np.flatnonzero(keep)[port.mean_closest(H, memc[keep])[0]])
+        last = min(nc - 1, c + delta)
+        want_merge = port.merge(omodel, Hc, cmag, clen, idx, c, c + 1, last, cutoff) if last >= c + 1 else 0
+        n_moved += want_next >= 0
+        n_merged += want_merge > c
+        if nxt[c] != want_next or ng[c] != want_good or mg[c] != want_merge:
+            print("[rank %d] update stage center %d MISMATCH: next %d vs %d, good %d vs %d, merge %d vs %d" % (
+                rank, c, nxt[c], want_next, ng[c], want_good, mg[c], want_merge), flush=True)
+            bad += 1
+    if n_moved == 0 or (rank == 0 and n_merged == 0):
+        print("[rank %d] update stage check is vacuous (moved %d, merged %d)" % (rank, n_moved, n_merged), flush=True)
+        bad += 1
     tot_bad = comm.all_reduce_sum([bad], torch, eng.device)[0]
     if rank == 0:
         print("multi_gpu_check world=%d n=%d: %s (sweep scored %d close %d; %d scan queries, %d marks)" % (

@@ -85,6 +85,35 @@ class OracleEngine:
         mg = np.concatenate([self.mag, mag.numpy()]).astype(np.uint64)
         return port.get_close(self.model, H, mg, ln, n, np.arange(n), cutoff)
 
+    def update_centers(self, rows, mag, length, off, members, cutoff):
+        H, ln, mg = self.full
+        H2 = np.concatenate([H, H[np.asarray(rows, dtype=np.int64)]])
+        mag2 = np.concatenate([mg, mag]).astype(np.uint64)
+        ln2 = np.concatenate([ln, length]).astype(np.uint64)
+        nxt, ng = np.full(len(rows), -1, dtype=np.int64), np.zeros(len(rows), dtype=np.int64)
+        for c in range(len(rows)):
+            mem = np.asarray(members[int(off[c]):int(off[c + 1])], dtype=np.uint64)
+            if len(mem) == 0:
+                continue
+            keep = port.filter_members(self.model, H2, mag2, ln2, H.shape[0] + c, mem, cutoff).astype(bool)
+            ng[c] = keep.sum()
+            if keep.any():
+                nxt[c] = np.flatnonzero(keep)[port.mean_closest(H, mem[keep])[0]]
+        return nxt, ng
+
+    def merge_centers(self, rows, mag, length, delta, cutoff):
+        H, _, _ = self.full
+        Hc = H[np.asarray(rows, dtype=np.int64)]
+        n = len(rows)
+        idx = np.arange(n)
+        out = np.zeros(n, dtype=np.int64)
+        for c in range(n):
+            last = min(n - 1, c + delta)
+            if last >= c + 1:
+                out[c] = port.merge(self.model, Hc, np.asarray(mag, dtype=np.uint64), np.asarray(length, dtype=np.uint64), idx,
+                                    c, c + 1, last, cutoff)
+        return out
+
     def sweep(self, q0, q1, upper_only, cutoff, max_out):
         H, ln, mag = self.full
         n = H.shape[0]
@@ -144,6 +173,82 @@ def _worker(rank, world, port_no, n_total, out):
             out.put((res["n_scored"], res["n_close"], sorted(map(tuple, sum(gathered, [])))))
     finally:
         tdist.destroy_process_group()
+
+
+def _update_case(n_total, seed=5):
+    """centers = every 3rd point (some with a stale magnitude), members = a window of points around each"""
+    rng = np.random.default_rng(seed)
+    seqs, _ = synth.make_range(n_total, 1000, 5, 0.08, seed=123)
+    pts = [port.get_point(s, 5, 1) for s in seqs]
+    H = np.stack([p["hist"] for p in pts])
+    mag = np.array([p["mag"] for p in pts], dtype=np.uint64)
+    ln = np.array([p["len"] for p in pts], dtype=np.uint64)
+    rows = np.arange(0, n_total, 3, dtype=np.uint64)
+    rows[6:9] = rows[5]                                      # a run of identical centers across the rank boundary: merges happen
+    rows[10:12] = rows[9]
+    cmag, clen = mag[rows].copy(), ln[rows].copy()
+    cmag[::2] += np.uint64(17)
+    off, mem = [0], []
+    for j, r in enumerate(rows):
+        lo, hi = max(0, int(r) - 7), min(n_total, int(r) + 8 + (j % 4) * 5)
+        if j == 2:
+            hi = lo                                          # an empty member list
+        mem.append(np.arange(lo, hi, dtype=np.uint64))
+        off.append(off[-1] + hi - lo)
+    return seqs, (H, ln.astype(np.int64), mag.astype(np.int64)), rows, cmag, clen, np.array(off, dtype=np.uint64), np.concatenate(mem)
+
+
+def _update_worker(rank, world, port_no, n_total, delta, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = port.Model.from_text(weights_text("weights_cfg1_id90"))
+        seqs, full, rows, cmag, clen, off, members = _update_case(n_total)
+        eng = OracleEngine([], 5, 1, model, 0)
+        eng.full = full                                      # the replicated point set (after the all-gather)
+        comm = mdist.Comm(tdist)
+        nxt, ng = mdist.update_pass(eng, comm, torch, rows, cmag, clen, off, members, 0.9)
+        mg = mdist.merge_pass(eng, comm, torch, rows, cmag, clen, delta, 0.9)
+        if rank == 0:
+            out.put((nxt.tolist(), ng.tolist(), mg.tolist()))
+    finally:
+        tdist.destroy_process_group()
+
+
+def test_balanced_ranges_cover_and_balance():
+    for world in (1, 2, 3, 8):
+        for w in ([], [5], [0, 0, 0], list(range(100)), [1000] + [1] * 50):
+            r = mdist.balanced_ranges(w, world)
+            assert len(r) == world and r[0][0] == 0 and r[-1][1] == len(w)
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1)) and all(lo <= hi for lo, hi in r)
+    r = mdist.balanced_ranges(np.ones(1000) * 50, 8)
+    sizes = [hi - lo for lo, hi in r]
+    assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_sharded_update_and_merge_pass_equal_single_process():
+    """mean_shift_update / merge for every center, centers split over 2 ranks == the same pass in one process"""
+    n_total, delta = 60, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    pno = _free_port()
+    procs = [ctx.Process(target=_update_worker, args=(r, 2, pno, n_total, delta, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    model = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    seqs, full, rows, cmag, clen, off, members = _update_case(n_total)
+    eng = OracleEngine([], 5, 1, model, 0)
+    eng.full = full
+    nxt, ng = eng.update_centers(rows, cmag, clen, off, members, 0.9)
+    mg = eng.merge_centers(rows, cmag, clen, delta, 0.9)
+    assert got == (nxt.tolist(), ng.tolist(), mg.tolist())
+    assert (nxt >= 0).any() and nxt[2] == -1 and (mg > 0).any()
 
 
 def _free_port():
