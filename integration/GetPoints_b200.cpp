@@ -34,6 +34,7 @@
 #include "nonltr/KmerHashTable.h"
 
 #include "device_b200.h"
+#include "fasta_records.h"
 
 namespace {
 
@@ -77,21 +78,6 @@ uint64_t min_bases()
 	static const char *min_env = std::getenv("MC2_K1_MIN_BASES");
 	return min_env ? std::strtoull(min_env, nullptr, 10) : (32ull << 20);
 }
-
-// the DNA code map of ChromosomeOneDigitDna::buildCodes (src/nonltr/ChromosomeOneDigitDna.cpp:48-68); -1 = not a nucleotide
-struct CodeTable {
-	signed char code[256];
-	CodeTable()
-	{
-		std::memset(code, -1, sizeof code);
-		const char *letters = "ACGTRYMKSWHBVDNX";
-		const signed char val[] = {0, 1, 2, 3, 2, 1, 0, 3, 2, 3, 1, 3, 0, 3, 1, 2};
-		for (int i = 0; letters[i]; i++) {
-			code[(unsigned char)letters[i]] = val[i];
-		}
-	}
-};
-const CodeTable g_codes;
 
 } // namespace
 
@@ -197,16 +183,9 @@ template bool mc2_batched_get_points<uint64_t>(const std::vector<Chromosome *> &
 // ---- FASTA file -> records (host) -> the input contract on the device ------------------------------------------------------
 namespace {
 
-// One FASTA file split into records with the reader's line rules: lines end at \n, \r\n or \r (safe_getline,
-// src/nonltr/ChromListMaker.cpp:24-47); a line starting with '>' opens a record and is its header, verbatim; lines starting
-// with a blank or a tab are skipped; every other line is appended to the current record as it is (:131-158).  The reference
-// reads each input file three times (find_k, the width detection of Runner::run, get_points); the records are split once and
-// kept until get_points has consumed them.
-struct FileRecords {
-	std::vector<std::string> headers;
-	std::vector<uint64_t> seq_off;
-	std::string text;
-};
+// The reference reads each input file three times (find_k, the width detection of Runner::run, get_points); the records are
+// split once (integration/fasta_records.h) and kept until get_points has consumed them.
+using mc2i::FileRecords;
 
 std::mutex g_files_mu;
 std::map<std::string, std::shared_ptr<FileRecords>> g_files;
@@ -236,41 +215,8 @@ std::shared_ptr<FileRecords> load_records(const std::string &fasta, bool is_sing
 		}
 	}
 	std::shared_ptr<FileRecords> rec = std::make_shared<FileRecords>();
-	rec->seq_off.push_back(0);
-	rec->text.reserve(raw.size());
-	const size_t sz = raw.size();
-	size_t pos = 0;
-	while (pos < sz) {
-		size_t e = pos;
-		while (e < sz && raw[e] != '\n' && raw[e] != '\r') {
-			e++;
-		}
-		const char first = e > pos ? raw[pos] : '\0';
-		if (first == '>') {
-			if (!rec->headers.empty()) {
-				rec->seq_off.push_back(rec->text.size());
-			}
-			rec->headers.push_back(raw.substr(pos, e - pos));
-		} else if (first == ' ' || first == '\t') {
-		} else if (e > pos) {
-			if (rec->headers.empty()) {
-				return nullptr; // bases before any header: the reference dereferences an unset pointer here
-			}
-			rec->text.append(raw, pos, e - pos);
-		}
-		pos = e;
-		if (pos < sz) {
-			pos += (raw[pos] == '\r' && pos + 1 < sz && raw[pos + 1] == '\n') ? 2 : 1;
-		}
-	}
-	if (rec->headers.empty()) {
+	if (!mc2i::split_fasta(raw, *rec)) {
 		return nullptr;
-	}
-	rec->seq_off.push_back(rec->text.size());
-	for (size_t i = 0; i + 1 < rec->seq_off.size(); i++) {
-		if (rec->seq_off[i + 1] == rec->seq_off[i]) {
-			return nullptr; // a record without bases shifts the reader's size list (ChromListMaker.cpp:105-107): its own business
-		}
 	}
 	slot = rec;
 	return rec;
@@ -300,17 +246,8 @@ bool mc2_batched_effective_length(const std::string &fasta, bool is_single_file,
 	}
 	const uint64_t n = rec->headers.size();
 	std::string doubled;
-	doubled.reserve(2 * rec->text.size());
-	std::vector<uint64_t> off(n + 1, 0);
-	for (uint64_t i = 0; i < n; i++) {
-		const uint64_t len = rec->seq_off[i + 1] - rec->seq_off[i];
-		doubled.append(len, 'A');
-		doubled.append(rec->text, rec->seq_off[i], len);
-		off[i + 1] = doubled.size();
-	}
-	for (char &c : doubled) { // plain Chromosome objects are never letter-checked: keep only what the segmentation looks at
-		c = (c == 'N' || c == 'n') ? 'N' : 'A';
-	}
+	std::vector<uint64_t> off;
+	mc2i::doubled_for_find_k(*rec, doubled, off);
 	std::vector<int32_t> segs;
 	std::vector<uint64_t> seg_off(n + 1);
 	{
@@ -420,28 +357,10 @@ bool mc2_batched_read_points(const std::string &fasta, bool is_single_file, uint
 #pragma omp parallel for schedule(dynamic, 256)
 	for (uint64_t i = 0; i < n; i++) {
 		std::string data(text, seq_off[i], seq_off[i + 1] - seq_off[i]);
-		for (char &c : data) {
-			c = (char)toupper((unsigned char)c);
-		}
-		if (seg_off[i + 1] > seg_off[i]) {
-			uint64_t sg = seg_off[i];
-			for (size_t j = 0; j < data.size(); j++) {
-				while (sg < seg_off[i + 1] && (int64_t)j > segs[2 * sg + 1]) {
-					sg++;
-				}
-				const bool inside = sg < seg_off[i + 1] && (int64_t)j >= segs[2 * sg];
-				const char c = data[j];
-				if (!inside && c == 'N') {
-					continue;
-				}
-				const signed char code = g_codes.code[(unsigned char)c];
-				if (code < 0) {
+		const char bad_letter = mc2i::encode_data_string(data, segs.data() + 2 * seg_off[i], seg_off[i + 1] - seg_off[i]);
+		if (bad_letter) {
 #pragma omp critical(mc2_bad_letter)
-					bad = std::string("ChromosomeOneDigit::encode() found invalid letter: ") + c;
-					break;
-				}
-				data[j] = (char)code;
-			}
+			bad = std::string("ChromosomeOneDigit::encode() found invalid letter: ") + bad_letter;
 		}
 		std::vector<T> values(bins.begin() + i * N, bins.begin() + (i + 1) * N);
 		Point<T> *p = new DivergencePoint<T>(values, data.size());
