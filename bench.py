@@ -53,6 +53,18 @@ def traffic_per_pair(key):
     return None, None
 
 
+def instr_per_pair(key):
+    """executed warp-instructions per pair of a kernel from the committed ncu capture (profiles/r1_traffic.json)"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        for k, v in d.items():
+            if k.startswith(key) and "warp_instr_per_pair" in v:
+                return float(v["warp_instr_per_pair"]), v["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -339,6 +351,21 @@ def run_ours(args, rank, world, local_rank):
             "k1": {"hist_per_s": (hi - lo) * args.steps / (count_ms * 1e-3) if count_ms > 0 else None,
                    "avg_launch_ms": count_ms / max(1, count_n),
                    "achieved_gbs": (hi - lo) * args.steps * (250 + N * eb + 40) / (count_ms * 1e-3) / 1e9 if count_ms > 0 else None}}
+    try:
+        # the roofline that actually binds the L2-resident sweep ("not HBM -- CUDA-core integer issue rate"):
+        # executed warp-instructions per second against the issue rate of the SMs at the clock sampled in the timed region
+        ipp, isrc = instr_per_pair("sweep_kernel")
+        sm_mhz = (clocks or {}).get("sm_mhz")
+        if ipp and sm_mhz and sweep_ms > 0:
+            issue_peak = ctx.sm_count * 4 * sm_mhz * 1e6
+            issue_ach = local_pairs / (sweep_ms * 1e-3) * ipp
+            line["roofline_issue"] = {"bound": "issue", "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9,
+                                      "unit": "Gwarp-instr/s", "frac": issue_ach / issue_peak, "warp_instr_per_pair": ipp,
+                                      "source": isrc, "kernel": roofline["kernel"],
+                                      "note": "secondary: issue slots of 4 schedulers x SMs at the sampled SM clock; the "
+                                              "instruction count per pair is the committed ncu figure, pairs/s is live"}
+    except Exception as e:
+        log("[bench] issue roofline skipped: %r" % (e,))
     if world == 1 and not args.no_extras:
         line["roofline_candidates"] = candidates_roofline(ctx, capi, model, k, eb, peak, peak_src)
         if args.workload != "cfg2":
