@@ -33,6 +33,9 @@
 #include "nonltr/ChromosomeOneDigitDna.h"
 #include "nonltr/KmerHashTable.h"
 
+#include <omp.h>
+
+#include "build_points.h"
 #include "device_b200.h"
 #include "fasta_records.h"
 
@@ -187,8 +190,14 @@ namespace {
 // split once (integration/fasta_records.h) and kept until get_points has consumed them.
 using mc2i::FileRecords;
 
+// per file: split once, by whichever caller comes first; other files load concurrently (get_points runs an `omp parallel
+// for` over files)
+struct FileSlot {
+	std::once_flag once;
+	std::shared_ptr<FileRecords> rec; // nullptr = declined (remembered), or consumed by get_points
+};
 std::mutex g_files_mu;
-std::map<std::string, std::shared_ptr<FileRecords>> g_files;
+std::map<std::string, std::shared_ptr<FileSlot>> g_files;
 
 // nullptr = declined: MC2_NO_BATCH=1, MC2_NO_DEVICE_READER=1, --single-file, a file below MC2_K1_MIN_BASES bytes, or a file
 // whose shape trips the reader's own corner cases (bases before any header, a record without bases)
@@ -197,37 +206,41 @@ std::shared_ptr<FileRecords> load_records(const std::string &fasta, bool is_sing
 	if (!mc2i::batching_enabled() || is_single_file || std::getenv("MC2_NO_DEVICE_READER")) {
 		return nullptr;
 	}
-	std::lock_guard<std::mutex> lock(g_files_mu);
-	auto it = g_files.find(fasta);
-	if (it != g_files.end()) {
-		return it->second;
-	}
-	std::shared_ptr<FileRecords> &slot = g_files[fasta]; // a declined file is remembered as nullptr
-	struct stat st;
-	if (stat(fasta.c_str(), &st) != 0 || (uint64_t)st.st_size < min_bases()) {
-		return nullptr;
-	}
-	std::string raw((size_t)st.st_size, '\0');
+	std::shared_ptr<FileSlot> slot;
 	{
+		std::lock_guard<std::mutex> lock(g_files_mu);
+		std::shared_ptr<FileSlot> &s = g_files[fasta];
+		if (!s) {
+			s = std::make_shared<FileSlot>();
+		}
+		slot = s;
+	}
+	std::call_once(slot->once, [&]() {
+		struct stat st;
+		if (stat(fasta.c_str(), &st) != 0 || (uint64_t)st.st_size < min_bases()) {
+			return;
+		}
+		std::string raw((size_t)st.st_size, '\0');
 		std::ifstream in(fasta.c_str(), std::ios::binary);
 		if (!in.read(&raw[0], st.st_size)) {
-			return nullptr;
+			return;
 		}
-	}
-	std::shared_ptr<FileRecords> rec = std::make_shared<FileRecords>();
-	if (!mc2i::split_fasta(raw, *rec)) {
-		return nullptr;
-	}
-	slot = rec;
-	return rec;
+		std::shared_ptr<FileRecords> rec = std::make_shared<FileRecords>();
+		if (mc2i::split_fasta(raw, *rec)) {
+			std::lock_guard<std::mutex> lock(g_files_mu);
+			slot->rec = rec;
+		}
+	});
+	std::lock_guard<std::mutex> lock(g_files_mu);
+	return slot->rec;
 }
 
 void drop_records(const std::string &fasta)
 {
 	std::lock_guard<std::mutex> lock(g_files_mu);
 	auto it = g_files.find(fasta);
-	if (it != g_files.end()) {
-		it->second.reset(); // stays declined-or-consumed: a later reader of the same file takes the reference's path
+	if (it != g_files.end() && it->second) {
+		it->second->rec.reset(); // consumed: a later reader of the same file takes the reference's path
 	}
 }
 
@@ -349,29 +362,10 @@ bool mc2_batched_read_points(const std::string &fasta, bool is_single_file, uint
 		mc2_seqs_free(sq);
 		mc2i::ok(rc);
 	}
-	// the host objects.  The sequence string is what ChromosomeOneDigit::encode leaves in `base` (ChromosomeOneDigit.cpp:
-	// 79-133): upper case; with at least one segment every letter becomes its code except an N outside the segments, which
-	// stays 'N'; without segments the upper-cased letters stay as they are.
-	std::vector<Point<T> *> made(n, nullptr);
-	std::string bad;
-#pragma omp parallel for schedule(dynamic, 256)
-	for (uint64_t i = 0; i < n; i++) {
-		std::string data(text, seq_off[i], seq_off[i + 1] - seq_off[i]);
-		const char bad_letter = mc2i::encode_data_string(data, segs.data() + 2 * seg_off[i], seg_off[i + 1] - seg_off[i]);
-		if (bad_letter) {
-#pragma omp critical(mc2_bad_letter)
-			bad = std::string("ChromosomeOneDigit::encode() found invalid letter: ") + bad_letter;
-		}
-		std::vector<T> values(bins.begin() + i * N, bins.begin() + (i + 1) * N);
-		Point<T> *p = new DivergencePoint<T>(values, data.size());
-		p->set_1mers(std::vector<uint64_t>(mers1.begin() + 4 * i, mers1.begin() + 4 * i + 4));
-		p->set_header(headers[i]);
-		p->set_length(len[i]);
-		p->set_data_str(data);
-		p->setK(k);
-		dynamic_cast<DivergencePoint<T> *>(p)->set_stddev(stddev[i]);
-		made[i] = p;
-	}
+	// the host objects (integration/build_points.h)
+	std::vector<Point<T> *> made;
+	const std::string bad = mc2i::build_points<T>(*rec, k, bins.data(), len.data(), mers1.data(), stddev.data(), segs.data(),
+						      seg_off.data(), (unsigned)omp_get_max_threads(), made);
 	ph.mark("host point objects");
 	if (!bad.empty()) {
 		throw InvalidInputException(bad);

@@ -17,14 +17,23 @@ pytestmark = pytest.mark.skipif(not (os.path.isdir(os.path.join(REF, "src", "non
                                 reason="reference sources / oracle/_ref not present")
 
 
-@pytest.fixture(scope="module")
-def harness(tmp_path_factory):
-    exe = str(tmp_path_factory.mktemp("reader") / "test_fasta_records")
+def _compile(tmp_path_factory, name):
+    exe = str(tmp_path_factory.mktemp(name) / name)
     inc = ["-I" + os.path.join(REF, "src", d) for d in ("", "clutil", "predict", "nonltr", "utility", "exception", "cluster")]
-    subprocess.check_call(["g++", "-std=c++11", "-O1", "-fopenmp", "-w", "-include", "cstdint", "-include", "limits"] + inc +
-                          ["-I" + os.path.join(ROOT, "integration"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_fasta_records.cpp"),
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-fopenmp", "-pthread", "-w", "-include", "cstdint", "-include", "limits"] + inc +
+                          ["-I" + os.path.join(ROOT, "integration"), "-o", exe, os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
                            "-L" + os.path.dirname(LIBREF), "-lmc2ref", "-Wl,-rpath," + os.path.dirname(LIBREF)])
     return exe
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    return _compile(tmp_path_factory, "test_fasta_records")
+
+
+@pytest.fixture(scope="module")
+def points_harness(tmp_path_factory):
+    return _compile(tmp_path_factory, "test_build_points")
 
 
 def _run(exe, path):
@@ -82,3 +91,24 @@ def test_corner_shapes_are_declined(harness, tmp_path):
         p.write_text(body)
         rc, out = _run(harness, str(p))
         assert rc == 0 and out == "DECLINED", (name, out)
+
+
+def test_host_points_equal_loader_get_point(points_harness, tmp_path):
+    """build_points (the host objects of the device reader, std::thread workers) == Loader<T>::get_point field by field, for
+    uint8 and uint16 histograms, 1 and 7 worker threads, more records than one work block"""
+    rng = np.random.default_rng(11)
+    text = ""
+    for j in range(700):
+        s = list(_dna(rng, int(rng.integers(40, 400))))
+        if j % 9 == 0:
+            a = int(rng.integers(0, len(s) - 30)); s[a:a + 25] = "N" * 25
+        if j % 13 == 0:
+            s[:5] = "nnnnn"
+        if j % 17 == 0:
+            s = list("A" * 700)                          # saturates uint8 bins
+        text += ">read_%d some description\n" % j + "".join(s) + "\n"
+    p = tmp_path / "many.fa"
+    p.write_text(text)
+    for k, threads in ((3, 1), (4, 7)):
+        r = subprocess.run([points_harness, str(p), str(k), str(threads)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.split() == ["OK", "700", "points", "OK", "700", "points"], r.stdout + r.stderr
