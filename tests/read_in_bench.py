@@ -1,7 +1,7 @@
 """Histogram stage of the relinked meshclust2 on a large single FASTA (default: the cfg3 shape, 100k x 1 kb): the reference's
 own `read_in_points` timestamp (FASTA parse + one Loader<T>::get_point per sequence, serial for a single file) next to the
 relinked binary's (same parse + ONE K1 batch on the device).  Both stop after training (--dump).
-usage: python tools/read_in_bench.py [n_sequences] [threads]"""
+usage: python tests/read_in_bench.py [n_sequences] [threads]"""
 import os, re, subprocess, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
