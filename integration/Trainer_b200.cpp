@@ -1,4 +1,5 @@
-// Trainer_b200.cpp — the ONE reference file that changes for the drop-in: a replacement for
+// Trainer_b200.cpp — the one reference file that is REPLACED for the drop-in (ClusterFactory.cpp and CRunner.cpp only gain the
+// few-line offers of integration/patch_*.py): a replacement for
 // src/cluster/Trainer.cpp that keeps Trainer<T>'s interface (src/cluster/Trainer.h:20-45, compiled from the reference
 // header, unmodified) and sends the candidate batches of get_close / filter / merge to libmeshclust2_b200 through the C
 // ABI (include/meshclust2_b200.h).  Everything else of MeShClust2 — CLI, FASTA I/O, mutation generator, GLM fit and
