@@ -500,8 +500,12 @@ bool mc2_batched_update(std::vector<Center<T>> &part, const Trainer<T> &trn, int
 	}
 	stage_all_centers<T>(d, part);
 	std::vector<int64_t> next((size_t)n);
-	ok(mc2_update_centers(d.ctx, d.model, d.centers, (uint64_t)n, d.points, off.data(), members.data(), trn.get_id(), next.data(),
-			      nullptr));
+	const int rc = mc2_update_centers(d.ctx, d.model, d.centers, (uint64_t)n, d.points, off.data(), members.data(), trn.get_id(),
+					  next.data(), nullptr);
+	if (rc == MC2_ERR_UNSUPPORTED) {
+		return false; // e.g. --bias below -0.5: the one-center calls handle it
+	}
+	ok(rc);
 	for (long j = 0; j < n; j++) {
 		Point<T> *center = part[j].getCenter();
 		if (next[(size_t)j] >= 0) {
