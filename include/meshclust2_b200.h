@@ -330,6 +330,13 @@ int mc2_all_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
 		  uint64_t max_out, uint64_t *out_q, uint64_t *out_d, double *out_score, uint64_t *n_out,
 		  uint64_t *n_scored);
 
+/* Diagnostic (tests): the integer reductions of the 1 KiB uint8 tile sweep for every (query, database) pair of the two row
+ * ranges, as dense row-major (q_end-q_begin) x (d_end-d_begin) uint32 matrices: need is a mask of 1 = sum|p-q|
+ * (Feature.cpp:858-871), 2 = sum p*q (Feature.cpp:1112-1124, 1170-1184), 4 = sum|cumP-cumQ| (Feature.cpp:1504-1518).
+ * Outputs not selected by `need` may be NULL.  No length window, no model. */
+int mc2_debug_tile_reductions(mc2_ctx *ctx, const mc2_hset *set_q, uint64_t q_begin, uint64_t q_end, const mc2_hset *set_d,
+			      uint64_t d_begin, uint64_t d_end, int32_t need, uint32_t *out_dot, uint32_t *out_emd, uint32_t *out_sad);
+
 /* DivergencePoint<T>::distance (src/clutil/DivergencePoint.cpp:70-82) for pairs of rows */
 int mc2_distance(mc2_ctx *ctx, const mc2_pairs *pairs, uint64_t *out);
 

@@ -38,7 +38,7 @@ SYMBOLS = [
     "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_count_kmers_into", "mc2_count_kmers_auto", "mc2_hset_largest_count", "mc2_width_for_count", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_update_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
     "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
-    "mc2_score_pairs", "mc2_get_close", "mc2_get_close_as", "mc2_filter", "mc2_filter_as", "mc2_merge", "mc2_all_pairs", "mc2_distance", "mc2_mean_closest", "mc2_closest",
+    "mc2_score_pairs", "mc2_get_close", "mc2_get_close_as", "mc2_filter", "mc2_filter_as", "mc2_merge", "mc2_all_pairs", "mc2_debug_tile_reductions", "mc2_distance", "mc2_mean_closest", "mc2_closest",
     "mc2_update_centers", "mc2_merge_centers",
     "mc2_bench_score_pairs", "mc2_bench_count_kmers", "mc2_encode_dna", "mc2_encode_dna_batch",
 ]
@@ -357,6 +357,17 @@ class Context:
                                    _p(od), _p(osc), C.byref(n_out), C.byref(n_scored)))
         got = min(n_out.value, max_out)
         return dict(q=oq[:got], d=od[:got], score=osc[:got], n_out=n_out.value, n_scored=n_scored.value)
+
+    def tile_reductions(self, set_q, set_d, need, q_range=None, d_range=None):
+        """Diagnostic: dense uint32 matrices {sad, dot, emd} (those in `need`: 1 | 2 | 4) of the tile sweep's reductions"""
+        q0, q1 = q_range if q_range else (0, len(set_q))
+        d0, d1 = d_range if d_range else (0, len(set_d))
+        shape = (q1 - q0, d1 - d0)
+        out = {k: np.zeros(shape, dtype=np.uint32) for k, bit in (("sad", 1), ("dot", 2), ("emd", 4)) if need & bit}
+        _check(lib().mc2_debug_tile_reductions(self.h, set_q.h, C.c_uint64(q0), C.c_uint64(q1), set_d.h, C.c_uint64(d0),
+                                               C.c_uint64(d1), int(need), _p(out["dot"]) if "dot" in out else None,
+                                               _p(out["emd"]) if "emd" in out else None, _p(out["sad"]) if "sad" in out else None))
+        return out
 
     def distance(self, set_a, set_b, ia, ib):
         p = self._pairs(set_a, set_b, ia, ib, len(ia))

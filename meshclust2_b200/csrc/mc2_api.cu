@@ -557,6 +557,7 @@ void mc2_ctx_destroy(mc2_ctx *ctx)
 	}
 	cudaFreeHost(ctx->h_slot);
 	cudaFree(ctx->d_slot);
+	cudaFree(ctx->d_sched);
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	cudaStreamDestroy(ctx->stream);
@@ -1020,6 +1021,7 @@ int mc2_count_kmers_into(mc2_ctx *ctx, const mc2_seqs *seqs, mc2_hset *dst)
 	MC2_REQUIRE(dst->n == seqs->n, "mc2_count_kmers_into: the set holds a different number of rows");
 	MC2_CUDA(cudaSetDevice(ctx->device));
 	dst->lane_off_valid = 0;
+	dst->cum16_valid = 0;
 	int rc = count_into(ctx, seqs, dst->k, dst->eb, 1, dst);
 	if (rc == MC2_OK) rc = refresh_max_sum(ctx, dst);
 	dst->counted = rc == MC2_OK;
@@ -1131,6 +1133,7 @@ int mc2_hset_update_from_device(mc2_ctx *ctx, mc2_hset *h, const void *d_bins, c
 		return MC2_OK;
 	}
 	h->lane_off_valid = 0;
+	h->cum16_valid = 0;
 	h->counted = 0;
 	MC2_CUDA(cudaMemcpyAsync(h->bins, d_bins, n * h->N * (u64)h->eb, cudaMemcpyDeviceToDevice, ctx->stream));
 	MC2_CUDA(cudaMemcpyAsync(h->len, d_len, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1169,6 +1172,8 @@ void mc2_hset_free(mc2_hset *h)
 	cudaFree(h->novf);
 	cudaFree(h->maxc);
 	cudaFree(h->lane_off);
+	cudaFree(h->cum16);
+	cudaFree(h->cumsum);
 	delete h;
 }
 
@@ -1249,6 +1254,7 @@ int mc2_hset_set_row(mc2_ctx *ctx, mc2_hset *dst, uint64_t dst_row, const mc2_hs
 	MC2_REQUIRE(dst->k == src->k && dst->eb == src->eb, "mc2_hset_set_row: sets differ in k or width");
 	MC2_REQUIRE(dst_row < dst->n && src_row < src->n, "mc2_hset_set_row: row out of range");
 	dst->lane_off_valid = 0;
+	dst->cum16_valid = 0;
 	dst->counted = 0;
 	cudaStream_t st = ctx->stream;
 	const u64 rb = dst->N * (u64)dst->eb;
@@ -1276,6 +1282,7 @@ int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t
 	// the destination's lane offsets stay valid when both sides have them (they are copied with the rows)
 	const bool keep_loff = dst->lane_off_valid && src->lane_off_valid && dst->lane_off && src->lane_off;
 	dst->lane_off_valid = keep_loff ? 1 : 0;
+	dst->cum16_valid = 0;
 	dst->counted = 0;
 	const int parts = 2 + (mag ? 1 : 0) + (len ? 1 : 0);
 	std::vector<u64> idx((size_t)parts * n);
@@ -1785,6 +1792,38 @@ int mc2_all_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
 		if (out_score) MC2_CUDA(cudaMemcpyAsync(out_score, x->d[B_OUTS].p, got * 8, cudaMemcpyDeviceToHost, st));
 		MC2_CUDA(cudaStreamSynchronize(st));
 	}
+	return check_err(ctx);
+}
+
+int mc2_debug_tile_reductions(mc2_ctx *ctx, const mc2_hset *set_q, uint64_t q_begin, uint64_t q_end, const mc2_hset *set_d,
+			      uint64_t d_begin, uint64_t d_end, int32_t need, uint32_t *out_dot, uint32_t *out_emd, uint32_t *out_sad)
+{
+	MC2_REQUIRE(ctx && set_q && set_d, "mc2_debug_tile_reductions: NULL argument");
+	MC2_REQUIRE(q_begin <= q_end && q_end <= set_q->n && d_begin <= d_end && d_end <= set_d->n, "mc2_debug_tile_reductions: row range out of bounds");
+	MC2_REQUIRE(set_q->eb == 1 && set_d->eb == 1 && set_q->N == 1024 && set_d->N == 1024, "mc2_debug_tile_reductions: needs k = 5 uint8 sets");
+	MC2_REQUIRE((need & 7) != 0 && (need & ~7) == 0, "mc2_debug_tile_reductions: need is a mask of 1 (sad), 2 (dot), 4 (emd)");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	const u64 cells = (q_end - q_begin) * (d_end - d_begin);
+	if (cells == 0) return MC2_OK;
+	CtxExtra *x = extra(ctx);
+	int rc = ensure(x->d[B_SCORE], cells * 4, false); if (rc) return rc;
+	rc = ensure(x->d[B_DIST], cells * 4, false); if (rc) return rc;
+	rc = ensure(x->d[B_CACHE], cells * 4, false); if (rc) return rc;
+	rc = ensure(x->d[B_MISC], 64, false); if (rc) return rc;
+	MC2_CUDA(cudaMemsetAsync(x->d[B_MISC].p, 0, 64, ctx->stream));
+	rc = reset_err(ctx);
+	DevModel dm;
+	memset(&dm, 0, sizeof dm);
+	if (rc == MC2_OK)
+		rc = launch_tile_sweep(ctx, dm, need, set_q, q_begin, q_end, set_d, d_begin, d_end, 0, 1.0, 0, nullptr, nullptr, nullptr,
+				       (u64 *)x->d[B_MISC].p, (u32 *)x->d[B_SCORE].p, (u32 *)x->d[B_DIST].p, (u32 *)x->d[B_CACHE].p);
+	if (rc == MC2_OK) rc = fetch_err(ctx);
+	if (rc != MC2_OK) return rc;
+	cudaStream_t st = ctx->stream;
+	if (out_dot && (need & 2)) MC2_CUDA(cudaMemcpyAsync(out_dot, x->d[B_SCORE].p, cells * 4, cudaMemcpyDeviceToHost, st));
+	if (out_emd && (need & 4)) MC2_CUDA(cudaMemcpyAsync(out_emd, x->d[B_DIST].p, cells * 4, cudaMemcpyDeviceToHost, st));
+	if (out_sad && (need & 1)) MC2_CUDA(cudaMemcpyAsync(out_sad, x->d[B_CACHE].p, cells * 4, cudaMemcpyDeviceToHost, st));
+	MC2_CUDA(cudaStreamSynchronize(st));
 	return check_err(ctx);
 }
 

@@ -100,6 +100,7 @@ struct mc2_ctx {
 	void *extra;      // CtxExtra (growable scratch buffers), owned by mc2_api.cu
 	int prof_on;      // per-kernel event timing enabled
 	int err_dirty;    // the device error word may be non-zero (set by reset_err, cleared by a clean check_err)
+	void *d_sched;    // tile schedule of the tile sweep (tile_sweep.cu), allocated on first use
 };
 
 namespace mc2 {
@@ -144,6 +145,11 @@ struct mc2_hset {
 	// dropped whenever bins change.
 	unsigned short *lane_off;
 	int lane_off_valid;
+	// 1 KiB uint8 rows with row sums < 65536: inclusive cumulative rows (u16, n x 1024) and each row's sum of them (u32),
+	// the EMD operands of the tile sweep (tile_sweep.cu).  Built lazily, dropped whenever bins change.
+	unsigned short *cum16;
+	u32 *cumsum;
+	int cum16_valid;
 };
 
 struct mc2_model {
@@ -197,6 +203,12 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 		     u64 *d_counters);
 int launch_distance(mc2_ctx *ctx, const PairArgs &a, u64 *d_out);
 int ensure_lane_off(mc2_ctx *ctx, const mc2_hset *h); // builds h->lane_off if the shape allows; no-op otherwise
+// tile_sweep.cu: the all-pairs sweep over 1 KiB uint8 rows as 64 x 128 pair tiles (TMA ring, tcgen05 Gram term, u16 cumulative EMD)
+int ensure_cum16(mc2_ctx *ctx, const mc2_hset *h);
+bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset *d);
+int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset *q, u64 q0, u64 q1, const mc2_hset *d, u64 d0, u64 d1,
+		      int upper_only, double cutoff, u64 max_out, u64 *d_out_q, u64 *d_out_d, double *d_out_score, u64 *d_counters,
+		      u32 *raw_dot, u32 *raw_emd, u32 *raw_sad);
 int launch_mean_closest(mc2_ctx *ctx, const mc2_hset *h, const u64 *d_members, u64 n, u64 *d_sums, double *d_mean, double *d_dist,
 			void *d_out, bool have_mean);
 int launch_update_batch(mc2_ctx *ctx, const mc2_hset *h, const u64 *d_member_off, const u64 *d_members, const uint8_t *d_close,
