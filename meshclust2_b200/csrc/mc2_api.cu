@@ -2,6 +2,7 @@
 // No compute happens on the host here; every entry point launches the sm_100a kernels in kmer_count.cu /
 // pair_score.cu / pair_tile.cu or fails loudly.
 #include "mc2_internal.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -224,6 +225,91 @@ static int d2h(mc2_ctx *ctx, void *dst, const void *src, size_t bytes)
 	return MC2_OK;
 }
 
+// Constants of the tile sweep's fp32 screen (tile_sweep.cu, screen_pairs).  Per single k present in the model the
+// normalised value of Feature::normalize_cache (Feature.cpp:136-154) is x = a*raw + b with a = +-1/range, b folded from
+// min, range and the 1 - v of distance-like singles.  Error model, eps = 2^-23 (twice the unit round-off):
+//   raw is a cancellation-free fp32 expression of exact integers, relative error <= 16 eps;
+//   |fl(x) - x| <= eps * 18 * (|x| + 2|b|) <= eps * gamma * u,  gamma = 18 * max(1, 2 max|b|),  u = 1 + max_k |x_k|;
+//   a combo of total degree P <= 4 in factors bounded by u with that error: |delta| <= u^4 * eps * (1.01 P gamma + P);
+//   weights in fp32 and the fused accumulation add eps * (2 + n_combos + 1) per term.
+// Hence |fp32 sum - exact sum| <= eps * (K1 * u^4 + K0); both constants are doubled before rounding to float.
+static void build_screen(DevModel &dm)
+{
+	dm.scr_ok = 0;
+	dm.scr_k1 = dm.scr_k0 = 0;
+	memset(dm.scr_a, 0, sizeof dm.scr_a);
+	memset(dm.scr_b, 0, sizeof dm.scr_b);
+	memset(dm.scr_w, 0, sizeof dm.scr_w);
+	if (!dm.fast_epi || dm.regression || dm.bias != 0.0 || dm.n_combos > MC2_SCR_MAX_COMBOS || (dm.need & NEED_LOG)) {
+		return;
+	}
+	const double eps = 1.1920928955078125e-07;
+	double beta = 0;
+	for (int k = 0; k < SC_COUNT; k++) {
+		if (dm.slot[k] < 0) {
+			continue;
+		}
+		if (!dm.crcp_ok[k] || !std::isfinite(dm.cmin[k])) {
+			return;
+		}
+		const double rcp = dm.crcp[k];
+		const double a = dm.csim[k] ? rcp : -rcp;
+		const double b = dm.csim[k] ? -dm.cmin[k] * rcp : 1.0 + dm.cmin[k] * rcp;
+		if (!(fabs(a) < 1e30 && fabs(b) < 1e6)) {
+			return;
+		}
+		dm.scr_a[k] = (float)a;
+		dm.scr_b[k] = (float)b;
+		beta = std::max(beta, fabs(b));
+	}
+	const double gamma = 18.0 * std::max(1.0, 2.0 * beta);
+	if (!(eps * gamma * 4 < 0.01)) {
+		return;
+	}
+	double K1 = 0;
+	for (int c = 0; c < MC2_SCR_MAX_COMBOS; c++) {
+		dm.scr_ka[c] = dm.scr_kb[c] = SC_COUNT; // the constant 1
+		dm.scr_pa2[c] = dm.scr_pb2[c] = 0;
+	}
+	for (int c = 0; c < dm.n_combos; c++) {
+		int pw[SC_COUNT] = {0};
+		int P = 0;
+		for (int t = 0; t < dm.nidx[c]; t++) {
+			const int code = dm.code[dm.idx[c][t]];
+			const int kind = dm.kind[c];
+			const int add = (kind == MC2_COMBO_X2Y2 || (kind == MC2_COMBO_XY2 && t == 1) || (kind == MC2_COMBO_X2Y && t == 0)) ? 2 : 1;
+			pw[code] += add;
+			P += add;
+		}
+		int nk = 0;
+		for (int k = 0; k < SC_COUNT; k++) {
+			if (pw[k] == 0) {
+				continue;
+			}
+			if (pw[k] > 2 || nk == 2) {
+				return; // more than two distinct singles, or one of them beyond its square: outside the screen's form
+			}
+			(nk == 0 ? dm.scr_ka[c] : dm.scr_kb[c]) = k;
+			(nk == 0 ? dm.scr_pa2[c] : dm.scr_pb2[c]) = pw[k] == 2;
+			nk++;
+		}
+		const double w = dm.weight[c + 1];
+		if (!(fabs(w) < 1e6)) {
+			return;
+		}
+		dm.scr_w[c + 1] = (float)w;
+		K1 += fabs(w) * (1.01 * P * gamma + P + 2 + dm.n_combos + 1);
+	}
+	if (!(fabs(dm.weight[0]) < 1e6)) {
+		return;
+	}
+	dm.scr_w[0] = (float)dm.weight[0];
+	const double K0 = (dm.n_combos + 2) * fabs(dm.weight[0]);
+	dm.scr_k1 = nextafterf((float)(2 * eps * K1), INFINITY);
+	dm.scr_k0 = nextafterf((float)(2 * eps * K0), INFINITY);
+	dm.scr_ok = 1;
+}
+
 static int model_need(const mc2_model_desc &d, DevModel &dm)
 {
 	memset(&dm, 0, sizeof dm);
@@ -308,6 +394,7 @@ static int model_need(const mc2_model_desc &d, DevModel &dm)
 		const double ar = fabs(dm.crange[c]);
 		dm.crcp_ok[c] = std::isfinite(dm.crcp[c]) && ar > 1e-100 && ar < 1e100;
 	}
+	build_screen(dm);
 	return MC2_OK;
 }
 
@@ -322,6 +409,10 @@ static int check_err(mc2_ctx *ctx)
 	if (e == 0) {
 		ctx->err_dirty = 0; // the device word is known to be zero: the next call need not clear it
 		return MC2_OK;
+	}
+	if (e & 16) {
+		set_error("tile sweep: a pipeline barrier timed out (internal error)");
+		return MC2_ERR_CUDA;
 	}
 	if (e & 4) {
 		set_error("invalid nucleotide code inside a segment (reference: InvalidInputException, KmerHashTable.cpp:138-149)");

@@ -46,6 +46,8 @@ enum SingleCode : int {
 	SC_COUNT
 };
 
+#define MC2_SCR_MAX_COMBOS 8
+
 // which reductions over the bins a model needs
 enum NeedBits : int { NEED_MIN = 1, NEED_DOT = 2, NEED_EMD = 4, NEED_LOG = 8 };
 
@@ -72,6 +74,14 @@ struct DevModel {
 	double cmin[SC_COUNT];
 	double crange[SC_COUNT];      // max - min, the divisor of Feature::normalize_cache (Feature.cpp:136-154)
 	double crcp[SC_COUNT];        // correctly rounded 1 / crange
+	// fp32 screen of the tile sweep (tile_sweep.cu): normalised single = scr_a * raw + scr_b; combo c is
+	// x[scr_ka[c]]^(1 + scr_pa2[c]) * x[scr_kb[c]]^(1 + scr_pb2[c]) with single CODES as indices (SC_COUNT = the constant 1);
+	// |fp32 sum - exact sum| <= scr_k1 * (1 + max |x|)^4 + scr_k0 (derivation: build_screen in mc2_api.cu)
+	int scr_ok;                   // 0: the model is outside what the screen covers -> every pair takes the exact path
+	float scr_a[SC_COUNT], scr_b[SC_COUNT];
+	float scr_w[MC2_SCR_MAX_COMBOS + 1];
+	int scr_ka[MC2_SCR_MAX_COMBOS], scr_kb[MC2_SCR_MAX_COMBOS], scr_pa2[MC2_SCR_MAX_COMBOS], scr_pb2[MC2_SCR_MAX_COMBOS];
+	float scr_k1, scr_k0;
 };
 
 // side-band SoA of a histogram set (device pointers)

@@ -30,29 +30,24 @@ namespace mc2 {
 
 namespace ts {
 
-constexpr int TQ = 64;          // query rows per tile (UMMA N, TMEM columns)
-constexpr int TD = 128;         // database rows per tile (UMMA M, TMEM lanes)
-constexpr int KC = 64;          // bins per pipeline stage
+constexpr int TQ = 64;          // query rows per tile (UMMA N, TMEM columns per region)
+constexpr int TD = 256;         // database rows per tile: two regions of 128 (UMMA M = 128 = the TMEM lanes)
 constexpr int NBINS = 1024;
-constexpr int NCHUNK = NBINS / KC;
-constexpr int NCW = 8;          // compute warps
-constexpr int THREADS = (NCW + 2) * 32;
-constexpr int CUMD_BYTES = TD * KC * 2;  // 16 KB, 128-byte rows, SWIZZLE_128B
-constexpr int CUMQ_BYTES = TQ * KC * 2;  //  8 KB
-constexpr int U8D_BYTES = TD * KC;       //  8 KB, 64-byte rows, SWIZZLE_64B
-constexpr int U8Q_BYTES = TQ * KC;       //  4 KB
-constexpr int STAGE_BYTES = CUMD_BYTES + CUMQ_BYTES + U8D_BYTES + U8Q_BYTES; // 36 KB (a stage keeps this layout whatever NEED is)
-constexpr int RED_BYTES = TQ * TD * 4;   // one staged reduction (32 KB)
+constexpr int KC_CUM = 64;      // bins per ring stage while the u16 cumulative rows stream (128-byte rows)
+constexpr int KC_U8 = 128;      // bins per ring stage while the u8 rows stream (128-byte rows)
+constexpr int NCW = 8;          // compute warps (CTA warps 2..9)
+constexpr int NEW = 4;          // epilogue warps (CTA warps 10..13), one per TMEM lane quarter
+constexpr int THREADS = (2 + NCW + NEW) * 32;
+constexpr int D_BYTES = TD * 128;        // 32 KB, SWIZZLE_128B
+constexpr int Q_BYTES = TQ * 128;        //  8 KB
+constexpr int STAGE_BYTES = D_BYTES + Q_BYTES; // 40 KB
+constexpr int STAGES = 4;
 constexpr int MAX_SUPER = 1024;          // entries of the tile schedule's prefix array
-
-__host__ __device__ constexpr int n_red(int need) { return ((need & NEED_DOT) ? 1 : 0) + ((need & NEED_EMD) ? 1 : 0) + ((need & NEED_MIN) ? 1 : 0); }
-__host__ __device__ constexpr int n_stages(int need)
-{
-	// 227 KB per CTA: staged reductions + candidate list (16 KB) + row info / schedule / barriers (16 KB) + ring
-	const int fixed = n_red(need) * RED_BYTES + 16384 + 16384 + 1024;
-	const int s = (227 * 1024 - fixed) / STAGE_BYTES;
-	return s > 4 ? 4 : s;
-}
+constexpr int LIST_CAP = 256;            // candidate records per epilogue warp
+// TMEM columns (512 allocated): Gram accumulators double buffered, EMD / SAD sums single buffered
+constexpr u32 TM_DOT = 0;                // + buf * 128 + region * 64
+constexpr u32 TM_EMD = 256;              // + region * 64
+constexpr u32 TM_SAD = 384;              // + region * 64
 
 struct Params {
 	u64 q0, q1, d0, d1;     // row ranges (query set / database set)
@@ -70,7 +65,6 @@ struct Params {
 	u32 n_super;
 	const u32 *sched;       // [n_super + 1] exclusive prefix of items per super-row (device)
 	int no_screen;          // experiments: skip the screen and the exact path (main-loop cost only)
-	int flush_mode;         // 0: packed sums flushed every 16 words (row sums <= 4095), 1: every 4 (<= 16383), 2: IDP.2A per word
 	// raw mode (tests): dense (q1-q0) x (d1-d0) matrices of the reductions instead of scoring
 	u32 *raw_dot, *raw_emd, *raw_sad;
 };
@@ -100,7 +94,7 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity, int *err)
 	u32 spins = 0;
 	while (!mbar_try(bar, parity)) {
 		if (++spins > (1u << 24)) {
-			atomicOr(err, 4);
+			atomicOr(err, 16);
 			__trap();
 		}
 	}
@@ -123,6 +117,21 @@ __device__ __forceinline__ void tc_mma_i8(u32 tmem_d, u64 desc_a, u64 desc_b, u3
 		     "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
 		     : "memory");
 }
+__device__ __forceinline__ void tc_ld4(u32 taddr, u32 (&v)[4])
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st32(u32 taddr, const u32 (&v)[32])
+{
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+		     "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+		     "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+		     "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+		     "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+		     : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ uint4 lds128(u32 addr)
 {
@@ -149,16 +158,16 @@ __device__ __forceinline__ u32 sad4(u32 a, u32 b, u32 c)
 	return d;
 }
 
-// K-major shared-memory operand descriptor for 64-byte rows under SWIZZLE_64B (cute::UMMA::SmemDescriptor: start >> 4 at
-// [0,14), leading byte offset >> 4 at [16,30) (1 for swizzled K-major), stride byte offset >> 4 at [32,46) = 8 rows x 64 B,
-// version 1 at [46,48), layout type at [61,64): 4 = SWIZZLE_64B)
-__device__ __forceinline__ u64 umma_desc_sw64(u32 saddr)
+// K-major shared-memory operand descriptor for 128-byte rows under SWIZZLE_128B (cute::UMMA::SmemDescriptor: start >> 4 at
+// [0,14), leading byte offset >> 4 at [16,30) (1 for swizzled K-major), stride byte offset >> 4 at [32,46) = 8 rows x 128 B,
+// version 1 at [46,48), layout type at [61,64): 2 = SWIZZLE_128B)
+__device__ __forceinline__ u64 umma_desc_sw128(u32 saddr)
 {
-	return (u64)((saddr & 0x3FFFFu) >> 4) | ((u64)1 << 16) | ((u64)(512 >> 4) << 32) | ((u64)1 << 46) | ((u64)4 << 61);
+	return (u64)((saddr & 0x3FFFFu) >> 4) | ((u64)1 << 16) | ((u64)(1024 >> 4) << 32) | ((u64)1 << 46) | ((u64)2 << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 at [4,6), a/b format U8 = 0, K-major both,
 // N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr u32 IDESC_U8 = (2u << 4) | ((u32)(TQ >> 3) << 17) | ((u32)(TD >> 4) << 24);
+constexpr u32 IDESC_U8 = (2u << 4) | ((u32)(TQ >> 3) << 17) | ((u32)(128 >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------------------------
 // tile schedule: super-rows of `group` query tiles; inside a super-row the items run database-tile major, query-tile
@@ -220,226 +229,228 @@ __device__ __forceinline__ Tile decode_item(const Params &p, const u32 *s_sched,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// per-chunk CUDA-core work of one compute warp: rows cw*8 .. cw*8+7 of the query tile x rows lane + 32 j of the database tile
+// CUDA-core work of one compute warp on one ring stage.  The thread owns database rows L and 128 + L of the tile
+// (L = 32 * (warp % 4) + lane, its TMEM lane) against the 32 query rows of its half: 64 accumulators.  Per 16-byte
+// step: 2 conflict-free row loads, 32 warp-uniform (broadcast) query loads, 512 (EMD) / 256 (SAD) arithmetic instructions.
+// 128-byte rows under SWIZZLE_128B: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4).
 // ---------------------------------------------------------------------------------------------------------------
-template <int NEED, int FLUSH>
-__device__ __forceinline__ void chunk_compute(u32 stage, int cw, int lane, u32 (&emd)[8][4], u32 (&sad)[8][4])
+template <bool IS_EMD>
+__device__ __forceinline__ void stage_compute(u32 stage, u32 lane_row, int half, u32 (&acc)[2][32])
 {
-	if constexpr ((NEED & NEED_EMD) != 0) {
-		// 128-byte rows, SWIZZLE_128B: 16-byte chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)
-		const u32 dbase = stage + (u32)lane * 128;
-		const u32 dsw = ((u32)lane & 7) << 4;
-		const u32 qbase = stage + CUMD_BYTES + (u32)cw * 1024;
+	const u32 dbase = stage + lane_row * 128;
+	const u32 dsw = (lane_row & 7) << 4;
+	const u32 qbase = stage + D_BYTES + (u32)half * 4096;
+	// the 16-byte steps stay a loop (a fully unrolled stage would be 70 KB of code, far beyond the instruction cache)
+#pragma unroll 1
+	for (u32 c = 0; c < 8; c++) {
+		const uint4 D0 = lds128(dbase + ((c << 4) ^ dsw));
+		const uint4 D1 = lds128(dbase + 16384 + ((c << 4) ^ dsw));
+		u32 cx[8]; // swizzled chunk offset for query rows with (row & 7) == j
 #pragma unroll
-		for (int g = 0; g < 2; g++) {
-			u32 acc[8][4];
-#pragma unroll
-			for (int ks = 0; ks < 4; ks++) {
-				const int c = g * 4 + ks;
-				uint4 D[4];
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					D[j] = lds128(dbase + (u32)j * 4096 + (((u32)c << 4) ^ dsw));
-				}
-#pragma unroll
-				for (int i = 0; i < 8; i++) {
-					const uint4 Q = lds128(qbase + (u32)i * 128 + (u32)((c ^ i) << 4));
-#pragma unroll
-					for (int j = 0; j < 4; j++) {
-						const u32 m0 = vmin2(Q.x, D[j].x), m1 = vmin2(Q.y, D[j].y);
-						const u32 m2 = vmin2(Q.z, D[j].z), m3 = vmin2(Q.w, D[j].w);
-						if constexpr (FLUSH == 2) {
-							emd[i][j] = dp2a_sum(m0, emd[i][j]);
-							emd[i][j] = dp2a_sum(m1, emd[i][j]);
-							emd[i][j] = dp2a_sum(m2, emd[i][j]);
-							emd[i][j] = dp2a_sum(m3, emd[i][j]);
-						} else if constexpr (FLUSH == 1) {
-							emd[i][j] = dp2a_sum(m0 + m1 + m2 + m3, emd[i][j]);
-						} else {
-							if (ks == 0) {
-								acc[i][j] = m0 + m1 + m2 + m3;
-							} else {
-								acc[i][j] += m0 + m1;
-								acc[i][j] += m2 + m3;
-							}
-						}
-					}
-				}
-			}
-			if constexpr (FLUSH == 0) {
-#pragma unroll
-				for (int i = 0; i < 8; i++) {
-#pragma unroll
-					for (int j = 0; j < 4; j++) {
-						emd[i][j] = dp2a_sum(acc[i][j], emd[i][j]);
-					}
-				}
-			}
+		for (int j = 0; j < 8; j++) {
+			cx[j] = qbase + ((c ^ (u32)j) << 4);
 		}
-	}
-	if constexpr ((NEED & NEED_MIN) != 0) {
-		// 64-byte rows, SWIZZLE_64B: 16-byte chunk c of row r sits at r*64 + ((c ^ ((r >> 1) & 3)) << 4)
-		const u32 dbase = stage + CUMD_BYTES + CUMQ_BYTES + (u32)lane * 64;
-		const u32 dsw = (((u32)lane >> 1) & 3) << 4;
-		const u32 qbase = stage + CUMD_BYTES + CUMQ_BYTES + U8D_BYTES + (u32)cw * 512;
 #pragma unroll
-		for (int c = 0; c < 4; c++) {
-			uint4 D[4];
-#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				D[j] = lds128(dbase + (u32)j * 2048 + (((u32)c << 4) ^ dsw));
+		for (int q = 0; q < 32; q++) {
+			const uint4 Q = lds128(cx[q & 7] + (u32)q * 128);
+			u32 a = acc[0][q], b = acc[1][q];
+			if constexpr (IS_EMD) {
+				// sum of min over the u16 pairs: VIMNMX.U16x2 (ALU pipe) + IDP.2A with weights (1, 1) (FMA pipe)
+				a = dp2a_sum(vmin2(Q.x, D0.x), a);
+				b = dp2a_sum(vmin2(Q.x, D1.x), b);
+				a = dp2a_sum(vmin2(Q.y, D0.y), a);
+				b = dp2a_sum(vmin2(Q.y, D1.y), b);
+				a = dp2a_sum(vmin2(Q.z, D0.z), a);
+				b = dp2a_sum(vmin2(Q.z, D1.z), b);
+				a = dp2a_sum(vmin2(Q.w, D0.w), a);
+				b = dp2a_sum(vmin2(Q.w, D1.w), b);
+			} else {
+				a = sad4(Q.x, D0.x, a);
+				b = sad4(Q.x, D1.x, b);
+				a = sad4(Q.y, D0.y, a);
+				b = sad4(Q.y, D1.y, b);
+				a = sad4(Q.z, D0.z, a);
+				b = sad4(Q.z, D1.z, b);
+				a = sad4(Q.w, D0.w, a);
+				b = sad4(Q.w, D1.w, b);
 			}
-#pragma unroll
-			for (int i = 0; i < 8; i++) {
-				const uint4 Q = lds128(qbase + (u32)i * 64 + (u32)((c ^ ((i >> 1) & 3)) << 4));
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					u32 s = sad[i][j];
-					s = sad4(Q.x, D[j].x, s);
-					s = sad4(Q.y, D[j].y, s);
-					s = sad4(Q.z, D[j].z, s);
-					s = sad4(Q.w, D[j].w, s);
-					sad[i][j] = s;
-				}
-			}
+			acc[0][q] = a;
+			acc[1][q] = b;
 		}
 	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fp32 screen: the GLM sum with a running bound on |computed - exact|.  Returns true when the pair may be close (or the
-// screen cannot tell): only `false` is a decision.  eps is 2^-23 (twice the unit round-off); every raw single below is a
-// cancellation-free expression of exact integers, at most 8 operations of <= 2 ulp each -> relative bound 16 eps.
+// fp32 screen: the GLM sum of NP pairs in single precision with a rigorous bound on |fp32 sum - exact sum| (constants and
+// derivation: build_screen in mc2_api.cu).  A pair whose bit is clear in the result is certainly not close; everything
+// else goes to the exact fp64 epilogue.  Every raw single is a cancellation-free expression of exact integers (at most 8
+// operations of <= 2 ulp); the NP pairs share the control flow, so the model's uniform branches are paid once per NP
+// pairs and the dependency chains interleave.  No local memory: combo products are built single by single.
 // ---------------------------------------------------------------------------------------------------------------
-struct RowF {          // per-row values staged in shared memory once per tile
-	u32 mag, sum;  // low words (valid when !big)
-	float magf, sumsqf, lenf, nnf; // nnf = N*sumsq - 2*mag*sum + mag^2 (pearson's centred norm, exact integer -> float)
-	u32 sumsq;
+struct RowF {          // per-row values of the screen
+	u32 mag, sum, sumsq; // low words (valid when !big)
+	u32 cs;        // sum of the row's cumulative sums (EMD identity)
+	float magf, lenf;
+	float rss;     // 1 / sqrt(sumsq)
+	float rnn;     // 1 / sqrt(N*sumsq - 2*mag*sum + mag^2)  (pearson's centred norm, exact integer -> float)
 	u32 big;       // mag or len outside the screen's comfortable range -> exact path
 };
 
-__device__ __forceinline__ bool screen_pair(const DevModel &dm, u32 dot, u32 emd, u32 sad, const RowF &P, const RowF &Q)
+__device__ __forceinline__ RowF make_rowf(const Sideband &sb, const u32 *cs, u64 row, bool ok, u64 &len)
 {
-	const float eps = 1.1920929e-07f;
-	float x[MC2_MAX_SINGLES], ex[MC2_MAX_SINGLES];
-#define MC2_SCR(CODE, RAW, DELTA)                                                                  \
-	{                                                                                          \
-		const float raw_ = (RAW);                                                          \
-		const float cmin_ = (float)dm.cmin[CODE], rcp_ = (float)dm.crcp[CODE];             \
-		const float t_ = raw_ - cmin_;                                                     \
-		const float v_ = t_ * rcp_;                                                        \
-		const float xv_ = dm.csim[CODE] ? v_ : 1.0f - v_;                                  \
-		x[dm.slot[CODE]] = xv_;                                                            \
-		ex[dm.slot[CODE]] = eps * (((DELTA)*fabsf(raw_) + fabsf(cmin_) + fabsf(t_)) * fabsf(rcp_) + 2.0f * fabsf(v_) + fabsf(xv_)); \
+	RowF r;
+	memset(&r, 0, sizeof r);
+	r.big = 1;
+	len = 0;
+	if (ok) {
+		const u64 mag = sb.mag[row], sum = sb.sum[row], sumsq = sb.sumsq[row];
+		len = sb.len[row];
+		r.mag = (u32)mag;
+		r.sum = (u32)sum;
+		r.sumsq = (u32)sumsq;
+		r.magf = (float)mag;
+		r.lenf = (float)len;
+		r.rss = rsqrtf((float)sumsq);
+		// the screen wants exact float lengths (their difference cancels) and 64-bit pearson terms
+		r.big = (mag >= (1ull << 26) || len >= (1ull << 24) || len == 0 || mag == 0) ? 1u : 0u;
+		const long long m = (long long)(mag & 0x3FFFFFFull);
+		r.rnn = rsqrtf((float)(1024ll * (long long)sumsq - 2ll * m * (long long)sum + m * m));
+		r.cs = cs ? cs[row] : 0u;
 	}
-	const u32 n2 = P.sumsq + Q.sumsq - 2u * dot; // exact: sum (p-q)^2 < 2^27 for 1024 uint8 bins
-	if (dm.slot[SC_MANHATTAN] >= 0) {
-		MC2_SCR(SC_MANHATTAN, (float)sad, 1.0f);
+	return r;
+}
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+	float r;
+	asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
+// sx: this thread's column of the epilogue's scratch, element (slot, t) at sx[(slot * NP + t) * (NEW * 32)]; slot = single
+// code, slot SC_COUNT holds the constant 1 (written once per kernel)
+template <int NEED, int NP>
+__device__ __forceinline__ u32 screen_pairs(const DevModel &dm, float *sx, const u32 (&dot)[NP], const u32 (&emd)[NP], const u32 (&sad)[NP],
+					    const RowF &P, const RowF *Q)
+{
+	constexpr int ET = NEW * 32;
+	float m[NP];
+#pragma unroll
+	for (int t = 0; t < NP; t++) {
+		m[t] = 0.0f;
 	}
-	if (dm.slot[SC_EUCLIDEAN] >= 0) {
-		MC2_SCR(SC_EUCLIDEAN, sqrtf((float)n2), 16.0f);
+	// one single: x = a * raw + b -> scratch; max |x| over the singles the model uses.  Branch-free: singles the model
+	// does not use are computed into slots nobody reads.
+#define MC2_SCR(CODE, RAW)                                                                       \
+	{                                                                                        \
+		const float a_ = dm.scr_a[CODE], b_ = dm.scr_b[CODE];                            \
+		const bool used_ = dm.slot[CODE] >= 0;                                           \
+		_Pragma("unroll") for (int t = 0; t < NP; t++)                                   \
+		{                                                                                \
+			const float x_ = __fmaf_rn(a_, (RAW), b_);                               \
+			sx[((CODE)*NP + t) * ET] = x_;                                           \
+			m[t] = fmaxf(m[t], used_ ? fabsf(x_) : 0.0f);                            \
+		}                                                                                \
 	}
-	if (dm.slot[SC_SIMRATIO] >= 0) {
-		const float d = (float)dot;
-		MC2_SCR(SC_SIMRATIO, __fdividef(d, d + sqrtf((float)n2)), 16.0f);
+	if constexpr ((NEED & NEED_DOT) != 0) {
+		float n2f[NP], dotf[NP], rt[NP];
+#pragma unroll
+		for (int t = 0; t < NP; t++) {
+			n2f[t] = (float)(P.sumsq + Q[t].sumsq - 2u * dot[t]); // exact integer: sum (p-q)^2 < 2^27 for 1024 uint8 bins
+			dotf[t] = (float)dot[t];
+			rt[t] = sqrt_approx(n2f[t]);
+		}
+		MC2_SCR(SC_EUCLIDEAN, rt[t])
+		MC2_SCR(SC_SIMRATIO, __fdividef(dotf[t], dotf[t] + rt[t]))
+		MC2_SCR(SC_NORMALIZED_VECTORS, dotf[t] * (P.rss * Q[t].rss))
+		MC2_SCR(SC_PEARSON, (float)(1024ll * (long long)dot[t] - (long long)P.mag * (long long)Q[t].sum - (long long)Q[t].mag * (long long)P.sum +
+					    (long long)P.mag * (long long)Q[t].mag) *
+					    (P.rnn * Q[t].rnn))
 	}
-	if (dm.slot[SC_NORMALIZED_VECTORS] >= 0) {
-		MC2_SCR(SC_NORMALIZED_VECTORS, (float)dot * rsqrtf(P.sumsqf * Q.sumsqf), 16.0f);
+	if constexpr ((NEED & NEED_MIN) != 0) {
+		float two_smin[NP];
+#pragma unroll
+		for (int t = 0; t < NP; t++) {
+			two_smin[t] = (float)(P.sum + Q[t].sum - sad[t]);
+		}
+		MC2_SCR(SC_MANHATTAN, (float)sad[t])
+		MC2_SCR(SC_INTERSECTION, __fdividef(two_smin[t], P.magf + Q[t].magf))
+		MC2_SCR(SC_KULCZYNSKI2, __fdividef(P.magf + Q[t].magf, 2.0f * (P.magf * (1.0f / 1024.0f)) * (Q[t].magf * (1.0f / 1024.0f))) * (0.5f * two_smin[t]))
 	}
-	if (dm.slot[SC_PEARSON] >= 0) {
-		const long long ndot = 1024ll * (long long)dot - (long long)P.mag * (long long)Q.sum - (long long)Q.mag * (long long)P.sum +
-				       (long long)P.mag * (long long)Q.mag;
-		MC2_SCR(SC_PEARSON, (float)ndot * rsqrtf(P.nnf * Q.nnf), 16.0f);
+	if constexpr ((NEED & NEED_EMD) != 0) {
+		MC2_SCR(SC_EMD, (float)emd[t])
 	}
-	if (dm.slot[SC_INTERSECTION] >= 0) {
-		MC2_SCR(SC_INTERSECTION, __fdividef((float)(P.sum + Q.sum - sad), P.magf + Q.magf), 16.0f);
-	}
-	if (dm.slot[SC_EMD] >= 0) {
-		MC2_SCR(SC_EMD, (float)emd, 1.0f);
-	}
-	if (dm.slot[SC_LENGTHD] >= 0) {
-		MC2_SCR(SC_LENGTHD, fabsf(P.lenf - Q.lenf), 4.0f);
-	}
-	if (dm.slot[SC_KULCZYNSKI2] >= 0) {
-		const float ap = P.magf * (1.0f / 1024.0f), aq = Q.magf * (1.0f / 1024.0f);
-		const float smin = 0.5f * (float)(P.sum + Q.sum - sad);
-		MC2_SCR(SC_KULCZYNSKI2, __fdividef(1024.0f * (ap + aq), 2.0f * ap * aq) * smin, 16.0f);
-	}
+	MC2_SCR(SC_LENGTHD, fabsf(P.lenf - Q[t].lenf))
 #undef MC2_SCR
-	float s = (float)dm.weight[0];
-	float M = fabsf(s), E = 0.0f;
+	float s[NP];
+#pragma unroll
+	for (int t = 0; t < NP; t++) {
+		s[t] = dm.scr_w[0];
+	}
 #pragma unroll 1
 	for (int c = 0; c < dm.n_combos; c++) {
-		const int *ix = dm.idx[c];
-		const int kind = dm.kind[c];
-		float v = 1.0f, hi = 1.0f, lo = 1.0f; // product, product of (|f| + e), product of |f|
-		const int n = dm.nidx[c];
-		for (int t = 0; t < n; t++) {
-			const float f = x[ix[t]], a = fabsf(f), b = a + ex[ix[t]];
-			int pw = 1;
-			if (kind == MC2_COMBO_X2Y2 || (kind == MC2_COMBO_XY2 && t == 1) || (kind == MC2_COMBO_X2Y && t == 0)) {
-				pw = 2;
-			}
-			v *= f;
-			hi *= b;
-			lo *= a;
-			if (pw == 2) {
-				v *= f;
-				hi *= b;
-				lo *= a;
-			}
+		const int ka = dm.scr_ka[c] * NP * ET, kb = dm.scr_kb[c] * NP * ET;
+		const bool pa2 = dm.scr_pa2[c] != 0, pb2 = dm.scr_pb2[c] != 0;
+		const float w = dm.scr_w[c + 1];
+#pragma unroll
+		for (int t = 0; t < NP; t++) {
+			const float xa = sx[ka + t * ET], xb = sx[kb + t * ET];
+			const float fa = pa2 ? xa * xa : xa, fb = pb2 ? xb * xb : xb;
+			s[t] = __fmaf_rn(w, fa * fb, s[t]);
 		}
-		const float w = (float)dm.weight[c + 1], aw = fabsf(w);
-		s += w * v;
-		E += aw * ((hi - lo) + 8.0f * eps * hi);
-		M += aw * hi;
 	}
-	E += 16.0f * eps * M;
-	if (!(M < 1.0e6f)) {
-		return true;
+	u32 maybe = 0;
+#pragma unroll
+	for (int t = 0; t < NP; t++) {
+		const float u = (1.0f + m[t]) * 1.001f, u2 = u * u;
+		const float e = __fmaf_rn(dm.scr_k1, u2 * u2, dm.scr_k0);
+		const bool reject = (e < 1.0f) && (s[t] + e < -1.0e-6f);
+		maybe |= reject ? 0u : (1u << t);
 	}
-	return !(s + E < -1.0e-6f);
+	return maybe;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int NEED> struct Smem {
-	static constexpr int STAGES = n_stages(NEED);
-	static constexpr int RING = 0;
-	static constexpr int RED = STAGES * STAGE_BYTES;                 // staged reductions: dot, emd, sad (those needed)
-	static constexpr int CAND = RED + n_red(NEED) * RED_BYTES;       // u16 pair indices, 8192 entries
-	static constexpr int ROWD = CAND + 16384;                        // RowF[TD]
-	static constexpr int ROWQ = ROWD + TD * (int)sizeof(RowF);       // RowF[TQ]
-	static constexpr int WINQ = ROWQ + TQ * (int)sizeof(RowF);       // u64 window [TQ][2]
-	static constexpr int LEND = WINQ + TQ * 16;                      // u64 len [TD]
-	static constexpr int SCHED = LEND + TD * 8;                      // u32 [MAX_SUPER + 1]
-	static constexpr int BARS = SCHED + (MAX_SUPER + 1) * 4 + 4;     // mbarriers
-	static constexpr int MISC = BARS + 16 * 8;                       // tmem base, candidate count
-	static constexpr int TOTAL = MISC + 64 + 1024; // + alignment slack
+struct Cand {
+	u32 pair; // region << 6 | query row in the tile
+	u32 dot, emd, sad;
 };
 
-template <int NEED, int FLUSH, bool RAW>
+struct Smem {
+	static constexpr int RING = 0;
+	static constexpr int LIST = STAGES * STAGE_BYTES;                         // Cand[NEW][LIST_CAP]
+	static constexpr int SCRX = LIST + NEW * LIST_CAP * (int)sizeof(Cand);    // float [SC_COUNT + 1][4][NEW * 32]: the screen's scratch
+	static constexpr int ROWQ = SCRX + (SC_COUNT + 1) * 4 * NEW * 32 * 4;      // RowF[2][TQ]
+	static constexpr int WINQ = ROWQ + 2 * TQ * (int)sizeof(RowF);            // u64 window [2][TQ][2]
+	static constexpr int SCHED = WINQ + 2 * TQ * 16;                          // u32 [MAX_SUPER + 1]
+	static constexpr int BARS = SCHED + (MAX_SUPER + 1) * 4 + 4;              // mbarriers
+	static constexpr int MISC = BARS + 24 * 8;                                // tmem base
+	static constexpr int TOTAL = MISC + 64 + 1024;                            // + alignment slack
+};
+
+template <int NEED, bool RAW>
 __global__ void __launch_bounds__(THREADS, 1)
 tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ Params p, const __grid_constant__ CUtensorMap mapCumD,
 		  const __grid_constant__ CUtensorMap mapCumQ, const __grid_constant__ CUtensorMap mapU8D,
 		  const __grid_constant__ CUtensorMap mapU8Q)
 {
-	using L = Smem<NEED>;
-	constexpr int STAGES = L::STAGES;
+	using L = Smem;
 	constexpr bool DOT = (NEED & NEED_DOT) != 0, EMD = (NEED & NEED_EMD) != 0, MIN = (NEED & NEED_MIN) != 0;
-	constexpr bool CUDA_STAGE = EMD || MIN;           // compute warps read the ring
-	constexpr bool U8_STAGE = DOT || MIN;             // the ring carries the u8 tiles
-	constexpr u32 TX_BYTES = (EMD ? CUMD_BYTES + CUMQ_BYTES : 0) + (U8_STAGE ? U8D_BYTES + U8Q_BYTES : 0);
+	constexpr bool U8_PHASE = DOT || MIN;
+	constexpr bool CUDA_RED = EMD || MIN;             // compute warps produce sums for the epilogue
+	constexpr int N_U8 = U8_PHASE ? NBINS / KC_U8 : 0;   // ring stages per tile while the u8 rows stream
+	constexpr int N_CUM = EMD ? NBINS / KC_CUM : 0;      // ... while the cumulative rows stream
 	extern __shared__ unsigned char smem_raw[];
 	// SWIZZLE_128B tiles and the UMMA descriptors want 1024-byte alignment: align by hand (the launch adds the slack)
 	unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 	const u32 sbase = smem_u32(smem);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	u32 *s_sched = reinterpret_cast<u32 *>(smem + L::SCHED);
-	const u32 bar_full = sbase + L::BARS, bar_empty = bar_full + 4 * 8, bar_tfull = bar_empty + 4 * 8, bar_tempty = bar_tfull + 2 * 8;
+	const u32 bar_full = sbase + L::BARS, bar_empty = bar_full + STAGES * 8, bar_tfull = bar_empty + STAGES * 8, bar_tempty = bar_tfull + 2 * 8;
+	const u32 bar_efull = bar_tempty + 2 * 8, bar_eempty = bar_efull + 8;
 	u32 *s_tmem = reinterpret_cast<u32 *>(smem + L::MISC);
-	u32 *s_ncand = s_tmem + 1;
 
 	for (u32 i = threadIdx.x; i <= p.n_super; i += blockDim.x) {
 		s_sched[i] = p.sched[i];
@@ -447,23 +458,24 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < STAGES; s++) {
 			mbar_init(bar_full + s * 8, 1);
-			mbar_init(bar_empty + s * 8, (CUDA_STAGE ? NCW : 0) + (DOT ? 1 : 0));
+			mbar_init(bar_empty + s * 8, NCW + 1); // every compute warp and the MMA thread release every stage
 		}
 		for (int b = 0; b < 2; b++) {
 			mbar_init(bar_tfull + b * 8, 1);
-			mbar_init(bar_tempty + b * 8, NCW);
+			mbar_init(bar_tempty + b * 8, NEW);
 		}
-		*s_ncand = 0;
+		mbar_init(bar_efull, NCW);
+		mbar_init(bar_eempty, NEW);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	if (DOT && warp == 1) { // TMEM: two 64-column accumulators
-		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(s_tmem)) : "memory");
+	if (warp == 1) { // the whole tensor memory: one CTA per SM
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
-	const u32 tmem_base = DOT ? *s_tmem : 0;
+	const u32 tmem_base = *s_tmem;
 	const u32 n_items = s_sched[p.n_super];
 
 	if (warp == 0) {
@@ -476,17 +488,16 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 					continue;
 				}
 				const int qrow = (int)(p.q0 + (u64)t.qt * TQ), drow = (int)(p.d0 + (u64)t.dt * TD);
-				for (int c = 0; c < NCHUNK; c++) {
+				for (int c = 0; c < N_U8 + N_CUM; c++) {
 					mbar_wait(bar_empty + s * 8, ph ^ 1, p.err);
 					const u32 st = sbase + s * STAGE_BYTES, fb = bar_full + s * 8;
-					mbar_expect_tx(fb, TX_BYTES);
-					if (EMD) {
-						tma_load_2d(st, &mapCumD, c * KC, drow, fb);
-						tma_load_2d(st + CUMD_BYTES, &mapCumQ, c * KC, qrow, fb);
-					}
-					if (U8_STAGE) {
-						tma_load_2d(st + CUMD_BYTES + CUMQ_BYTES, &mapU8D, c * KC, drow, fb);
-						tma_load_2d(st + CUMD_BYTES + CUMQ_BYTES + U8D_BYTES, &mapU8Q, c * KC, qrow, fb);
+					mbar_expect_tx(fb, STAGE_BYTES);
+					if (c < N_U8) {
+						tma_load_2d(st, &mapU8D, c * KC_U8, drow, fb);
+						tma_load_2d(st + D_BYTES, &mapU8Q, c * KC_U8, qrow, fb);
+					} else {
+						tma_load_2d(st, &mapCumD, (c - N_U8) * KC_CUM, drow, fb);
+						tma_load_2d(st + D_BYTES, &mapCumQ, (c - N_U8) * KC_CUM, qrow, fb);
 					}
 					if (++s == (u32)STAGES) {
 						s = 0;
@@ -497,7 +508,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 		}
 	} else if (warp == 1) {
 		// ===== MMA issuer =====
-		if (DOT && lane == 0) {
+		if (lane == 0) {
 			u32 s = 0, ph = 0, it = 0;
 			for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
 				const Tile t = decode_item(p, s_sched, item);
@@ -505,95 +516,66 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 					continue;
 				}
 				const u32 buf = it & 1;
-				mbar_wait(bar_tempty + buf * 8, ((it >> 1) & 1) ^ 1, p.err);
-				tc_fence_after();
-				const u32 tacc = tmem_base + buf * TQ;
-				for (int c = 0; c < NCHUNK; c++) {
-					mbar_wait(bar_full + s * 8, ph, p.err);
+				if (DOT) {
+					mbar_wait(bar_tempty + buf * 8, ((it >> 1) & 1) ^ 1, p.err);
 					tc_fence_after();
-					const u32 a = sbase + s * STAGE_BYTES + CUMD_BYTES + CUMQ_BYTES, b = a + U8D_BYTES;
+				}
+				for (int c = 0; c < N_U8 + N_CUM; c++) {
+					mbar_wait(bar_full + s * 8, ph, p.err);
+					if (DOT && c < N_U8) {
+						tc_fence_after();
+						const u32 a = sbase + s * STAGE_BYTES, b = a + D_BYTES;
 #pragma unroll
-					for (int k = 0; k < KC / 32; k++) {
-						tc_mma_i8(tacc, umma_desc_sw64(a + k * 32), umma_desc_sw64(b + k * 32), IDESC_U8, (c | k) != 0);
+						for (int r = 0; r < 2; r++) {
+#pragma unroll
+							for (int k = 0; k < KC_U8 / 32; k++) {
+								tc_mma_i8(tmem_base + TM_DOT + buf * 128 + r * 64, umma_desc_sw128(a + r * 16384 + k * 32),
+									  umma_desc_sw128(b + k * 32), IDESC_U8, (c | k) != 0);
+							}
+						}
+						tc_commit(bar_empty + s * 8);
+						if (c == N_U8 - 1) {
+							tc_commit(bar_tfull + buf * 8);
+						}
+					} else {
+						mbar_arrive(bar_empty + s * 8);
 					}
-					tc_commit(bar_empty + s * 8);
 					if (++s == (u32)STAGES) {
 						s = 0;
 						ph ^= 1;
 					}
 				}
-				tc_commit(bar_tfull + buf * 8);
 				it++;
 			}
 		}
-	} else {
+	} else if (warp < 2 + NCW) {
 		// ===== compute warps =====
 		const int cw = warp - 2;
-		const int ctid = threadIdx.x - 64; // 0..255
+		const u32 quarter = (u32)warp & 3;          // the TMEM lanes this warp may touch: 32 * quarter ..
+		const int half = cw >> 2;                   // query rows 32 * half .. of the tile
+		const u32 lane_row = quarter * 32 + (u32)lane;
+		const u32 tlane = (quarter * 32) << 16;
 		u32 s = 0, ph = 0, it = 0;
-		RowF *s_rowD = reinterpret_cast<RowF *>(smem + L::ROWD);
-		RowF *s_rowQ = reinterpret_cast<RowF *>(smem + L::ROWQ);
-		u64 *s_winQ = reinterpret_cast<u64 *>(smem + L::WINQ);
-		u64 *s_lenD = reinterpret_cast<u64 *>(smem + L::LEND);
-		unsigned short *s_cand = reinterpret_cast<unsigned short *>(smem + L::CAND);
-		u32 *s_dot = reinterpret_cast<u32 *>(smem + L::RED);
-		u32 *s_emd = s_dot + (DOT ? TQ * TD : 0);
-		u32 *s_sad = s_emd + (EMD ? TQ * TD : 0);
 		for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
 			const Tile t = decode_item(p, s_sched, item);
 			if (!t.valid) {
 				continue;
 			}
-			const u64 qrow0 = p.q0 + (u64)t.qt * TQ, drow0 = p.d0 + (u64)t.dt * TD;
-			// row info for the epilogue: issued now, consumed after the main loop
-			if (!RAW && ctid < TQ + TD) {
-				const bool isq = ctid >= TD;
-				const u64 row = isq ? qrow0 + (ctid - TD) : drow0 + ctid;
-				const bool ok = isq ? row < p.q1 : row < p.d1;
-				const Sideband &sb = isq ? p.sbQ : p.sbD;
-				RowF r;
-				u64 len = 0;
-				memset(&r, 0, sizeof r);
-				r.big = 1;
-				if (ok) {
-					const u64 mag = sb.mag[row], sum = sb.sum[row], sumsq = sb.sumsq[row];
-					len = sb.len[row];
-					r.mag = (u32)mag;
-					r.sum = (u32)sum;
-					r.sumsq = (u32)sumsq;
-					r.magf = (float)mag;
-					r.sumsqf = (float)sumsq;
-					r.lenf = (float)len;
-					// the screen wants exact float lengths (their difference cancels) and 64-bit pearson terms
-					r.big = (mag >= (1ull << 26) || len >= (1ull << 24) || len == 0 || mag == 0) ? 1u : 0u;
-					const long long nn = 1024ll * (long long)sumsq - 2ll * (long long)(mag & 0x3FFFFFFull) * (long long)sum +
-							     (long long)(mag & 0x3FFFFFFull) * (long long)(mag & 0x3FFFFFFull);
-					r.nnf = (float)nn;
-				}
-				if (isq) {
-					s_rowQ[ctid - TD] = r;
-					// FC_Runner.cpp:435-444: size_t truncation of len * id and len / id; an empty window marks an unused row
-					s_winQ[2 * (ctid - TD)] = ok ? (u64)((double)len * p.cutoff) : 1;
-					s_winQ[2 * (ctid - TD) + 1] = ok ? (u64)((double)len / p.cutoff) : 0;
-				} else {
-					s_rowD[ctid] = r;
-					s_lenD[ctid] = ok ? len : ~0ull;
-				}
-			}
-			u32 emd[8][4], sad[8][4];
+			bool tmem_free = false;
+			if (U8_PHASE) {
+				u32 acc[2][32];
+				if (MIN) {
 #pragma unroll
-			for (int i = 0; i < 8; i++) {
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					emd[i][j] = 0;
-					sad[i][j] = 0;
+					for (int q = 0; q < 32; q++) {
+						acc[0][q] = acc[1][q] = 0;
+					}
 				}
-			}
-			if (CUDA_STAGE) {
 #pragma unroll 1
-				for (int c = 0; c < NCHUNK; c++) {
+				for (int c = 0; c < N_U8; c++) {
 					mbar_wait(bar_full + s * 8, ph, p.err);
-					chunk_compute<NEED, FLUSH>(sbase + s * STAGE_BYTES, cw, lane, emd, sad);
+					if (MIN) {
+						stage_compute<false>(sbase + s * STAGE_BYTES, lane_row, half, acc);
+					}
 					__syncwarp();
 					if (lane == 0) {
 						mbar_arrive(bar_empty + s * 8);
@@ -603,133 +585,228 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 						ph ^= 1;
 					}
 				}
+				if (MIN) {
+					mbar_wait(bar_eempty, (it & 1) ^ 1, p.err); // the epilogue is done with the previous tile's sums
+					tc_fence_after();
+					tmem_free = true;
+					tc_st32(tmem_base + tlane + TM_SAD + half * 32, acc[0]);
+					tc_st32(tmem_base + tlane + TM_SAD + 64 + half * 32, acc[1]);
+				}
 			}
-			// ---- epilogue: reductions -> shared memory ----
-			if (EMD || MIN) {
+			if (EMD) {
+				u32 acc[2][32];
 #pragma unroll
-				for (int i = 0; i < 8; i++) {
-#pragma unroll
-					for (int j = 0; j < 4; j++) {
-						const int idx = (cw * 8 + i) * TD + lane + 32 * j;
-						if (EMD) s_emd[idx] = emd[i][j];
-						if (MIN) s_sad[idx] = sad[i][j];
+				for (int q = 0; q < 32; q++) {
+					acc[0][q] = acc[1][q] = 0;
+				}
+#pragma unroll 1
+				for (int c = 0; c < N_CUM; c++) {
+					mbar_wait(bar_full + s * 8, ph, p.err);
+					stage_compute<true>(sbase + s * STAGE_BYTES, lane_row, half, acc);
+					__syncwarp();
+					if (lane == 0) {
+						mbar_arrive(bar_empty + s * 8);
+					}
+					if (++s == (u32)STAGES) {
+						s = 0;
+						ph ^= 1;
 					}
 				}
-			}
-			if (DOT) {
-				const u32 buf = it & 1;
-				mbar_wait(bar_tfull + buf * 8, (it >> 1) & 1, p.err);
-				tc_fence_after();
-				// warp w may read TMEM lanes 32 (w % 4) ..; compute warps 0-3 take accumulator columns 0-31, 4-7 columns 32-63
-				const u32 quarter = (u32)warp & 3, chalf = (u32)cw >> 2;
-				u32 v[32];
-				const u32 taddr = tmem_base + buf * TQ + chalf * 32 + ((quarter * 32) << 16);
-				asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-					     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-					     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-					       "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-					       "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-					       "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-					     : "r"(taddr)
-					     : "memory");
-				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-				for (int c = 0; c < 32; c++) {
-					s_dot[(chalf * 32 + c) * TD + quarter * 32 + lane] = v[c];
+				if (!tmem_free) {
+					mbar_wait(bar_eempty, (it & 1) ^ 1, p.err);
+					tc_fence_after();
 				}
+				tc_st32(tmem_base + tlane + TM_EMD + half * 32, acc[0]);
+				tc_st32(tmem_base + tlane + TM_EMD + 64 + half * 32, acc[1]);
+			}
+			if (CUDA_RED) {
+				tc_st_wait();
 				tc_fence_before();
 				__syncwarp();
 				if (lane == 0) {
-					mbar_arrive(bar_tempty + buf * 8);
+					mbar_arrive(bar_efull);
 				}
-			}
-			named_sync(1, NCW * 32);
-			// ---- epilogue: one pair per thread at a time ----
-			u32 scored = 0;
-			for (int pi = ctid; pi < TQ * TD; pi += NCW * 32) {
-				const int ql = pi >> 7, dl = pi & (TD - 1);
-				const u64 q = qrow0 + ql, d = drow0 + dl;
-				if constexpr (RAW) {
-					if (q < p.q1 && d < p.d1) {
-						const u64 o = (q - p.q0) * (p.d1 - p.d0) + (d - p.d0);
-						if (DOT) p.raw_dot[o] = s_dot[pi];
-						if (EMD) p.raw_emd[o] = p.csQ[q] + p.csD[d] - 2u * s_emd[pi];
-						if (MIN) p.raw_sad[o] = s_sad[pi];
-					}
-				} else {
-					const u64 lc = s_lenD[dl];
-					bool go = lc >= s_winQ[2 * ql] && lc <= s_winQ[2 * ql + 1] && (!p.upper_only || d > q);
-					if (go) {
-						scored++;
-						const RowF &P = s_rowD[dl], &Q = s_rowQ[ql];
-						bool cand = !p.no_screen;
-						if (cand && !(P.big | Q.big)) {
-							const u32 dotv = DOT ? s_dot[pi] : 0;
-							const u32 emdv = EMD ? p.csQ[q] + p.csD[d] - 2u * s_emd[pi] : 0;
-							cand = screen_pair(dm, dotv, emdv, MIN ? s_sad[pi] : 0, P, Q);
-						}
-						if (cand) {
-							const u32 slot = atomicAdd(s_ncand, 1u);
-							s_cand[slot] = (unsigned short)pi;
-						}
-					}
-				}
-			}
-			if constexpr (!RAW) {
-				named_sync(1, NCW * 32);
-				const u32 ncand = *s_ncand;
-				for (u32 base = 0; base < ncand; base += NCW * 32) {
-					const u32 e = base + (u32)ctid;
-					int close = 0;
-					double score = 0, d0v;
-					u64 q = 0, d = 0;
-					if (e < ncand) {
-						const int pi = s_cand[e];
-						const int ql = pi >> 7, dl = pi & (TD - 1);
-						q = qrow0 + ql;
-						d = drow0 + dl;
-						const Side sd = load_side(p.sbD, d), sq = load_side(p.sbQ, q);
-						RedN r;
-						r.jeff = r.js = 0;
-						r.dot = DOT ? s_dot[pi] : 0;
-						r.emd = EMD ? (u64)(p.csQ[q] + p.csD[d] - 2u * s_emd[pi]) : 0;
-						r.smin = MIN ? (sd.sum + sq.sum - (u64)s_sad[pi]) >> 1 : 0;
-						const int bad = eval_pair_fast(dm, NBINS, r, sd, sq, true, score, d0v, close);
-						if (bad) {
-							atomicOr(p.err, bad & 1 ? 1 : 2);
-						}
-					}
-					const unsigned cm = __ballot_sync(0xffffffffu, close);
-					u64 obase = 0;
-					if (lane == 0 && cm) {
-						obase = atomicAdd(p.counters, (u64)__popc(cm));
-					}
-					obase = __shfl_sync(0xffffffffu, obase, 0);
-					if (close) {
-						const u64 idx = obase + __popc(cm & ((1u << lane) - 1));
-						if (idx < p.max_out) {
-							p.out_q[idx] = q;
-							p.out_d[idx] = d;
-							p.out_score[idx] = score;
-						}
-					}
-				}
-				scored = __reduce_add_sync(0xffffffffu, scored);
-				if (lane == 0 && scored) {
-					atomicAdd(p.counters + 1, (u64)scored);
-				}
-			}
-			named_sync(1, NCW * 32); // staged reductions, candidate list and row info are free again
-			if (ctid == 0) {
-				*s_ncand = 0;
 			}
 			it++;
+		}
+	} else {
+		// ===== epilogue warps: thread = TMEM lane (database rows L and 128 + L), all 64 query columns of each region =====
+		const int ew = warp - 2 - NCW;
+		const int etid = threadIdx.x - (2 + NCW) * 32; // 0 .. NEW * 32 - 1
+		const u32 quarter = (u32)warp & 3;
+		const u32 lane_row = quarter * 32 + (u32)lane;
+		const u32 tlane = (quarter * 32) << 16;
+		RowF *s_rowQ = reinterpret_cast<RowF *>(smem + L::ROWQ);
+		u64 *s_winQ = reinterpret_cast<u64 *>(smem + L::WINQ);
+		Cand *s_list = reinterpret_cast<Cand *>(smem + L::LIST) + ew * LIST_CAP;
+		float *sx = reinterpret_cast<float *>(smem + L::SCRX) + etid;
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			sx[(SC_COUNT * 4 + t) * (NEW * 32)] = 1.0f;
+		}
+		u32 it = 0;
+		u64 scored_total = 0;
+		for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
+			const Tile t = decode_item(p, s_sched, item);
+			if (!t.valid) {
+				continue;
+			}
+			const u64 qrow0 = p.q0 + (u64)t.qt * TQ, drow0 = p.d0 + (u64)t.dt * TD;
+			const int par = it & 1; // query-row info is double buffered: one barrier per tile is enough
+			RowF PD[2];
+			u64 lenD[2];
+			if (!RAW) {
+				if (etid < TQ) {
+					const u64 row = qrow0 + etid;
+					const bool ok = row < p.q1;
+					u64 len;
+					s_rowQ[par * TQ + etid] = make_rowf(p.sbQ, p.csQ, row, ok, len);
+					// FC_Runner.cpp:435-444: size_t truncation of len * id and len / id; an empty window marks an unused row
+					s_winQ[(par * TQ + etid) * 2] = ok ? (u64)((double)len * p.cutoff) : 1;
+					s_winQ[(par * TQ + etid) * 2 + 1] = ok ? (u64)((double)len / p.cutoff) : 0;
+				}
+#pragma unroll
+				for (int r = 0; r < 2; r++) {
+					const u64 row = drow0 + r * 128 + lane_row;
+					const bool ok = row < p.d1;
+					PD[r] = make_rowf(p.sbD, p.csD, row, ok, lenD[r]);
+					if (!ok) {
+						lenD[r] = ~0ull;
+					}
+				}
+				named_sync(2, NEW * 32);
+			}
+			const u32 buf = it & 1;
+			if (CUDA_RED) {
+				mbar_wait(bar_efull, it & 1, p.err);
+			}
+			if (DOT) {
+				mbar_wait(bar_tfull + buf * 8, (it >> 1) & 1, p.err);
+			}
+			tc_fence_after();
+			u32 n_list = 0, scored = 0;
+#pragma unroll 1
+			for (int r = 0; r < 2; r++) {
+#pragma unroll 1
+				for (int qc = 0; qc < TQ; qc += 4) {
+					u32 vd[4] = {0, 0, 0, 0}, ve[4] = {0, 0, 0, 0}, vs[4] = {0, 0, 0, 0};
+					if (DOT) tc_ld4(tmem_base + tlane + TM_DOT + buf * 128 + r * 64 + qc, vd);
+					if (EMD) tc_ld4(tmem_base + tlane + TM_EMD + r * 64 + qc, ve);
+					if (MIN) tc_ld4(tmem_base + tlane + TM_SAD + r * 64 + qc, vs);
+					tc_ld_wait();
+					const u64 d = drow0 + r * 128 + lane_row;
+					if constexpr (RAW) {
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							const u64 q = qrow0 + qc + k;
+							if (q < p.q1 && d < p.d1) {
+								const u64 o = (q - p.q0) * (p.d1 - p.d0) + (d - p.d0);
+								if (DOT) p.raw_dot[o] = vd[k];
+								if (EMD) p.raw_emd[o] = p.csQ[q] + p.csD[d] - 2u * ve[k];
+								if (MIN) p.raw_sad[o] = vs[k];
+							}
+						}
+					} else {
+						const RowF *Q = s_rowQ + par * TQ + qc;
+						u32 go = 0;
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							const u64 lo = s_winQ[(par * TQ + qc + k) * 2], hi = s_winQ[(par * TQ + qc + k) * 2 + 1];
+							const bool g = lenD[r] >= lo && lenD[r] <= hi && (!p.upper_only || d > qrow0 + qc + k);
+							go |= g ? (1u << k) : 0u;
+							if (EMD) ve[k] = g ? Q[k].cs + PD[r].cs - 2u * ve[k] : 0u;
+						}
+						scored += __popc(go);
+						u32 cand = p.no_screen ? 0u : go;
+						const bool can_screen = dm.scr_ok != 0;
+						const u32 anybig = PD[r].big | Q[0].big | Q[1].big | Q[2].big | Q[3].big;
+						if (can_screen && __any_sync(0xffffffffu, cand != 0 && !anybig)) {
+							const u32 maybe = screen_pairs<NEED, 4>(dm, sx, vd, ve, vs, PD[r], Q);
+							if (!anybig) {
+								cand &= maybe;
+							}
+						}
+						// candidate records -> the warp's list (ballot-compacted), flushed through the exact epilogue when full
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							const bool c = (cand >> k) & 1;
+							const unsigned m = __ballot_sync(0xffffffffu, c);
+							if (c) {
+								Cand rec;
+								rec.pair = ((u32)r << 6) | (u32)(qc + k) | ((u32)lane << 8);
+								rec.dot = vd[k];
+								rec.emd = ve[k];
+								rec.sad = vs[k];
+								s_list[n_list + __popc(m & ((1u << lane) - 1))] = rec;
+							}
+							n_list += __popc(m);
+						}
+						if (n_list > LIST_CAP - 128 || (r == 1 && qc == TQ - 4)) {
+							__syncwarp();
+							for (u32 base = 0; base < n_list; base += 32) {
+								const u32 e = base + (u32)lane;
+								int close = 0;
+								double score = 0, d0v;
+								u64 cq = 0, cd = 0;
+								if (e < n_list) {
+									const Cand c = s_list[e];
+									cq = qrow0 + (c.pair & 63);
+									cd = drow0 + ((c.pair >> 6) & 1) * 128 + quarter * 32 + ((c.pair >> 8) & 31);
+									const Side sd = load_side(p.sbD, cd), sq = load_side(p.sbQ, cq);
+									RedN rd;
+									rd.jeff = rd.js = 0;
+									rd.dot = c.dot;
+									rd.emd = c.emd;
+									rd.smin = MIN ? (sd.sum + sq.sum - (u64)c.sad) >> 1 : 0;
+									const int bad = eval_pair_fast(dm, NBINS, rd, sd, sq, true, score, d0v, close);
+									if (bad) {
+										atomicOr(p.err, bad & 1 ? 1 : 2);
+									}
+								}
+								const unsigned cm = __ballot_sync(0xffffffffu, close);
+								u64 obase = 0;
+								if (lane == 0 && cm) {
+									obase = atomicAdd(p.counters, (u64)__popc(cm));
+								}
+								obase = __shfl_sync(0xffffffffu, obase, 0);
+								if (close) {
+									const u64 idx = obase + __popc(cm & ((1u << lane) - 1));
+									if (idx < p.max_out) {
+										p.out_q[idx] = cq;
+										p.out_d[idx] = cd;
+										p.out_score[idx] = score;
+									}
+								}
+							}
+							__syncwarp();
+							n_list = 0;
+						}
+					}
+				}
+			}
+			// TMEM reads of this tile are complete: hand the buffers back
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) {
+				if (CUDA_RED) mbar_arrive(bar_eempty);
+				if (DOT) mbar_arrive(bar_tempty + buf * 8);
+			}
+			scored_total += scored;
+			it++;
+		}
+		if (!RAW) {
+			// u64 warp sum through two 32-bit halves
+			const u32 lo = __reduce_add_sync(0xffffffffu, (u32)(scored_total & 0xFFFFu));
+			const u32 hi = __reduce_add_sync(0xffffffffu, (u32)(scored_total >> 16));
+			if (lane == 0 && (lo | hi)) {
+				atomicAdd(p.counters + 1, ((u64)hi << 16) + lo);
+			}
 		}
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (DOT && warp == 1) {
-		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
+	if (warp == 1) {
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 	}
 }
 
@@ -828,7 +905,7 @@ static EncodeTiledFn encode_fn()
 	return fn;
 }
 
-// rows of 1024 elements (u8 or u16), box = 64 elements x `box_rows` rows
+// rows of 1024 elements (u8 or u16), box = 128 bytes x `box_rows` rows, SWIZZLE_128B
 static int make_map(CUtensorMap *m, const void *base, u64 n_rows, int elem_bytes, int box_rows)
 {
 	EncodeTiledFn fn = encode_fn();
@@ -838,10 +915,10 @@ static int make_map(CUtensorMap *m, const void *base, u64 n_rows, int elem_bytes
 	}
 	const cuuint64_t dims[2] = {1024, n_rows};
 	const cuuint64_t strides[1] = {(cuuint64_t)1024 * elem_bytes};
-	const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+	const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
 	const cuuint32_t es[2] = {1, 1};
 	const CUresult r = fn(m, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims,
-			      strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, elem_bytes == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+			      strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
 			      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		set_error("tile sweep: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
@@ -861,22 +938,11 @@ bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset 
 	return shape && model && q->n < (1ull << 31) && d->n < (1ull << 31);
 }
 
-template <int NEED, bool RAW> static int launch_need(int flush, int grid, cudaStream_t st, const DevModel &dm, const ts::Params &p, const CUtensorMap *m)
+template <int NEED, bool RAW> static int launch_need(int grid, cudaStream_t st, const DevModel &dm, const ts::Params &p, const CUtensorMap *m)
 {
-	const int smem = ts::Smem<NEED>::TOTAL;
-#define MC2_TS_GO(F)                                                                                                           \
-	{                                                                                                                      \
-		MC2_CUDA(cudaFuncSetAttribute(ts::tile_sweep_kernel<NEED, F, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-		ts::tile_sweep_kernel<NEED, F, RAW><<<grid, ts::THREADS, smem, st>>>(dm, p, m[0], m[1], m[2], m[3]);                \
-	}
-	if constexpr ((NEED & NEED_EMD) != 0) {
-		if (flush == 0) MC2_TS_GO(0)
-		else if (flush == 1) MC2_TS_GO(1)
-		else MC2_TS_GO(2)
-	} else {
-		MC2_TS_GO(0)
-	}
-#undef MC2_TS_GO
+	const int smem = ts::Smem::TOTAL;
+	MC2_CUDA(cudaFuncSetAttribute(ts::tile_sweep_kernel<NEED, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	ts::tile_sweep_kernel<NEED, RAW><<<grid, ts::THREADS, smem, st>>>(dm, p, m[0], m[1], m[2], m[3]);
 	return MC2_OK;
 }
 
@@ -921,13 +987,7 @@ int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset
 	p.group = group;
 	p.n_super = (p.nqt + group - 1) / group;
 	p.sched = d_sched;
-	const u64 ms = q->max_sum > d->max_sum ? q->max_sum : d->max_sum;
-	p.flush_mode = ms <= 4095 ? 0 : (ms <= 16383 ? 1 : 2);
 	p.no_screen = getenv("MC2_TS_NOSCREEN") != nullptr;
-	if (const char *e = getenv("MC2_TS_FLUSH")) { // experiments: force a (legal) more frequent flush
-		const int f = atoi(e);
-		if (f > p.flush_mode && f <= 2) p.flush_mode = f;
-	}
 	p.raw_dot = raw_dot; p.raw_emd = raw_emd; p.raw_sad = raw_sad;
 	// the kernel reads the item count from the last prefix entry; it must fit 32 bits
 	if ((u64)p.n_super * group * p.ndt >= (1ull << 32)) {
@@ -956,8 +1016,8 @@ int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset
 	switch (need & 7) {
 #define MC2_TS_CASE(n)                                                                                  \
 	case n:                                                                                         \
-		rc = raw ? launch_need<n, true>(p.flush_mode, grid, ctx->stream, dm, p, maps)           \
-			 : launch_need<n, false>(p.flush_mode, grid, ctx->stream, dm, p, maps);         \
+		rc = raw ? launch_need<n, true>(grid, ctx->stream, dm, p, maps)           \
+			 : launch_need<n, false>(grid, ctx->stream, dm, p, maps);         \
 		break;
 		MC2_TS_CASE(1)
 		MC2_TS_CASE(2)
