@@ -35,9 +35,17 @@ constexpr int TD = 256;         // database rows per tile: two regions of 128 (U
 constexpr int NBINS = 1024;
 constexpr int KC_CUM = 64;      // bins per ring stage while the u16 cumulative rows stream (128-byte rows)
 constexpr int KC_U8 = 128;      // bins per ring stage while the u8 rows stream (128-byte rows)
-constexpr int NCW = 8;          // compute warps (CTA warps 2..9)
-constexpr int NEW = 4;          // epilogue warps (CTA warps 10..13), one per TMEM lane quarter
-constexpr int THREADS = (2 + NCW + NEW) * 32;
+#ifndef MC2_TS_NCW
+#define MC2_TS_NCW 16
+#endif
+constexpr int NCW = MC2_TS_NCW; // compute warps (CTA warps 4 .. 4 + NCW - 1, whole warpgroups): 8 or 16
+constexpr int QN = TQ / (NCW / 4); // query rows per compute thread (x 2 database rows): 32 or 16 accumulator pairs
+constexpr int NEW = 4;          // epilogue warps (CTA warps 12..15: warpgroup 3), one per TMEM lane quarter
+constexpr int THREADS = (4 + NCW + NEW) * 32; // warpgroup 0: TMA producer, MMA issuer, two idle warps
+// setmaxnreg per warpgroup.  8 compute warps: launch 128 / thread, control 40, compute 168, epilogue 128.
+// 16 compute warps: launch 80 / thread, control 40, compute 80 (unchanged), epilogue 120.  The pool is what the launch
+// allocated (threads x launch registers): the sums below must not exceed it.
+constexpr int REGS_CTRL = 40, REGS_COMPUTE = NCW == 8 ? 168 : 80, REGS_EPI = NCW == 8 ? 128 : 120;
 constexpr int D_BYTES = TD * 128;        // 32 KB, SWIZZLE_128B
 constexpr int Q_BYTES = TQ * 128;        //  8 KB
 constexpr int STAGE_BYTES = D_BYTES + Q_BYTES; // 40 KB
@@ -46,7 +54,7 @@ constexpr int MAX_SUPER = 1024;          // entries of the tile schedule's prefi
 constexpr int LIST_CAP = 256;            // candidate records per epilogue warp
 // TMEM columns (512 allocated): Gram accumulators double buffered, EMD / SAD sums single buffered
 constexpr u32 TM_DOT = 0;                // + buf * 128 + region * 64
-constexpr u32 TM_EMD = 256;              // + region * 64
+constexpr u32 TM_EMD = 256;              // + ebuf * 128 + region * 64 (double buffered when no SAD sums are needed)
 constexpr u32 TM_SAD = 384;              // + region * 64
 
 struct Params {
@@ -81,10 +89,12 @@ __device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes)
 __device__ __forceinline__ void mbar_arrive(u32 bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ bool mbar_try(u32 bar, u32 parity)
 {
+	// the suspend-time hint (ns) lets the hardware park the warp instead of returning at once: a polling warp would
+	// take issue slots from the compute warps that share its scheduler
 	u32 ok;
-	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
 		     : "=r"(ok)
-		     : "r"(bar), "r"(parity)
+		     : "r"(bar), "r"(parity), "r"(10000u)
 		     : "memory");
 	return ok != 0;
 }
@@ -93,7 +103,7 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity, int *err)
 {
 	u32 spins = 0;
 	while (!mbar_try(bar, parity)) {
-		if (++spins > (1u << 24)) {
+		if (++spins > (1u << 20)) {
 			atomicOr(err, 16);
 			__trap();
 		}
@@ -131,6 +141,15 @@ __device__ __forceinline__ void tc_st32(u32 taddr, const u32 (&v)[32])
 		     "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
 		     : "memory");
 }
+__device__ __forceinline__ void tc_st16(u32 taddr, const u32 (&v)[16])
+{
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(v[0]),
+		     "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]),
+		     "r"(v[13]), "r"(v[14]), "r"(v[15])
+		     : "memory");
+}
+__device__ __forceinline__ void tc_st(u32 taddr, const u32 (&v)[32]) { tc_st32(taddr, v); }
+__device__ __forceinline__ void tc_st(u32 taddr, const u32 (&v)[16]) { tc_st16(taddr, v); }
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ uint4 lds128(u32 addr)
@@ -235,47 +254,48 @@ __device__ __forceinline__ Tile decode_item(const Params &p, const u32 *s_sched,
 // 128-byte rows under SWIZZLE_128B: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool IS_EMD>
-__device__ __forceinline__ void stage_compute(u32 stage, u32 lane_row, int half, u32 (&acc)[2][32])
+__device__ __forceinline__ void stage_compute(const unsigned char *stage, u32 lane_row, int qsel, u32 (&acc)[2][QN])
 {
-	const u32 dbase = stage + lane_row * 128;
-	const u32 dsw = (lane_row & 7) << 4;
-	const u32 qbase = stage + D_BYTES + (u32)half * 4096;
-	// the 16-byte steps stay a loop (a fully unrolled stage would be 70 KB of code, far beyond the instruction cache)
-#pragma unroll 1
-	for (u32 c = 0; c < 8; c++) {
-		const uint4 D0 = lds128(dbase + ((c << 4) ^ dsw));
-		const uint4 D1 = lds128(dbase + 16384 + ((c << 4) ^ dsw));
-		u32 cx[8]; // swizzled chunk offset for query rows with (row & 7) == j
+	// plain loads (not asm): the compiler may order and pipeline them freely inside the stage
+	const uint4 *dptr = reinterpret_cast<const uint4 *>(stage) + lane_row * 8;
+	const uint4 *qptr = reinterpret_cast<const uint4 *>(stage + D_BYTES) + qsel * (QN * 8);
+	const u32 dsw = lane_row & 7;
+	// fully unrolled over the eight 16-byte steps: every query-row address is an immediate offset (the swizzle XOR folds at
+	// compile time), ~2.3 k instructions per stage
+	uint4 D0 = dptr[dsw], D1 = dptr[1024 + dsw];
 #pragma unroll
-		for (int j = 0; j < 8; j++) {
-			cx[j] = qbase + ((c ^ (u32)j) << 4);
+	for (int c = 0; c < 8; c++) {
+		const uint4 E0 = D0, E1 = D1;
+		if (c < 7) { // next step's rows are requested before this step's arithmetic
+			D0 = dptr[(u32)(c + 1) ^ dsw];
+			D1 = dptr[1024 + ((u32)(c + 1) ^ dsw)];
 		}
 #pragma unroll
-		for (int q = 0; q < 32; q++) {
-			const uint4 Q = lds128(cx[q & 7] + (u32)q * 128);
-			u32 a = acc[0][q], b = acc[1][q];
-			if constexpr (IS_EMD) {
-				// sum of min over the u16 pairs: VIMNMX.U16x2 (ALU pipe) + IDP.2A with weights (1, 1) (FMA pipe)
-				a = dp2a_sum(vmin2(Q.x, D0.x), a);
-				b = dp2a_sum(vmin2(Q.x, D1.x), b);
-				a = dp2a_sum(vmin2(Q.y, D0.y), a);
-				b = dp2a_sum(vmin2(Q.y, D1.y), b);
-				a = dp2a_sum(vmin2(Q.z, D0.z), a);
-				b = dp2a_sum(vmin2(Q.z, D1.z), b);
-				a = dp2a_sum(vmin2(Q.w, D0.w), a);
-				b = dp2a_sum(vmin2(Q.w, D1.w), b);
-			} else {
-				a = sad4(Q.x, D0.x, a);
-				b = sad4(Q.x, D1.x, b);
-				a = sad4(Q.y, D0.y, a);
-				b = sad4(Q.y, D1.y, b);
-				a = sad4(Q.z, D0.z, a);
-				b = sad4(Q.z, D1.z, b);
-				a = sad4(Q.w, D0.w, a);
-				b = sad4(Q.w, D1.w, b);
+		for (int g = 0; g < QN / 4; g++) {
+			uint4 Q[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int q = g * 4 + j;
+				Q[j] = qptr[q * 8 + (c ^ (q & 7))];
 			}
-			acc[0][q] = a;
-			acc[1][q] = b;
+			// word by word over the four query rows x two database rows: eight independent accumulator chains
+#define MC2_STEP(W)                                                                       \
+	_Pragma("unroll") for (int j = 0; j < 4; j++)                                     \
+	{                                                                                 \
+		const int q = g * 4 + j;                                                  \
+		if constexpr (IS_EMD) {                                                   \
+			acc[0][q] = dp2a_sum(vmin2(Q[j].W, E0.W), acc[0][q]);             \
+			acc[1][q] = dp2a_sum(vmin2(Q[j].W, E1.W), acc[1][q]);             \
+		} else {                                                                  \
+			acc[0][q] = sad4(Q[j].W, E0.W, acc[0][q]);                        \
+			acc[1][q] = sad4(Q[j].W, E1.W, acc[1][q]);                        \
+		}                                                                         \
+	}
+			MC2_STEP(x)
+			MC2_STEP(y)
+			MC2_STEP(z)
+			MC2_STEP(w)
+#undef MC2_STEP
 		}
 	}
 }
@@ -424,9 +444,10 @@ struct Smem {
 	static constexpr int SCRX = LIST + NEW * LIST_CAP * (int)sizeof(Cand);    // float [SC_COUNT + 1][4][NEW * 32]: the screen's scratch
 	static constexpr int ROWQ = SCRX + (SC_COUNT + 1) * 4 * NEW * 32 * 4;      // RowF[2][TQ]
 	static constexpr int WINQ = ROWQ + 2 * TQ * (int)sizeof(RowF);            // u64 window [2][TQ][2]
-	static constexpr int SCHED = WINQ + 2 * TQ * 16;                          // u32 [MAX_SUPER + 1]
+	static constexpr int WIN32 = WINQ + 2 * TQ * 16;                          // uint2 window [2][TQ], saturated to 32 bits
+	static constexpr int SCHED = WIN32 + 2 * TQ * 8;                          // u32 [MAX_SUPER + 1]
 	static constexpr int BARS = SCHED + (MAX_SUPER + 1) * 4 + 4;              // mbarriers
-	static constexpr int MISC = BARS + 24 * 8;                                // tmem base
+	static constexpr int MISC = BARS + 32 * 8;                                // tmem base
 	static constexpr int TOTAL = MISC + 64 + 1024;                            // + alignment slack
 };
 
@@ -442,6 +463,11 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 	constexpr bool CUDA_RED = EMD || MIN;             // compute warps produce sums for the epilogue
 	constexpr int N_U8 = U8_PHASE ? NBINS / KC_U8 : 0;   // ring stages per tile while the u8 rows stream
 	constexpr int N_CUM = EMD ? NBINS / KC_CUM : 0;      // ... while the cumulative rows stream
+	// Gram + EMD models: every third stage carries u8 rows (for the MMA issuer only), so the compute warps never sit
+	// through a whole u8 phase; otherwise the u8 stages come first, then the cumulative ones
+	constexpr bool INTERLEAVE = DOT && EMD && !MIN;
+	auto stage_is_u8 = [](int c) { return INTERLEAVE ? (c % 3 == 2) : (c < N_U8); };
+	auto stage_index = [](int c) { return INTERLEAVE ? (c % 3 == 2 ? c / 3 : c - c / 3) : (c < N_U8 ? c : c - N_U8); };
 	extern __shared__ unsigned char smem_raw[];
 	// SWIZZLE_128B tiles and the UMMA descriptors want 1024-byte alignment: align by hand (the launch adds the slack)
 	unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -449,7 +475,8 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	u32 *s_sched = reinterpret_cast<u32 *>(smem + L::SCHED);
 	const u32 bar_full = sbase + L::BARS, bar_empty = bar_full + STAGES * 8, bar_tfull = bar_empty + STAGES * 8, bar_tempty = bar_tfull + 2 * 8;
-	const u32 bar_efull = bar_tempty + 2 * 8, bar_eempty = bar_efull + 8;
+	const u32 bar_efull = bar_tempty + 2 * 8, bar_eempty = bar_efull + 2 * 8; // [2] each
+	constexpr int EBUFS = MIN ? 1 : 2; // EMD sums in TMEM: two buffers unless the SAD sums need the columns
 	u32 *s_tmem = reinterpret_cast<u32 *>(smem + L::MISC);
 
 	for (u32 i = threadIdx.x; i <= p.n_super; i += blockDim.x) {
@@ -464,8 +491,10 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 			mbar_init(bar_tfull + b * 8, 1);
 			mbar_init(bar_tempty + b * 8, NEW);
 		}
-		mbar_init(bar_efull, NCW);
-		mbar_init(bar_eempty, NEW);
+		for (int b = 0; b < 2; b++) {
+			mbar_init(bar_efull + b * 8, NCW);
+			mbar_init(bar_eempty + b * 8, NEW);
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 1) { // the whole tensor memory: one CTA per SM
@@ -480,6 +509,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 
 	if (warp == 0) {
 		// ===== TMA producer =====
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
 		if (lane == 0) {
 			u32 s = 0, ph = 0;
 			for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -492,12 +522,12 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 					mbar_wait(bar_empty + s * 8, ph ^ 1, p.err);
 					const u32 st = sbase + s * STAGE_BYTES, fb = bar_full + s * 8;
 					mbar_expect_tx(fb, STAGE_BYTES);
-					if (c < N_U8) {
-						tma_load_2d(st, &mapU8D, c * KC_U8, drow, fb);
-						tma_load_2d(st + D_BYTES, &mapU8Q, c * KC_U8, qrow, fb);
+					if (stage_is_u8(c)) {
+						tma_load_2d(st, &mapU8D, stage_index(c) * KC_U8, drow, fb);
+						tma_load_2d(st + D_BYTES, &mapU8Q, stage_index(c) * KC_U8, qrow, fb);
 					} else {
-						tma_load_2d(st, &mapCumD, (c - N_U8) * KC_CUM, drow, fb);
-						tma_load_2d(st + D_BYTES, &mapCumQ, (c - N_U8) * KC_CUM, qrow, fb);
+						tma_load_2d(st, &mapCumD, stage_index(c) * KC_CUM, drow, fb);
+						tma_load_2d(st + D_BYTES, &mapCumQ, stage_index(c) * KC_CUM, qrow, fb);
 					}
 					if (++s == (u32)STAGES) {
 						s = 0;
@@ -508,6 +538,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 		}
 	} else if (warp == 1) {
 		// ===== MMA issuer =====
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
 		if (lane == 0) {
 			u32 s = 0, ph = 0, it = 0;
 			for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -522,7 +553,8 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				}
 				for (int c = 0; c < N_U8 + N_CUM; c++) {
 					mbar_wait(bar_full + s * 8, ph, p.err);
-					if (DOT && c < N_U8) {
+					if (DOT && stage_is_u8(c)) {
+						const int ku = stage_index(c);
 						tc_fence_after();
 						const u32 a = sbase + s * STAGE_BYTES, b = a + D_BYTES;
 #pragma unroll
@@ -530,11 +562,11 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 #pragma unroll
 							for (int k = 0; k < KC_U8 / 32; k++) {
 								tc_mma_i8(tmem_base + TM_DOT + buf * 128 + r * 64, umma_desc_sw128(a + r * 16384 + k * 32),
-									  umma_desc_sw128(b + k * 32), IDESC_U8, (c | k) != 0);
+									  umma_desc_sw128(b + k * 32), IDESC_U8, (ku | k) != 0);
 							}
 						}
 						tc_commit(bar_empty + s * 8);
-						if (c == N_U8 - 1) {
+						if (ku == N_U8 - 1) {
 							tc_commit(bar_tfull + buf * 8);
 						}
 					} else {
@@ -548,11 +580,17 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				it++;
 			}
 		}
-	} else if (warp < 2 + NCW) {
+	} else if (warp < 4) {
+		// idle: their registers go to the other warpgroups
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+	} else if (warp < 4 + NCW) {
 		// ===== compute warps =====
-		const int cw = warp - 2;
+		if (NCW == 8) {
+			asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
+		}
+		const int cw = warp - 4;
 		const u32 quarter = (u32)warp & 3;          // the TMEM lanes this warp may touch: 32 * quarter ..
-		const int half = cw >> 2;                   // query rows 32 * half .. of the tile
+		const int qsel = cw >> 2;                   // query rows QN * qsel .. of the tile
 		const u32 lane_row = quarter * 32 + (u32)lane;
 		const u32 tlane = (quarter * 32) << 16;
 		u32 s = 0, ph = 0, it = 0;
@@ -562,11 +600,38 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				continue;
 			}
 			bool tmem_free = false;
-			if (U8_PHASE) {
-				u32 acc[2][32];
+			const u32 eb = EBUFS == 2 ? (it & 1) : 0, eit = EBUFS == 2 ? (it >> 1) : it; // buffer and its use count
+			if (INTERLEAVE) {
+				u32 acc[2][QN];
+#pragma unroll
+				for (int q = 0; q < QN; q++) {
+					acc[0][q] = acc[1][q] = 0;
+				}
+#pragma unroll 1
+				for (int c = 0; c < N_U8 + N_CUM; c++) {
+					mbar_wait(bar_full + s * 8, ph, p.err);
+					if (c % 3 != 2) {
+						stage_compute<true>(smem + s * STAGE_BYTES, lane_row, qsel, acc);
+					}
+					__syncwarp();
+					if (lane == 0) {
+						mbar_arrive(bar_empty + s * 8);
+					}
+					if (++s == (u32)STAGES) {
+						s = 0;
+						ph ^= 1;
+					}
+				}
+				mbar_wait(bar_eempty + eb * 8, (eit & 1) ^ 1, p.err); // the epilogue is done with this buffer's previous sums
+				tc_fence_after();
+				tc_st(tmem_base + tlane + TM_EMD + eb * 128 + qsel * QN, acc[0]);
+				tc_st(tmem_base + tlane + TM_EMD + eb * 128 + 64 + qsel * QN, acc[1]);
+			}
+			if (!INTERLEAVE && U8_PHASE) {
+				u32 acc[2][QN];
 				if (MIN) {
 #pragma unroll
-					for (int q = 0; q < 32; q++) {
+					for (int q = 0; q < QN; q++) {
 						acc[0][q] = acc[1][q] = 0;
 					}
 				}
@@ -574,7 +639,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				for (int c = 0; c < N_U8; c++) {
 					mbar_wait(bar_full + s * 8, ph, p.err);
 					if (MIN) {
-						stage_compute<false>(sbase + s * STAGE_BYTES, lane_row, half, acc);
+						stage_compute<false>(smem + s * STAGE_BYTES, lane_row, qsel, acc);
 					}
 					__syncwarp();
 					if (lane == 0) {
@@ -586,23 +651,23 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 					}
 				}
 				if (MIN) {
-					mbar_wait(bar_eempty, (it & 1) ^ 1, p.err); // the epilogue is done with the previous tile's sums
+					mbar_wait(bar_eempty + eb * 8, (eit & 1) ^ 1, p.err); // the epilogue is done with this buffer's previous sums
 					tc_fence_after();
 					tmem_free = true;
-					tc_st32(tmem_base + tlane + TM_SAD + half * 32, acc[0]);
-					tc_st32(tmem_base + tlane + TM_SAD + 64 + half * 32, acc[1]);
+					tc_st(tmem_base + tlane + TM_SAD + qsel * QN, acc[0]);
+					tc_st(tmem_base + tlane + TM_SAD + 64 + qsel * QN, acc[1]);
 				}
 			}
-			if (EMD) {
-				u32 acc[2][32];
+			if (!INTERLEAVE && EMD) {
+				u32 acc[2][QN];
 #pragma unroll
-				for (int q = 0; q < 32; q++) {
+				for (int q = 0; q < QN; q++) {
 					acc[0][q] = acc[1][q] = 0;
 				}
 #pragma unroll 1
 				for (int c = 0; c < N_CUM; c++) {
 					mbar_wait(bar_full + s * 8, ph, p.err);
-					stage_compute<true>(sbase + s * STAGE_BYTES, lane_row, half, acc);
+					stage_compute<true>(smem + s * STAGE_BYTES, lane_row, qsel, acc);
 					__syncwarp();
 					if (lane == 0) {
 						mbar_arrive(bar_empty + s * 8);
@@ -613,31 +678,35 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 					}
 				}
 				if (!tmem_free) {
-					mbar_wait(bar_eempty, (it & 1) ^ 1, p.err);
+					mbar_wait(bar_eempty + eb * 8, (eit & 1) ^ 1, p.err);
 					tc_fence_after();
 				}
-				tc_st32(tmem_base + tlane + TM_EMD + half * 32, acc[0]);
-				tc_st32(tmem_base + tlane + TM_EMD + 64 + half * 32, acc[1]);
+				tc_st(tmem_base + tlane + TM_EMD + eb * 128 + qsel * QN, acc[0]);
+				tc_st(tmem_base + tlane + TM_EMD + eb * 128 + 64 + qsel * QN, acc[1]);
 			}
 			if (CUDA_RED) {
 				tc_st_wait();
 				tc_fence_before();
 				__syncwarp();
 				if (lane == 0) {
-					mbar_arrive(bar_efull);
+					mbar_arrive(bar_efull + eb * 8);
 				}
 			}
 			it++;
 		}
 	} else {
 		// ===== epilogue warps: thread = TMEM lane (database rows L and 128 + L), all 64 query columns of each region =====
-		const int ew = warp - 2 - NCW;
-		const int etid = threadIdx.x - (2 + NCW) * 32; // 0 .. NEW * 32 - 1
+		if (NCW != 8) {
+			asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+		}
+		const int ew = warp - 4 - NCW;
+		const int etid = threadIdx.x - (4 + NCW) * 32; // 0 .. NEW * 32 - 1
 		const u32 quarter = (u32)warp & 3;
 		const u32 lane_row = quarter * 32 + (u32)lane;
 		const u32 tlane = (quarter * 32) << 16;
 		RowF *s_rowQ = reinterpret_cast<RowF *>(smem + L::ROWQ);
 		u64 *s_winQ = reinterpret_cast<u64 *>(smem + L::WINQ);
+		uint2 *s_win32 = reinterpret_cast<uint2 *>(smem + L::WIN32);
 		Cand *s_list = reinterpret_cast<Cand *>(smem + L::LIST) + ew * LIST_CAP;
 		float *sx = reinterpret_cast<float *>(smem + L::SCRX) + etid;
 #pragma unroll
@@ -662,8 +731,11 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 					u64 len;
 					s_rowQ[par * TQ + etid] = make_rowf(p.sbQ, p.csQ, row, ok, len);
 					// FC_Runner.cpp:435-444: size_t truncation of len * id and len / id; an empty window marks an unused row
-					s_winQ[(par * TQ + etid) * 2] = ok ? (u64)((double)len * p.cutoff) : 1;
-					s_winQ[(par * TQ + etid) * 2 + 1] = ok ? (u64)((double)len / p.cutoff) : 0;
+					const u64 wlo = ok ? (u64)((double)len * p.cutoff) : 1, whi = ok ? (u64)((double)len / p.cutoff) : 0;
+					s_winQ[(par * TQ + etid) * 2] = wlo;
+					s_winQ[(par * TQ + etid) * 2 + 1] = whi;
+					// 32-bit copy for lengths below 2^32 (everything real); a saturated bound sends the pair to the 64-bit compare
+					s_win32[par * TQ + etid] = make_uint2(wlo > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)wlo, whi >= 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)whi);
 				}
 #pragma unroll
 				for (int r = 0; r < 2; r++) {
@@ -677,8 +749,9 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				named_sync(2, NEW * 32);
 			}
 			const u32 buf = it & 1;
+			const u32 eb = EBUFS == 2 ? (it & 1) : 0, eit = EBUFS == 2 ? (it >> 1) : it;
 			if (CUDA_RED) {
-				mbar_wait(bar_efull, it & 1, p.err);
+				mbar_wait(bar_efull + eb * 8, eit & 1, p.err);
 			}
 			if (DOT) {
 				mbar_wait(bar_tfull + buf * 8, (it >> 1) & 1, p.err);
@@ -691,10 +764,11 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				for (int qc = 0; qc < TQ; qc += 4) {
 					u32 vd[4] = {0, 0, 0, 0}, ve[4] = {0, 0, 0, 0}, vs[4] = {0, 0, 0, 0};
 					if (DOT) tc_ld4(tmem_base + tlane + TM_DOT + buf * 128 + r * 64 + qc, vd);
-					if (EMD) tc_ld4(tmem_base + tlane + TM_EMD + r * 64 + qc, ve);
+					if (EMD) tc_ld4(tmem_base + tlane + TM_EMD + eb * 128 + r * 64 + qc, ve);
 					if (MIN) tc_ld4(tmem_base + tlane + TM_SAD + r * 64 + qc, vs);
 					tc_ld_wait();
 					const u64 d = drow0 + r * 128 + lane_row;
+					const u32 len32 = RAW ? 0u : (lenD[r] >= 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)lenD[r]);
 					if constexpr (RAW) {
 #pragma unroll
 						for (int k = 0; k < 4; k++) {
@@ -711,8 +785,12 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 						u32 go = 0;
 #pragma unroll
 						for (int k = 0; k < 4; k++) {
-							const u64 lo = s_winQ[(par * TQ + qc + k) * 2], hi = s_winQ[(par * TQ + qc + k) * 2 + 1];
-							const bool g = lenD[r] >= lo && lenD[r] <= hi && (!p.upper_only || d > qrow0 + qc + k);
+							const uint2 w = s_win32[par * TQ + qc + k];
+							bool inwin = len32 >= w.x && len32 <= w.y;
+							if (len32 == 0xFFFFFFFFu || w.y == 0xFFFFFFFFu) { // beyond 32 bits: the exact 64-bit window
+								inwin = lenD[r] >= s_winQ[(par * TQ + qc + k) * 2] && lenD[r] <= s_winQ[(par * TQ + qc + k) * 2 + 1];
+							}
+							const bool g = inwin && (!p.upper_only || d > qrow0 + qc + k);
 							go |= g ? (1u << k) : 0u;
 							if (EMD) ve[k] = g ? Q[k].cs + PD[r].cs - 2u * ve[k] : 0u;
 						}
@@ -727,6 +805,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 							}
 						}
 						// candidate records -> the warp's list (ballot-compacted), flushed through the exact epilogue when full
+						if (__any_sync(0xffffffffu, cand != 0)) {
 #pragma unroll
 						for (int k = 0; k < 4; k++) {
 							const bool c = (cand >> k) & 1;
@@ -740,6 +819,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 								s_list[n_list + __popc(m & ((1u << lane) - 1))] = rec;
 							}
 							n_list += __popc(m);
+						}
 						}
 						if (n_list > LIST_CAP - 128 || (r == 1 && qc == TQ - 4)) {
 							__syncwarp();
@@ -788,7 +868,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) {
-				if (CUDA_RED) mbar_arrive(bar_eempty);
+				if (CUDA_RED) mbar_arrive(bar_eempty + eb * 8);
 				if (DOT) mbar_arrive(bar_tempty + buf * 8);
 			}
 			scored_total += scored;
