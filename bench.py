@@ -10,7 +10,11 @@ A step = one pass of the hot path over one batch of synthetic mutated-template D
 N > 1: one process per GPU (torchrun); sequences sharded for K1, histogram shards all-gathered over NCCL, the sweep
 split by folded query-row blocks; total work fixed ("strong" scaling).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2] [--n-seqs N]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4|cfg5] [--n-seqs N]
+
+--workload cfg4 / cfg5 print the same kind of line for BASELINE configs[3] (long records, k=8, uint16) and configs[4]
+(1M x 1 kb candidate scans + one update / merge pass, sharded over the ranks); the default cfg3 run carries both as
+`also_cfg4` / `also_cfg5` blocks so that the driver's own run times them.
 """
 import argparse
 import json
@@ -33,36 +37,46 @@ WORKLOADS = {
     "cfg3": dict(synth="cfg3", desc="BASELINE configs[2]: 100k x 1 kb, k=5, uint8, all-pairs feature+GLM sweep (id 0.9)"),
     # BASELINE.json configs[1] shape: 10k 16S-like 1.5 kb (hot-path content of the train+cluster run: K1 + candidate scans)
     "cfg2": dict(synth="cfg2", desc="BASELINE configs[1] shape: 10k x 1.5 kb 16S-like, k=5, uint8, K1 + all-pairs candidate sweep (id 0.9)"),
+    # BASELINE.json configs[3]: 5k long records (5 contigs x 10 kb joined by 50 N, --single-file), k=8, uint16 (128 KiB rows)
+    "cfg4": dict(synth=None, desc="BASELINE configs[3]: 5k x 50 kb --single-file records, k=8, uint16 (65,536-bin rows), K1 + all-pairs sweep (id 0.9)"),
+    # BASELINE.json configs[4]: 1M x 1 kb, candidate scans of the mean-shift accumulate stage + update / merge passes at --delta 5
+    "cfg5": dict(synth=None, desc="BASELINE configs[4]: 1M x 1 kb, k=5, uint8, Trainer::get_close candidate scans sharded over the ranks + one update / merge pass (--delta 5)"),
 }
+N_DEFAULT = {"cfg3": 100000, "cfg2": 10000, "cfg4": 5000, "cfg5": 1000000}
+
+
+def workload_config(name, n_total, k, eb):
+    """The `config` object: identical in both arms (the driver compares them key by key)."""
+    return {"workload": WORKLOADS[name]["desc"], "n_sequences": int(n_total), "k": int(k), "elem_bytes": int(eb),
+            "pairs_per_step": int(n_total) * (int(n_total) - 1) // 2, "model": os.path.basename(WEIGHTS), "cutoff": 0.9}
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def profile_entry(key):
+    """per-kernel figures read off the committed ncu --set full captures (profiles/r2_traffic.json, then r1_traffic.json):
+    dram_bytes_per_pair, warp_instr_per_pair, tensor_pipe_pct, source"""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            for k, v in d.items():
+                if k.startswith(key):
+                    return v
+        except Exception:
+            pass
+    return {}
+
+
 def traffic_per_pair(key):
-    """DRAM bytes per pair of a kernel from the committed ncu --set full capture (profiles/r1_traffic.json)"""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        d = json.load(open(p))
-        for k, v in d.items():
-            if k.startswith(key):
-                return float(v["dram_bytes_per_pair"]), v["source"]
-    except Exception:
-        pass
-    return None, None
+    v = profile_entry(key)
+    return (float(v["dram_bytes_per_pair"]), v.get("source")) if "dram_bytes_per_pair" in v else (None, None)
 
 
 def instr_per_pair(key):
-    """executed warp-instructions per pair of a kernel from the committed ncu capture (profiles/r1_traffic.json)"""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        for k, v in d.items():
-            if k.startswith(key) and "warp_instr_per_pair" in v:
-                return float(v["warp_instr_per_pair"]), v["source"]
-    except Exception:
-        pass
-    return None, None
+    v = profile_entry(key)
+    return (float(v["warp_instr_per_pair"]), v.get("source")) if "warp_instr_per_pair" in v else (None, None)
 
 
 def peaks():
@@ -142,7 +156,12 @@ class ClockSampler:
 def load_workload(name, n_override, lo, hi):
     from meshclust2_b200 import synth
     t0 = time.time()
-    seqs, _, k, eb = synth.make_config_range(WORKLOADS[name]["synth"], lo=lo, hi=hi, n=n_override)
+    if name == "cfg4":
+        n = n_override or N_DEFAULT["cfg4"]
+        seqs = synth.make_single_file(n, 5, 10000, seed=4)[lo:hi]
+        k, eb = 8, 2
+    else:
+        seqs, _, k, eb = synth.make_config_range(WORKLOADS[name]["synth"] or name, lo=lo, hi=hi, n=n_override)
     log("[bench] generated %d synthetic sequences [%d,%d) in %.1fs" % (len(seqs), lo, hi, time.time() - t0))
     return seqs, k, eb
 
@@ -199,7 +218,8 @@ def cpu_leg(seqs, k, eb, n_total, n_scored_total, cutoff, hist_sample, pair_samp
     del order
     return dict(value=n_scored_total / t_step, unit=UNIT, cores=threads, kind=kind,
                 sample="%d sequences through Loader<T>::get_point (%.2fs) + %d in-window pairs through Predictor<T>::close "
-                       "(%.2fs), %d OpenMP threads; extrapolated to the step's %d histograms + %d pairs" % (
+                       "(%.2fs), %d OpenMP threads; extrapolated to the step's %d histograms + %d pairs; the pairs are drawn "
+                       "at random over the sample (worse cache locality than fastcar's query-major loop)" % (
                            hs, t_hist, len(ia), t_pairs, threads, n_total, n_scored_total),
                 hist_per_s=hist_rate, pairs_per_s_kernel=pair_rate, seconds=t_hist + t_pairs, n_close_sample=n_close)
 
@@ -207,24 +227,24 @@ def cpu_leg(seqs, k, eb, n_total, n_scored_total, cutoff, hist_sample, pair_samp
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n_total = args.n or {"cfg3": 100000, "cfg2": 10000}[args.workload]
-    nsamp = min(n_total, args.cpu_hist_sample)
-    seqs, k, eb = load_workload(args.workload, args.n, 0, nsamp)
+    n_total = args.n or N_DEFAULT[args.workload]
+    nsamp = min(n_total, args.cpu_hist_sample if args.workload != "cfg4" else 256)
+    seqs, k, eb = load_workload(args.workload, args.n if args.workload != "cfg4" else nsamp, 0, nsamp)
     n_scored_total = n_total * (n_total - 1) // 2          # synthetic lengths are within the 0.9 window (L +/- 5 %)
+    pair_sample = args.cpu_pair_sample if args.workload != "cfg4" else 200000
     vals, secs = [], []
     leg = None
     for s in range(args.warmup + args.steps):
-        leg = cpu_leg(seqs, k, eb, n_total, n_scored_total, 0.9, nsamp, args.cpu_pair_sample, seed=s)
+        leg = cpu_leg(seqs, k, eb, n_total, n_scored_total, 0.9, nsamp, pair_sample, seed=s)
         if s >= args.warmup:
             vals.append(leg["value"])
             secs.append(leg["seconds"])
     v = float(np.mean(vals))
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOADS[args.workload]["desc"], "n_sequences": n_total, "k": k, "elem_bytes": eb,
-                       "pairs_per_step": n_scored_total, "model": os.path.basename(WEIGHTS),
-                       "note": "each step is a bounded sample; value is the workload-equivalent rate"},
+            "dtype": "u8" if eb == 1 else "u16", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args.workload, n_total, k, eb),
+            "notes": {"sampling": "each step is a bounded sample; value is the workload-equivalent rate"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": leg["cores"], "kind": leg["kind"], "sample": leg["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -242,7 +262,32 @@ def run_ours(args, rank, world, local_rank):
         tdist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         tdist = tdist_mod
     comm = mdist.Comm(tdist)
-    n_total = args.n or {"cfg3": 100000, "cfg2": 10000}[args.workload]
+    n_total = args.n or N_DEFAULT[args.workload]
+    if args.workload == "cfg5":
+        # the candidate-scan form: a step = 16 Trainer::get_close scans over the whole sharded set
+        ctx = capi.Context(local_rank)
+        model = ctx.model_from_file(WEIGHTS)
+        peak, peak_src = peaks()
+        blk = cfg5_block(ctx, capi, mdist, torch, comm, model, model.meta["id"], local_rank, peak, n_total=n_total,
+                         n_queries=16 * args.steps)
+        cs = blk["candidate_scan"]
+        line = {"metric": METRIC, "value": cs["pairs_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 4,
+                "ms_per_step": cs["ms_per_query"] * 16, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic (histograms generated directly)", "config": workload_config("cfg5", n_total, 5, 1),
+                "notes": {"step": "16 get_close scans over all candidates; 4 warm-up scans"},
+                "e2e": {"value": cs["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 * (n_total // world + 64),
+                        "from": "mc2_get_close through the C ABI: marks and the arg-max come back to the host every scan"},
+                "gpu_launches": int(ctx.launches),
+                "roofline": {"bound": "hbm", "achieved": cs["achieved_gbs"], "peak": peak * world, "unit": "GB/s",
+                             "frac": cs["frac_of_hbm_per_gpu"], "traffic": None, "kernel": "pair_fast_kernel<u8> (one query vs shard)",
+                             "algorithmic_bytes_per_unit": 1057, "peak_source": peak_src},
+                "cfg5": blk}
+        if rank == 0:
+            emit(line)
+        ctx.close()
+        if tdist is not None:
+            tdist.destroy_process_group()
+        return
     per, bounds = mdist.shard_bounds(n_total, world)
     lo, hi = bounds[rank]
     seqs, k, eb = load_workload(args.workload, args.n, lo, hi)
@@ -319,57 +364,94 @@ def run_ours(args, rank, world, local_rank):
     h2d = int(text.nbytes + text_off.nbytes)
     d2h = int(len(res_e["survivors"]) * 24 + 16 * len(res_e["blocks"]))
 
-    # roofline of the dominant kernel (the sweep): algorithmic bytes = candidate form, N*w + 24 + 9 per pair
+    # roofline of the dominant kernel (the sweep).  SURVEY.md 8(d), all-pairs tile sweep row: "not HBM -- CUDA-core integer
+    # issue rate for sum-min and sum|cum diff|, tensor pipe for sum p*q".  Algorithmic CUDA-core work of the benchmarked model
+    # (Gram term + EMD): the EMD's N bins at the densest instructions the ISA has for 16-bit cumulative values, 2 bins per
+    # VIMNMX.U16x2 and 2 per IDP.2A -> N lane-instructions = N/32 warp-instructions per pair; the Gram term's 2N integer
+    # ops per pair run on the tensor pipe.  Peak = the same instruction pair measured in this process (mc2_bench_issue_rate).
     N = 4 ** k
-    bytes_per_pair = N * eb + 24 + 9
     sweep_ms, sweep_n = ktime[3]
     count_ms, count_n = ktime[1]
     peak, peak_src = peaks()
     local_pairs = res["local_scored"] * args.steps
-    achieved = local_pairs * bytes_per_pair / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
-    tpp, tsrc = traffic_per_pair("sweep_kernel")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": tpp * local_pairs / max(1, sweep_n) if tpp else None, "traffic_source": tsrc,
-                "kernel": "sweep_kernel<u8,NEED_DOT|NEED_EMD>",
-                "algorithmic_bytes_per_unit": bytes_per_pair, "units_per_launch": local_pairs / max(1, sweep_n),
+    tile = (k == 5 and eb == 1)
+    kernel_name = "tile_sweep_kernel<NEED_DOT|NEED_EMD> (TMA ring + tcgen05 u8 MMA + VIMNMX.U16x2/IDP.2A EMD)" if tile else \
+        "sweep_wide_kernel<u16,NEED_DOT|NEED_EMD>"
+    prof = profile_entry("tile_sweep_kernel" if tile else "sweep_wide_kernel")
+    pairs_per_s_kernel = local_pairs / (sweep_ms * 1e-3) if sweep_ms > 0 else 0.0
+    try:
+        probe = ctx.issue_rate()
+    except Exception as e:
+        log("[bench] issue-rate probe failed: %r" % (e,))
+        probe = None
+    # tile sweep: N/32; wide rows (u16 bins, no cumulative rows): Gram term on CUDA cores as well, N/2 IDP.2A more
+    alg_wi = N / 32.0 if tile else (N + N / 2) / 32.0
+    ach = pairs_per_s_kernel * alg_wi
+    tpp = prof.get("dram_bytes_per_pair")
+    roofline = {"bound": "alu", "achieved": ach / 1e9, "peak": probe / 1e9 if probe else None, "unit": "Gwarp-instr/s",
+                "frac": ach / probe if probe else None,
+                "traffic": tpp * local_pairs / max(1, sweep_n) if tpp else None, "traffic_source": prof.get("source"),
+                "kernel": kernel_name,
+                "algorithmic_ops_per_unit": alg_wi, "algorithmic_ops_unit": "warp-instructions per pair",
+                "algorithmic_ops_note": "EMD over N=4^k bins on 16-bit cumulative values: N/2 VIMNMX.U16x2 + N/2 IDP.2A lane-"
+                                        "instructions (2 bins each)" + ("" if tile else " + N/2 IDP.2A for the Gram term") +
+                                        "; SURVEY 8(d) counts the same work as N byte-ops per reduction at 4 bins per SIMD op "
+                                        "(N/4 lane-instructions + accumulation), which no sm_100a instruction offers for 16-bit data",
+                "units_per_launch": local_pairs / max(1, sweep_n),
                 "avg_launch_ms": sweep_ms / max(1, sweep_n), "launches": sweep_n,
-                "kernel_share_of_step": sweep_ms / ms if ms > 0 else None, "peak_source": peak_src,
-                "note": "candidate-form bytes (each scored pair streams one database row, query row resident); at this "
-                        "size the 4^k x n set is L2-resident, so the kernel is ALU-issue bound, see DESIGN.md"}
+                "kernel_share_of_step": sweep_ms / ms if ms > 0 else None,
+                "peak_source": "mc2_bench_issue_rate: VIMNMX.U16x2 + IDP.2A, register operands, 32 warps / SM, measured in this process",
+                "pairs_per_s": pairs_per_s_kernel,
+                "hbm": {"achieved_gbs": (tpp * pairs_per_s_kernel / 1e9) if tpp else None, "peak_gbs": peak, "peak_source": peak_src,
+                        "frac": (tpp * pairs_per_s_kernel / 1e9 / peak) if tpp else None,
+                        "note": "measured DRAM bytes per pair (ncu) x live pairs/s: the sweep is not HBM bound"},
+                "tensor": {"int_ops_per_pair": 2 * N if tile else 0, "achieved_tops": pairs_per_s_kernel * 2 * N / 1e12 if tile else 0.0,
+                           "pipe_active_pct": prof.get("tensor_pipe_pct"),
+                           "note": "Gram term sum p*q: tcgen05.mma kind::i8 (u8 x u8 -> s32, exact) into TMEM; it is ~1 % of the "
+                                   "tensor pipe because the CUDA-core EMD term paces the tile"}}
+    ipp = prof.get("warp_instr_per_pair")
+    sm_mhz = (clocks or {}).get("sm_mhz")
+    if ipp and sm_mhz:
+        issue_peak = ctx.sm_count * 4 * sm_mhz * 1e6
+        roofline["issue"] = {"executed_warp_instr_per_pair": ipp, "achieved": pairs_per_s_kernel * ipp / 1e9, "peak": issue_peak / 1e9,
+                             "unit": "Gwarp-instr/s", "frac": pairs_per_s_kernel * ipp / issue_peak,
+                             "note": "slot occupancy (counts overhead as work): executed instructions per pair from the committed "
+                                     "ncu capture x live pairs/s over 4 schedulers x SMs x sampled clock"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload]["desc"], "n_sequences": n_total, "k": k, "elem_bytes": eb,
-                       "pairs_scored_per_step": n_scored, "pairs_close_per_step": res["n_close"],
-                       "model": os.path.basename(WEIGHTS), "parallelism": "row-block x%d, NCCL all-gather of histograms" % world,
-                       "l2": "L2 flushed between steps (256 MB memset inside the timed region)"},
+            "dtype": "u8" if eb == 1 else "u16", "data": "synthetic",
+            "config": workload_config(args.workload, n_total, k, eb),
+            "notes": {"pairs_scored_per_step": n_scored, "pairs_close_per_step": res["n_close"],
+                      "parallelism": "row-block x%d, NCCL all-gather of histograms" % world,
+                      "l2": "L2 flushed between steps (256 MB memset inside the timed region)",
+                      "e2e_steps": e2e_steps},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "ms_per_step": ms_e / e2e_steps,
+                    "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
                     "from": "raw sequence text in page-locked host memory (mc2_seqs_from_text_into -> mc2_count_kmers_into -> "
                             "mc2_all_pairs; survivors copied back)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "k1": {"hist_per_s": (hi - lo) * args.steps / (count_ms * 1e-3) if count_ms > 0 else None,
                    "avg_launch_ms": count_ms / max(1, count_n),
-                   "achieved_gbs": (hi - lo) * args.steps * (250 + N * eb + 40) / (count_ms * 1e-3) / 1e9 if count_ms > 0 else None}}
-    try:
-        # the roofline that actually binds the L2-resident sweep ("not HBM -- CUDA-core integer issue rate"):
-        # executed warp-instructions per second against the issue rate of the SMs at the clock sampled in the timed region
-        ipp, isrc = instr_per_pair("sweep_kernel")
-        sm_mhz = (clocks or {}).get("sm_mhz")
-        if ipp and sm_mhz and sweep_ms > 0:
-            issue_peak = ctx.sm_count * 4 * sm_mhz * 1e6
-            issue_ach = local_pairs / (sweep_ms * 1e-3) * ipp
-            line["roofline_issue"] = {"bound": "issue", "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9,
-                                      "unit": "Gwarp-instr/s", "frac": issue_ach / issue_peak, "warp_instr_per_pair": ipp,
-                                      "source": isrc, "kernel": roofline["kernel"],
-                                      "note": "secondary: issue slots of 4 schedulers x SMs at the sampled SM clock; the "
-                                              "instruction count per pair is the committed ncu figure, pairs/s is live"}
-    except Exception as e:
-        log("[bench] issue roofline skipped: %r" % (e,))
-    if world == 1 and not args.no_extras:
-        line["roofline_candidates"] = candidates_roofline(ctx, capi, model, k, eb, peak, peak_src)
-        if args.workload != "cfg2":
+                   "achieved_gbs": (hi - lo) * args.steps * (np.mean([len(x) for x in seqs]) / 4 + N * eb + 40) / (count_ms * 1e-3) / 1e9 if count_ms > 0 and seqs else None}}
+    if line["k1"]["achieved_gbs"]:
+        line["k1"]["frac_of_hbm"] = line["k1"]["achieved_gbs"] / peak
+    if not args.no_extras:
+        if world == 1 and tile:
+            line["roofline_candidates"] = candidates_roofline(ctx, capi, model, k, eb, peak, peak_src)
+        if world == 1 and args.workload == "cfg3":
             line["also_cfg2"] = small_workload(ctx, capi, mdist, torch, model, cutoff)
+            if rank == 0:
+                try:
+                    line["also_cfg2"]["e2e_cluster"] = e2e_cluster_block()
+                except Exception as e:
+                    log("[bench] e2e_cluster extra failed: %r" % (e,))
+        if args.workload == "cfg3":
+            try:
+                if world == 1:
+                    line["also_cfg4"] = cfg4_block(ctx, capi, model, cutoff, peak)
+                line["also_cfg5"] = cfg5_block(ctx, capi, mdist, torch, comm, model, cutoff, local_rank, peak)
+            except Exception as e:                      # an extra, never the reason a bench line is lost
+                log("[bench] cfg4 / cfg5 extra failed: %r" % (e,))
     if rank == 0 and world == 1 and not args.no_cpu:
         t0 = time.time()
         cb = cpu_leg(seqs, k, eb, n_total, n_scored, cutoff, args.cpu_hist_sample, args.cpu_pair_sample)
@@ -384,13 +466,16 @@ def run_ours(args, rank, world, local_rank):
 
 def pin_inputs(capi, enc):
     """page-lock the step's host inputs (the encoded batch) so the timed H2D copies are DMA transfers from pinned memory"""
+    done = []
     for key in ("codes", "seq_off", "segs", "seg_off"):
         enc[key] = np.ascontiguousarray(enc[key])
         if enc[key].nbytes:
             try:
                 capi.host_register(enc[key])
+                done.append(enc[key])
             except capi.Mc2Error as e:          # e.g. a locked-memory limit: the copies still work, just through pageable memory
                 log("[bench] could not page-lock %s: %s" % (key, e))
+    return done
 
 
 def small_workload(ctx, capi, mdist, torch, model, cutoff, steps=20):
@@ -399,7 +484,7 @@ def small_workload(ctx, capi, mdist, torch, model, cutoff, steps=20):
     from meshclust2_b200 import synth
     seqs, _, k, eb = synth.make_config_range("cfg2", 0, None)
     enc = capi.encode_batch(seqs)
-    pin_inputs(capi, enc)
+    pinned = pin_inputs(capi, enc)
     eng = mdist.GpuEngine(capi, ctx, torch, model, k, eb, 0)
     n = len(seqs)
     eng.set_local_sequences(ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"]), n, n)
@@ -410,6 +495,7 @@ def small_workload(ctx, capi, mdist, torch, model, cutoff, steps=20):
     for arr in (text, text_off):
         try:
             capi.host_register(arr)
+            pinned.append(arr)
         except capi.Mc2Error:
             pass
     out = {}
@@ -431,6 +517,12 @@ def small_workload(ctx, capi, mdist, torch, model, cutoff, steps=20):
         out["update_stage"] = update_stage(ctx, capi, model, eng.full, cutoff)
     except Exception as e:                              # an extra, never the reason a bench line is lost
         log("[bench] update-stage extra failed: %r" % (e,))
+    ctx.sync()
+    for arr in pinned:       # a page-locked range must be released before its memory goes back to the allocator: a later
+        try:                 # array landing on the same addresses would make its copies fail
+            capi.host_unregister(arr)
+        except capi.Mc2Error:
+            pass
     out["workload"] = WORKLOADS["cfg2"]["desc"]
     out["pairs_scored_per_step"] = res["n_scored"]
     out["pairs_close_per_step"] = res["n_close"]
@@ -495,6 +587,185 @@ def update_stage(ctx, capi, model, hs, cutoff, delta=5, per_cluster=5, passes=5)
     return {"centers": nc, "member_pairs_per_pass": int(off[-1]), "batched_ms_per_pass": t_b * 1e3,
             "per_center_calls_ms_per_pass": t_p * 1e3, "speedup": t_p / t_b, "same_choices": same,
             "sample": "per-center form timed on the first %d centers and scaled to %d" % (limit, nc)}
+
+
+def cfg4_block(ctx, capi, model, cutoff, peak, n=5000):
+    """BASELINE configs[3] in the same run: 5k --single-file records (5 contigs x 10 kb joined by 50 N), k = 8, uint16
+    histograms (65,536 bins = 128 KiB rows): K1 rate and the all-pairs sweep (sweep_wide_kernel), device-timed."""
+    from meshclust2_b200 import synth
+    t0 = time.time()
+    seqs = synth.make_single_file(n, 5, 10000, seed=4)
+    enc = capi.encode_batch(seqs)
+    log("[bench] cfg4: %d records generated + encoded in %.1fs" % (n, time.time() - t0))
+    sq = ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
+    L = float(np.mean([len(x) for x in seqs]))
+    for _ in range(2):
+        k1_ms = ctx.bench_count_kmers(sq, 8, 2, iters=3, flush_l2=True)
+    hs, largest, eb = ctx.count_kmers_auto(sq, 8)
+    if eb != 2:
+        hs.free()
+        hs = ctx.count_kmers(sq, 8, 2)
+    out = {"workload": WORKLOADS["cfg4"]["desc"], "n_records": n, "mean_length": L, "largest_count": int(largest),
+           "detected_elem_bytes": int(eb)}
+    k1_bytes = n * (L / 4 + 65536 * 2 + 40)
+    out["k1"] = {"ms": k1_ms, "hist_per_s": n / (k1_ms * 1e-3), "achieved_gbs": k1_bytes / (k1_ms * 1e-3) / 1e9,
+                 "frac_of_hbm": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_hist": k1_bytes / n}
+    ms_best, r = None, None
+    for _ in range(3):
+        ctx.flush_l2(256 << 20)
+        ctx.timer_start()
+        r = ctx.all_pairs(model, hs, hs, cutoff, upper_only=True, max_out=1 << 22)
+        ms = ctx.timer_stop()
+        ms_best = ms if ms_best is None else min(ms_best, ms)
+    pps = r["n_scored"] / (ms_best * 1e-3)
+    prof = profile_entry("sweep_wide_kernel")
+    tpp = prof.get("dram_bytes_per_pair")
+    out["sweep"] = {"ms": ms_best, "pairs_scored": r["n_scored"], "pairs_close": r["n_out"], "pairs_per_s": pps,
+                    "kernel": "sweep_wide_kernel<u16> (query row in shared memory, candidate rows streamed)",
+                    "candidate_form_gbs": pps * 131105 / 1e9,
+                    "dram_gbs": pps * tpp / 1e9 if tpp else None, "dram_frac_of_hbm": pps * tpp / 1e9 / peak if tpp else None,
+                    "note": "131,105 algorithmic bytes per pair in the one-vs-many form; in the all-pairs form the CTAs walk the "
+                            "candidate rows in step and L2 serves most re-reads, so DRAM traffic per pair is the ncu figure"}
+    hs.free()
+    sq.free()
+    return out
+
+
+def cfg5_block(ctx, capi, mdist, torch, comm, model, cutoff, local_rank, peak, n_total=1000000, n_queries=64, delta=5):
+    """BASELINE configs[4] in the same run: 1M x 1 kb (k = 5, uint8) histograms RANGE-PARTITIONED over the ranks (1 GiB in
+    all), Trainer::get_close candidate scans of the accumulate stage (the query row broadcast from its owner, every rank
+    scanning its shard with mc2_get_close, one triple per rank combined) and one update + merge pass of the update stage at
+    --delta 5 over the replicated set (mc2_update_centers / mc2_merge_centers, centers split over the ranks).
+    Histograms are generated directly (template rows + noise), bypassing FASTA, as SURVEY 8(d) allows for pair kernels."""
+    world, rank = comm.world, comm.rank
+    per, bounds = mdist.shard_bounds(n_total, world)
+    lo, hi = bounds[rank]
+    N = 1024
+    rng = np.random.default_rng([55, rank])
+    trng = np.random.default_rng(55)
+    base = trng.integers(1, 6, size=(10000, N), dtype=np.uint8)            # 10,000 templates x 100 variants
+    tid = (np.arange(lo, hi) % 10000)
+    H = base[tid]
+    flip = rng.random(H.shape) < 0.02
+    H = np.where(flip, np.clip(H.astype(np.int16) + rng.integers(-1, 2, size=H.shape), 1, 255).astype(np.uint8), H)
+    ln = (950 + (tid * 7919) % 100).astype(np.uint64)
+    eng = mdist.GpuEngine(capi, ctx, torch, model, 5, 1, local_rank)
+    eng.local_hset = ctx.hset_from_host(H, 5, length=ln)
+    eng.n_local, eng.per = hi - lo, per
+    del H
+    out = {"workload": WORKLOADS["cfg5"]["desc"], "n_sequences": n_total, "ranks": world}
+    # accumulate-stage scans: n_queries get_close calls, each over all 1M candidates
+    qs = [(q * 15485863) % n_total for q in range(n_queries)]
+    for q in qs[:4]:
+        mdist.candidate_scan(eng, comm, torch, q, n_total, cutoff)
+    comm.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_close = 0
+    for q in qs:
+        r = mdist.candidate_scan(eng, comm, torch, q, n_total, cutoff)
+        n_close += int(np.count_nonzero(r["marks_local"]))
+    torch.cuda.synchronize()
+    comm.barrier()
+    dt = comm.all_reduce_max(time.perf_counter() - t0, torch, eng.device)
+    out["candidate_scan"] = {"queries": n_queries, "candidates_per_query": n_total, "ms_per_query": dt / n_queries * 1e3,
+                             "pairs_per_s": n_queries * n_total / dt, "achieved_gbs": n_queries * n_total * 1057 / dt / 1e9,
+                             "frac_of_hbm_per_gpu": n_queries * n_total * 1057 / dt / 1e9 / (peak * world),
+                             "timing": "host wall clock around the whole distributed call (broadcast + scan + combine), max over ranks",
+                             "close_marks_rank0": n_close}
+    # update stage: one pass over centers = every 100th point, members = the 2*delta+1 neighbouring clusters' points
+    try:
+        if world > 1:
+            eng.full = None
+            bins, length, mag = eng.export_local()
+            bins = comm.all_gather_rows(bins, torch); length = comm.all_gather_rows(length, torch); mag = comm.all_gather_rows(mag, torch)
+            eng.install_full(bins, length, mag, per * world)
+            del bins
+        else:
+            eng.use_local_as_full()
+        nfull = len(eng.full)
+        per_cluster = 5
+        nc = min(nfull // per_cluster, 20000)
+        rows = np.arange(nc, dtype=np.uint64) * per_cluster
+        off = np.zeros(nc + 1, dtype=np.uint64)
+        mem = []
+        for j in range(nc):
+            a, b = max(0, j - delta) * per_cluster, min(nc, j + delta + 1) * per_cluster
+            mem.append(np.arange(a, b, dtype=np.uint64))
+            off[j + 1] = off[j] + np.uint64(b - a)
+        members = np.concatenate(mem)
+        side = eng.full.download(0, nc * per_cluster)                   # the centers' own magnitudes and lengths
+        cm = side["mag"][::per_cluster].astype(np.uint64)
+        cl = side["len"][::per_cluster].astype(np.uint64)
+        del side
+        mdist.update_pass(eng, comm, torch, rows, cm, cl, off, members, cutoff)
+        comm.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nxt, ng = mdist.update_pass(eng, comm, torch, rows, cm, cl, off, members, cutoff)
+        mg = mdist.merge_pass(eng, comm, torch, rows, cm, cl, delta, cutoff)
+        torch.cuda.synchronize(); comm.barrier()
+        dtu = comm.all_reduce_max(time.perf_counter() - t0, torch, eng.device)
+        out["update_stage"] = {"centers": int(nc), "delta": delta, "member_pairs": int(off[-1]), "merge_pairs": int(nc * delta),
+                               "ms_per_pass": dtu * 1e3, "pairs_per_s": (int(off[-1]) + nc * delta) / dtu,
+                               "moved": int(np.count_nonzero(nxt >= 0)), "merged": int(np.count_nonzero(mg > 0))}
+    except Exception as e:
+        log("[bench] cfg5 update stage failed: %r" % (e,))
+    try:
+        if eng.full is not None and eng.full is not eng.local_hset:
+            eng.full.free()
+        eng.local_hset.free()
+    except Exception:
+        pass
+    return out
+
+
+def e2e_cluster_block(threads_list=None):
+    """BASELINE configs[1] as the full job it names: the reference's own meshclust2 binary (oracle/_ref/meshclust2) next to
+    the same binary relinked against this library (oracle/_ref/meshclust2_b200) on the 10k x 1.5 kb
+    synthetic 16S-like FASTA at --id 0.9; wall clock of the whole process, clusters compared as sets."""
+    import re
+    import tempfile
+    from meshclust2_b200 import synth
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "meshclust2")
+    our_bin = os.path.join(ROOT, "oracle", "_ref", "meshclust2_b200")
+    if not (os.path.exists(ref_bin) and os.path.exists(our_bin)):
+        return {"unavailable": "oracle/_ref binaries not built on this box"}
+    seqs, tids, _, _ = synth.make_config_range("cfg2", 0, None)
+    tmp = tempfile.mkdtemp()
+    fasta = os.path.join(tmp, "in.fa")
+    open(fasta, "w").write(synth.to_fasta(seqs, tids))
+
+    def clusters(path):
+        out, cur = [], None
+        for ln_ in open(path):
+            if ln_.startswith(">Cluster"):
+                cur = set()
+                out.append(cur)
+            else:
+                m = re.search(r">(\S+)", ln_)
+                if m:
+                    cur.add(m.group(1).rstrip("."))
+        return {frozenset(c) for c in out if c}
+
+    res = {"workload": "meshclust2 --id 0.9 on 10k x 1.5 kb (BASELINE configs[1]), whole process wall clock", "runs": []}
+    for threads in (threads_list or [os.cpu_count() or 1, 1]):
+        got = {}
+        for name, binary in (("reference", ref_bin), ("b200", our_bin)):
+            wd = os.path.join(tmp, "%s_%d" % (name, threads))
+            os.makedirs(wd, exist_ok=True)
+            outp = os.path.join(wd, "out.clstr")
+            t0 = time.time()
+            r = subprocess.run([binary, "--id", "0.9", "--threads", str(threads), fasta, "--output", outp], cwd=wd,
+                               capture_output=True, text=True, timeout=600)
+            got[name] = (time.time() - t0, r.returncode, clusters(outp) if r.returncode == 0 else None)
+        same = got["reference"][2] is not None and got["reference"][2] == got["b200"][2]
+        res["runs"].append({"threads": threads, "reference_s": got["reference"][0], "b200_s": got["b200"][0],
+                            "rc": [got["reference"][1], got["b200"][1]],
+                            "clusters": len(got["reference"][2]) if got["reference"][2] is not None else None,
+                            "identical_clusters": bool(same),
+                            "note": None if threads == 1 else "the reference's OpenMP training is not reproducible run to run "
+                                                              "(SURVEY section 4): identical clusters are asserted at --threads 1"})
+    return res
 
 
 def candidates_roofline(ctx, capi, model, k, eb, peak, peak_src, n=1 << 20):

@@ -330,6 +330,11 @@ int mc2_all_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
 		  uint64_t max_out, uint64_t *out_q, uint64_t *out_d, double *out_score, uint64_t *n_out,
 		  uint64_t *n_scored);
 
+/* Measured issue rate (warp-instructions per second, whole GPU) of the tile sweep's inner instruction pair -- VIMNMX.U16x2 on
+ * the ALU pipe feeding IDP.2A on the FMA pipe, register operands only, 32 resident warps per SM: the denominator of
+ * bench.py's roofline for the CUDA-core EMD term ("achieved ... vs a measured ALU peak"). */
+int mc2_bench_issue_rate(mc2_ctx *ctx, int iters, double *warp_instr_per_s);
+
 /* Diagnostic (tests): the integer reductions of the 1 KiB uint8 tile sweep for every (query, database) pair of the two row
  * ranges, as dense row-major (q_end-q_begin) x (d_end-d_begin) uint32 matrices: need is a mask of 1 = sum|p-q|
  * (Feature.cpp:858-871), 2 = sum p*q (Feature.cpp:1112-1124, 1170-1184), 4 = sum|cumP-cumQ| (Feature.cpp:1504-1518).

@@ -40,7 +40,7 @@ SYMBOLS = [
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
     "mc2_score_pairs", "mc2_get_close", "mc2_get_close_as", "mc2_filter", "mc2_filter_as", "mc2_merge", "mc2_all_pairs", "mc2_debug_tile_reductions", "mc2_distance", "mc2_mean_closest", "mc2_closest",
     "mc2_update_centers", "mc2_merge_centers",
-    "mc2_bench_score_pairs", "mc2_bench_count_kmers", "mc2_encode_dna", "mc2_encode_dna_batch",
+    "mc2_bench_score_pairs", "mc2_bench_count_kmers", "mc2_bench_issue_rate", "mc2_encode_dna", "mc2_encode_dna_batch",
 ]
 
 
@@ -357,6 +357,12 @@ class Context:
                                    _p(od), _p(osc), C.byref(n_out), C.byref(n_scored)))
         got = min(n_out.value, max_out)
         return dict(q=oq[:got], d=od[:got], score=osc[:got], n_out=n_out.value, n_scored=n_scored.value)
+
+    def issue_rate(self, iters=100000):
+        """measured warp-instructions / s of the VIMNMX.U16x2 + IDP.2A pair (roofline denominator of the tile sweep)"""
+        out = C.c_double()
+        _check(lib().mc2_bench_issue_rate(self.h, int(iters), C.byref(out)))
+        return out.value
 
     def tile_reductions(self, set_q, set_d, need, q_range=None, d_range=None):
         """Diagnostic: dense uint32 matrices {sad, dot, emd} (those in `need`: 1 | 2 | 4) of the tile sweep's reductions"""

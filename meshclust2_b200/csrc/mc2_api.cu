@@ -1886,6 +1886,30 @@ int mc2_all_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
 	return check_err(ctx);
 }
 
+int mc2_bench_issue_rate(mc2_ctx *ctx, int iters, double *warp_instr_per_s)
+{
+	MC2_REQUIRE(ctx && warp_instr_per_s && iters > 0, "mc2_bench_issue_rate: bad argument");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	CtxExtra *x = extra(ctx);
+	int rc = ensure(x->d[B_MISC], (size_t)ctx->sm_count * 4 * 256 * 4 + 64, false); if (rc) return rc;
+	u64 wi = 0;
+	rc = launch_issue_probe(ctx, iters, (u32 *)x->d[B_MISC].p, &wi); // warm-up (clocks, instruction cache)
+	if (rc != MC2_OK) return rc;
+	float ms = 0;
+	for (int rep = 0; rep < 3; rep++) { // best of three
+		MC2_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+		rc = launch_issue_probe(ctx, iters, (u32 *)x->d[B_MISC].p, &wi);
+		if (rc != MC2_OK) return rc;
+		MC2_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+		MC2_CUDA(cudaEventSynchronize(ctx->ev1));
+		float t = 0;
+		MC2_CUDA(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+		if (rep == 0 || t < ms) ms = t;
+	}
+	*warp_instr_per_s = ms > 0 ? (double)wi / (ms * 1e-3) : 0.0;
+	return MC2_OK;
+}
+
 int mc2_debug_tile_reductions(mc2_ctx *ctx, const mc2_hset *set_q, uint64_t q_begin, uint64_t q_end, const mc2_hset *set_d,
 			      uint64_t d_begin, uint64_t d_end, int32_t need, uint32_t *out_dot, uint32_t *out_emd, uint32_t *out_sad)
 {

@@ -216,6 +216,7 @@ int ensure_lane_off(mc2_ctx *ctx, const mc2_hset *h); // builds h->lane_off if t
 // tile_sweep.cu: the all-pairs sweep over 1 KiB uint8 rows as 64 x 128 pair tiles (TMA ring, tcgen05 Gram term, u16 cumulative EMD)
 int ensure_cum16(mc2_ctx *ctx, const mc2_hset *h);
 bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset *d);
+int launch_issue_probe(mc2_ctx *ctx, int iters, u32 *d_out, u64 *warp_instr);
 int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset *q, u64 q0, u64 q1, const mc2_hset *d, u64 d0, u64 d1,
 		      int upper_only, double cutoff, u64 max_out, u64 *d_out_q, u64 *d_out_d, double *d_out_score, u64 *d_counters,
 		      u32 *raw_dot, u32 *raw_emd, u32 *raw_sad);

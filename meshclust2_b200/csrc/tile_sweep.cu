@@ -939,6 +939,34 @@ __global__ void __launch_bounds__(256) cum16_kernel(const unsigned char *__restr
 	}
 }
 
+// issue-rate probe: the tile sweep's inner pair of instructions (VIMNMX.U16x2 on the ALU pipe feeding IDP.2A on the FMA
+// pipe), 16 independent chains per thread, 32 resident warps per SM, no memory traffic: the measured denominator of
+// bench.py's roofline for the CUDA-core EMD term
+__global__ void __launch_bounds__(256) issue_probe_kernel(u32 *out, u32 seed, int iters)
+{
+	u32 a = threadIdx.x * 2654435761u + seed, b = a ^ 0x5bd1e995u;
+	u32 c[16];
+#pragma unroll
+	for (int i = 0; i < 16; i++) {
+		c[i] = a + i;
+	}
+	for (int it = 0; it < iters; it++) {
+#pragma unroll
+		for (int i = 0; i < 16; i++) {
+			u32 m;
+			asm volatile("min.u16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(c[i]));
+			asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(c[i]) : "r"(m), "r"(0x0101u), "r"(c[i]));
+		}
+		a += b;
+	}
+	u32 s = 0;
+#pragma unroll
+	for (int i = 0; i < 16; i++) {
+		s += c[i];
+	}
+	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 } // namespace ts
 
 int ensure_cum16(mc2_ctx *ctx, const mc2_hset *hc)
@@ -963,6 +991,16 @@ int ensure_cum16(mc2_ctx *ctx, const mc2_hset *hc)
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
 	h->cum16_valid = 1;
+	return MC2_OK;
+}
+
+int launch_issue_probe(mc2_ctx *ctx, int iters, u32 *d_out, u64 *warp_instr)
+{
+	const int grid = ctx->sm_count * 4;
+	ts::issue_probe_kernel<<<grid, 256, 0, ctx->stream>>>(d_out, 1u, iters);
+	ctx->launches++;
+	MC2_CUDA(cudaGetLastError());
+	*warp_instr = (u64)grid * 8 * (u64)iters * 32; // 16 x (VIMNMX + IDP.2A) per iteration and warp
 	return MC2_OK;
 }
 
