@@ -351,6 +351,7 @@ def run_ours(args, rank, world, local_rank):
     ms, res, launches, ktime, clocks = timed(step_resident, args.steps, sample_clocks=True)
     n_scored = res["n_scored"]
     value = n_scored * args.steps / (ms * 1e-3)
+    log("[bench] rank %d per-kind device ms per step: %s" % (rank, {kk: round(v[0] / args.steps, 3) for kk, v in ktime.items()}))
     log("[bench] rank %d resident: %.1f ms/step, %d pairs scored, %d close, %d launches" % (
         rank, ms / args.steps, n_scored, res["n_close"], launches))
     # end to end from host buffers

@@ -39,6 +39,32 @@ def rect_row_blocks(n, world, rank):
     return [(lo, hi)] if hi > lo else []
 
 
+class Survivors:
+    """This rank's survivor pairs of one step, block by block, WITHOUT copying them together: an engine may hand back views
+    of its own (page-locked, per-block) buffers, valid until its next step.  tolist() / array() build the [m, 2] form."""
+
+    def __init__(self):
+        self.parts = []
+
+    def add(self, pairs):
+        if isinstance(pairs, tuple):
+            self.parts.append((np.asarray(pairs[0]), np.asarray(pairs[1])))
+        else:
+            pairs = np.asarray(pairs).reshape(-1, 2)
+            self.parts.append((pairs[:, 0], pairs[:, 1]))
+
+    def __len__(self):
+        return int(sum(len(q) for q, _ in self.parts))
+
+    def array(self):
+        if not self.parts:
+            return np.zeros((0, 2), dtype=np.uint64)
+        return np.stack([np.concatenate([q for q, _ in self.parts]), np.concatenate([d for _, d in self.parts])], axis=1)
+
+    def tolist(self):
+        return self.array().tolist()
+
+
 class Comm:
     """Thin wrapper so single-process runs need no process group."""
 
@@ -79,7 +105,7 @@ def all_pairs_step(engine, comm, torch, n_total, cutoff, upper_only=True, blocks
     engine.export_local()           -> (bins [per, N] tensor, length [per] int64 tensor, mag [per] int64 tensor) padded
     engine.install_full(bins, length, mag, n_total)   make the gathered set the sweep's database
     engine.use_local_as_full()      single rank: the counted shard is the database (no copy, no collective)
-    engine.sweep(q0, q1, upper_only, cutoff, max_out) -> (n_survivors, n_scored, survivors array [m,2])
+    engine.sweep(q0, q1, upper_only, cutoff, max_out) -> (n_survivors, n_scored, survivors: array [m,2] or (q[m], d[m]))
     Returns dict(n_scored, n_close, survivors (this rank's), blocks)."""
     engine.count()
     if comm.world == 1:
@@ -100,15 +126,14 @@ def all_pairs_step(engine, comm, torch, n_total, cutoff, upper_only=True, blocks
     blocks = (folded_row_blocks(n_total, comm.world, comm.rank, blocks_per_rank) if upper_only
               else rect_row_blocks(n_total, comm.world, comm.rank))
     n_scored = n_close = 0
-    surv = []
+    surv = Survivors()
     for q0, q1 in blocks:
         ns, sc, pairs = engine.sweep(q0, q1, upper_only, cutoff, max_out)
         n_close += ns
         n_scored += sc
-        surv.append(pairs)
+        surv.add(pairs)
     tot_scored, tot_close = comm.all_reduce_sum([n_scored, n_close], torch, engine.device)
-    return dict(n_scored=tot_scored, n_close=tot_close, local_scored=n_scored, local_close=n_close,
-                survivors=np.concatenate(surv) if surv else np.zeros((0, 2), dtype=np.uint64), blocks=blocks)
+    return dict(n_scored=tot_scored, n_close=tot_close, local_scored=n_scored, local_close=n_close, survivors=surv, blocks=blocks)
 
 
 def candidate_scan(engine, comm, torch, q_global, n_total, cutoff):
@@ -243,6 +268,7 @@ class GpuEngine:
         return self.seqs
 
     def count(self):
+        self._slot = 0          # a new step: the per-block survivor buffers are free again
         # steady state: recount into the same device allocation (cudaMalloc / cudaFree stall the device)
         hs = getattr(self, "local_hset", None)
         if hs is not None and len(hs) == len(self.seqs):
@@ -325,20 +351,28 @@ class GpuEngine:
         return self.ctx.merge_centers(self.model, sc, len(rows), delta, cutoff)
 
     def sweep(self, q0, q1, upper_only, cutoff, max_out):
-        # survivor buffers: allocated once, page-locked, reused by every sweep of this engine (fresh pageable arrays cost
-        # page faults + a staged copy per call)
-        if getattr(self, "_surv", None) is None or len(self._surv[0]) < max_out:
-            for old in getattr(self, "_surv_pinned", None) or ():
-                self.capi.host_unregister(old)
+        # survivor buffers: one page-locked triple per block of a step, allocated once and reused by every step (fresh
+        # pageable arrays cost page faults + a staged copy per call; a shared triple would force a host copy per block)
+        slots = getattr(self, "_surv_slots", None)
+        if slots is None:
+            slots = self._surv_slots = []
+        slot = getattr(self, "_slot", 0)
+        self._slot = slot + 1
+        while len(slots) <= slot:
+            slots.append(None)
+        if slots[slot] is None or len(slots[slot][0]) < max_out:
+            if slots[slot] is not None:
+                for old in slots[slot][3]:
+                    self.capi.host_unregister(old)
             bufs = (np.zeros(max_out, dtype=np.uint64), np.zeros(max_out, dtype=np.uint64), np.zeros(max_out, dtype=np.float64))
-            self._surv_pinned = []
+            pinned = []
             for b in bufs:
                 try:
                     self.capi.host_register(b)
-                    self._surv_pinned.append(b)
+                    pinned.append(b)
                 except self.capi.Mc2Error:      # locked-memory limit: pageable buffers still work
                     pass
-            self._surv = bufs
+            slots[slot] = bufs + (pinned,)
         r = self.ctx.all_pairs(self.model, self.full, self.full, cutoff, q_range=(q0, q1), upper_only=upper_only,
-                               max_out=max_out, out=self._surv)
-        return r["n_out"], r["n_scored"], np.stack([r["q"], r["d"]], axis=1)
+                               max_out=max_out, out=slots[slot][:3])
+        return r["n_out"], r["n_scored"], (r["q"], r["d"])
