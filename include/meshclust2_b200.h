@@ -175,6 +175,16 @@ int mc2_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, m
  * guard and hashes k characters from the segment start, reading past it (quirk Q6) - there is no result to reproduce. */
 int mc2_count_kmers_auto(mc2_ctx *ctx, const mc2_seqs *seqs, int k, uint64_t *largest_count, int *elem_bytes,
 			 mc2_hset **out);
+/* Multi-GPU exchange without staging copies (per-rank K1 shards all-gathered into the full set):
+ * mc2_hset_alloc makes an n-row set with zeroed rows; mc2_count_kmers_into_rows runs K1 (Loader<T>::get_point,
+ * src/clutil/Loader.cpp:138-179) for `seqs` straight into rows [first_row, first_row + n_seqs) of it; the caller then
+ * lets the collective (e.g. an in-place NCCL all-gather) write the other ranks' bins / mag / len through the device
+ * pointers (mc2_hset_device_bins, mc2_hset_device_sideband) and calls mc2_hset_refresh, which recomputes the true bin
+ * sums (and the magnitudes when set_mag != 0) and drops every derived cache. */
+int mc2_hset_alloc(mc2_ctx *ctx, uint64_t n, int k, int elem_bytes, mc2_hset **out);
+int mc2_count_kmers_into_rows(mc2_ctx *ctx, const mc2_seqs *seqs, mc2_hset *dst, uint64_t first_row);
+int mc2_hset_refresh(mc2_ctx *ctx, mc2_hset *h, int32_t set_mag);
+
 /* "Largest count" of a set produced by mc2_count_kmers(_into/_auto); MC2_ERR_UNSUPPORTED for sets built from
  * histograms (their multiplicities before saturation are unknown). */
 int mc2_hset_largest_count(const mc2_hset *h, uint64_t *largest_count);

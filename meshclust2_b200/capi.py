@@ -35,7 +35,7 @@ SYMBOLS = [
     "mc2_abi_version", "mc2_last_error", "mc2_device_count", "mc2_ctx_create", "mc2_ctx_destroy", "mc2_ctx_sync",
     "mc2_ctx_device", "mc2_ctx_sm_count", "mc2_ctx_stream", "mc2_timer_start", "mc2_timer_stop",
     "mc2_ctx_launch_count", "mc2_ctx_profile", "mc2_ctx_kernel_time", "mc2_ctx_flush_l2", "mc2_seqs_upload", "mc2_seqs_upload_into", "mc2_seqs_from_text", "mc2_seqs_from_text_into", "mc2_seqs_download_segments", "mc2_seqs_total_segments", "mc2_host_register", "mc2_host_unregister", "mc2_seqs_free", "mc2_seqs_count",
-    "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_count_kmers_into", "mc2_count_kmers_auto", "mc2_hset_largest_count", "mc2_width_for_count", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_update_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
+    "mc2_seqs_total_bases", "mc2_count_kmers", "mc2_count_kmers_into", "mc2_count_kmers_auto", "mc2_hset_largest_count", "mc2_hset_alloc", "mc2_count_kmers_into_rows", "mc2_hset_refresh", "mc2_width_for_count", "mc2_kmer_table_increment", "mc2_hset_from_host", "mc2_hset_from_device", "mc2_hset_update_from_device", "mc2_hset_device_sideband", "mc2_hset_free",
     "mc2_hset_count", "mc2_hset_k", "mc2_hset_elem_bytes", "mc2_hset_device_bins", "mc2_hset_download", "mc2_hset_copy_to_device",
     "mc2_hset_set_sideband", "mc2_hset_set_row", "mc2_hset_assign_rows", "mc2_model_create", "mc2_model_free", "mc2_model_desc_from_file",
     "mc2_score_pairs", "mc2_get_close", "mc2_get_close_as", "mc2_filter", "mc2_filter_as", "mc2_merge", "mc2_all_pairs", "mc2_debug_tile_reductions", "mc2_distance", "mc2_mean_closest", "mc2_closest",
@@ -248,6 +248,15 @@ class Context:
         _check(lib().mc2_hset_from_host(self.h, _p(bins), C.c_uint64(n), k, bins.dtype.itemsize, _p(mag), _p(length),
                                         C.byref(out)))
         return HistSet(self, out)
+
+    def hset_alloc(self, n, k, elem_bytes):
+        """an n-row set with zeroed rows, to be filled by count_kmers_into_rows / a collective + refresh()"""
+        out = C.c_void_p()
+        _check(lib().mc2_hset_alloc(self.h, C.c_uint64(n), k, elem_bytes, C.byref(out)))
+        return HistSet(self, out)
+
+    def count_kmers_into_rows(self, seqs, hset, first_row):
+        _check(lib().mc2_count_kmers_into_rows(self.h, seqs.h, hset.h, C.c_uint64(first_row)))
 
     def hset_from_device(self, d_bins, n, k, elem_bytes, d_len, d_mag=None):
         """d_bins / d_len / d_mag: raw device pointers (ints), e.g. torch_tensor.data_ptr()"""
@@ -505,6 +514,10 @@ class HistSet:
     def update_from_device(self, d_bins, d_len, d_mag=None):
         _check(lib().mc2_hset_update_from_device(self.ctx.h, self.h, C.c_void_p(d_bins), C.c_void_p(d_mag) if d_mag else None,
                                                  C.c_void_p(d_len)))
+
+    def refresh(self, set_mag=False):
+        """after external writes through the device pointers: recompute the true sums, drop the derived caches"""
+        _check(lib().mc2_hset_refresh(self.ctx.h, self.h, int(set_mag)))
 
     def device_sideband(self, which):
         """0 mag, 1 len, 2 sum, 3 sumsq -> raw device pointer"""

@@ -1057,6 +1057,80 @@ int mc2_count_kmers(mc2_ctx *ctx, const mc2_seqs *seqs, int k, int elem_bytes, m
 	return MC2_OK;
 }
 
+int mc2_hset_alloc(mc2_ctx *ctx, uint64_t n, int k, int elem_bytes, mc2_hset **out)
+{
+	MC2_REQUIRE(ctx && out, "mc2_hset_alloc: NULL argument");
+	*out = nullptr;
+	int rc = check_k_eb(k, elem_bytes);
+	if (rc != MC2_OK) return rc;
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	mc2_hset *h = nullptr;
+	rc = alloc_hset(ctx, n, k, elem_bytes, &h);
+	if (rc != MC2_OK) return rc;
+	const u64 nn = n ? n : 1;
+	cudaStream_t st = ctx->stream;
+	cudaError_t e = cudaMemsetAsync(h->bins, 0, nn * h->N * (u64)elem_bytes, st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(h->mag, 0, nn * 8, st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(h->sum, 0, nn * 8, st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(h->sumsq, 0, nn * 8, st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(h->len, 0, nn * 8, st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(h->mers1, 0, nn * 32, st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(h->stddev, 0, nn * 8, st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(h->novf, 0, nn * 4, st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(h->maxc, 0, nn * 4, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) {
+		mc2_hset_free(h);
+		return cuda_fail(e, "mc2_hset_alloc", __FILE__, __LINE__);
+	}
+	*out = h;
+	return MC2_OK;
+}
+
+int mc2_count_kmers_into_rows(mc2_ctx *ctx, const mc2_seqs *seqs, mc2_hset *dst, uint64_t first_row)
+{
+	MC2_REQUIRE(ctx && seqs && dst, "mc2_count_kmers_into_rows: NULL argument");
+	MC2_REQUIRE(first_row <= dst->n && seqs->n <= dst->n - first_row, "mc2_count_kmers_into_rows: rows out of range");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	dst->lane_off_valid = 0;
+	dst->cum16_valid = 0;
+	dst->counted = 0;
+	if (seqs->n == 0) {
+		return MC2_OK;
+	}
+	// a window of the destination set: the same arrays, offset by first_row
+	mc2_hset view = *dst;
+	view.n = seqs->n;
+	view.bins = (char *)dst->bins + first_row * dst->N * (u64)dst->eb;
+	view.mag = dst->mag + first_row;
+	view.sum = dst->sum + first_row;
+	view.sumsq = dst->sumsq + first_row;
+	view.len = dst->len + first_row;
+	view.mers1 = dst->mers1 + first_row * 4;
+	view.stddev = dst->stddev + first_row;
+	view.novf = dst->novf + first_row;
+	view.maxc = dst->maxc + first_row;
+	view.lane_off = nullptr;
+	view.cum16 = nullptr;
+	view.cumsum = nullptr;
+	return count_into(ctx, seqs, dst->k, dst->eb, 1, &view);
+}
+
+int mc2_hset_refresh(mc2_ctx *ctx, mc2_hset *h, int32_t set_mag)
+{
+	MC2_REQUIRE(ctx && h, "mc2_hset_refresh: NULL argument");
+	MC2_CUDA(cudaSetDevice(ctx->device));
+	h->lane_off_valid = 0;
+	h->cum16_valid = 0;
+	h->counted = 0;
+	if (h->n == 0) {
+		return MC2_OK;
+	}
+	int rc = launch_sideband(ctx, h, set_mag != 0);
+	if (rc == MC2_OK) rc = refresh_max_sum(ctx, h);
+	return rc;
+}
+
 int mc2_hset_largest_count(const mc2_hset *h, uint64_t *largest_count)
 {
 	MC2_REQUIRE(h && largest_count, "mc2_hset_largest_count: NULL argument");

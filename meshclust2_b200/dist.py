@@ -107,10 +107,14 @@ def all_pairs_step(engine, comm, torch, n_total, cutoff, upper_only=True, blocks
     engine.use_local_as_full()      single rank: the counted shard is the database (no copy, no collective)
     engine.sweep(q0, q1, upper_only, cutoff, max_out) -> (n_survivors, n_scored, survivors: array [m,2] or (q[m], d[m]))
     Returns dict(n_scored, n_close, survivors (this rank's), blocks)."""
-    engine.count()
-    if comm.world == 1:
+    if comm.world > 1 and hasattr(engine, "count_and_gather_in_place"):
+        # the product engine: K1 writes this rank's rows straight into the full set, the all-gathers run in place on it
+        engine.count_and_gather_in_place(comm, n_total)
+    elif comm.world == 1:
+        engine.count()
         engine.use_local_as_full()
     else:
+        engine.count()
         bins, length, mag = engine.export_local()
         bins = comm.all_gather_rows(bins, torch)
         length = comm.all_gather_rows(length, torch)
@@ -267,8 +271,17 @@ class GpuEngine:
         self.seqs = self.ctx.upload_seqs(enc["codes"], enc["seq_off"], enc["segs"], enc["seg_off"])
         return self.seqs
 
+    def _local(self):
+        """(set, first row, rows) of this rank's shard: its own set after count(), a window of the full set after
+        count_and_gather_in_place()"""
+        base = getattr(self, "_local_in_full", None)
+        if base is not None:
+            return self.full, base, self.n_local
+        return self.local_hset, 0, len(self.local_hset)
+
     def count(self):
         self._slot = 0          # a new step: the per-block survivor buffers are free again
+        self._local_in_full = None
         # steady state: recount into the same device allocation (cudaMalloc / cudaFree stall the device)
         hs = getattr(self, "local_hset", None)
         if hs is not None and len(hs) == len(self.seqs):
@@ -278,10 +291,43 @@ class GpuEngine:
                 hs.free()
             self.local_hset = self.ctx.count_kmers(self.seqs, self.k, self.eb)
 
+    class _DevArray:
+        """a raw device allocation as a __cuda_array_interface__ object (torch.as_tensor wraps it without a copy)"""
+
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+    def count_and_gather_in_place(self, comm, n_total):
+        """K1 for this rank's shard into rows [rank * per, ...) of the full set, then ONE in-place all-gather each for the
+        bins, the lengths and the magnitudes (NCCL reads every rank's own slice of the output buffer): no export copy, no
+        install copy, no compaction -- the padding rows of the tail shard sit past n_total and are never swept."""
+        torch = self.torch
+        self._slot = 0
+        rows = self.per * comm.world
+        full = getattr(self, "_gfull", None)
+        if full is None or len(full) != rows:
+            if full is not None:
+                full.free()
+            full = self._gfull = self.ctx.hset_alloc(rows, self.k, self.eb)
+            ts = {1: "|u1", 2: "<u2", 4: "<u4", 8: "<u8"}[self.eb]
+            self._gt = (torch.as_tensor(self._DevArray(full.device_bins(), (rows, self.N), ts), device=self.device),
+                        torch.as_tensor(self._DevArray(full.device_sideband(1), (rows,), "<i8"), device=self.device),
+                        torch.as_tensor(self._DevArray(full.device_sideband(0), (rows,), "<i8"), device=self.device))
+        self.ctx.count_kmers_into_rows(self.seqs, full, comm.rank * self.per)    # synchronises the ctx stream
+        lo = comm.rank * self.per
+        for t in self._gt:
+            comm.dist.all_gather_into_tensor(t, t[lo:lo + self.per])
+        torch.cuda.synchronize(self.device)
+        full.refresh(set_mag=False)
+        self.full = full
+        self.n_total = n_total
+        self._local_in_full = comm.rank * self.per      # this rank's shard lives inside the full set
+
     def use_local_as_full(self):
-        if self.full is not None and self.full is not self.local_hset:
+        if self.full is not None and self.full is not self.local_hset and self.full is not getattr(self, "_gfull", None):
             self.full.free()
         self.full = self.local_hset
+        self.n_total = None
 
     def export_local(self):
         torch = self.torch
@@ -298,6 +344,7 @@ class GpuEngine:
 
     def install_full(self, bins, length, mag, n_total):
         self.torch.cuda.synchronize(self.device)
+        self.n_total = None
         if self.full is not None and self.full is not self.local_hset and len(self.full) == n_total:
             self.full.update_from_device(bins.data_ptr(), length.data_ptr(), mag.data_ptr())
             return
@@ -315,7 +362,8 @@ class GpuEngine:
     def local_query(self, row_local):
         bins, length, mag = self.empty_query()
         self.torch.cuda.synchronize(self.device)
-        self.local_hset.copy_to_device(bins.data_ptr(), mag.data_ptr(), length.data_ptr(), row_local, 1)
+        hs, base, _ = self._local()
+        hs.copy_to_device(bins.data_ptr(), mag.data_ptr(), length.data_ptr(), base + row_local, 1)
         return bins, length, mag
 
     def scan_local(self, bins, length, mag, cutoff):
@@ -324,10 +372,10 @@ class GpuEngine:
             self._qset = self.ctx.hset_from_device(bins.data_ptr(), 1, self.k, self.eb, length.data_ptr(), mag.data_ptr())
         else:
             self._qset.update_from_device(bins.data_ptr(), length.data_ptr(), mag.data_ptr())
-        n = len(self.local_hset)
+        hs, base, n = self._local()
         if n == 0:
             return -1, -1.0, True, np.zeros(0, dtype=np.uint8)
-        return self.ctx.get_close(self.model, self._qset, 0, self.local_hset, cand_begin=0, n_cand=n, cutoff=cutoff)
+        return self.ctx.get_close(self.model, self._qset, 0, hs, cand_begin=base, n_cand=n, cutoff=cutoff)
 
     # ---- update stage (update_pass / merge_pass) over the replicated set self.full ----
     def _stage_centers(self, rows, mag, length):
@@ -373,6 +421,7 @@ class GpuEngine:
                 except self.capi.Mc2Error:      # locked-memory limit: pageable buffers still work
                     pass
             slots[slot] = bufs + (pinned,)
-        r = self.ctx.all_pairs(self.model, self.full, self.full, cutoff, q_range=(q0, q1), upper_only=upper_only,
-                               max_out=max_out, out=slots[slot][:3])
+        nd = min(len(self.full), getattr(self, "n_total", None) or len(self.full))   # rows past n_total are shard padding
+        r = self.ctx.all_pairs(self.model, self.full, self.full, cutoff, q_range=(q0, q1), d_range=(0, nd),
+                               upper_only=upper_only, max_out=max_out, out=slots[slot][:3])
         return r["n_out"], r["n_scored"], (r["q"], r["d"])
