@@ -305,7 +305,9 @@ int mc2_filter(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_c, uint
 	       const uint64_t *members, uint64_t n_members, double id, uint8_t *keep);
 
 /* Trainer<T>::merge (src/cluster/Trainer.cpp:74-109): center row rows[cur] vs rows[begin..last] of `centers`;
- * *out = chosen index in [begin,last] or 0 when none is close. */
+ * *out = chosen index in [begin,last] or 0 when none is close. 
+ * MC2_ERR_UNSUPPORTED for a regression model or a bias outside [-0.5, 0.5): the reference merges on round(score) == 1
+ * (Trainer.cpp:100-103), the device flags round(score) > 0; callers then apply the rule to mc2_score_pairs outputs. */
 int mc2_merge(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *centers, const uint64_t *rows, int64_t cur,
 	      int64_t begin, int64_t last, double id, int64_t *out);
 

@@ -41,6 +41,27 @@
 
 namespace {
 
+// owning handles: the device objects are released on every path out of a scope, exceptions included
+struct SeqsHandle {
+	mc2_seqs *p = nullptr;
+	~SeqsHandle()
+	{
+		if (p) {
+			mc2_seqs_free(p);
+		}
+	}
+};
+struct HsetHandle {
+	mc2_hset *p = nullptr;
+	~HsetHandle()
+	{
+		if (p) {
+			mc2_hset_free(p);
+		}
+	}
+};
+
+
 template <class T>
 struct DeviceWidth {
 	static const int bytes = 0; // int / double histograms: not a device width
@@ -266,12 +287,10 @@ bool mc2_batched_effective_length(const std::string &fasta, bool is_single_file,
 	{
 		std::lock_guard<std::mutex> lock(mc2i::device_mutex());
 		mc2_ctx *ctx = mc2i::shared_ctx();
-		mc2_seqs *sq = nullptr;
-		mc2i::ok(mc2_seqs_from_text(ctx, doubled.data(), off.data(), n, &sq));
-		segs.resize(2 * mc2_seqs_total_segments(sq));
-		const int rc = mc2_seqs_download_segments(ctx, sq, segs.data(), seg_off.data(), nullptr);
-		mc2_seqs_free(sq);
-		mc2i::ok(rc);
+		SeqsHandle sq;
+		mc2i::ok(mc2_seqs_from_text(ctx, doubled.data(), off.data(), n, &sq.p));
+		segs.resize(2 * mc2_seqs_total_segments(sq.p));
+		mc2i::ok(mc2_seqs_download_segments(ctx, sq.p, segs.data(), seg_off.data(), nullptr));
 	}
 	sum_effective = 0;
 	for (size_t s2 = 0; s2 + 1 < segs.size(); s2 += 2) {
@@ -292,17 +311,17 @@ bool mc2_batched_largest_count(const std::string &fasta, bool is_single_file, in
 	}
 	std::lock_guard<std::mutex> lock(mc2i::device_mutex());
 	mc2_ctx *ctx = mc2i::shared_ctx();
-	mc2_seqs *sq = nullptr;
-	int rc = mc2_seqs_from_text(ctx, rec->text.data(), rec->seq_off.data(), rec->headers.size(), &sq);
+	SeqsHandle sq;
+	HsetHandle hs;
+	int rc = mc2_seqs_from_text(ctx, rec->text.data(), rec->seq_off.data(), rec->headers.size(), &sq.p);
 	if (rc == MC2_ERR_INPUT) {
 		throw InvalidInputException(std::string("Invalid nucleotide: ") + mc2_last_error());
 	}
 	mc2i::ok(rc);
-	mc2_hset *hs = nullptr;
+	// (when the largest count exceeds 255, mc2_count_kmers_auto counts a second time at the wider width; that set is not
+	// needed here, but the call is the one that declines on segments shorter than k)
 	int eb = 0;
-	rc = mc2_count_kmers_auto(ctx, sq, k, &largest, &eb, &hs);
-	mc2_hset_free(hs);
-	mc2_seqs_free(sq);
+	rc = mc2_count_kmers_auto(ctx, sq.p, k, &largest, &eb, &hs.p);
 	if (rc == MC2_ERR_INPUT) {
 		return false;
 	}
@@ -338,8 +357,10 @@ bool mc2_batched_read_points(const std::string &fasta, bool is_single_file, uint
 		std::lock_guard<std::mutex> lock(mc2i::device_mutex());
 		mc2_ctx *ctx = mc2i::shared_ctx();
 		ph.mark("wait for the CUDA context");
-		mc2_seqs *sq = nullptr;
-		mc2_hset *hs = nullptr;
+		SeqsHandle sqh;
+		HsetHandle hsh;
+		mc2_seqs *&sq = sqh.p;
+		mc2_hset *&hs = hsh.p;
 		int rc = mc2_seqs_from_text(ctx, text.data(), seq_off.data(), n, &sq);
 		ph.mark("mc2_seqs_from_text");
 		if (rc == MC2_ERR_INPUT) {
@@ -358,8 +379,6 @@ bool mc2_batched_read_points(const std::string &fasta, bool is_single_file, uint
 					       maxc.data());
 		}
 		ph.mark("histograms back");
-		mc2_hset_free(hs);
-		mc2_seqs_free(sq);
 		mc2i::ok(rc);
 	}
 	// the host objects (integration/build_points.h)

@@ -23,15 +23,18 @@
 #include "clutil/DivergencePoint.h"
 #include "predict/Predictor.h"
 
+#include <atomic>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
 #include <map>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
+#include <unordered_map>
 
 #include "meshclust2_b200.h"
 #include "device_b200.h"
@@ -45,7 +48,11 @@ using mc2i::ok;
 struct Device {
 	mc2_ctx *ctx = nullptr;
 	mc2_model *model = nullptr;
-	mc2_hset *points = nullptr;   // row = Point::get_id()
+	mc2_hset *points = nullptr;   // row = Point::get_id(); rows are filled as their points are first seen (see rows_of)
+	uint64_t cap = 0;             // rows allocated in `points`
+	std::vector<uint8_t> present; // row id holds the histogram of the point that currently carries that id
+	std::vector<const void *> owner; // the point object a row was filled from (NULL: filled from a center clone)
+	std::vector<uint64_t> hmag, hlen; // host copies of the rows' side-band (needed when the set is re-allocated)
 	mc2_hset *scratch = nullptr;  // assembled center rows (filter: 1, merge: <= 1 + delta)
 	uint64_t scratch_rows = 0;
 	mc2_hset *centers = nullptr;  // every center of an update / merge pass (batched stage)
@@ -95,6 +102,7 @@ struct Prewarm {
 	mc2_hset *points = nullptr;
 	std::string err;
 	bool started = false;
+	std::atomic<bool> cancel{false};
 	~Prewarm()
 	{
 		if (th.joinable()) {
@@ -147,7 +155,125 @@ mc2_model_desc describe(const Feature<T> &feat, const matrix::Matrix &weights)
 	return d;
 }
 
-// lazily mirror the Trainer's state on the device: the model once, the points (indexed by their final ids) once
+// The device mirror of the points is keyed by Point::get_id() and filled lazily.  CRunner assigns the final ids after the
+// Trainer was built when --no-train-list files are given (src/cluster/CRunner.cpp:576-592: the extra points are appended, the
+// whole vector re-sorted and re-numbered), so a row may hold the histogram of a point that no longer carries that id.  Every
+// real point is therefore checked against the object its row was filled from; the first mismatch drops the whole mirror and
+// the rows are refilled from the objects actually seen.  Center clones carry the id of the point whose bins they copied
+// (DivergencePoint::set copies points + id, src/clutil/DivergencePoint.cpp:182-190), so a clone can fill a missing row too.
+template <class T>
+void grow_points(Device &d, uint64_t need)
+{
+	if (need <= d.cap) {
+		return;
+	}
+	uint64_t cap = std::max<uint64_t>(need, d.cap + d.cap / 2 + 1024);
+	const size_t N = (size_t)1 << (2 * d.k);
+	mc2_hset *fresh = nullptr;
+	{
+		std::vector<T> ones((size_t)cap * N, 1);
+		std::vector<uint64_t> len1(cap, 1);
+		ok(mc2_hset_from_host(d.ctx, ones.data(), cap, d.k, (int)sizeof(T), nullptr, len1.data(), &fresh));
+	}
+	if (d.points) {
+		std::vector<uint64_t> idx, mag, len;
+		for (uint64_t r = 0; r < d.present.size(); r++) {
+			if (d.present[r]) {
+				idx.push_back(r);
+				mag.push_back(d.hmag[r]);
+				len.push_back(d.hlen[r]);
+			}
+		}
+		if (!idx.empty()) {
+			ok(mc2_hset_assign_rows(d.ctx, fresh, idx.size(), idx.data(), d.points, idx.data(), mag.data(), len.data()));
+		}
+		mc2_hset_free(d.points);
+	}
+	d.points = fresh;
+	d.cap = cap;
+	d.present.resize(cap, 0);
+	d.owner.resize(cap, nullptr);
+	d.hmag.resize(cap, 0);
+	d.hlen.resize(cap, 0);
+}
+
+// rows of `objs` in the device mirror; real = the objects are the points themselves (not center clones)
+template <class T>
+void rows_of(Device &d, const std::vector<Point<T> *> &objs, bool real, std::vector<uint64_t> &rows)
+{
+	rows.resize(objs.size());
+	for (int attempt = 0; attempt < 2; attempt++) {
+		std::vector<size_t> missing;
+		bool stale = false;
+		uint64_t max_id = 0;
+		for (size_t i = 0; i < objs.size(); i++) {
+			const uint64_t id = objs[i]->get_id();
+			rows[i] = id;
+			max_id = std::max(max_id, id);
+			if (id >= d.cap || !d.present[id]) {
+				missing.push_back(i);
+			} else if (real && d.owner[id] != nullptr && d.owner[id] != (const void *)objs[i]) {
+				stale = true;
+				break;
+			}
+		}
+		if (stale) {
+			// the ids were re-assigned after the rows were filled: forget everything, refill from what is seen
+			std::fill(d.present.begin(), d.present.end(), 0);
+			std::fill(d.owner.begin(), d.owner.end(), nullptr);
+			continue;
+		}
+		if (missing.empty()) {
+			return;
+		}
+		grow_points<T>(d, max_id + 1);
+		// one upload for all missing rows of this call (a row may be asked for twice: keep the first)
+		const size_t N = (size_t)1 << (2 * d.k);
+		std::vector<size_t> uniq;
+		for (size_t i : missing) {
+			const uint64_t id = objs[i]->get_id();
+			if (!d.present[id]) {
+				d.present[id] = 1;
+				d.owner[id] = real ? (const void *)objs[i] : nullptr;
+				uniq.push_back(i);
+			}
+		}
+		std::vector<T> bins(uniq.size() * N);
+		std::vector<uint64_t> mag(uniq.size()), len(uniq.size()), dst(uniq.size()), src(uniq.size());
+		for (size_t u = 0; u < uniq.size(); u++) {
+			const DivergencePoint<T> &q = dp<T>(objs[uniq[u]]);
+			const uint64_t id = objs[uniq[u]]->get_id();
+			std::copy(q.points.begin(), q.points.end(), bins.begin() + u * N);
+			// the row's own magnitude is the true bin sum: queries and centers pass theirs explicitly (quirk Q4)
+			uint64_t sum = 0;
+			for (const T &v : q.points) {
+				sum += (uint64_t)v;
+			}
+			mag[u] = d.hmag[id] = real ? q.getPseudoMagnitude() : sum;
+			len[u] = d.hlen[id] = q.get_length();
+			dst[u] = id;
+			src[u] = u;
+		}
+		mc2_hset *tmp = nullptr;
+		ok(mc2_hset_from_host(d.ctx, bins.data(), uniq.size(), d.k, (int)sizeof(T), mag.data(), len.data(), &tmp));
+		const int rc = mc2_hset_assign_rows(d.ctx, d.points, uniq.size(), dst.data(), tmp, src.data(), mag.data(), len.data());
+		mc2_hset_free(tmp);
+		ok(rc);
+		return;
+	}
+	throw std::runtime_error("meshclust2_b200 integration: point ids changed while a batch was being staged");
+}
+
+template <class T>
+uint64_t row_of(Device &d, Point<T> *obj, bool real)
+{
+	std::vector<Point<T> *> one{obj};
+	std::vector<uint64_t> rows;
+	rows_of<T>(d, one, real, rows);
+	return rows[0];
+}
+
+// lazily mirror the Trainer's state on the device: the model once, the points as they are seen
 template <class T>
 Device &device_for(const void *key, const Feature<T> &feat, const matrix::Matrix &weights, const std::vector<Point<T> *> &points,
 		   int k)
@@ -160,20 +286,31 @@ Device &device_for(const void *key, const Feature<T> &feat, const matrix::Matrix
 	Stopwatch sw(g_time.init, once);
 	d.k = k;
 	d.n = points.size();
-	const size_t N = (size_t)1 << (2 * k);
 	auto pre = g_pre.find(key);
 	if (pre != g_pre.end() && pre->second.started) {
 		Prewarm &w = pre->second;
+		w.cancel = true; // a thread still waiting for the device mutex (held by our caller) gives up; a finished one is joined
 		if (w.th.joinable()) {
 			w.th.join();
 		}
-		bool in_order = w.err.empty() && w.ctx && w.points;
-		for (size_t i = 0; in_order && i < points.size(); i++) {
-			in_order = points[i]->get_id() == i;
-		}
-		if (in_order) {
+		if (w.err.empty() && w.ctx && w.points) {
+			// rows were uploaded in the order of the Trainer's vector; rows_of() verifies every row against its object
 			d.ctx = w.ctx;
 			d.points = w.points;
+			d.cap = points.size();
+			d.present.assign(d.cap, 1);
+			d.owner.assign(d.cap, nullptr);
+			d.hmag.resize(d.cap);
+			d.hlen.resize(d.cap);
+			for (size_t i = 0; i < points.size(); i++) {
+				d.owner[i] = (const void *)points[i];
+				d.hmag[i] = dp<T>(points[i]).getPseudoMagnitude();
+				d.hlen[i] = points[i]->get_length();
+				if (points[i]->get_id() != i) {
+					d.present[i] = 0; // not where its id says: will be refilled on first use
+					d.owner[i] = nullptr;
+				}
+			}
 		} else if (w.points) {
 			mc2_hset_free(w.points);
 		}
@@ -183,23 +320,16 @@ Device &device_for(const void *key, const Feature<T> &feat, const matrix::Matrix
 	}
 	if (!d.ctx) {
 		d.ctx = mc2i::shared_ctx();
-		std::vector<T> bins(d.n * N);
-		std::vector<uint64_t> mag(d.n), len(d.n);
-		for (Point<T> *p : points) {
-			const uint64_t id = p->get_id();
-			if (id >= d.n) {
-				throw std::runtime_error("meshclust2_b200 integration: point ids must be 0..n-1 (no --no-train-list support)");
-			}
-			const DivergencePoint<T> &q = dp<T>(p);
-			std::copy(q.points.begin(), q.points.end(), bins.begin() + id * N);
-			mag[id] = q.getPseudoMagnitude();
-			len[id] = q.get_length();
-		}
-		ok(mc2_hset_from_host(d.ctx, bins.data(), d.n, k, (int)sizeof(T), mag.data(), len.data(), &d.points));
+	}
+	if (!d.points) {
+		grow_points<T>(d, std::max<uint64_t>(points.size(), 1));
+		std::vector<uint64_t> rows;
+		rows_of<T>(d, points, true, rows); // the training-time points in one upload
 	}
 	mc2_model_desc desc = describe<T>(feat, weights);
 	ok(mc2_model_create(d.ctx, &desc, &d.model));
 	d.scratch_rows = 64;
+	const size_t N = (size_t)1 << (2 * k);
 	std::vector<T> zero(d.scratch_rows * N, 1);
 	std::vector<uint64_t> ones(d.scratch_rows, 1);
 	ok(mc2_hset_from_host(d.ctx, zero.data(), d.scratch_rows, k, (int)sizeof(T), nullptr, ones.data(), &d.scratch));
@@ -222,7 +352,6 @@ void start_prewarm(const void *key, const std::vector<Point<T> *> &points, int k
 	const std::vector<Point<T> *> *pts = &points;
 	w.th = std::thread([wp, pts, k]() {
 		try {
-			wp->ctx = mc2i::shared_ctx();
 			const size_t n = pts->size(), N = (size_t)1 << (2 * k);
 			std::vector<T> bins(n * N);
 			std::vector<uint64_t> mag(n), len(n);
@@ -232,6 +361,16 @@ void start_prewarm(const void *key, const std::vector<Point<T> *> &points, int k
 				mag[i] = q.getPseudoMagnitude();
 				len[i] = q.get_length();
 			}
+			// one caller per context (include/meshclust2_b200.h): the reader of --no-train-list files may be using the
+			// shared context right now.  device_for() runs with the mutex held and sets `cancel` before it joins.
+			std::unique_lock<std::mutex> lk(mc2i::device_mutex(), std::defer_lock);
+			while (!lk.try_lock()) {
+				if (wp->cancel) {
+					return;
+				}
+				std::this_thread::sleep_for(std::chrono::microseconds(100));
+			}
+			wp->ctx = mc2i::shared_ctx();
 			if (mc2_hset_from_host(wp->ctx, bins.data(), n, k, (int)sizeof(T), mag.data(), len.data(), &wp->points) != MC2_OK) {
 				throw std::runtime_error(mc2_last_error());
 			}
@@ -246,10 +385,10 @@ template <class T>
 void stage_into(Device &d, mc2_hset *into, const std::vector<Point<T> *> &cs)
 {
 	const uint64_t m = cs.size();
-	std::vector<uint64_t> dst(m), src(m), mag(m), len(m);
+	std::vector<uint64_t> dst(m), src, mag(m), len(m);
+	rows_of<T>(d, cs, false, src);
 	for (uint64_t i = 0; i < m; i++) {
 		dst[i] = i;
-		src[i] = cs[i]->get_id();
 		mag[i] = dp<T>(cs[i]).getPseudoMagnitude();
 		len[i] = cs[i]->get_length();
 	}
@@ -300,13 +439,14 @@ std::tuple<Point<T> *, double, size_t, size_t> Trainer<T>::get_close(Point<T> *p
 	Device &d = device_for<T>(this, *feat, weights, points, k);
 	Stopwatch sw(g_time.get_close, g_time.n_get_close);
 	std::vector<uint64_t> cand;
+	std::vector<Point<T> *> cand_pts;
 	std::vector<bvec_iterator<T>> where;
 	// same trip count as the reference's `omp parallel for` over the iterator range: iend - istart (bvec_iterator::operator-),
 	// which is 0 when only empty bins lie between the two positions
 	const int64_t n_iter = iend - istart;
 	bvec_iterator<T> i = istart;
 	for (int64_t t = 0; t < n_iter; t++) {
-		cand.push_back((*i).first->get_id());
+		cand_pts.push_back((*i).first);
 		where.push_back(i);
 		if (t + 1 < n_iter) {
 			++i;
@@ -314,15 +454,17 @@ std::tuple<Point<T> *, double, size_t, size_t> Trainer<T>::get_close(Point<T> *p
 	}
 	std::tuple<Point<T> *, double, size_t, size_t> result(NULL, -1, 0, 0);
 	is_min_r = true;
-	if (cand.empty()) {
+	if (cand_pts.empty()) {
 		return result;
 	}
+	rows_of<T>(d, cand_pts, true, cand);
+	const uint64_t qrow = row_of<T>(d, p, false); // the query may be a clone: addressed by the id it carries
 	int64_t best = -1;
 	double best_dist = -1;
 	int32_t is_min = 1;
 	std::vector<uint8_t> marks(cand.size());
 	// the query is the row of the point whose bins it carries, with its own (possibly stale) magnitude and length
-	ok(mc2_get_close_as(d.ctx, d.model, d.points, p->get_id(), dp<T>(p).getPseudoMagnitude(), p->get_length(), d.points,
+	ok(mc2_get_close_as(d.ctx, d.model, d.points, qrow, dp<T>(p).getPseudoMagnitude(), p->get_length(), d.points,
 			    cand.data(), 0, cand.size(), cutoff, &best, &best_dist, &is_min, marks.data()));
 	for (size_t j = 0; j < cand.size(); j++) {
 		if (marks[j]) {
@@ -358,7 +500,33 @@ long Trainer<T>::merge(vector<Center<T>> &centers, long current, long begin, lon
 		rows[i] = i;
 	}
 	int64_t out = 0;
-	ok(mc2_merge(d.ctx, d.model, d.scratch, rows.data(), 0, 1, (int64_t)cs.size() - 1, get_id(), &out));
+	const int rc = mc2_merge(d.ctx, d.model, d.scratch, rows.data(), 0, 1, (int64_t)cs.size() - 1, get_id(), &out);
+	if (rc == MC2_ERR_UNSUPPORTED) {
+		// --bias outside [-0.5, 0.5): the device's close flag (round(score) > 0) is not the reference's rule
+		// (round(classify_sum(sum)) == 1, src/cluster/Trainer.cpp:100-103).  Scores and first-combo values still come from
+		// the device; the rule is applied here exactly as the reference's loop applies it (later tie wins, :104).
+		const size_t m = cs.size() - 1;
+		mc2_pairs pr = mc2_pairs();
+		pr.set_a = pr.set_b = d.scratch;
+		pr.n_pairs = m;
+		pr.ia = rows.data() + 1;
+		pr.b_begin = 0;
+		pr.b_broadcast = 1;
+		pr.len_filter = 1;
+		pr.anchor_is_b = 1;
+		pr.cutoff = get_id();
+		std::vector<double> score(m), dist(m);
+		std::vector<uint8_t> skipped(m);
+		ok(mc2_score_pairs(d.ctx, d.model, &pr, score.data(), dist.data(), nullptr, nullptr, nullptr, skipped.data()));
+		std::pair<long, double> best = std::make_pair(0L, std::numeric_limits<double>::min());
+		for (size_t j = 0; j < m; j++) {
+			if (!skipped[j] && round(score[j]) == 1) {
+				best = best.second > dist[j] ? best : std::make_pair(begin + (long)j, dist[j]);
+			}
+		}
+		return best.first;
+	}
+	ok(rc);
 	return out == 0 ? 0 : begin + (out - 1);
 }
 
@@ -391,11 +559,14 @@ void Trainer<T>::filter(Point<T> *p, vector<pair<Point<T> *, bool>> &vec) const
 		std::lock_guard<std::mutex> lock(g_mu);
 		Device &d = device_for<T>(this, *feat, weights, points, k);
 		Stopwatch sw(g_time.filter, g_time.n_filter);
-		std::vector<uint64_t> rows(vec.size());
+		std::vector<uint64_t> rows;
+		std::vector<Point<T> *> pts(vec.size());
 		for (size_t j = 0; j < vec.size(); j++) {
-			rows[j] = vec[j].first->get_id();
+			pts[j] = vec[j].first;
 		}
-		ok(mc2_filter_as(d.ctx, d.model, d.points, p->get_id(), dp<T>(p).getPseudoMagnitude(), p->get_length(), d.points,
+		rows_of<T>(d, pts, true, rows);
+		const uint64_t crow = row_of<T>(d, p, false);
+		ok(mc2_filter_as(d.ctx, d.model, d.points, crow, dp<T>(p).getPseudoMagnitude(), p->get_length(), d.points,
 				 rows.data(), rows.size(), get_id(), keep.data()));
 	}
 	size_t w = 0;
@@ -419,10 +590,12 @@ Point<T> *Trainer<T>::closest(Point<double> *p, vector<pair<Point<T> *, bool>> &
 	std::lock_guard<std::mutex> lock(g_mu);
 	Device &d = device_for<T>(this, *feat, weights, points, k);
 	Stopwatch sw(g_time.closest, g_time.n_closest);
-	std::vector<uint64_t> rows(vec.size());
+	std::vector<uint64_t> rows;
+	std::vector<Point<T> *> pts(vec.size());
 	for (size_t j = 0; j < vec.size(); j++) {
-		rows[j] = vec[j].first->get_id();
+		pts[j] = vec[j].first;
 	}
+	rows_of<T>(d, pts, true, rows);
 	const std::vector<double> &mean = p->get_data();
 	int64_t best = -1;
 	double bd = 0;
@@ -492,12 +665,12 @@ bool mc2_batched_update(std::vector<Center<T>> &part, const Trainer<T> &trn, int
 		const long i_begin = std::max(0L, j - delta), i_end = std::min(j + (long)delta, n - 1);
 		for (long i = i_begin; i <= i_end; i++) {
 			for (Point<T> *p : part[i].getPoints()) {
-				members.push_back(p->get_id());
 				who.push_back(p);
 			}
 		}
-		off[(size_t)j + 1] = members.size();
+		off[(size_t)j + 1] = who.size();
 	}
+	rows_of<T>(d, who, true, members);
 	stage_all_centers<T>(d, part);
 	std::vector<int64_t> next((size_t)n);
 	const int rc = mc2_update_centers(d.ctx, d.model, d.centers, (uint64_t)n, d.points, off.data(), members.data(), trn.get_id(),
@@ -535,7 +708,11 @@ bool mc2_batched_merge(std::vector<Center<T>> &centers, const Trainer<T> &trn, i
 		Device &d = it->second;
 		Stopwatch sw(g_time.merge_batch, g_time.n_merge_batch);
 		stage_all_centers<T>(d, centers);
-		ok(mc2_merge_centers(d.ctx, d.model, d.centers, centers.size(), delta, trn.get_id(), ret.data()));
+		const int rc = mc2_merge_centers(d.ctx, d.model, d.centers, centers.size(), delta, trn.get_id(), ret.data());
+		if (rc == MC2_ERR_UNSUPPORTED) {
+			return false; // --bias outside [-0.5, 0.5): the per-center calls apply the reference's rule on the host
+		}
+		ok(rc);
 	}
 	for (size_t i = 0; i < centers.size(); i++) {
 		if (ret[i] > (int64_t)i) {

@@ -56,9 +56,9 @@ struct EarlyContext {
 		if (th.joinable()) {
 			th.join();
 		}
-		if (ctx) {
-			mc2_ctx_destroy(ctx);
-		}
+		// The context is NOT destroyed here: static objects of other translation units (the Trainer's prewarm threads,
+		// the device mirrors) may still be using it, and their destruction order against this one is unspecified.  The
+		// process is exiting; the driver releases the context.
 	}
 } g_early;
 

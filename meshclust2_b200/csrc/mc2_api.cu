@@ -171,6 +171,19 @@ static int sync_stage(mc2_ctx *ctx)
 	return MC2_OK;
 }
 
+// Entry points that stage copies end with sync_stage(); an early error return between a d2h() and that sync leaves entries
+// behind whose destination may be gone by the next call.  Every public entry point that stages starts by dropping them.
+static void drop_stale_stage(mc2_ctx *ctx)
+{
+	CtxExtra *x = extra_of(ctx);
+	if (!x->deferred.empty() || x->stage_used) {
+		cudaStreamSynchronize(ctx->stream);
+		cudaGetLastError();
+		x->deferred.clear();
+		x->stage_used = 0;
+	}
+}
+
 static const size_t kStageBytes = 4u << 20, kStageMaxCopy = 1u << 20;
 
 static char *stage_take(mc2_ctx *ctx, size_t bytes)
@@ -1444,6 +1457,7 @@ int mc2_hset_assign_rows(mc2_ctx *ctx, mc2_hset *dst, uint64_t n, const uint64_t
 		return MC2_OK;
 	}
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	// the destination's lane offsets stay valid when both sides have them (they are copied with the rows)
 	const bool keep_loff = dst->lane_off_valid && src->lane_off_valid && dst->lane_off && src->lane_off;
 	dst->lane_off_valid = keep_loff ? 1 : 0;
@@ -1706,6 +1720,7 @@ int mc2_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs *pairs
 {
 	MC2_REQUIRE(ctx && model && pairs, "mc2_score_pairs: NULL argument");
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	CtxExtra *x = extra(ctx);
 	PairArgs a;
 	int rc = fill_pair_args(ctx, pairs, a, x);
@@ -1806,6 +1821,7 @@ static int get_close_impl(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *
 	MC2_REQUIRE(ctx && model && set_q && set_c && best && best_dist && is_min, "mc2_get_close: NULL argument");
 	MC2_REQUIRE(q < set_q->n, "mc2_get_close: query row out of range");
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	*best = -1;
 	*best_dist = -1;
 	*is_min = 1;
@@ -1855,6 +1871,7 @@ static int filter_impl(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set
 	MC2_REQUIRE(ctx && model && set_c && set_m && (n_members == 0 || (members && keep)), "mc2_filter: NULL argument");
 	MC2_REQUIRE(center < set_c->n, "mc2_filter: center row out of range");
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	if (n_members == 0) return MC2_OK;
 	mc2_pairs p;
 	memset(&p, 0, sizeof p);
@@ -1890,7 +1907,14 @@ int mc2_merge(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *centers, con
 {
 	MC2_REQUIRE(ctx && model && centers && rows && out, "mc2_merge: NULL argument");
 	MC2_REQUIRE(cur >= 0 && begin >= 0, "mc2_merge: negative index");
+	// Trainer<T>::merge merges on round(classify_sum(sum)) == 1 (src/cluster/Trainer.cpp:100-103); the kernels flag
+	// round(score) > 0, which is the same set only while logistic + bias stays below 1.5 and above -0.5
+	if (model->dm.regression || model->dm.bias >= 0.5 || model->dm.bias < -0.5) {
+		set_error("mc2_merge: needs a classifier with -0.5 <= bias < 0.5");
+		return MC2_ERR_UNSUPPORTED;
+	}
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	*out = 0;
 	if (last < begin) return MC2_OK;
 	mc2_pairs p;
@@ -2020,6 +2044,7 @@ int mc2_distance(mc2_ctx *ctx, const mc2_pairs *pairs, uint64_t *out)
 {
 	MC2_REQUIRE(ctx && pairs && out, "mc2_distance: NULL argument");
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	CtxExtra *x = extra(ctx);
 	PairArgs a;
 	int rc = fill_pair_args(ctx, pairs, a, x);
@@ -2059,6 +2084,7 @@ static int mean_closest_impl(mc2_ctx *ctx, const mc2_hset *set, const uint64_t *
 		MC2_REQUIRE(members[j] < set->n, "mc2_mean_closest: member row out of range");
 	}
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	CtxExtra *x = extra(ctx);
 	const u64 N = set->N;
 	int rc = ensure(x->d[B_IA], n * 8, false); if (rc) return rc;
@@ -2117,6 +2143,7 @@ int mc2_update_centers(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *cen
 	const u64 m = member_off[n_centers];
 	MC2_REQUIRE(m == 0 || members, "mc2_update_centers: members is NULL");
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	if (m == 0) {
 		for (u64 c = 0; c < n_centers; c++) {
 			next[c] = -1;
@@ -2174,8 +2201,13 @@ int mc2_merge_centers(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *cent
 {
 	MC2_REQUIRE(ctx && model && centers && (n_centers == 0 || out), "mc2_merge_centers: NULL argument");
 	MC2_REQUIRE(n_centers <= centers->n && delta >= 0, "mc2_merge_centers: bad center count or delta");
+	if (model->dm.regression || model->dm.bias >= 0.5 || model->dm.bias < -0.5) { // see mc2_merge
+		set_error("mc2_merge_centers: needs a classifier with -0.5 <= bias < 0.5");
+		return MC2_ERR_UNSUPPORTED;
+	}
 	if (n_centers == 0) return MC2_OK;
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	std::vector<uint64_t> off(n_centers + 1), ia, ib;
 	for (u64 c = 0; c < n_centers; c++) {
 		off[c] = ia.size();
@@ -2227,6 +2259,7 @@ int mc2_bench_score_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_pairs 
 {
 	MC2_REQUIRE(ctx && model && pairs && avg_ms && iters > 0, "mc2_bench_score_pairs: bad argument");
 	MC2_CUDA(cudaSetDevice(ctx->device));
+	drop_stale_stage(ctx);
 	CtxExtra *x = extra(ctx);
 	PairArgs a;
 	int rc = fill_pair_args(ctx, pairs, a, x);

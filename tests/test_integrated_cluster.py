@@ -34,10 +34,10 @@ def parse_clstr(path):
     return {frozenset(c) for c in clusters if c}
 
 
-def run(binary, fasta, workdir, out, env=None):
+def run(binary, fasta, workdir, out, env=None, extra=()):
     os.makedirs(workdir, exist_ok=True)
-    r = subprocess.run([binary, "--id", "0.9", "--sample", "800", "--num-templates", "120", "--threads", "1", fasta,
-                        "--output", out], cwd=workdir, capture_output=True, text=True, timeout=900,
+    r = subprocess.run([binary, "--id", "0.9", "--sample", "800", "--num-templates", "120", "--threads", "1", fasta] +
+                       list(extra) + ["--output", out], cwd=workdir, capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     # what Runner::find_k and the width detection of Runner::run print (CRunner.cpp:497-498, :93, :109-121)
@@ -63,4 +63,24 @@ def test_same_clusters_as_the_reference(tmp_path):
         assert w_ref == w_our                   # same host training code, same seeds
         c_our = parse_clstr(str(tmp_path / (tag + ".clstr")))
         assert sum(len(c) for c in c_our) == 800
+        assert c_ref == c_our, "%s: clusters differ: %d vs %d clusters, %d in common" % (tag, len(c_ref), len(c_our), len(c_ref & c_our))
+
+
+def test_no_train_list_same_clusters(tmp_path):
+    """--no-train-list: the extra files' points join after the classifier was trained and every id is re-assigned
+    (src/cluster/CRunner.cpp:576-592); the device mirror must follow the new numbering"""
+    seqs, tids = synth.make_set(600, 1000, 90, 0.08, seed=17)
+    train, extra = str(tmp_path / "train.fa"), str(tmp_path / "extra.fa")
+    open(train, "w").write(synth.to_fasta(seqs[:350], tids[:350]))
+    open(extra, "w").write("".join(">x%d template_%d\n%s\n" % (i, tids[350 + i], s.decode()) for i, s in enumerate(seqs[350:])))
+    lst = str(tmp_path / "list.txt")
+    open(lst, "w").write(extra + "\n")
+    args = ("--no-train-list", lst)
+    w_ref, _ = run(REF, train, str(tmp_path / "ref"), str(tmp_path / "ref.clstr"), extra=args)
+    c_ref = parse_clstr(str(tmp_path / "ref.clstr"))
+    assert sum(len(c) for c in c_ref) == 600
+    for tag, env in (("batched", {}), ("percall", {"MC2_NO_BATCH": "1"}), ("noprewarm", {"MC2_NO_PREWARM": "1"})):
+        w_our, _ = run(OURS, train, str(tmp_path / tag), str(tmp_path / (tag + ".clstr")), env, extra=args)
+        assert w_ref == w_our
+        c_our = parse_clstr(str(tmp_path / (tag + ".clstr")))
         assert c_ref == c_our, "%s: clusters differ: %d vs %d clusters, %d in common" % (tag, len(c_ref), len(c_our), len(c_ref & c_our))

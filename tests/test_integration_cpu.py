@@ -46,3 +46,24 @@ def test_host_logic_reproduces_the_reference(stub_binary, tmp_path):
         assert w == w_ref, tag
         c = parse_clstr(str(tmp_path / (tag + ".clstr")))
         assert c == c_ref, "%s: %d vs %d clusters, %d in common" % (tag, len(c_ref), len(c), len(c_ref & c))
+
+
+@pytest.mark.timeout(600)
+def test_no_train_list_host_logic(stub_binary, tmp_path):
+    """--no-train-list (src/cluster/CRunner.cpp:576-592): points appended and every id re-assigned after the Trainer was
+    built; the integration's id-keyed device mirror must notice and refill itself (integration/Trainer_b200.cpp rows_of)"""
+    seqs, tids = synth.make_set(400, 1000, 60, 0.08, seed=17)
+    train, extra = str(tmp_path / "train.fa"), str(tmp_path / "extra.fa")
+    open(train, "w").write(synth.to_fasta(seqs[:250], tids[:250]))
+    open(extra, "w").write("".join(">x%d template_%d\n%s\n" % (i, tids[250 + i], s.decode()) for i, s in enumerate(seqs[250:])))
+    lst = str(tmp_path / "list.txt")
+    open(lst, "w").write(extra + "\n")
+    args = ("--no-train-list", lst)
+    w_ref, _ = run(REF, train, str(tmp_path / "ref"), str(tmp_path / "ref.clstr"), extra=args)
+    c_ref = parse_clstr(str(tmp_path / "ref.clstr"))
+    assert sum(len(c) for c in c_ref) == 400
+    for tag, env in (("batched", {}), ("percall", {"MC2_NO_BATCH": "1"}), ("noprewarm", {"MC2_NO_PREWARM": "1"})):
+        w, _ = run(stub_binary, train, str(tmp_path / tag), str(tmp_path / (tag + ".clstr")), env, extra=args)
+        assert w == w_ref, tag
+        c = parse_clstr(str(tmp_path / (tag + ".clstr")))
+        assert c == c_ref, "%s: %d vs %d clusters, %d in common" % (tag, len(c_ref), len(c), len(c_ref & c))
