@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include <string>
 #include "../../include/meshclust2_b200.h"
 
@@ -84,6 +85,31 @@ struct DevModel {
 	float scr_k1, scr_k0;
 };
 
+// Mailbox of the resident scan server: the accumulate stage of the mean-shift driver issues one Trainer::get_close per
+// query, each depending on the previous result (src/cluster/ClusterFactory.cpp:560-605), tens of candidates at a time, so
+// the cost of a call is launch + copy latency.  The host writes a request into this mapped page-locked block and bumps
+// `seq`; a resident CTA polls it, scores the candidates, reduces the arg-max and writes the answer back; the host polls
+// `seq_done`.  No launch, no memcpy, no stream synchronisation per call.
+#define MC2_SCAN_CAP 512        // longer candidate lists take the launch path
+#define MC2_SCAN_INLINE 10      // candidates that travel inside the request header
+struct ScanMailbox {
+	// Request header: 32 words = four 64-byte lines, fetched by the server with ONE coalesced read per poll.  The host
+	// writes word 0 (the sequence number) last and repeats it in the last word of lines 1-3, so a header whose four
+	// copies agree is complete even if the lines were fetched separately.
+	//  [0] seq  [1] q_row  [2] q_mag  [3] q_len  [4] cand_begin  [5] cutoff (double bits)  [6] n_cand | has_list << 32 | ovr << 33
+	//  [7] quit  [8] binsQ  [9] binsC  [10] magQ  [11] sumQ  [12] sumsqQ  [13] lenQ  [14] N  [15] seq
+	//  [16] magC  [17] sumC  [18] sumsqC  [19] lenC  [20..22] cand 0-2  [23] seq  [24..30] cand 3-9  [31] seq
+	volatile unsigned long long w[32];
+	unsigned long long cand[MC2_SCAN_CAP];      // the whole list when it is longer than MC2_SCAN_INLINE
+	// answer (written by the device): one 64-byte line, seq_done last
+	//  [0] best  [1] best_dist (double bits)  [2] is_min | err << 32  [3..6] marks of the first 32 candidates  [7] seq_done
+	volatile unsigned long long r[8];
+	volatile int running;
+	int pad1[15];
+	unsigned char marks[MC2_SCAN_CAP];          // all marks when there are more than 32 candidates
+};
+static_assert(offsetof(ScanMailbox, cand) == 256, "the scan server reads the request header as 32 eight-byte words");
+
 // side-band SoA of a histogram set (device pointers)
 struct Sideband {
 	const u64 *mag;   // pseudo-magnitude as the host object reports it (may be stale, quirk Q4)
@@ -111,6 +137,12 @@ struct mc2_ctx {
 	int prof_on;      // per-kernel event timing enabled
 	int err_dirty;    // the device error word may be non-zero (set by reset_err, cleared by a clean check_err)
 	void *d_sched;    // tile schedule of the tile sweep (tile_sweep.cu), allocated on first use
+	// resident scan server (pair_score.cu scan_server_kernel): mailbox in mapped page-locked memory, its own stream
+	mc2::ScanMailbox *mb;
+	cudaStream_t server_stream;
+	u64 mb_seq;           // sequence number of the last request posted
+	u64 server_model_uid; // model the running server was launched with
+	int server_eb;
 };
 
 namespace mc2 {
@@ -166,6 +198,7 @@ struct mc2_model {
 	mc2_ctx *ctx;
 	mc2_model_desc desc;
 	mc2::DevModel dm;
+	u64 uid; // identifies the model a resident scan server was started with
 };
 
 namespace mc2 {
@@ -217,6 +250,8 @@ int ensure_lane_off(mc2_ctx *ctx, const mc2_hset *h); // builds h->lane_off if t
 int ensure_cum16(mc2_ctx *ctx, const mc2_hset *h);
 bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset *d);
 int launch_issue_probe(mc2_ctx *ctx, int iters, u32 *d_out, u64 *warp_instr);
+// pair_score.cu: start the resident scan server for 1- or 2-byte bins on ctx->server_stream
+int launch_scan_server(mc2_ctx *ctx, const DevModel &dm, int eb, u64 first_seq);
 int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset *q, u64 q0, u64 q1, const mc2_hset *d, u64 d0, u64 d1,
 		      int upper_only, double cutoff, u64 max_out, u64 *d_out_q, u64 *d_out_d, double *d_out_score, u64 *d_counters,
 		      u32 *raw_dot, u32 *raw_emd, u32 *raw_sad);

@@ -2129,6 +2129,248 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 	return MC2_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Resident scan server (see ScanMailbox in mc2_internal.cuh): Trainer<T>::get_close (src/cluster/Trainer.cpp:23-71) for
+// small candidate lists without a launch per call.  One CTA of 16 warps; a warp scores one candidate at a time with the
+// same row reduction and the same fp64 epilogue as pair_fast_kernel, the CTA reduces the first maximum of the first
+// combo value over the in-window candidates (strict >, initial -1: Trainer.cpp:52-56) and the close marks.
+// The server leaves after MC2_SCAN_IDLE_NS without a request, so nothing that waits for an idle device (cudaFree,
+// cudaMalloc) waits longer than that.
+// ------------------------------------------------------------------------------------------------
+#ifndef MC2_SCAN_IDLE_NS
+#define MC2_SCAN_IDLE_NS 300000ull
+#endif
+__device__ __forceinline__ unsigned long long ld_sys_u64(const volatile unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512, 1) scan_server_kernel(const __grid_constant__ DevModel dm, ScanMailbox *mb, u64 first_seq)
+{
+	__shared__ unsigned long long s_hdr[32];      // the request header
+	__shared__ unsigned long long s_cand[MC2_SCAN_CAP];
+	__shared__ double s_dist[MC2_SCAN_CAP];
+	__shared__ unsigned char s_flag[MC2_SCAN_CAP]; // 1 close, 2 skipped / not scored
+	__shared__ double s_bd[16];
+	__shared__ long long s_bi[16];
+	__shared__ int s_any[16], s_err, s_go;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	constexpr int NW = 16;
+	u64 last = first_seq - 1;
+	for (;;) {
+		if (warp == 0) {
+			// every poll fetches the whole header with one coalesced read; it is taken when its four sequence copies agree
+			const unsigned long long t0 = global_ns();
+			int go = 0;
+			for (;;) {
+				const unsigned long long v = ld_sys_u64(&mb->w[lane]);
+				const unsigned long long s0 = __shfl_sync(0xffffffffu, v, 0);
+				const bool whole = __shfl_sync(0xffffffffu, v, 15) == s0 && __shfl_sync(0xffffffffu, v, 23) == s0 &&
+						   __shfl_sync(0xffffffffu, v, 31) == s0;
+				if (s0 != last && whole) {
+					s_hdr[lane] = v;
+					go = 1;
+					break;
+				}
+				if (__shfl_sync(0xffffffffu, v, 7) != 0 || global_ns() - t0 > MC2_SCAN_IDLE_NS) {
+					break;
+				}
+			}
+			if (lane == 0) {
+				s_go = go;
+				s_err = 0;
+			}
+		}
+		__syncthreads();
+		if (!s_go) {
+			break;
+		}
+		last = s_hdr[0];
+		const u64 q_row = s_hdr[1];
+		const u32 n = (u32)(s_hdr[6] & 0xFFFFFFFFull);
+		const bool has_list = (s_hdr[6] >> 32) & 1, ovr = (s_hdr[6] >> 33) & 1;
+		const double cutoff = __longlong_as_double((long long)s_hdr[5]);
+		if (has_list) {
+			if (n <= MC2_SCAN_INLINE) {
+				if (threadIdx.x < n) {
+					s_cand[threadIdx.x] = threadIdx.x < 3 ? s_hdr[20 + threadIdx.x] : s_hdr[24 + threadIdx.x - 3];
+				}
+			} else {
+				for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
+					s_cand[j] = ld_sys_u64(&mb->cand[j]);
+				}
+			}
+			__syncthreads();
+		}
+		const u64 N = s_hdr[14];
+		const u32 slabs = (u32)(N * sizeof(T) / 1024);
+		const T *Q = reinterpret_cast<const T *>(s_hdr[8]) + q_row * N;
+		const T *C = reinterpret_cast<const T *>(s_hdr[9]);
+		const u64 *magQ = reinterpret_cast<const u64 *>(s_hdr[10]), *sumQ = reinterpret_cast<const u64 *>(s_hdr[11]);
+		const u64 *sumsqQ = reinterpret_cast<const u64 *>(s_hdr[12]), *lenQ = reinterpret_cast<const u64 *>(s_hdr[13]);
+		const u64 *magC = reinterpret_cast<const u64 *>(s_hdr[16]), *sumC = reinterpret_cast<const u64 *>(s_hdr[17]);
+		const u64 *sumsqC = reinterpret_cast<const u64 *>(s_hdr[18]), *lenC = reinterpret_cast<const u64 *>(s_hdr[19]);
+		Side sq;
+		sq.mag = ovr ? s_hdr[2] : magQ[q_row];
+		sq.len = ovr ? s_hdr[3] : lenQ[q_row];
+		sq.sum = sumQ[q_row];
+		sq.sumsq = sumsqQ[q_row];
+		// length window on the candidate, anchored at the query (Trainer.cpp:39-48: u64 truncation)
+		const u64 min_len = (u64)((double)sq.len * cutoff), max_len = (u64)((double)sq.len / cutoff);
+		// a warp reduces its (up to 32) candidates one after the other, keeping candidate i's sums in lane i; then the
+		// lanes run the fp64 epilogue side by side
+		const u32 chunk = (n + NW - 1) / NW;
+		const u32 first = (u32)warp * chunk;
+		RedN mine;
+		mine.smin = mine.dot = mine.emd = 0;
+		mine.jeff = mine.js = 0;
+		u64 my_c = 0, my_len = 0;
+		bool my_go = false;
+		for (u32 i = 0; i < chunk && first + i < n; i++) {
+			const u64 c = has_list ? s_cand[first + i] : s_hdr[4] + first + i;
+			const u64 lc = lenC[c];
+			const bool inwin = lc >= min_len && lc <= max_len;
+			if (inwin) {
+				const RedN r = reduce_rows_fast<T, 7>(C + c * N, Q, slabs, lane, true);
+				if (lane == (int)i) {
+					mine = r;
+				}
+			}
+			if (lane == (int)i) {
+				my_c = c;
+				my_len = lc;
+				my_go = inwin;
+			}
+		}
+		if ((u32)lane < chunk && first + lane < n) {
+			const u32 j = first + lane;
+			if (my_go) {
+				Side sc;
+				sc.mag = magC[my_c];
+				sc.sum = sumC[my_c];
+				sc.sumsq = sumsqC[my_c];
+				sc.len = my_len;
+				if (sizeof(T) == 1) {
+					mine.smin = (sc.sum + sq.sum - mine.smin) >> 1; // 8-bit rows reduce sum |p-q|
+				}
+				double score, d0;
+				int close;
+				const int bad = eval_pair_fast(dm, N, mine, sc, sq, true, score, d0, close); // compute(candidate, query)
+				if (bad) {
+					atomicOr(&s_err, bad & 1 ? 1 : 2);
+				}
+				s_dist[j] = d0;
+				s_flag[j] = close ? 1 : 0;
+			} else {
+				s_dist[j] = 0;
+				s_flag[j] = 2;
+			}
+		}
+		__syncthreads();
+		// first maximum over the scored candidates (strict >, initial -1), any close
+		double bd = -1.0;
+		long long bi = -1;
+		int any = 0;
+		for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
+			const unsigned char f = s_flag[j];
+			if (f & 2) {
+				continue;
+			}
+			any |= f & 1;
+			const double d = s_dist[j];
+			if (d > bd) {
+				bd = d;
+				bi = (long long)j;
+			}
+		}
+		for (int o = 16; o > 0; o >>= 1) {
+			const double d2 = __shfl_xor_sync(0xffffffffu, bd, o);
+			const long long i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+			any |= __shfl_xor_sync(0xffffffffu, any, o);
+			if (i2 >= 0 && (bi < 0 || d2 > bd || (d2 == bd && i2 < bi))) {
+				bd = d2;
+				bi = i2;
+			}
+		}
+		if (lane == 0) {
+			s_bd[warp] = bd;
+			s_bi[warp] = bi;
+			s_any[warp] = any;
+		}
+		__syncthreads();
+		// the answer: marks beyond the first 32 into the byte array, everything else into one 64-byte line, the
+		// sequence number last and after a system-wide fence
+		if (n > 32) {
+			for (u32 w = threadIdx.x; w < (n + 7) / 8; w += blockDim.x) {
+				unsigned long long v = 0;
+				for (u32 b = 0; b < 8 && w * 8 + b < n; b++) {
+					v |= (unsigned long long)(s_flag[w * 8 + b] & 1) << (8 * b);
+				}
+				reinterpret_cast<unsigned long long *>(mb->marks)[w] = v;
+			}
+		}
+		if (warp == 0) {
+			bd = -1.0;
+			bi = -1;
+			any = 0;
+			for (int w = 0; w < NW; w++) {
+				any |= s_any[w];
+				if (s_bi[w] >= 0 && (bi < 0 || s_bd[w] > bd || (s_bd[w] == bd && s_bi[w] < bi))) {
+					bd = s_bd[w];
+					bi = s_bi[w];
+				}
+			}
+			unsigned long long v = 0;
+			if (lane == 0) {
+				v = (unsigned long long)bi;
+			} else if (lane == 1) {
+				v = (unsigned long long)__double_as_longlong(bi >= 0 ? bd : -1.0);
+			} else if (lane == 2) {
+				v = (unsigned long long)(any ? 0 : 1) | ((unsigned long long)(unsigned)s_err << 32);
+			} else if (lane < 7) {
+				for (u32 b = 0; b < 8; b++) {
+					const u32 j = (u32)(lane - 3) * 8 + b;
+					v |= (unsigned long long)(j < n ? (s_flag[j] & 1) : 0) << (8 * b);
+				}
+			}
+			if (lane < 7) {
+				mb->r[lane] = v;
+			}
+		}
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			mb->r[7] = last;
+			__threadfence_system();
+		}
+	}
+	if (threadIdx.x == 0) {
+		mb->running = 0;
+		__threadfence_system();
+	}
+}
+
+int launch_scan_server(mc2_ctx *ctx, const DevModel &dm, int eb, u64 first_seq)
+{
+	if (eb == 1) {
+		scan_server_kernel<uint8_t><<<1, 512, 0, ctx->server_stream>>>(dm, ctx->mb, first_seq);
+	} else {
+		scan_server_kernel<uint16_t><<<1, 512, 0, ctx->server_stream>>>(dm, ctx->mb, first_seq);
+	}
+	ctx->launches++;
+	MC2_CUDA(cudaGetLastError());
+	return MC2_OK;
+}
+
 // exclusive prefix of the bin sums at the 32 lane boundaries of every 1 KiB uint8 row (see mc2_hset::lane_off)
 __global__ void __launch_bounds__(256) lane_off_kernel(const unsigned char *__restrict__ bins, u64 n, unsigned short *__restrict__ out)
 {
