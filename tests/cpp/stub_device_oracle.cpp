@@ -316,11 +316,48 @@ int mc2_score_pairs(mc2_ctx *, const mc2_model *model, const mc2_pairs *p, doubl
 		if (mc2o_score_pair(&model->m, p->set_a->eb, p->set_a->N, &a, &b, cch, &d0, &sum, &sc, &cl) != 0) {
 			return fail(MC2_ERR_FEATURE, "stub: a single feature failed");
 		}
+		if (model->regression) { // Predictor::p_predict (src/predict/Predictor.cpp:284-300): the clamped sum, no logistic
+			sc = sum < 0 ? 0 : (sum > 1 ? 1 : sum);
+			cl = 0;
+		}
 		if (score) score[j] = sc;
 		if (dist) dist[j] = d0;
 		if (close) close[j] = (uint8_t)cl;
 		if (skipped) skipped[j] = 0;
 	}
+	return MC2_OK;
+}
+
+int mc2_all_pairs(mc2_ctx *, const mc2_model *model, const mc2_hset *set_q, uint64_t q_begin, uint64_t q_end, const mc2_hset *set_d,
+		  uint64_t d_begin, uint64_t d_end, int32_t upper_only, double cutoff, uint64_t max_out, uint64_t *out_q, uint64_t *out_d,
+		  double *out_score, uint64_t *n_out, uint64_t *n_scored)
+{
+	uint64_t no = 0, ns = 0;
+	for (uint64_t q = q_begin; q < q_end; q++) {
+		mc2o_point b = point_of(set_q, q);
+		const uint64_t lo = (uint64_t)((double)b.len * cutoff), hi = (uint64_t)((double)b.len / cutoff);
+		for (uint64_t d = d_begin; d < d_end; d++) {
+			if (upper_only && d <= q) continue;
+			mc2o_point a = point_of(set_d, d);
+			if (a.len < lo || a.len > hi) continue;
+			double cch[MC2O_MAX_SINGLES], d0 = 0, sum = 0, sc = 0;
+			int cl = 0;
+			if (mc2o_score_pair(&model->m, set_d->eb, set_d->N, &a, &b, cch, &d0, &sum, &sc, &cl) != 0) {
+				return fail(MC2_ERR_FEATURE, "stub: a single feature failed");
+			}
+			ns++;
+			if (cl) {
+				if (no < max_out) {
+					if (out_q) out_q[no] = q;
+					if (out_d) out_d[no] = d;
+					if (out_score) out_score[no] = sc;
+				}
+				no++;
+			}
+		}
+	}
+	*n_out = no;
+	if (n_scored) *n_scored = ns;
 	return MC2_OK;
 }
 
