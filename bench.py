@@ -423,7 +423,7 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "u8" if eb == 1 else "u16", "data": "synthetic",
             "config": workload_config(args.workload, n_total, k, eb),
             "notes": {"pairs_scored_per_step": n_scored, "pairs_close_per_step": res["n_close"],
-                      "parallelism": "row-block x%d, NCCL all-gather of histograms" % world,
+                      "parallelism": "equal-pair-count query-row ranges x%d (one sweep launch per rank), in-place NCCL all-gather of histograms" % world,
                       "l2": "L2 flushed between steps (256 MB memset inside the timed region)",
                       "e2e_steps": e2e_steps},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
@@ -439,6 +439,10 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_extras:
         if world == 1 and tile:
             line["roofline_candidates"] = candidates_roofline(ctx, capi, model, k, eb, peak, peak_src)
+            try:
+                line["slow_singles"] = slow_singles_block(ctx, capi, peak)
+            except Exception as e:
+                log("[bench] slow-singles extra failed: %r" % (e,))
         if world == 1 and args.workload == "cfg3":
             line["also_cfg2"] = small_workload(ctx, capi, mdist, torch, model, cutoff)
             if rank == 0:
@@ -720,6 +724,30 @@ def cfg5_block(ctx, capi, mdist, torch, comm, model, cutoff, local_rank, peak, n
     return out
 
 
+def slow_singles_block(ctx, capi, peak, n=1 << 18):
+    """the two "slow" singles (jefferey_divergence, jensen_shannon: per-bin fp64 logarithms, Feature.cpp:1230-1263,
+    :983-1009) run pair_generic_kernel; one query vs 2^18 candidate rows, device-timed."""
+    rng = np.random.default_rng(2)
+    base = rng.integers(1, 7, size=(4096, 1024), dtype=np.uint8)
+    H = base[rng.integers(0, 4096, n)]
+    ln = rng.integers(950, 1050, n).astype(np.uint64)
+    hs = ctx.hset_from_host(H, 5, length=ln)
+    del H
+    out = {}
+    for name, flags in (("jefferey_divergence", [128]), ("jensen_shannon", [536870912]), ("both", [128, 536870912])):
+        singles = [(f, 0.0, 1.0) for f in flags]
+        combos = [(0, [i]) for i in range(len(flags))]
+        gm = ctx.model(capi.make_desc(singles, combos, [0.5] + [-1.0] * len(flags)))
+        for _ in range(2):
+            ms, _nc = ctx.bench_score_pairs(gm, hs, hs, n_pairs=n, a_begin=0, b_begin=3, b_bc=1, iters=5, flush_l2=False)
+        out[name] = {"ms": ms, "pairs_per_s": n / (ms * 1e-3), "log_evals_per_s": n * 1024 * (1 if name != "both" else 2) * (1 if name == "jefferey_divergence" else 2 if name == "jensen_shannon" else 1.5) / (ms * 1e-3),
+                     "hbm_frac": n * 1057 / (ms * 1e-3) / 1e9 / peak}
+    hs.free()
+    out["kernel"] = "pair_generic_kernel<u8> (fp64 log per bin; bound by the fp64 / special-function pipes, not HBM)"
+    out["candidates"] = n
+    return out
+
+
 def e2e_cluster_block(threads_list=None):
     """BASELINE configs[1] as the full job it names: the reference's own meshclust2 binary (oracle/_ref/meshclust2) next to
     the same binary relinked against this library (oracle/_ref/meshclust2_b200) on the 10k x 1.5 kb
@@ -820,7 +848,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--n-seqs", dest="n", type=int, default=None, help="override the number of sequences (smoke runs)")
-    ap.add_argument("--blocks-per-rank", type=int, default=2, help="folded query-row block pairs per rank and step")
+    ap.add_argument("--blocks-per-rank", type=int, default=1, help="contiguous equal-pair-count query-row ranges (= sweep launches) per rank and step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--cpu-hist-sample", type=int, default=100000)

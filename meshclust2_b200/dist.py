@@ -32,6 +32,32 @@ def folded_row_blocks(n, world, rank, blocks_per_rank=8):
     return sorted(out)
 
 
+def triangle_row_blocks(n, world, rank, blocks_per_rank=1):
+    """Query-row blocks of an upper-triangular sweep for `rank`: CONTIGUOUS row ranges holding equal numbers of pairs
+    (row q pairs with n - 1 - q later rows, so the ranges get longer towards the end), `blocks_per_rank` of them per rank.
+    One range per rank means one sweep launch per rank and step: every launch pays a tail of up to one tile per SM."""
+    B = max(1, world * blocks_per_rank)
+    total = n * (n - 1) // 2
+    edges = [0]
+    for j in range(1, B):
+        target = total * j // B
+        lo, hi = edges[-1], n
+        while lo < hi:                              # smallest x with pairs(rows < x) >= target
+            mid = (lo + hi) // 2
+            if mid * (n - 1) - mid * (mid - 1) // 2 >= target:
+                hi = mid
+            else:
+                lo = mid + 1
+        edges.append(lo)
+    edges.append(n)
+    out = []
+    for b in range(rank * blocks_per_rank, (rank + 1) * blocks_per_rank):
+        q0, q1 = edges[b], edges[b + 1]
+        if q1 > q0:
+            out.append((q0, q1))
+    return out
+
+
 def rect_row_blocks(n, world, rank):
     """Query-row blocks of a rectangular (query set x database) sweep: plain contiguous split."""
     _, b = shard_bounds(n, world)
@@ -98,7 +124,7 @@ class Comm:
         return float(t.item())
 
 
-def all_pairs_step(engine, comm, torch, n_total, cutoff, upper_only=True, blocks_per_rank=8, max_out=1 << 20):
+def all_pairs_step(engine, comm, torch, n_total, cutoff, upper_only=True, blocks_per_rank=1, max_out=1 << 20):
     """One pass of the hot path over a batch: local K1 -> all-gather -> row-block K2 sweep.
 
     engine.count()                  K1 over this rank's shard
@@ -127,7 +153,7 @@ def all_pairs_step(engine, comm, torch, n_total, cutoff, upper_only=True, blocks
             idx = torch.as_tensor(keep, device=bins.device)
             bins, length, mag = bins[idx].contiguous(), length[idx].contiguous(), mag[idx].contiguous()
         engine.install_full(bins, length, mag, n_total)
-    blocks = (folded_row_blocks(n_total, comm.world, comm.rank, blocks_per_rank) if upper_only
+    blocks = (triangle_row_blocks(n_total, comm.world, comm.rank, blocks_per_rank) if upper_only
               else rect_row_blocks(n_total, comm.world, comm.rank))
     n_scored = n_close = 0
     surv = Survivors()

@@ -29,6 +29,9 @@ def test_shard_bounds_and_blocks_cover_everything():
             assert sorted(rows) == list(range(n)), (n, world)
             rows = [q for r in range(world) for q0, q1 in mdist.rect_row_blocks(n, world, r) for q in range(q0, q1)]
             assert sorted(rows) == list(range(n))
+            for bpr in (1, 3):
+                rows = [q for r in range(world) for q0, q1 in mdist.triangle_row_blocks(n, world, r, bpr) for q in range(q0, q1)]
+                assert rows == list(range(n)), (n, world, bpr)
 
 
 def test_folded_blocks_balance_the_triangle():
@@ -37,6 +40,17 @@ def test_folded_blocks_balance_the_triangle():
     for r in range(world):
         work.append(sum((n - 1 - q0 + n - q1) * (q1 - q0) / 2 for q0, q1 in mdist.folded_row_blocks(n, world, r)))
     assert max(work) / min(work) < 1.01
+
+
+def test_triangle_ranges_balance_the_triangle():
+    """one contiguous range per rank, equal pair counts (the ranges grow towards the end of the set)"""
+    n, world = 100000, 8
+    work = []
+    for r in range(world):
+        (q0, q1), = mdist.triangle_row_blocks(n, world, r)
+        work.append((n - 1 - q0 + n - q1) * (q1 - q0) / 2)
+    assert sum(work) == n * (n - 1) / 2
+    assert max(work) / min(work) < 1.001
 
 
 class OracleEngine:
