@@ -440,6 +440,10 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and tile:
             line["roofline_candidates"] = candidates_roofline(ctx, capi, model, k, eb, peak, peak_src)
             try:
+                line["gram_term"] = gram_term_block(ctx, capi, eng.full, n_total, cutoff)
+            except Exception as e:
+                log("[bench] gram-term extra failed: %r" % (e,))
+            try:
                 line["slow_singles"] = slow_singles_block(ctx, capi, peak)
             except Exception as e:
                 log("[bench] slow-singles extra failed: %r" % (e,))
@@ -721,6 +725,48 @@ def cfg5_block(ctx, capi, mdist, torch, comm, model, cutoff, local_rank, peak, n
         eng.local_hset.free()
     except Exception:
         pass
+    return out
+
+
+def gram_term_block(ctx, capi, hs, n_total, cutoff, nq=10000):
+    """The Gram term sum p*q on the tensor pipe next to the CUDA-core form: a model over the three singles that need only
+    that reduction (euclidean Feature.cpp:1112-1124, normalized_vectors :1170-1184, pearson :794-811) sweeps the first nq
+    query rows of the bench's own histogram set twice -- tile_sweep_kernel (TMA + tcgen05.mma kind::i8 into TMEM) and, with
+    MC2_SWEEP_LEGACY set for the call, sweep_kernel (IDP.4A from registers) -- device-timed, survivors compared."""
+    singles = [(1 << 3, 0.0, 60.0), (1 << 5, 0.0, 1.0), (1 << 9, 0.0, 1.0)]        # Feature.h FEAT_TYPE bits of the three
+    combos = [(0, [0]), (0, [1]), (0, [2])]
+    nq = min(nq, n_total)
+    # threshold: the 99.9th percentile of the summed normalised singles over a random pair sample (about 1 pair in 1000 close)
+    rng = np.random.default_rng(9)
+    probe = ctx.model(capi.make_desc(singles, combos, [0.0, 1.0, 1.0, 1.0]))
+    ia = rng.integers(0, nq, 50000).astype(np.uint64)
+    ib = rng.integers(0, n_total, 50000).astype(np.uint64)
+    cache = ctx.score_pairs(probe, hs, hs, ia=ia, ib=ib, want=("cache",))["cache"]
+    thr = float(np.quantile(cache.sum(axis=1), 0.999))
+    gm = ctx.model(capi.make_desc(singles, combos, [-8.0 * thr, 8.0, 8.0, 8.0]))
+    out = {"model": "euclidean + normalized_vectors + pearson (needs only sum p*q and the per-row side band)", "query_rows": nq,
+           "database_rows": n_total}
+    keep = {}
+    for name, env in (("tensor_core_tile_sweep", None), ("cuda_core_sweep", "1")):
+        if env:
+            os.environ["MC2_SWEEP_LEGACY"] = env
+        try:
+            best = None
+            for _ in range(3):
+                ctx.timer_start()
+                r = ctx.all_pairs(gm, hs, hs, cutoff, q_range=(0, nq), d_range=(0, n_total), upper_only=True, max_out=1 << 22)
+                ms = ctx.timer_stop()
+                best = ms if best is None else min(best, ms)
+        finally:
+            os.environ.pop("MC2_SWEEP_LEGACY", None)
+        keep[name] = r
+        out[name] = {"ms": best, "pairs_per_s": r["n_scored"] / (best * 1e-3), "pairs_scored": int(r["n_scored"]), "pairs_close": int(r["n_out"]),
+                     "gram_int_ops_per_s": r["n_scored"] * 2 * 1024 / (best * 1e-3)}
+    a, b = keep["tensor_core_tile_sweep"], keep["cuda_core_sweep"]
+    sa = set(zip(a["q"].tolist(), a["d"].tolist()))
+    sb = set(zip(b["q"].tolist(), b["d"].tolist()))
+    out["same_survivors"] = bool(sa == sb and a["n_scored"] == b["n_scored"])
+    out["speedup"] = out["cuda_core_sweep"]["ms"] / out["tensor_core_tile_sweep"]["ms"]
     return out
 
 

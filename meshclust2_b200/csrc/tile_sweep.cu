@@ -4,22 +4,27 @@
 // every (query, database) pair inside the length window gets the model's reductions, the GLM score and the cutoff
 // (Feature.cpp:136-171, Trainer.cpp:112-120, Predictor.cpp:323-333), survivors are appended to a list.
 //
-// One persistent CTA per SM walks 64 (query) x 128 (database) pair tiles.  Per tile the 1024 bins are streamed through a
-// shared-memory ring in 16 chunks of 64 bins by TMA (cp.async.bulk.tensor, hardware swizzle), and three engines consume
-// each chunk:
-//   S_pq  = sum p*q              tcgen05.mma kind::i8 (u8 x u8 -> s32, exact), accumulator 128 x 64 in TMEM, issued by one
-//                                thread; the accumulator is double buffered so the next tile's MMAs overlap the epilogue.
-//   S_emd = sum |cumP - cumQ|    CUDA cores on precomputed u16 cumulative rows (mc2_hset::cum16), through the identity
-//                                sum|a-b| = sum a + sum b - 2 sum min(a,b): VIMNMX.U16x2 (2 bins / instruction), packed
-//                                16-bit partial sums added three at a time (IADD3) and flushed into a 32-bit accumulator
-//                                with IDP.2A before a half can overflow.  Thread tile 8 query x 4 database rows: the
-//                                query rows are warp-uniform shared-memory broadcasts, the database rows conflict-free
-//                                128-bit loads from the swizzled tile.
-//   S_sad = sum |p - q|          VABSDIFF4.U8.ACC on the u8 tile (4 bins / instruction)  -> S_min = (sumP+sumQ-S_sad)/2
-// Epilogue per tile: reductions -> shared memory; one pair per thread at a time: length window (FC_Runner.cpp:435-444),
-// an fp32 evaluation of the GLM sum with a running error bound that can only REJECT (sum + bound < -1e-6 => not close
-// whatever the rounding); everything else goes through the exact fp64 epilogue shared with the other pair kernels
-// (eval_pair_fast), so scores and decisions are the same bits as theirs.
+// One persistent CTA per SM (24 warps, warp specialised, registers re-dealt per warpgroup with setmaxnreg) walks
+// 64 (query) x 256 (database) pair tiles in the order of a precomputed schedule (database-tile major inside super-rows
+// of query tiles, so concurrently running CTAs share tiles in L2).  Per tile the 1024 bins stream through a 4-stage
+// shared-memory ring of 40 KB stages filled by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, one elected producer thread):
+// 16 stages of 64 bins of the u16 cumulative rows and 8 stages of 128 bins of the u8 rows, interleaved 2 : 1.
+//   S_pq  = sum p*q              tcgen05.mma kind::i8 (u8 x u8 -> s32, exact) issued by one thread straight from the
+//                                ring: two 128 x 64 accumulators (database rows = TMEM lanes) per tile, double buffered in
+//                                TMEM so the next tile's MMAs overlap the epilogue.
+//   S_emd = sum |cumP - cumQ|    16 compute warps on precomputed u16 cumulative rows (mc2_hset::cum16, cum16_kernel)
+//                                through sum|a-b| = sum a + sum b - 2 sum min(a,b): VIMNMX.U16x2 (2 bins / instruction,
+//                                ALU pipe) feeding IDP.2A with weights 0x0101 (FMA pipe) into a 32-bit accumulator: two
+//                                instructions per two bins.  A thread owns database rows L and 128 + L (L = its TMEM lane)
+//                                against 16 query rows: its rows are conflict-free 128-bit loads from the swizzled
+//                                tile, the query rows warp-uniform shared-memory broadcasts, 32 accumulators in registers.
+//                                The sums go to TMEM (tcgen05.st) for the epilogue warps, double buffered.
+//   S_sad = sum |p - q|          VABSDIFF4.U8.ACC on the u8 stages (4 bins / instruction) -> S_min = (sumP+sumQ-S_sad)/2
+// Epilogue (4 warps, thread = TMEM lane): tcgen05.ld of 4 query columns at a time; length window
+// (FC_Runner.cpp:435-444) in 32 bits with an exact 64-bit path for lengths >= 2^32; an fp32 evaluation of the GLM sum
+// with a rigorous host-derived error bound that can only REJECT (sum + bound < -1e-6 => not close whatever the
+// rounding); the rest is ballot-compacted into a per-warp list and goes, one pair per lane, through the exact fp64
+// epilogue shared with the other pair kernels (eval_pair_fast), so scores and decisions are the same bits as theirs.
 #include "mc2_internal.cuh"
 #include "pair_eval.cuh"
 #include <cuda.h>
@@ -249,8 +254,9 @@ __device__ __forceinline__ Tile decode_item(const Params &p, const u32 *s_sched,
 
 // ---------------------------------------------------------------------------------------------------------------
 // CUDA-core work of one compute warp on one ring stage.  The thread owns database rows L and 128 + L of the tile
-// (L = 32 * (warp % 4) + lane, its TMEM lane) against the 32 query rows of its half: 64 accumulators.  Per 16-byte
-// step: 2 conflict-free row loads, 32 warp-uniform (broadcast) query loads, 512 (EMD) / 256 (SAD) arithmetic instructions.
+// (L = 32 * (warp % 4) + lane, its TMEM lane) against the QN query rows of its share: 2 * QN accumulators (QN = 16 with
+// 16 compute warps).  Per 16-byte step: 2 conflict-free row loads, QN warp-uniform (broadcast) query loads, 16 * QN (EMD:
+// VIMNMX.U16x2 + IDP.2A per word) or 8 * QN (SAD: VABSDIFF4 per word) arithmetic instructions.
 // 128-byte rows under SWIZZLE_128B: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool IS_EMD>
@@ -1047,7 +1053,7 @@ static int make_map(CUtensorMap *m, const void *base, u64 n_rows, int elem_bytes
 
 bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset *d)
 {
-	static const bool off = getenv("MC2_SWEEP_LEGACY") != nullptr;
+	const bool off = getenv("MC2_SWEEP_LEGACY") != nullptr; // read per call: bench.py times both forms in one process
 	if (off) {
 		return false;
 	}

@@ -489,3 +489,35 @@ def test_get_close_as_and_filter_as_equal_staged_centers(built_lib, ctx, golden)
             ln2 = np.append(ln, np.uint64(qlen)).astype(np.uint64)
             o = port.get_close(m, H2, mag2, ln2, len(H), cand, 0.9)
             assert b[0] == o[0] and abs(b[1] - o[1]) <= 1e-9 and b[2] == o[2] and np.array_equal(b[3], o[3])
+
+
+def test_get_close_one_million_candidates_vs_oracle(built_lib, ctx):
+    """BASELINE configs[4] size: Trainer<T>::get_close (src/cluster/Trainer.cpp:23-71) of one center against 10^6 candidate
+    rows (1 GB of uint8 histograms, well past L2) == the oracle's get_close over the same 10^6 rows: the marks of all
+    candidates, the best candidate, its distance and the is-minimum flag; contiguous range and explicit list agree."""
+    rng = np.random.default_rng(21)
+    n = 1000000
+    base = rng.integers(1, 12, size=(4096, 1024), dtype=np.uint8)
+    H = base[rng.integers(0, 4096, n)]
+    rows = np.arange(n)
+    for _ in range(24):                                     # 24 bins of every row nudged: related rows, few exact duplicates
+        H[rows, rng.integers(0, 1024, n)] += 1
+    ln = rng.integers(900, 1100, n).astype(np.uint64)
+    mag = H.sum(axis=1, dtype=np.uint64)
+    hs = ctx.hset_from_host(H, 5, length=ln)
+    m = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    gm = ctx.model_from_file(weights_path("weights_cfg1_id90"))
+    for q in (5, 999999):
+        best, bd, ismin, marks = ctx.get_close(gm, hs, q, hs, cand_begin=0, n_cand=n, cutoff=0.9)
+        ob, obd, omin, omarks = port.get_close(m, H, mag, ln, q, rows, 0.9)
+        assert best == ob and ismin == omin and abs(bd - obd) <= 1e-9, q
+        diff = np.flatnonzero(marks != omarks)
+        if len(diff):                                       # only scores within 1e-9 of the decision boundary may differ
+            o = port.score_pairs(m, H, mag, ln, diff, np.full(len(diff), q))
+            assert np.abs(o["score"] - 0.5).max() <= 1e-9, q
+        assert 10 < int(marks.sum()) < n // 100
+        sub = np.sort(np.unique(np.concatenate([np.flatnonzero(marks), rows[::997]]))).astype(np.uint64)
+        b2, bd2, min2, marks2 = ctx.get_close(gm, hs, q, hs, cand=sub, cutoff=0.9)
+        assert sub[b2] == best and bd2 == bd and min2 == ismin
+        assert np.array_equal(marks2, marks[sub.astype(np.int64)])
+    hs.free()
