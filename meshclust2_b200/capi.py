@@ -304,12 +304,18 @@ class Context:
                                      _p(out["cache"]), _p(out["raw"]), _p(out["skipped"])))
         return out
 
-    def get_close(self, model, set_q, q, set_c, cand=None, cand_begin=0, n_cand=None, cutoff=0.9):
+    def get_close(self, model, set_q, q, set_c, cand=None, cand_begin=0, n_cand=None, cutoff=0.9, marks=None):
+        """marks: optional uint8 buffer of >= n_cand bytes to fill (e.g. page-locked and reused across calls); its first n_cand
+        bytes are returned"""
         cand = _u64(cand)
         if n_cand is None:
             n_cand = len(cand)
         best, bd, ismin = C.c_int64(), C.c_double(), C.c_int32()
-        marks = np.zeros(n_cand, dtype=np.uint8)
+        if marks is None:
+            marks = np.zeros(n_cand, dtype=np.uint8)
+        else:
+            assert marks.dtype == np.uint8 and marks.flags.c_contiguous and len(marks) >= n_cand
+            marks = marks[:n_cand]
         _check(lib().mc2_get_close(self.h, model.h, set_q.h, C.c_uint64(q), set_c.h, _p(cand), C.c_uint64(cand_begin),
                                    C.c_uint64(n_cand), C.c_double(cutoff), C.byref(best), C.byref(bd), C.byref(ismin),
                                    _p(marks)))

@@ -32,19 +32,25 @@ def folded_row_blocks(n, world, rank, blocks_per_rank=8):
     return sorted(out)
 
 
-def triangle_row_blocks(n, world, rank, blocks_per_rank=1):
-    """Query-row blocks of an upper-triangular sweep for `rank`: CONTIGUOUS row ranges holding equal numbers of pairs
-    (row q pairs with n - 1 - q later rows, so the ranges get longer towards the end), `blocks_per_rank` of them per rank.
+def triangle_row_blocks(n, world, rank, blocks_per_rank=1, row_overhead=160):
+    """Query-row blocks of an upper-triangular sweep for `rank`: CONTIGUOUS row ranges of equal cost (so they get longer
+    towards the end of the set), `blocks_per_rank` of them per rank.  Row q costs its n - 1 - q pairs plus `row_overhead`
+    pair slots: the tile kernel pays whole 64 x 256 tiles along the diagonal (about half a tile width + half a tile height
+    of unused slots per query row), which would otherwise make the last rank, whose range is mostly diagonal, the slowest.
     One range per rank means one sweep launch per rank and step: every launch pays a tail of up to one tile per SM."""
     B = max(1, world * blocks_per_rank)
-    total = n * (n - 1) // 2
+
+    def cost(x):                                    # rows [0, x)
+        return x * (n - 1) - x * (x - 1) // 2 + row_overhead * x
+
+    total = cost(n)
     edges = [0]
     for j in range(1, B):
         target = total * j // B
         lo, hi = edges[-1], n
-        while lo < hi:                              # smallest x with pairs(rows < x) >= target
+        while lo < hi:                              # smallest x with cost(rows < x) >= target
             mid = (lo + hi) // 2
-            if mid * (n - 1) - mid * (mid - 1) // 2 >= target:
+            if cost(mid) >= target:
                 hi = mid
             else:
                 lo = mid + 1
@@ -174,27 +180,36 @@ def candidate_scan(engine, comm, torch, q_global, n_total, cutoff):
 
     engine.local_query(row_local)      -> (bins[1,N], length[1], mag[1]) tensors of a local row
     engine.scan_local(bins, length, mag, cutoff) -> (best_local_pos or -1, best_dist, is_min, marks[local_n])
-    Returns dict(best=global row or -1, best_dist, is_min, marks_local, shard=(lo, hi))."""
+    Returns dict(best=global row or -1, best_dist, is_min, marks_local, shard=(lo, hi)); marks_local may be a view of a
+    buffer the engine reuses: it is valid until the next scan."""
     per, bounds = shard_bounds(n_total, comm.world)
     owner = min(q_global // per, comm.world - 1) if per else 0
     lo, hi = bounds[comm.rank]
-    if comm.rank == owner:
-        bins, length, mag = engine.local_query(q_global - bounds[owner][0])
+    if comm.dist is None and hasattr(engine, "scan_row"):
+        # one rank: the query row already sits in the set being scanned
+        best, bd, is_min, marks = engine.scan_row(q_global - lo, cutoff)
     else:
-        bins, length, mag = engine.empty_query()
-    if comm.dist is not None:
-        for t in (bins, length, mag):
-            comm.dist.broadcast(t, src=owner)
-    best, bd, is_min, marks = engine.scan_local(bins, length, mag, cutoff)
+        if comm.rank == owner:
+            bins, length, mag = engine.local_query(q_global - bounds[owner][0])
+        else:
+            bins, length, mag = engine.empty_query()
+        if comm.dist is not None:
+            pack = engine.query_pack() if hasattr(engine, "query_pack") else None
+            if pack is not None:                    # the three tensors are views of one buffer: one broadcast
+                comm.dist.broadcast(pack, src=owner)
+            else:
+                for t in (bins, length, mag):
+                    comm.dist.broadcast(t, src=owner)
+        best, bd, is_min, marks = engine.scan_local(bins, length, mag, cutoff)
     # combine: larger dist wins, ties go to the smaller global index (the sequential first maximum)
-    mine = torch.tensor([bd if best >= 0 else -1.0, float(lo + best if best >= 0 else -1), 0.0 if is_min else 1.0],
-                        dtype=torch.float64, device=engine.device)
+    triple = [bd if best >= 0 else -1.0, float(lo + best if best >= 0 else -1), 0.0 if is_min else 1.0]
     if comm.dist is not None:
+        mine = torch.tensor(triple, dtype=torch.float64, device=engine.device)
         allv = torch.empty((comm.world * 3,), dtype=torch.float64, device=engine.device)
         comm.dist.all_gather_into_tensor(allv, mine)
         allv = allv.cpu().numpy().reshape(comm.world, 3)
     else:
-        allv = mine.cpu().numpy().reshape(1, 3)
+        allv = np.array([triple])
     gbest, gdist = -1, -1.0
     for dist_r, idx_r, _ in allv:
         if idx_r >= 0 and (gbest < 0 or dist_r > gdist or (dist_r == gdist and idx_r < gbest)):
@@ -380,17 +395,37 @@ class GpuEngine:
                                               mag.data_ptr())
 
     # ---- sharded candidate scan (candidate_scan) ----
+    def query_pack(self):
+        """the query message of a distributed scan: length (8 bytes) | magnitude (8) | bins, ONE device buffer kept for the
+        engine's life, so a scan costs one broadcast and no allocation"""
+        if getattr(self, "_qpack", None) is None:
+            self._qpack = self.torch.zeros((16 + self.N * self.eb,), dtype=self.torch.uint8, device=self.device)
+        return self._qpack
+
     def empty_query(self):
-        torch = self.torch
-        return (torch.ones((1, self.N), dtype=self._dt, device=self.device),
-                torch.zeros((1,), dtype=torch.int64, device=self.device), torch.zeros((1,), dtype=torch.int64, device=self.device))
+        torch, pack = self.torch, self.query_pack()
+        return pack[16:].view(self._dt).view(1, self.N), pack[0:8].view(torch.int64), pack[8:16].view(torch.int64)
 
     def local_query(self, row_local):
         bins, length, mag = self.empty_query()
-        self.torch.cuda.synchronize(self.device)
         hs, base, _ = self._local()
         hs.copy_to_device(bins.data_ptr(), mag.data_ptr(), length.data_ptr(), base + row_local, 1)
+        self.ctx.sync()                                 # the copy ran on the context's stream; the broadcast runs on torch's
         return bins, length, mag
+
+    def _marks(self, n):
+        """page-locked mark buffer reused by every scan (a fresh pageable array costs page faults and a staged copy per call)"""
+        buf = getattr(self, "_marks_buf", None)
+        if buf is None or len(buf) < n:
+            if buf is not None and self._marks_pinned:
+                self.capi.host_unregister(buf)
+            buf = self._marks_buf = np.zeros(max(n, 1 << 16), dtype=np.uint8)
+            try:
+                self.capi.host_register(buf)
+                self._marks_pinned = True
+            except self.capi.Mc2Error:          # locked-memory limit: a pageable buffer still works
+                self._marks_pinned = False
+        return buf
 
     def scan_local(self, bins, length, mag, cutoff):
         self.torch.cuda.synchronize(self.device)
@@ -401,7 +436,12 @@ class GpuEngine:
         hs, base, n = self._local()
         if n == 0:
             return -1, -1.0, True, np.zeros(0, dtype=np.uint8)
-        return self.ctx.get_close(self.model, self._qset, 0, hs, cand_begin=base, n_cand=n, cutoff=cutoff)
+        return self.ctx.get_close(self.model, self._qset, 0, hs, cand_begin=base, n_cand=n, cutoff=cutoff, marks=self._marks(n))
+
+    def scan_row(self, row_local, cutoff):
+        """get_close of a row of the local shard against the whole shard (what a scan is with one rank)"""
+        hs, base, n = self._local()
+        return self.ctx.get_close(self.model, hs, base + row_local, hs, cand_begin=base, n_cand=n, cutoff=cutoff, marks=self._marks(n))
 
     # ---- update stage (update_pass / merge_pass) over the replicated set self.full ----
     def _stage_centers(self, rows, mag, length):
