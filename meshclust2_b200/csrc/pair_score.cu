@@ -1267,14 +1267,18 @@ struct ArgOut {
 };
 
 // flags_out (may be NULL): the close flags copied next to the result so that one device->host copy returns both
+// Block b reduces candidates [b * chunk, min(n, (b + 1) * chunk)) into out[b] (absolute positions); one block with
+// chunk >= n is the whole reduction, several blocks leave partial records for argmax_combine_kernel.
 __global__ void __launch_bounds__(1024) argmax_kernel(const double *dist, const uint8_t *skipped, const uint8_t *close, u64 n,
-						      int mode, ArgOut *out, uint8_t *flags_out)
+						      int mode, ArgOut *out, uint8_t *flags_out, u64 chunk)
 {
 	if (flags_out) {
 		for (u64 i = threadIdx.x; i < n; i += blockDim.x) {
 			flags_out[i] = close[i];
 		}
 	}
+	const u64 i_begin = (u64)blockIdx.x * chunk, i_end = i_begin + chunk < n ? i_begin + chunk : n;
+	out += blockIdx.x;
 	__shared__ double s_d[32];
 	__shared__ long long s_i[32];
 	__shared__ int s_any[32];
@@ -1283,7 +1287,7 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const double *dist, const 
 	long long bi = mode == 0 ? -1 : 0;
 	bool has = false; // mode 1: whether bi was set by a candidate
 	int any = 0;
-	for (u64 i = threadIdx.x; i < n; i += blockDim.x) {
+	for (u64 i = i_begin + threadIdx.x; i < i_end; i += blockDim.x) {
 		if (skipped[i]) {
 			continue;
 		}
@@ -1358,6 +1362,35 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const double *dist, const 
 			out->has = mode == 0 ? (bi >= 0) : (int)has;
 		}
 	}
+}
+
+// partial records of consecutive candidate ranges, in range order -> the result (same tie rules as above: mode 0 keeps
+// the earlier range on ties, mode 1 the later one)
+__global__ void argmax_combine_kernel(const ArgOut *parts, int n_parts, int mode, ArgOut *out)
+{
+	if (threadIdx.x != 0) {
+		return;
+	}
+	double bd = mode == 0 ? -1.0 : 2.2250738585072014e-308;
+	long long bi = mode == 0 ? -1 : 0;
+	bool has = false;
+	int any = 0;
+	for (int b = 0; b < n_parts; b++) {
+		const ArgOut p = parts[b];
+		any |= !p.is_min;
+		if (!p.has) {
+			continue;
+		}
+		if (mode == 0 ? (!has || p.best_dist > bd) : (!has || !(bd > p.best_dist))) {
+			bd = p.best_dist;
+			bi = p.best;
+			has = true;
+		}
+	}
+	out->best = bi;
+	out->best_dist = bd;
+	out->is_min = !any;
+	out->has = (int)has;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1968,7 +2001,18 @@ int launch_argmax(mc2_ctx *ctx, const double *dist, const uint8_t *skipped, cons
 		  uint8_t *d_flags_out)
 {
 	prof_begin(ctx, 4);
-	argmax_kernel<<<1, 1024, 0, ctx->stream>>>(dist, skipped, close, n, mode, reinterpret_cast<ArgOut *>(d_out), d_flags_out);
+	if (n < 32768 || d_flags_out) {
+		argmax_kernel<<<1, 1024, 0, ctx->stream>>>(dist, skipped, close, n, mode, reinterpret_cast<ArgOut *>(d_out), d_flags_out, n);
+	} else {
+		// long scans (10^5 .. 10^6 candidates): up to 96 blocks leave partial records in the result slot's spare bytes
+		// (d_out is the context's 4 KB slot; the result and the error word use its first 128 bytes)
+		const u64 chunk = n / 96 + 1 > 8192 ? n / 96 + 1 : 8192;
+		const int parts = (int)((n + chunk - 1) / chunk);
+		ArgOut *d_parts = reinterpret_cast<ArgOut *>(reinterpret_cast<char *>(d_out) + 128);
+		argmax_kernel<<<parts, 1024, 0, ctx->stream>>>(dist, skipped, close, n, mode, d_parts, nullptr, chunk);
+		argmax_combine_kernel<<<1, 32, 0, ctx->stream>>>(d_parts, parts, mode, reinterpret_cast<ArgOut *>(d_out));
+		ctx->launches++;
+	}
 	prof_end(ctx);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
