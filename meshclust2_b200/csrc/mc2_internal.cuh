@@ -47,6 +47,15 @@ enum SingleCode : int {
 	SC_COUNT
 };
 
+// slots of the tile sweep's screen scratch: the nine fast singles, densely, then the constant 1
+#define MC2_SCR_SLOTS 10
+__host__ __device__ constexpr int scr_slot(int code)
+{
+	return code == SC_MANHATTAN ? 0 : code == SC_EUCLIDEAN ? 1 : code == SC_NORMALIZED_VECTORS ? 2 : code == SC_PEARSON ? 3 :
+	       code == SC_INTERSECTION ? 4 : code == SC_EMD ? 5 : code == SC_LENGTHD ? 6 : code == SC_KULCZYNSKI2 ? 7 :
+	       code == SC_SIMRATIO ? 8 : 9;
+}
+
 #define MC2_SCR_MAX_COMBOS 8
 
 // which reductions over the bins a model needs

@@ -4,7 +4,7 @@
 // every (query, database) pair inside the length window gets the model's reductions, the GLM score and the cutoff
 // (Feature.cpp:136-171, Trainer.cpp:112-120, Predictor.cpp:323-333), survivors are appended to a list.
 //
-// One persistent CTA per SM (24 warps, warp specialised, registers re-dealt per warpgroup with setmaxnreg) walks
+// One persistent CTA per SM (28 warps, warp specialised, registers re-dealt per warpgroup with setmaxnreg) walks
 // 64 (query) x 256 (database) pair tiles in the order of a precomputed schedule (database-tile major inside super-rows
 // of query tiles, so concurrently running CTAs share tiles in L2).  Per tile the 1024 bins stream through a 4-stage
 // shared-memory ring of 40 KB stages filled by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, one elected producer thread):
@@ -20,7 +20,8 @@
 //                                tile, the query rows warp-uniform shared-memory broadcasts, 32 accumulators in registers.
 //                                The sums go to TMEM (tcgen05.st) for the epilogue warps, double buffered.
 //   S_sad = sum |p - q|          VABSDIFF4.U8.ACC on the u8 stages (4 bins / instruction) -> S_min = (sumP+sumQ-S_sad)/2
-// Epilogue (4 warps, thread = TMEM lane): tcgen05.ld of 4 query columns at a time; length window
+// Epilogue (8 warps, thread = TMEM lane, two warps per lane quarter splitting the query columns; one warp per scheduler
+// is latency bound and stalls the compute warps at the tile hand-over): tcgen05.ld of 2 query columns at a time; length window
 // (FC_Runner.cpp:435-444) in 32 bits with an exact 64-bit path for lengths >= 2^32; an fp32 evaluation of the GLM sum
 // with a rigorous host-derived error bound that can only REJECT (sum + bound < -1e-6 => not close whatever the
 // rounding); the rest is ballot-compacted into a per-warp list and goes, one pair per lane, through the exact fp64
@@ -45,18 +46,34 @@ constexpr int KC_U8 = 128;      // bins per ring stage while the u8 rows stream 
 #endif
 constexpr int NCW = MC2_TS_NCW; // compute warps (CTA warps 4 .. 4 + NCW - 1, whole warpgroups): 8 or 16
 constexpr int QN = TQ / (NCW / 4); // query rows per compute thread (x 2 database rows): 32 or 16 accumulator pairs
-constexpr int NEW = 4;          // epilogue warps (CTA warps 12..15: warpgroup 3), one per TMEM lane quarter
+// measured on 100 k x 1 kb (bench model): 4 epilogue warps x 4 pairs 95.6 ms per 1.8e9 pairs, 8 x 2: 91.5 ms, 8 x 4 (list
+// flushed at every hit for lack of shared memory): 94.8 ms, 4 x 2: 105.7 ms
+#ifndef MC2_TS_NEW
+#define MC2_TS_NEW 8
+#endif
+#ifndef MC2_TS_NP
+#define MC2_TS_NP 2
+#endif
+constexpr int NEW = MC2_TS_NEW; // epilogue warps (after the compute warps, whole warpgroups): NEW / 4 per TMEM lane quarter, each
+                                // taking TQ / (NEW / 4) query columns of both regions
+constexpr int NP = MC2_TS_NP;   // pairs a thread of the epilogue screens at a time (query columns per tcgen05.ld)
+constexpr int QE = TQ / (NEW / 4); // query columns per epilogue warp
 constexpr int THREADS = (4 + NCW + NEW) * 32; // warpgroup 0: TMA producer, MMA issuer, two idle warps
-// setmaxnreg per warpgroup.  8 compute warps: launch 128 / thread, control 40, compute 168, epilogue 128.
-// 16 compute warps: launch 80 / thread, control 40, compute 80 (unchanged), epilogue 120.  The pool is what the launch
-// allocated (threads x launch registers): the sums below must not exceed it.
-constexpr int REGS_CTRL = 40, REGS_COMPUTE = NCW == 8 ? 168 : 80, REGS_EPI = NCW == 8 ? 128 : 120;
+// setmaxnreg per warpgroup.  The pool is what the launch allocated (threads x launch registers, at most 64 K): the
+// per-role sums below must not exceed it.
+//   8 compute + 4 epilogue warps: launch 128, control 40, compute 168, epilogue 128
+//  16 compute + 4 epilogue warps: launch  80, control 40, compute  80, epilogue 120
+//  16 compute + 8 epilogue warps: launch  72, control 24, compute  80, epilogue  80
+constexpr int REGS_LAUNCH = NEW == 8 ? 72 : (NCW == 8 ? 128 : 80);
+constexpr int REGS_CTRL = NEW == 8 ? 24 : 40, REGS_COMPUTE = NCW == 8 ? 168 : 80, REGS_EPI = NEW == 8 ? 80 : (NCW == 8 ? 128 : 120);
+static_assert(128 * REGS_CTRL + NCW * 32 * REGS_COMPUTE + NEW * 32 * REGS_EPI <= THREADS * REGS_LAUNCH, "register pool");
+static_assert(THREADS * REGS_LAUNCH <= 65536, "register file");
 constexpr int D_BYTES = TD * 128;        // 32 KB, SWIZZLE_128B
 constexpr int Q_BYTES = TQ * 128;        //  8 KB
 constexpr int STAGE_BYTES = D_BYTES + Q_BYTES; // 40 KB
 constexpr int STAGES = 4;
-constexpr int MAX_SUPER = 1024;          // entries of the tile schedule's prefix array
-constexpr int LIST_CAP = 256;            // candidate records per epilogue warp
+constexpr int MAX_SUPER = (NEW == 8 && NP == 4) ? 512 : 1024; // entries of the tile schedule's prefix array (shared memory is tight with the large scratch)
+constexpr int LIST_CAP = NEW == 8 ? 128 : 256; // candidate records per epilogue warp
 // TMEM columns (512 allocated): Gram accumulators double buffered, EMD / SAD sums single buffered
 constexpr u32 TM_DOT = 0;                // + buf * 128 + region * 64
 constexpr u32 TM_EMD = 256;              // + ebuf * 128 + region * 64 (double buffered when no SAD sums are needed)
@@ -78,6 +95,7 @@ struct Params {
 	u32 n_super;
 	const u32 *sched;       // [n_super + 1] exclusive prefix of items per super-row (device)
 	int no_screen;          // experiments: skip the screen and the exact path (main-loop cost only)
+	u32 sleep_ctrl, sleep_comp, sleep_epi; // experiments: back-off of the three roles' barrier waits (ns)
 	// raw mode (tests): dense (q1-q0) x (d1-d0) matrices of the reductions instead of scoring
 	u32 *raw_dot, *raw_emd, *raw_sad;
 };
@@ -103,11 +121,16 @@ __device__ __forceinline__ bool mbar_try(u32 bar, u32 parity)
 		     : "memory");
 	return ok != 0;
 }
-// bounded wait: a pipeline bug must end in an error, never in a hung GPU
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity, int *err)
+// bounded wait: a pipeline bug must end in an error, never in a hung GPU.  sleep_ns > 0: a warp that finds the barrier
+// not ready leaves the scheduler for that long instead of polling (its poll loop would take issue slots from the
+// compute warps of the same SM sub-partition)
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity, int *err, u32 sleep_ns = 0)
 {
 	u32 spins = 0;
 	while (!mbar_try(bar, parity)) {
+		if (sleep_ns) {
+			__nanosleep(sleep_ns);
+		}
 		if (++spins > (1u << 20)) {
 			atomicOr(err, 16);
 			__trap();
@@ -136,6 +159,12 @@ __device__ __forceinline__ void tc_ld4(u32 taddr, u32 (&v)[4])
 {
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld2(u32 taddr, u32 (&v)[2])
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ldn(u32 taddr, u32 (&v)[4]) { tc_ld4(taddr, v); }
+__device__ __forceinline__ void tc_ldn(u32 taddr, u32 (&v)[2]) { tc_ld2(taddr, v); }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_st32(u32 taddr, const u32 (&v)[32])
 {
@@ -216,7 +245,9 @@ __global__ void __launch_bounds__(1024) sched_kernel(Params p, u32 *sched)
 		const u32 f = first_dt(p, s * p.group);
 		c = f < p.ndt ? (p.ndt - f) * p.group : 0;
 	}
-	cnt[s] = c;
+	if (s < (u32)MAX_SUPER) {
+		cnt[s] = c;
+	}
 	__syncthreads();
 	if (s == 0) {
 		u32 run = 0;
@@ -354,7 +385,7 @@ __device__ __forceinline__ float sqrt_approx(float x)
 }
 
 // sx: this thread's column of the epilogue's scratch, element (slot, t) at sx[(slot * NP + t) * (NEW * 32)]; slot = single
-// code, slot SC_COUNT holds the constant 1 (written once per kernel)
+// slot (scr_slot), the last slot holds the constant 1 (written once per kernel)
 template <int NEED, int NP>
 __device__ __forceinline__ u32 screen_pairs(const DevModel &dm, float *sx, const u32 (&dot)[NP], const u32 (&emd)[NP], const u32 (&sad)[NP],
 					    const RowF &P, const RowF *Q)
@@ -374,7 +405,7 @@ __device__ __forceinline__ u32 screen_pairs(const DevModel &dm, float *sx, const
 		_Pragma("unroll") for (int t = 0; t < NP; t++)                                   \
 		{                                                                                \
 			const float x_ = __fmaf_rn(a_, (RAW), b_);                               \
-			sx[((CODE)*NP + t) * ET] = x_;                                           \
+			sx[(scr_slot(CODE) * NP + t) * ET] = x_;                                           \
 			m[t] = fmaxf(m[t], used_ ? fabsf(x_) : 0.0f);                            \
 		}                                                                                \
 	}
@@ -447,8 +478,8 @@ struct Cand {
 struct Smem {
 	static constexpr int RING = 0;
 	static constexpr int LIST = STAGES * STAGE_BYTES;                         // Cand[NEW][LIST_CAP]
-	static constexpr int SCRX = LIST + NEW * LIST_CAP * (int)sizeof(Cand);    // float [SC_COUNT + 1][4][NEW * 32]: the screen's scratch
-	static constexpr int ROWQ = SCRX + (SC_COUNT + 1) * 4 * NEW * 32 * 4;      // RowF[2][TQ]
+	static constexpr int SCRX = LIST + NEW * LIST_CAP * (int)sizeof(Cand);    // float [MC2_SCR_SLOTS][NP][NEW * 32]: the screen's scratch
+	static constexpr int ROWQ = SCRX + MC2_SCR_SLOTS * NP * NEW * 32 * 4;     // RowF[2][TQ]
 	static constexpr int WINQ = ROWQ + 2 * TQ * (int)sizeof(RowF);            // u64 window [2][TQ][2]
 	static constexpr int WIN32 = WINQ + 2 * TQ * 16;                          // uint2 window [2][TQ], saturated to 32 bits
 	static constexpr int SCHED = WIN32 + 2 * TQ * 8;                          // u32 [MAX_SUPER + 1]
@@ -456,6 +487,7 @@ struct Smem {
 	static constexpr int MISC = BARS + 32 * 8;                                // tmem base
 	static constexpr int TOTAL = MISC + 64 + 1024;                            // + alignment slack
 };
+static_assert(Smem::TOTAL <= 232448, "shared memory per CTA");
 
 template <int NEED, bool RAW>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -525,7 +557,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				}
 				const int qrow = (int)(p.q0 + (u64)t.qt * TQ), drow = (int)(p.d0 + (u64)t.dt * TD);
 				for (int c = 0; c < N_U8 + N_CUM; c++) {
-					mbar_wait(bar_empty + s * 8, ph ^ 1, p.err);
+					mbar_wait(bar_empty + s * 8, ph ^ 1, p.err, p.sleep_ctrl);
 					const u32 st = sbase + s * STAGE_BYTES, fb = bar_full + s * 8;
 					mbar_expect_tx(fb, STAGE_BYTES);
 					if (stage_is_u8(c)) {
@@ -554,11 +586,11 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				}
 				const u32 buf = it & 1;
 				if (DOT) {
-					mbar_wait(bar_tempty + buf * 8, ((it >> 1) & 1) ^ 1, p.err);
+					mbar_wait(bar_tempty + buf * 8, ((it >> 1) & 1) ^ 1, p.err, p.sleep_ctrl);
 					tc_fence_after();
 				}
 				for (int c = 0; c < N_U8 + N_CUM; c++) {
-					mbar_wait(bar_full + s * 8, ph, p.err);
+					mbar_wait(bar_full + s * 8, ph, p.err, p.sleep_ctrl);
 					if (DOT && stage_is_u8(c)) {
 						const int ku = stage_index(c);
 						tc_fence_after();
@@ -591,7 +623,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
 	} else if (warp < 4 + NCW) {
 		// ===== compute warps =====
-		if (NCW == 8) {
+		if (REGS_COMPUTE > REGS_LAUNCH) {
 			asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
 		}
 		const int cw = warp - 4;
@@ -615,7 +647,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				}
 #pragma unroll 1
 				for (int c = 0; c < N_U8 + N_CUM; c++) {
-					mbar_wait(bar_full + s * 8, ph, p.err);
+					mbar_wait(bar_full + s * 8, ph, p.err, p.sleep_comp);
 					if (c % 3 != 2) {
 						stage_compute<true>(smem + s * STAGE_BYTES, lane_row, qsel, acc);
 					}
@@ -628,7 +660,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 						ph ^= 1;
 					}
 				}
-				mbar_wait(bar_eempty + eb * 8, (eit & 1) ^ 1, p.err); // the epilogue is done with this buffer's previous sums
+				mbar_wait(bar_eempty + eb * 8, (eit & 1) ^ 1, p.err, p.sleep_comp); // the epilogue is done with this buffer's previous sums
 				tc_fence_after();
 				tc_st(tmem_base + tlane + TM_EMD + eb * 128 + qsel * QN, acc[0]);
 				tc_st(tmem_base + tlane + TM_EMD + eb * 128 + 64 + qsel * QN, acc[1]);
@@ -643,7 +675,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				}
 #pragma unroll 1
 				for (int c = 0; c < N_U8; c++) {
-					mbar_wait(bar_full + s * 8, ph, p.err);
+					mbar_wait(bar_full + s * 8, ph, p.err, p.sleep_comp);
 					if (MIN) {
 						stage_compute<false>(smem + s * STAGE_BYTES, lane_row, qsel, acc);
 					}
@@ -657,7 +689,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 					}
 				}
 				if (MIN) {
-					mbar_wait(bar_eempty + eb * 8, (eit & 1) ^ 1, p.err); // the epilogue is done with this buffer's previous sums
+					mbar_wait(bar_eempty + eb * 8, (eit & 1) ^ 1, p.err, p.sleep_comp); // the epilogue is done with this buffer's previous sums
 					tc_fence_after();
 					tmem_free = true;
 					tc_st(tmem_base + tlane + TM_SAD + qsel * QN, acc[0]);
@@ -672,7 +704,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 				}
 #pragma unroll 1
 				for (int c = 0; c < N_CUM; c++) {
-					mbar_wait(bar_full + s * 8, ph, p.err);
+					mbar_wait(bar_full + s * 8, ph, p.err, p.sleep_comp);
 					stage_compute<true>(smem + s * STAGE_BYTES, lane_row, qsel, acc);
 					__syncwarp();
 					if (lane == 0) {
@@ -684,7 +716,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 					}
 				}
 				if (!tmem_free) {
-					mbar_wait(bar_eempty + eb * 8, (eit & 1) ^ 1, p.err);
+					mbar_wait(bar_eempty + eb * 8, (eit & 1) ^ 1, p.err, p.sleep_comp);
 					tc_fence_after();
 				}
 				tc_st(tmem_base + tlane + TM_EMD + eb * 128 + qsel * QN, acc[0]);
@@ -702,7 +734,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 		}
 	} else {
 		// ===== epilogue warps: thread = TMEM lane (database rows L and 128 + L), all 64 query columns of each region =====
-		if (NCW != 8) {
+		if (REGS_EPI > REGS_LAUNCH) {
 			asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
 		}
 		const int ew = warp - 4 - NCW;
@@ -716,9 +748,10 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 		Cand *s_list = reinterpret_cast<Cand *>(smem + L::LIST) + ew * LIST_CAP;
 		float *sx = reinterpret_cast<float *>(smem + L::SCRX) + etid;
 #pragma unroll
-		for (int t = 0; t < 4; t++) {
-			sx[(SC_COUNT * 4 + t) * (NEW * 32)] = 1.0f;
+		for (int t = 0; t < NP; t++) {
+			sx[(scr_slot(SC_COUNT) * NP + t) * (NEW * 32)] = 1.0f;
 		}
+		const int qc0 = (ew >> 2) * QE; // this warp's query columns: qc0 .. qc0 + QE - 1
 		u32 it = 0;
 		u64 scored_total = 0;
 		for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -757,27 +790,27 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 			const u32 buf = it & 1;
 			const u32 eb = EBUFS == 2 ? (it & 1) : 0, eit = EBUFS == 2 ? (it >> 1) : it;
 			if (CUDA_RED) {
-				mbar_wait(bar_efull + eb * 8, eit & 1, p.err);
+				mbar_wait(bar_efull + eb * 8, eit & 1, p.err, p.sleep_epi);
 			}
 			if (DOT) {
-				mbar_wait(bar_tfull + buf * 8, (it >> 1) & 1, p.err);
+				mbar_wait(bar_tfull + buf * 8, (it >> 1) & 1, p.err, p.sleep_epi);
 			}
 			tc_fence_after();
 			u32 n_list = 0, scored = 0;
 #pragma unroll 1
 			for (int r = 0; r < 2; r++) {
 #pragma unroll 1
-				for (int qc = 0; qc < TQ; qc += 4) {
-					u32 vd[4] = {0, 0, 0, 0}, ve[4] = {0, 0, 0, 0}, vs[4] = {0, 0, 0, 0};
-					if (DOT) tc_ld4(tmem_base + tlane + TM_DOT + buf * 128 + r * 64 + qc, vd);
-					if (EMD) tc_ld4(tmem_base + tlane + TM_EMD + eb * 128 + r * 64 + qc, ve);
-					if (MIN) tc_ld4(tmem_base + tlane + TM_SAD + r * 64 + qc, vs);
+				for (int qc = qc0; qc < qc0 + QE; qc += NP) {
+					u32 vd[NP] = {}, ve[NP] = {}, vs[NP] = {};
+					if (DOT) tc_ldn(tmem_base + tlane + TM_DOT + buf * 128 + r * 64 + qc, vd);
+					if (EMD) tc_ldn(tmem_base + tlane + TM_EMD + eb * 128 + r * 64 + qc, ve);
+					if (MIN) tc_ldn(tmem_base + tlane + TM_SAD + r * 64 + qc, vs);
 					tc_ld_wait();
 					const u64 d = drow0 + r * 128 + lane_row;
 					const u32 len32 = RAW ? 0u : (lenD[r] >= 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)lenD[r]);
 					if constexpr (RAW) {
 #pragma unroll
-						for (int k = 0; k < 4; k++) {
+						for (int k = 0; k < NP; k++) {
 							const u64 q = qrow0 + qc + k;
 							if (q < p.q1 && d < p.d1) {
 								const u64 o = (q - p.q0) * (p.d1 - p.d0) + (d - p.d0);
@@ -790,7 +823,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 						const RowF *Q = s_rowQ + par * TQ + qc;
 						u32 go = 0;
 #pragma unroll
-						for (int k = 0; k < 4; k++) {
+						for (int k = 0; k < NP; k++) {
 							const uint2 w = s_win32[par * TQ + qc + k];
 							bool inwin = len32 >= w.x && len32 <= w.y;
 							if (len32 == 0xFFFFFFFFu || w.y == 0xFFFFFFFFu) { // beyond 32 bits: the exact 64-bit window
@@ -803,9 +836,13 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 						scored += __popc(go);
 						u32 cand = p.no_screen ? 0u : go;
 						const bool can_screen = dm.scr_ok != 0;
-						const u32 anybig = PD[r].big | Q[0].big | Q[1].big | Q[2].big | Q[3].big;
+						u32 anybig = PD[r].big;
+#pragma unroll
+						for (int k = 0; k < NP; k++) {
+							anybig |= Q[k].big;
+						}
 						if (can_screen && __any_sync(0xffffffffu, cand != 0 && !anybig)) {
-							const u32 maybe = screen_pairs<NEED, 4>(dm, sx, vd, ve, vs, PD[r], Q);
+							const u32 maybe = screen_pairs<NEED, NP>(dm, sx, vd, ve, vs, PD[r], Q);
 							if (!anybig) {
 								cand &= maybe;
 							}
@@ -813,7 +850,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 						// candidate records -> the warp's list (ballot-compacted), flushed through the exact epilogue when full
 						if (__any_sync(0xffffffffu, cand != 0)) {
 #pragma unroll
-						for (int k = 0; k < 4; k++) {
+						for (int k = 0; k < NP; k++) {
 							const bool c = (cand >> k) & 1;
 							const unsigned m = __ballot_sync(0xffffffffu, c);
 							if (c) {
@@ -827,7 +864,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 							n_list += __popc(m);
 						}
 						}
-						if (n_list > LIST_CAP - 128 || (r == 1 && qc == TQ - 4)) {
+						if (n_list > LIST_CAP - 32 * NP || (r == 1 && qc == qc0 + QE - NP)) {
 							__syncwarp();
 							for (u32 base = 0; base < n_list; base += 32) {
 								const u32 e = base + (u32)lane;
@@ -1112,6 +1149,9 @@ int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset
 	p.n_super = (p.nqt + group - 1) / group;
 	p.sched = d_sched;
 	p.no_screen = getenv("MC2_TS_NOSCREEN") != nullptr;
+	p.sleep_ctrl = getenv("MC2_TS_SLEEP_CTRL") ? (u32)atoi(getenv("MC2_TS_SLEEP_CTRL")) : 0;
+	p.sleep_comp = getenv("MC2_TS_SLEEP_COMP") ? (u32)atoi(getenv("MC2_TS_SLEEP_COMP")) : 0;
+	p.sleep_epi = getenv("MC2_TS_SLEEP_EPI") ? (u32)atoi(getenv("MC2_TS_SLEEP_EPI")) : 0;
 	p.raw_dot = raw_dot; p.raw_emd = raw_emd; p.raw_sad = raw_sad;
 	// the kernel reads the item count from the last prefix entry; it must fit 32 bits
 	if ((u64)p.n_super * group * p.ndt >= (1ull << 32)) {
