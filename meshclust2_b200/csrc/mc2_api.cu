@@ -1830,7 +1830,8 @@ int mc2_get_close_as(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q
 // the launch path.  MC2_NO_SCAN_SERVER=1 (read per call, so tests can compare both paths in one process) turns it off.
 static bool scan_server_eligible(const mc2_model *model, const mc2_hset *set_q, const mc2_hset *set_c, uint64_t n_cand)
 {
-	// measured (tools/call_latency_raw.py): 12 us at 8 candidates, 17 us at 64, 45 us at 512 against 33 us for the launch path
+	// measured from C++ (tools/call_latency.cpp): 8.7 us at <= 16 candidates, 12 us at 64, 17 us at 192; the launch path
+	// costs 32 us whatever the count
 	if (n_cand > 192 || getenv("MC2_NO_SCAN_SERVER")) {
 		return false;
 	}
@@ -1920,11 +1921,11 @@ static int scan_server_call(mc2_ctx *ctx, const mc2_model *model, const mc2_hset
 	}
 	const auto t0 = std::chrono::steady_clock::now();
 	unsigned spins = 0;
-	while (mb->r[7] != seq) {
+	while (mb->r[7] != seq || mb->r[3] != seq) {
 		if (!mb->running) {
 			// the server left (idle) at the moment the request was posted: start it again for this request
 			std::atomic_thread_fence(std::memory_order_seq_cst);
-			if (mb->r[7] == seq) break;
+			if (mb->r[7] == seq && mb->r[3] == seq) break;
 			MC2_CUDA(cudaStreamSynchronize(ctx->server_stream));
 			int rc = scan_server_start(ctx, model, set_q->eb, seq);
 			if (rc != MC2_OK) return rc;
@@ -1949,9 +1950,11 @@ static int scan_server_call(mc2_ctx *ctx, const mc2_model *model, const mc2_hset
 	*best_dist = bdv.d;
 	*is_min = (int)(mb->r[2] & 0xFFFFFFFFull);
 	if (marks) {
-		if (n_cand <= 32) {
-			unsigned long long m4[4] = {mb->r[3], mb->r[4], mb->r[5], mb->r[6]};
-			memcpy(marks, m4, n_cand);
+		if (n_cand <= MC2_SCAN_MARKS_INLINE) {
+			const unsigned long long m3[3] = {mb->r[4], mb->r[5], mb->r[6]};
+			for (u64 j = 0; j < n_cand; j++) {
+				marks[j] = (uint8_t)((m3[j >> 6] >> (j & 63)) & 1);
+			}
 		} else {
 			memcpy(marks, mb->marks, n_cand);
 		}

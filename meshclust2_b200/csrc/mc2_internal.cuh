@@ -101,6 +101,7 @@ struct DevModel {
 // `seq_done`.  No launch, no memcpy, no stream synchronisation per call.
 #define MC2_SCAN_CAP 512        // longer candidate lists take the launch path
 #define MC2_SCAN_INLINE 10      // candidates that travel inside the request header
+#define MC2_SCAN_MARKS_INLINE 192 // marks that travel inside the answer line (one bit each)
 struct ScanMailbox {
 	// Request header: 32 words = four 64-byte lines, fetched by the server with ONE coalesced read per poll.  The host
 	// writes word 0 (the sequence number) last and repeats it in the last word of lines 1-3, so a header whose four
@@ -110,12 +111,13 @@ struct ScanMailbox {
 	//  [16] magC  [17] sumC  [18] sumsqC  [19] lenC  [20..22] cand 0-2  [23] seq  [24..30] cand 3-9  [31] seq
 	volatile unsigned long long w[32];
 	unsigned long long cand[MC2_SCAN_CAP];      // the whole list when it is longer than MC2_SCAN_INLINE
-	// answer (written by the device): one 64-byte line, seq_done last
-	//  [0] best  [1] best_dist (double bits)  [2] is_min | err << 32  [3..6] marks of the first 32 candidates  [7] seq_done
+	// answer (written by the device with one eight-lane store): one 64-byte line, the sequence number closing both halves
+	//  [0] best  [1] best_dist (double bits)  [2] is_min | err << 32  [3] seq_done  [4..6] mark bits of the first 192 candidates
+	//  [7] seq_done
 	volatile unsigned long long r[8];
 	volatile int running;
 	int pad1[15];
-	unsigned char marks[MC2_SCAN_CAP];          // all marks when there are more than 32 candidates
+	unsigned char marks[MC2_SCAN_CAP];          // all marks when there are more than MC2_SCAN_MARKS_INLINE candidates
 };
 static_assert(offsetof(ScanMailbox, cand) == 256, "the scan server reads the request header as 32 eight-byte words");
 

@@ -2277,32 +2277,77 @@ __global__ void __launch_bounds__(512, 1) scan_server_kernel(const __grid_consta
 		RedN mine;
 		mine.smin = mine.dot = mine.emd = 0;
 		mine.jeff = mine.js = 0;
+		// lane i owns candidate first + i: its row index and side-band are requested now, all loads in flight together
+		// (one dependent round trip to memory instead of three)
 		u64 my_c = 0, my_len = 0;
-		bool my_go = false;
-		for (u32 i = 0; i < chunk && first + i < n; i++) {
-			const u64 c = has_list ? s_cand[first + i] : s_hdr[4] + first + i;
-			const u64 lc = lenC[c];
-			const bool inwin = lc >= min_len && lc <= max_len;
-			if (inwin) {
-				const RedN r = reduce_rows_fast<T, 7>(C + c * N, Q, slabs, lane, true);
-				if (lane == (int)i) {
+		Side sc;
+		sc.mag = sc.sum = sc.sumsq = sc.len = 0;
+		const bool mine_valid = (u32)lane < chunk && first + lane < n;
+		if (mine_valid) {
+			my_c = has_list ? s_cand[first + lane] : s_hdr[4] + first + lane;
+			my_len = lenC[my_c];
+			sc.mag = magC[my_c];
+			sc.sum = sumC[my_c];
+			sc.sumsq = sumsqC[my_c];
+			sc.len = my_len;
+		}
+		const bool my_go = mine_valid && my_len >= min_len && my_len <= max_len;
+		const unsigned go_mask = __ballot_sync(0xffffffffu, my_go);
+		if (my_go && chunk > 1) {
+			// the warp reduces its candidates one after the other: pull all their rows towards L2 now, so only the first
+			// one pays the trip to HBM
+			const char *row = reinterpret_cast<const char *>(C + my_c * N);
+			const u32 bytes = (u32)(N * sizeof(T)) < 4096u ? (u32)(N * sizeof(T)) : 4096u;
+			for (u32 o = 0; o < bytes; o += 128) {
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+			}
+		}
+		if (slabs == 1) {
+			// 1 KiB rows: the query's slab and its lane sum are loaded once, and the next wanted candidate's row is
+			// requested before the current one is reduced
+			const Row8 qv = ld_row_keep(reinterpret_cast<const char *>(Q) + lane * 32);
+			const int qsum = lane_sum<T>(qv);
+			unsigned todo = go_mask;
+			Row8 cur = qv;
+			if (todo) {
+				const u64 c0 = __shfl_sync(0xffffffffu, my_c, __ffs(todo) - 1);
+				cur = ld_row_stream(reinterpret_cast<const char *>(C + c0 * N) + lane * 32);
+			}
+			while (todo) {
+				const int i = __ffs(todo) - 1;
+				todo &= todo - 1;
+				Row8 nxt = cur;
+				if (todo) {
+					const u64 c1 = __shfl_sync(0xffffffffu, my_c, __ffs(todo) - 1);
+					nxt = ld_row_stream(reinterpret_cast<const char *>(C + c1 * N) + lane * 32);
+				}
+				int carry = 0;
+				u32 a_min = 0, lo = 0, hi = 0, e = 0;
+				slab_reduce<T, 7>(cur, qv, qsum, carry, a_min, lo, hi, e);
+				RedN r;
+				r.smin = warp_sum_u64(a_min);
+				r.dot = warp_sum_u64((u64)lo + ((u64)hi << 8));
+				r.emd = warp_sum_u64(e);
+				r.jeff = r.js = 0;
+				if (lane == i) {
 					mine = r;
 				}
+				cur = nxt;
 			}
-			if (lane == (int)i) {
-				my_c = c;
-				my_len = lc;
-				my_go = inwin;
+		} else {
+			for (u32 i = 0; i < chunk && first + i < n; i++) {
+				const u64 c = __shfl_sync(0xffffffffu, my_c, (int)i);
+				if ((go_mask >> i) & 1) {
+					const RedN r = reduce_rows_fast<T, 7>(C + c * N, Q, slabs, lane, true);
+					if (lane == (int)i) {
+						mine = r;
+					}
+				}
 			}
 		}
 		if ((u32)lane < chunk && first + lane < n) {
 			const u32 j = first + lane;
 			if (my_go) {
-				Side sc;
-				sc.mag = magC[my_c];
-				sc.sum = sumC[my_c];
-				sc.sumsq = sumsqC[my_c];
-				sc.len = my_len;
 				if (sizeof(T) == 1) {
 					mine.smin = (sc.sum + sq.sum - mine.smin) >> 1; // 8-bit rows reduce sum |p-q|
 				}
@@ -2351,16 +2396,24 @@ __global__ void __launch_bounds__(512, 1) scan_server_kernel(const __grid_consta
 			s_any[warp] = any;
 		}
 		__syncthreads();
-		// the answer: marks beyond the first 32 into the byte array, everything else into one 64-byte line, the
-		// sequence number last and after a system-wide fence
-		if (n > 32) {
+		// the answer: ONE 64-byte line written by one store instruction of eight lanes, the sequence number closing each of
+		// its two 32-byte halves (the host takes the line when both agree), so no fence and no second write sit between the
+		// result and its publication.  The marks of up to 192 candidates travel in the line as a bit mask; longer lists
+		// go to the byte array first, fenced system-wide before the line is written.
+		if (n > MC2_SCAN_MARKS_INLINE) {
+			bool wrote = false;
 			for (u32 w = threadIdx.x; w < (n + 7) / 8; w += blockDim.x) {
 				unsigned long long v = 0;
 				for (u32 b = 0; b < 8 && w * 8 + b < n; b++) {
 					v |= (unsigned long long)(s_flag[w * 8 + b] & 1) << (8 * b);
 				}
 				reinterpret_cast<unsigned long long *>(mb->marks)[w] = v;
+				wrote = true;
 			}
+			if (wrote) {
+				__threadfence_system();
+			}
+			__syncthreads();
 		}
 		if (warp == 0) {
 			bd = -1.0;
@@ -2380,22 +2433,23 @@ __global__ void __launch_bounds__(512, 1) scan_server_kernel(const __grid_consta
 				v = (unsigned long long)__double_as_longlong(bi >= 0 ? bd : -1.0);
 			} else if (lane == 2) {
 				v = (unsigned long long)(any ? 0 : 1) | ((unsigned long long)(unsigned)s_err << 32);
-			} else if (lane < 7) {
-				for (u32 b = 0; b < 8; b++) {
-					const u32 j = (u32)(lane - 3) * 8 + b;
-					v |= (unsigned long long)(j < n ? (s_flag[j] & 1) : 0) << (8 * b);
+			} else if (lane == 3 || lane == 7) {
+				v = last;
+			}
+			// mark bits: six ballots over the first 192 flags, two per 64-bit word, kept by lanes 4..6
+#pragma unroll
+			for (int h = 0; h < 6; h++) {
+				const u32 j = (u32)h * 32 + (u32)lane;
+				const unsigned bits = __ballot_sync(0xffffffffu, j < n && j < MC2_SCAN_MARKS_INLINE && (s_flag[j] & 1));
+				if (lane == 4 + (h >> 1)) {
+					v |= (unsigned long long)bits << (32 * (h & 1));
 				}
 			}
-			if (lane < 7) {
+			if (lane < 8) {
 				mb->r[lane] = v;
 			}
 		}
-		__threadfence_system();
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			mb->r[7] = last;
-			__threadfence_system();
-		}
+		__syncthreads(); // s_flag / s_bd are rewritten by the next request
 	}
 	if (threadIdx.x == 0) {
 		mb->running = 0;
