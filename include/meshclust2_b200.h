@@ -347,10 +347,12 @@ int mc2_all_pairs(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q, u
  * bench.py's roofline for the CUDA-core EMD term ("achieved ... vs a measured ALU peak"). */
 int mc2_bench_issue_rate(mc2_ctx *ctx, int iters, double *warp_instr_per_s);
 
-/* Diagnostic (tests): the integer reductions of the 1 KiB uint8 tile sweep for every (query, database) pair of the two row
- * ranges, as dense row-major (q_end-q_begin) x (d_end-d_begin) uint32 matrices: need is a mask of 1 = sum|p-q|
- * (Feature.cpp:858-871), 2 = sum p*q (Feature.cpp:1112-1124, 1170-1184), 4 = sum|cumP-cumQ| (Feature.cpp:1504-1518).
- * Outputs not selected by `need` may be NULL.  No length window, no model. */
+/* Diagnostic (tests): the integer reductions of the tile sweep for every (query, database) pair of the two row ranges, as
+ * dense row-major (q_end-q_begin) x (d_end-d_begin) uint32 matrices: need is a mask of 1 = sum|p-q| (Feature.cpp:858-871),
+ * 2 = sum p*q (Feature.cpp:1112-1124, 1170-1184), 4 = sum|cumP-cumQ| (Feature.cpp:1504-1518).  Outputs not selected by
+ * `need` may be NULL.  No length window, no model.  Sets of uint8 / uint16 rows of whole 1 KiB slabs (k >= 5, at most 4^8
+ * bins) whose row sums fit 16 bits once the pseudo-count per bin is taken out; MC2_ERR_UNSUPPORTED when the rows do not
+ * fit the tile form (a uint16 bin above 255, a bin below the pseudo-count in rows that need it taken out). */
 int mc2_debug_tile_reductions(mc2_ctx *ctx, const mc2_hset *set_q, uint64_t q_begin, uint64_t q_end, const mc2_hset *set_d,
 			      uint64_t d_begin, uint64_t d_end, int32_t need, uint32_t *out_dot, uint32_t *out_emd, uint32_t *out_sad);
 

@@ -1134,6 +1134,7 @@ int mc2_count_kmers_into_rows(mc2_ctx *ctx, const mc2_seqs *seqs, mc2_hset *dst,
 	view.maxc = dst->maxc + first_row;
 	view.lane_off = nullptr;
 	view.cum16 = nullptr;
+	view.plane8 = nullptr;
 	view.cumsum = nullptr;
 	return count_into(ctx, seqs, dst->k, dst->eb, 1, &view);
 }
@@ -1360,6 +1361,7 @@ void mc2_hset_free(mc2_hset *h)
 	cudaFree(h->maxc);
 	cudaFree(h->lane_off);
 	cudaFree(h->cum16);
+	cudaFree(h->plane8);
 	cudaFree(h->cumsum);
 	delete h;
 }
@@ -2177,7 +2179,7 @@ int mc2_debug_tile_reductions(mc2_ctx *ctx, const mc2_hset *set_q, uint64_t q_be
 {
 	MC2_REQUIRE(ctx && set_q && set_d, "mc2_debug_tile_reductions: NULL argument");
 	MC2_REQUIRE(q_begin <= q_end && q_end <= set_q->n && d_begin <= d_end && d_end <= set_d->n, "mc2_debug_tile_reductions: row range out of bounds");
-	MC2_REQUIRE(set_q->eb == 1 && set_d->eb == 1 && set_q->N == 1024 && set_d->N == 1024, "mc2_debug_tile_reductions: needs k = 5 uint8 sets");
+	MC2_REQUIRE(tile_sweep_shape_ok(set_q, set_d), "mc2_debug_tile_reductions: needs uint8 / uint16 sets of whole 1 KiB slabs whose rows fit the tile form");
 	MC2_REQUIRE((need & 7) != 0 && (need & ~7) == 0, "mc2_debug_tile_reductions: need is a mask of 1 (sad), 2 (dot), 4 (emd)");
 	MC2_CUDA(cudaSetDevice(ctx->device));
 	const u64 cells = (q_end - q_begin) * (d_end - d_begin);

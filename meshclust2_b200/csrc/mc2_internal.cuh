@@ -198,11 +198,14 @@ struct mc2_hset {
 	// dropped whenever bins change.
 	unsigned short *lane_off;
 	int lane_off_valid;
-	// 1 KiB uint8 rows with row sums < 65536: inclusive cumulative rows (u16, n x 1024) and each row's sum of them (u32),
-	// the EMD operands of the tile sweep (tile_sweep.cu).  Built lazily, dropped whenever bins change.
+	// Operands of the tile sweep (tile_sweep.cu; uint8 / uint16 rows of whole 1 KiB slabs): inclusive cumulative rows of
+	// (bin - cum_base) as u16 (n x N), each row's sum of them (u32), and for uint16 bins the rows as bytes.  Built lazily,
+	// dropped whenever bins change.  cum16_valid: 0 not built, 1 built, -1 the set cannot be served with cum_base.
 	unsigned short *cum16;
 	u32 *cumsum;
+	unsigned char *plane8;
 	int cum16_valid;
+	int cum_base;
 };
 
 struct mc2_model {
@@ -258,8 +261,9 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 int launch_distance(mc2_ctx *ctx, const PairArgs &a, u64 *d_out);
 int ensure_lane_off(mc2_ctx *ctx, const mc2_hset *h); // builds h->lane_off if the shape allows; no-op otherwise
 // tile_sweep.cu: the all-pairs sweep over 1 KiB uint8 rows as 64 x 128 pair tiles (TMA ring, tcgen05 Gram term, u16 cumulative EMD)
-int ensure_cum16(mc2_ctx *ctx, const mc2_hset *h);
+int ensure_tile_operands(mc2_ctx *ctx, const mc2_hset *h, int base);
 bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset *d);
+bool tile_sweep_shape_ok(const mc2_hset *q, const mc2_hset *d);
 int launch_issue_probe(mc2_ctx *ctx, int iters, u32 *d_out, u64 *warp_instr);
 // pair_score.cu: start the resident scan server for 1- or 2-byte bins on ctx->server_stream
 int launch_scan_server(mc2_ctx *ctx, const DevModel &dm, int eb, u64 first_seq);

@@ -2084,10 +2084,15 @@ int launch_all_pairs(mc2_ctx *ctx, const DevModel &dm, const mc2_hset *q, u64 q0
 		     int upper_only, double cutoff, u64 max_out, u64 *d_out_q, u64 *d_out_d, double *d_out_score,
 		     u64 *d_counters)
 {
-	// 1 KiB uint8 rows with a classifier the fast epilogue covers: 64 x 128 pair tiles (tile_sweep.cu)
+	// uint8 / uint16 rows of whole 1 KiB slabs with a classifier the fast epilogue covers: 64 x 256 pair tiles
+	// (tile_sweep.cu).  Its operand pass may still find the rows unfit (a uint16 bin above 255, a bin below the
+	// pseudo-count): nothing has been written then, and the row-streaming kernels below take the call.
 	if (tile_sweep_supported(dm, q, d)) {
-		return launch_tile_sweep(ctx, dm, dm.need & 7, q, q0, q1, d, d0, d1, upper_only, cutoff, max_out, d_out_q, d_out_d, d_out_score,
-					 d_counters, nullptr, nullptr, nullptr);
+		const int rc = launch_tile_sweep(ctx, dm, dm.need & 7, q, q0, q1, d, d0, d1, upper_only, cutoff, max_out, d_out_q, d_out_d,
+						 d_out_score, d_counters, nullptr, nullptr, nullptr);
+		if (rc != MC2_ERR_UNSUPPORTED) {
+			return rc;
+		}
 	}
 	PairArgs a;
 	memset(&a, 0, sizeof a);

@@ -38,7 +38,7 @@ namespace ts {
 
 constexpr int TQ = 64;          // query rows per tile (UMMA N, TMEM columns per region)
 constexpr int TD = 256;         // database rows per tile: two regions of 128 (UMMA M = 128 = the TMEM lanes)
-constexpr int NBINS = 1024;
+constexpr int NBINS = 1024;      // bins per slab; rows are Params::n_slabs slabs long
 constexpr int KC_CUM = 64;      // bins per ring stage while the u16 cumulative rows stream (128-byte rows)
 constexpr int KC_U8 = 128;      // bins per ring stage while the u8 rows stream (128-byte rows)
 #ifndef MC2_TS_NCW
@@ -93,6 +93,7 @@ struct Params {
 	u32 nqt, ndt;           // tiles along each side
 	u32 group;              // query tiles per super-row of the schedule
 	u32 n_super;
+	u32 n_slabs;            // bins per row / 1024 (1 for k = 5, 64 for k = 8)
 	const u32 *sched;       // [n_super + 1] exclusive prefix of items per super-row (device)
 	int no_screen;          // experiments: skip the screen and the exact path (main-loop cost only)
 	u32 sleep_ctrl, sleep_comp, sleep_epi; // experiments: back-off of the three roles' barrier waits (ns)
@@ -499,13 +500,13 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 	constexpr bool DOT = (NEED & NEED_DOT) != 0, EMD = (NEED & NEED_EMD) != 0, MIN = (NEED & NEED_MIN) != 0;
 	constexpr bool U8_PHASE = DOT || MIN;
 	constexpr bool CUDA_RED = EMD || MIN;             // compute warps produce sums for the epilogue
-	constexpr int N_U8 = U8_PHASE ? NBINS / KC_U8 : 0;   // ring stages per tile while the u8 rows stream
-	constexpr int N_CUM = EMD ? NBINS / KC_CUM : 0;      // ... while the cumulative rows stream
+	const int N_U8 = U8_PHASE ? (int)p.n_slabs * (NBINS / KC_U8) : 0;   // ring stages per tile while the u8 rows stream
+	const int N_CUM = EMD ? (int)p.n_slabs * (NBINS / KC_CUM) : 0;      // ... while the cumulative rows stream
 	// Gram + EMD models: every third stage carries u8 rows (for the MMA issuer only), so the compute warps never sit
 	// through a whole u8 phase; otherwise the u8 stages come first, then the cumulative ones
 	constexpr bool INTERLEAVE = DOT && EMD && !MIN;
-	auto stage_is_u8 = [](int c) { return INTERLEAVE ? (c % 3 == 2) : (c < N_U8); };
-	auto stage_index = [](int c) { return INTERLEAVE ? (c % 3 == 2 ? c / 3 : c - c / 3) : (c < N_U8 ? c : c - N_U8); };
+	auto stage_is_u8 = [N_U8](int c) { return INTERLEAVE ? (c % 3 == 2) : (c < N_U8); };
+	auto stage_index = [N_U8](int c) { return INTERLEAVE ? (c % 3 == 2 ? c / 3 : c - c / 3) : (c < N_U8 ? c : c - N_U8); };
 	extern __shared__ unsigned char smem_raw[];
 	// SWIZZLE_128B tiles and the UMMA descriptors want 1024-byte alignment: align by hand (the launch adds the slack)
 	unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -835,7 +836,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 						}
 						scored += __popc(go);
 						u32 cand = p.no_screen ? 0u : go;
-						const bool can_screen = dm.scr_ok != 0;
+						const bool can_screen = dm.scr_ok != 0 && p.n_slabs == 1; // the screen's constants and bound are for 1024 bins
 						u32 anybig = PD[r].big;
 #pragma unroll
 						for (int k = 0; k < NP; k++) {
@@ -881,7 +882,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 									rd.dot = c.dot;
 									rd.emd = c.emd;
 									rd.smin = MIN ? (sd.sum + sq.sum - (u64)c.sad) >> 1 : 0;
-									const int bad = eval_pair_fast(dm, NBINS, rd, sd, sq, true, score, d0v, close);
+									const int bad = eval_pair_fast(dm, (u64)p.n_slabs * NBINS, rd, sd, sq, true, score, d0v, close);
 									if (bad) {
 										atomicOr(p.err, bad & 1 ? 1 : 2);
 									}
@@ -982,6 +983,97 @@ __global__ void __launch_bounds__(256) cum16_kernel(const unsigned char *__restr
 	}
 }
 
+// The general form: rows of n_slabs x 1024 bins of T (uint8 / uint16), cumulative values of (bin - base).  Both operands of
+// sum |cumP - cumQ| carry the same pseudo-count per bin, so subtracting it from every bin of both rows leaves every
+// difference of cumulative values unchanged -- and brings rows whose sums reach 65536 only through the 4^k pseudo-counts
+// (k >= 6) back into 16 bits.  For uint16 bins the kernel also writes the row as bytes (the tensor-core and VABSDIFF4
+// operands).  flags: 1 a bin below base, 2 a uint16 bin above 255, 4 a cumulative value beyond 16 bits -- any of them
+// means the set cannot take the tile sweep with this base.
+template <typename T>
+__global__ void __launch_bounds__(256) cum_wide_kernel(const T *__restrict__ bins, u64 n, u32 n_slabs, u32 base, unsigned short *__restrict__ cum,
+						       u32 *__restrict__ cumsum, unsigned char *__restrict__ plane, int *flags)
+{
+	const int lane = threadIdx.x & 31;
+	const u64 warps_total = (u64)gridDim.x * (blockDim.x >> 5);
+	const u64 N = (u64)n_slabs * 1024;
+	int bad = 0;
+	for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps_total) {
+		u32 carry = 0, cs = 0;
+		for (u32 s = 0; s < n_slabs; s++) {
+			const u64 at = r * N + (u64)s * 1024 + (u64)lane * 32;
+			u32 v[32];
+			if (sizeof(T) == 1) {
+				const uint4 *src = reinterpret_cast<const uint4 *>(bins + at);
+				const uint4 a = __ldg(src), b = __ldg(src + 1);
+				const u32 w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+				for (int i = 0; i < 32; i++) {
+					v[i] = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+				}
+			} else {
+				const uint4 *src = reinterpret_cast<const uint4 *>(bins + at);
+				u32 w[16];
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					const uint4 a = __ldg(src + i);
+					w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
+				}
+				u32 pk[8];
+#pragma unroll
+				for (int i = 0; i < 32; i++) {
+					v[i] = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+					bad |= v[i] > 255u ? 2 : 0;
+				}
+#pragma unroll
+				for (int i = 0; i < 8; i++) {
+					pk[i] = (v[4 * i] & 0xFFu) | ((v[4 * i + 1] & 0xFFu) << 8) | ((v[4 * i + 2] & 0xFFu) << 16) | ((v[4 * i + 3] & 0xFFu) << 24);
+				}
+				uint4 *dp = reinterpret_cast<uint4 *>(plane + at);
+				dp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+				dp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+			}
+			u32 tot = 0;
+#pragma unroll
+			for (int i = 0; i < 32; i++) {
+				bad |= v[i] < base ? 1 : 0;
+				v[i] -= base;
+				tot += v[i];
+			}
+			u32 x = tot;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const u32 y = __shfl_up_sync(0xffffffffu, x, d);
+				if (lane >= d) {
+					x += y;
+				}
+			}
+			u32 run = carry + x - tot;
+			u32 out[16];
+#pragma unroll
+			for (int i = 0; i < 16; i++) {
+				const u32 c0 = run + v[2 * i], c1 = c0 + v[2 * i + 1];
+				run = c1;
+				cs += c0 + c1;
+				out[i] = (c0 & 0xFFFFu) | (c1 << 16);
+			}
+			bad |= run > 0xFFFFu ? 4 : 0; // cumulative values are non-decreasing: the lane's last one bounds the others
+			uint4 *dst = reinterpret_cast<uint4 *>(cum + at);
+			dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+			dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+			dst[2] = make_uint4(out[8], out[9], out[10], out[11]);
+			dst[3] = make_uint4(out[12], out[13], out[14], out[15]);
+			carry += __shfl_sync(0xffffffffu, x, 31);
+		}
+		cs = __reduce_add_sync(0xffffffffu, cs);
+		if (lane == 0) {
+			cumsum[r] = cs;
+		}
+	}
+	if (bad) {
+		atomicOr(flags, bad);
+	}
+}
+
 // issue-rate probe: the tile sweep's inner pair of instructions (VIMNMX.U16x2 on the ALU pipe feeding IDP.2A on the FMA
 // pipe), 16 independent chains per thread, 32 resident warps per SM, no memory traffic: the measured denominator of
 // bench.py's roofline for the CUDA-core EMD term
@@ -1012,29 +1104,62 @@ __global__ void __launch_bounds__(256) issue_probe_kernel(u32 *out, u32 seed, in
 
 } // namespace ts
 
-int ensure_cum16(mc2_ctx *ctx, const mc2_hset *hc)
+// Operands of the tile sweep for one set: u16 cumulative rows of (bin - base) + their sums, and for uint16 bins the
+// byte plane.  cum16_valid: 0 not built, 1 built for cum_base, -1 this set cannot be served with cum_base (cached until
+// the bins change).  1 KiB uint8 rows with base 0 (the bench shape) need no check on the device and no synchronisation.
+int ensure_tile_operands(mc2_ctx *ctx, const mc2_hset *hc, int base)
 {
 	mc2_hset *h = const_cast<mc2_hset *>(hc);
-	if (h->eb != 1 || h->N != 1024 || h->max_sum >= 65536 || h->n == 0) {
-		h->cum16_valid = 0;
-		return MC2_OK;
+	if (h->n == 0) {
+		return MC2_ERR_UNSUPPORTED;
 	}
-	if (h->cum16_valid) {
-		return MC2_OK;
+	if (h->cum16_valid != 0 && h->cum_base == base) {
+		return h->cum16_valid > 0 ? MC2_OK : MC2_ERR_UNSUPPORTED;
+	}
+	const u64 N = h->N;
+	if ((h->eb != 1 && h->eb != 2) || N % 1024 != 0 || N > 65536 || h->max_sum >= 65536 + (u64)base * N) {
+		h->cum16_valid = -1;
+		h->cum_base = base;
+		return MC2_ERR_UNSUPPORTED;
 	}
 	if (!h->cum16) {
-		MC2_CUDA(cudaMalloc((void **)&h->cum16, h->n * 2048));
+		MC2_CUDA(cudaMalloc((void **)&h->cum16, h->n * N * 2));
 		MC2_CUDA(cudaMalloc((void **)&h->cumsum, h->n * 4));
 	}
+	if (h->eb == 2 && !h->plane8) {
+		MC2_CUDA(cudaMalloc((void **)&h->plane8, h->n * N));
+	}
+	h->cum_base = base;
 	u64 want = (h->n + 7) / 8, cap = (u64)ctx->sm_count * 8;
 	int grid = (int)(want < cap ? want : cap);
+	if (h->eb == 1 && N == 1024 && base == 0) {
+		prof_begin(ctx, 5);
+		ts::cum16_kernel<<<grid, 256, 0, ctx->stream>>>((const unsigned char *)h->bins, h->n, h->cum16, h->cumsum);
+		prof_end(ctx);
+		ctx->launches++;
+		MC2_CUDA(cudaGetLastError());
+		h->cum16_valid = 1;
+		return MC2_OK;
+	}
+	// the general form reports what it met in a word of the context's result slot (bytes 3072..3075, unused otherwise)
+	int *d_flags = reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->d_slot) + 3072);
+	MC2_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->stream));
 	prof_begin(ctx, 5);
-	ts::cum16_kernel<<<grid, 256, 0, ctx->stream>>>((const unsigned char *)h->bins, h->n, h->cum16, h->cumsum);
+	if (h->eb == 1) {
+		ts::cum_wide_kernel<unsigned char><<<grid, 256, 0, ctx->stream>>>((const unsigned char *)h->bins, h->n, (u32)(N / 1024), (u32)base,
+										      h->cum16, h->cumsum, nullptr, d_flags);
+	} else {
+		ts::cum_wide_kernel<unsigned short><<<grid, 256, 0, ctx->stream>>>((const unsigned short *)h->bins, h->n, (u32)(N / 1024), (u32)base,
+										       h->cum16, h->cumsum, h->plane8, d_flags);
+	}
 	prof_end(ctx);
 	ctx->launches++;
 	MC2_CUDA(cudaGetLastError());
-	h->cum16_valid = 1;
-	return MC2_OK;
+	int flags = 0;
+	MC2_CUDA(cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	MC2_CUDA(cudaStreamSynchronize(ctx->stream));
+	h->cum16_valid = flags ? -1 : 1;
+	return flags ? MC2_ERR_UNSUPPORTED : MC2_OK;
 }
 
 int launch_issue_probe(mc2_ctx *ctx, int iters, u32 *d_out, u64 *warp_instr)
@@ -1066,16 +1191,16 @@ static EncodeTiledFn encode_fn()
 	return fn;
 }
 
-// rows of 1024 elements (u8 or u16), box = 128 bytes x `box_rows` rows, SWIZZLE_128B
-static int make_map(CUtensorMap *m, const void *base, u64 n_rows, int elem_bytes, int box_rows)
+// rows of `row_elems` elements (u8 or u16), box = 128 bytes x `box_rows` rows, SWIZZLE_128B
+static int make_map(CUtensorMap *m, const void *base, u64 n_rows, u64 row_elems, int elem_bytes, int box_rows)
 {
 	EncodeTiledFn fn = encode_fn();
 	if (!fn) {
 		set_error("tile sweep: cuTensorMapEncodeTiled is not available from this driver");
 		return MC2_ERR_CUDA;
 	}
-	const cuuint64_t dims[2] = {1024, n_rows};
-	const cuuint64_t strides[1] = {(cuuint64_t)1024 * elem_bytes};
+	const cuuint64_t dims[2] = {row_elems, n_rows};
+	const cuuint64_t strides[1] = {(cuuint64_t)row_elems * elem_bytes};
 	const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
 	const cuuint32_t es[2] = {1, 1};
 	const CUresult r = fn(m, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims,
@@ -1088,15 +1213,33 @@ static int make_map(CUtensorMap *m, const void *base, u64 n_rows, int elem_bytes
 	return MC2_OK;
 }
 
+// the base both sets' cumulative rows are built with: 0 when the row sums themselves fit 16 bits, else the pseudo-count
+static int tile_base(const mc2_hset *q, const mc2_hset *d)
+{
+	return (q->max_sum < 65536 && d->max_sum < 65536) ? 0 : 1;
+}
+
+// what the host can tell without touching the data: rows of whole 1 KiB slabs of uint8 / uint16 bins, at most 65536 bins
+// (32-bit sums of 16-bit cumulative values), row sums that fit 16 bits once the pseudo-counts are taken out
+bool tile_sweep_shape_ok(const mc2_hset *q, const mc2_hset *d)
+{
+	const int base = tile_base(q, d);
+	const u64 N = q->N;
+	const bool shape = q->eb == d->eb && (q->eb == 1 || q->eb == 2) && N == d->N && N % 1024 == 0 && N <= 65536 && q->n > 0 && d->n > 0 &&
+			   q->n < (1ull << 31) && d->n < (1ull << 31);
+	const bool sums = q->max_sum < 65536 + (u64)base * N && d->max_sum < 65536 + (u64)base * N;
+	const bool known_bad = (q->cum16_valid < 0 && q->cum_base == base) || (d->cum16_valid < 0 && d->cum_base == base);
+	return shape && sums && !known_bad;
+}
+
 bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset *d)
 {
 	const bool off = getenv("MC2_SWEEP_LEGACY") != nullptr; // read per call: bench.py times both forms in one process
 	if (off) {
 		return false;
 	}
-	const bool shape = q->eb == 1 && d->eb == 1 && q->N == 1024 && d->N == 1024 && q->max_sum < 65536 && d->max_sum < 65536;
 	const bool model = dm.fast_epi && !dm.regression && dm.bias == 0.0 && !(dm.need & NEED_LOG) && (dm.need & 7) != 0;
-	return shape && model && q->n < (1ull << 31) && d->n < (1ull << 31);
+	return model && tile_sweep_shape_ok(q, d);
 }
 
 template <int NEED, bool RAW> static int launch_need(int grid, cudaStream_t st, const DevModel &dm, const ts::Params &p, const CUtensorMap *m)
@@ -1117,15 +1260,16 @@ int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset
 	u32 *d_sched = (u32 *)ctx->d_sched;
 	const bool raw = raw_dot || raw_emd || raw_sad;
 	int rc;
-	if (need & NEED_EMD) {
-		rc = ensure_cum16(ctx, q);
-		if (rc != MC2_OK) return rc;
-		rc = ensure_cum16(ctx, d);
-		if (rc != MC2_OK) return rc;
-		if (!q->cum16_valid || !d->cum16_valid) {
-			set_error("tile sweep: cumulative rows unavailable for this set");
-			return MC2_ERR_UNSUPPORTED;
+	// operands first: a set that cannot be served (a bin below the pseudo-count, a uint16 bin above 255) is known before
+	// anything is written, and the caller falls back to the row-streaming kernels
+	const int base = tile_base(q, d);
+	if ((need & NEED_EMD) || q->eb == 2) {
+		rc = ensure_tile_operands(ctx, q, base);
+		if (rc == MC2_OK && d != q) rc = ensure_tile_operands(ctx, d, base);
+		if (rc == MC2_ERR_UNSUPPORTED) {
+			set_error("tile sweep: this set's rows do not fit the tile form");
 		}
+		if (rc != MC2_OK) return rc;
 	}
 	ts::Params p;
 	memset(&p, 0, sizeof p);
@@ -1147,6 +1291,7 @@ int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset
 	}
 	p.group = group;
 	p.n_super = (p.nqt + group - 1) / group;
+	p.n_slabs = (u32)(q->N / 1024);
 	p.sched = d_sched;
 	p.no_screen = getenv("MC2_TS_NOSCREEN") != nullptr;
 	p.sleep_ctrl = getenv("MC2_TS_SLEEP_CTRL") ? (u32)atoi(getenv("MC2_TS_SLEEP_CTRL")) : 0;
@@ -1163,15 +1308,15 @@ int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset
 	CUtensorMap maps[4];
 	memset(maps, 0, sizeof maps);
 	if (need & NEED_EMD) {
-		rc = make_map(&maps[0], d->cum16, d->n, 2, ts::TD);
+		rc = make_map(&maps[0], d->cum16, d->n, d->N, 2, ts::TD);
 		if (rc != MC2_OK) return rc;
-		rc = make_map(&maps[1], q->cum16, q->n, 2, ts::TQ);
+		rc = make_map(&maps[1], q->cum16, q->n, q->N, 2, ts::TQ);
 		if (rc != MC2_OK) return rc;
 	}
 	if (need & (NEED_DOT | NEED_MIN)) {
-		rc = make_map(&maps[2], d->bins, d->n, 1, ts::TD);
+		rc = make_map(&maps[2], d->eb == 2 ? (const void *)d->plane8 : d->bins, d->n, d->N, 1, ts::TD);
 		if (rc != MC2_OK) return rc;
-		rc = make_map(&maps[3], q->bins, q->n, 1, ts::TQ);
+		rc = make_map(&maps[3], q->eb == 2 ? (const void *)q->plane8 : q->bins, q->n, q->N, 1, ts::TQ);
 		if (rc != MC2_OK) return rc;
 	}
 	const int grid = ctx->sm_count;

@@ -131,3 +131,100 @@ def test_tile_sweep_random_models(built_lib, ctx, seed):
     assert set(got) - edge == set(want) - edge
     for k in set(got) & set(want):
         assert abs(got[k] - want[k]) <= 1e-9
+
+
+def _wide_hist(rng, n, k, eb, mean_extra):
+    """rows of 4^k bins >= 1 (the pseudo-count) plus sparse k-mer counts: about mean_extra counted k-mers per row"""
+    N = 4 ** k
+    H = np.ones((n, N), dtype=np.int64)
+    for r in range(n):
+        idx = rng.integers(0, N, mean_extra)
+        np.add.at(H[r], idx, 1)
+    return H.astype(port.DTYPES[eb])
+
+
+@pytest.mark.parametrize("k,eb,extra", [(6, 1, 30000), (6, 2, 30000), (6, 2, 64000), (7, 2, 50000), (8, 2, 50000), (5, 2, 3000)])
+def test_tile_reductions_wide_rows_bit_exact(built_lib, ctx, k, eb, extra):
+    """rows of several 1 KiB slabs (k = 6 .. 8) and uint16 bins: row sums reach 65536 only through the 4^k pseudo-counts, which
+    the cumulative rows leave out (the differences cumP - cumQ do not change); uint16 bins travel as a byte plane"""
+    rng = np.random.default_rng(1000 * k + eb)
+    nq, nd = (70, 150) if k < 8 else (66, 130)
+    Hq, Hd = _wide_hist(rng, nq, k, eb, extra), _wide_hist(rng, nd, k, eb, extra)
+    Hd[5] = 1                                               # nothing but pseudo-counts
+    hq = ctx.hset_from_host(Hq, k, mag=None, length=np.full(nq, 1000, dtype=np.uint64))
+    hd = ctx.hset_from_host(Hd, k, mag=None, length=np.full(nd, 1000, dtype=np.uint64))
+    got = ctx.tile_reductions(hq, hd, 7)
+    dot, emd, sad = _np_reductions(Hq, Hd)
+    assert np.array_equal(got["dot"].astype(np.int64), dot)
+    assert np.array_equal(got["emd"].astype(np.int64), emd)
+    assert np.array_equal(got["sad"].astype(np.int64), sad)
+
+
+@pytest.mark.parametrize("k,eb", [(6, 1), (6, 2), (7, 2)])
+def test_tile_sweep_wide_rows_vs_oracle(built_lib, ctx, k, eb):
+    """the sweep over multi-slab rows through the tile form == the oracle's work() loop (every in-window pair takes the exact
+    epilogue there: the fp32 screen is for 1 KiB rows)"""
+    from meshclust2_b200 import capi
+    rng = np.random.default_rng(77 + k + eb)
+    n = 200
+    base = _wide_hist(rng, 25, k, eb, 20000).astype(np.int64)
+    H = base[rng.integers(0, 25, n)]
+    for r in range(n):                                      # related rows: a few hundred extra k-mers each
+        np.add.at(H[r], rng.integers(0, 4 ** k, 300), 1)
+    H = H.astype(port.DTYPES[eb])
+    ln = rng.integers(18000, 22000, n).astype(np.uint64)
+    mag = H.sum(axis=1, dtype=np.uint64)
+    flags = [port.FEAT[x] for x in ("euclidean", "emd", "manhattan", "pearson", "length_difference")]
+    om = all_singles_model(flags, H, mag, ln, rng, n_combos=4)
+    # intercept such that about one pair in ten is close
+    iu, ju = np.triu_indices(n, 1)
+    sc = np.clip(port.score_pairs(om, H, mag, ln, ju, iu)["score"], 1e-12, 1 - 1e-12)
+    om.weights[0] = float(om.weights[0]) - float(np.quantile(np.log(sc / (1 - sc)), 0.9))
+    hs = ctx.hset_from_host(H, k, mag=mag, length=ln)
+    gm = ctx.model(to_desc(capi, om))
+    r = ctx.all_pairs(gm, hs, hs, 0.9, upper_only=True, max_out=n * n)
+    want, scored = _oracle_sweep(om, H, mag, ln, 0.9, (0, n), (0, n), True)
+    got = {(int(q), int(d)): s for q, d, s in zip(r["q"], r["d"], r["score"])}
+    assert r["n_scored"] == scored
+    edge = {kk for kk, s in want.items() if abs(s - 0.5) <= 1e-9}
+    assert set(got) - edge == set(want) - edge
+    for kk in set(got) & set(want):
+        assert abs(got[kk] - want[kk]) <= 1e-9
+    assert 0 < len(want) < scored
+    # the same through the row-streaming kernels
+    import os
+    os.environ["MC2_SWEEP_LEGACY"] = "1"
+    try:
+        r2 = ctx.all_pairs(gm, hs, hs, 0.9, upper_only=True, max_out=n * n)
+    finally:
+        os.environ.pop("MC2_SWEEP_LEGACY", None)
+    got2 = {(int(q), int(d)): s for q, d, s in zip(r2["q"], r2["d"], r2["score"])}
+    assert got2 == got and r2["n_scored"] == r["n_scored"]
+
+
+def test_tile_sweep_declines_unfit_rows(built_lib, ctx):
+    """a uint16 bin above 255, or a zero bin in rows whose sums need the pseudo-counts taken out: the tile form declines
+    (nothing written) and the sweep is served by the row-streaming kernels with the same answers as the oracle"""
+    from meshclust2_b200 import capi
+    rng = np.random.default_rng(5)
+    n, k = 120, 6
+    for case in ("big_bin", "zero_bin"):
+        H = _wide_hist(rng, n, k, 2, 30000 if case == "big_bin" else 64000).astype(np.int64)
+        if case == "big_bin":
+            H[7, 100] = 300
+        else:
+            H[9, 5] = 0
+        H = H.astype(np.uint16)
+        ln = rng.integers(19000, 21000, n).astype(np.uint64)
+        mag = H.sum(axis=1, dtype=np.uint64)
+        hs = ctx.hset_from_host(H, k, mag=mag, length=ln)
+        with pytest.raises(capi.Mc2Error):
+            ctx.tile_reductions(hs, hs, 7)
+        om = all_singles_model([port.FEAT["euclidean"], port.FEAT["emd"]], H, mag, ln, rng, n_combos=2)
+        gm = ctx.model(to_desc(capi, om))
+        r = ctx.all_pairs(gm, hs, hs, 0.9, upper_only=True, max_out=n * n)
+        want, scored = _oracle_sweep(om, H, mag, ln, 0.9, (0, n), (0, n), True)
+        got = {(int(q), int(d)): s for q, d, s in zip(r["q"], r["d"], r["score"])}
+        assert r["n_scored"] == scored
+        edge = {kk for kk, s in want.items() if abs(s - 0.5) <= 1e-9}
+        assert set(got) - edge == set(want) - edge
