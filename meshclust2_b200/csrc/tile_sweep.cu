@@ -490,7 +490,8 @@ struct Smem {
 };
 static_assert(Smem::TOTAL <= 232448, "shared memory per CTA");
 
-template <int NEED, bool RAW>
+// ONE: rows of one 1 KiB slab (k = 5), stage counts known at compile time; otherwise Params::n_slabs slabs per row
+template <int NEED, bool RAW, bool ONE>
 __global__ void __launch_bounds__(THREADS, 1)
 tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ Params p, const __grid_constant__ CUtensorMap mapCumD,
 		  const __grid_constant__ CUtensorMap mapCumQ, const __grid_constant__ CUtensorMap mapU8D,
@@ -500,8 +501,9 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 	constexpr bool DOT = (NEED & NEED_DOT) != 0, EMD = (NEED & NEED_EMD) != 0, MIN = (NEED & NEED_MIN) != 0;
 	constexpr bool U8_PHASE = DOT || MIN;
 	constexpr bool CUDA_RED = EMD || MIN;             // compute warps produce sums for the epilogue
-	const int N_U8 = U8_PHASE ? (int)p.n_slabs * (NBINS / KC_U8) : 0;   // ring stages per tile while the u8 rows stream
-	const int N_CUM = EMD ? (int)p.n_slabs * (NBINS / KC_CUM) : 0;      // ... while the cumulative rows stream
+	const int n_slabs = ONE ? 1 : (int)p.n_slabs;
+	const int N_U8 = U8_PHASE ? n_slabs * (NBINS / KC_U8) : 0;   // ring stages per tile while the u8 rows stream
+	const int N_CUM = EMD ? n_slabs * (NBINS / KC_CUM) : 0;      // ... while the cumulative rows stream
 	// Gram + EMD models: every third stage carries u8 rows (for the MMA issuer only), so the compute warps never sit
 	// through a whole u8 phase; otherwise the u8 stages come first, then the cumulative ones
 	constexpr bool INTERLEAVE = DOT && EMD && !MIN;
@@ -836,7 +838,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 						}
 						scored += __popc(go);
 						u32 cand = p.no_screen ? 0u : go;
-						const bool can_screen = dm.scr_ok != 0 && p.n_slabs == 1; // the screen's constants and bound are for 1024 bins
+						const bool can_screen = dm.scr_ok != 0 && n_slabs == 1; // the screen's constants and bound are for 1024 bins
 						u32 anybig = PD[r].big;
 #pragma unroll
 						for (int k = 0; k < NP; k++) {
@@ -882,7 +884,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 									rd.dot = c.dot;
 									rd.emd = c.emd;
 									rd.smin = MIN ? (sd.sum + sq.sum - (u64)c.sad) >> 1 : 0;
-									const int bad = eval_pair_fast(dm, (u64)p.n_slabs * NBINS, rd, sd, sq, true, score, d0v, close);
+									const int bad = eval_pair_fast(dm, (u64)n_slabs * NBINS, rd, sd, sq, true, score, d0v, close);
 									if (bad) {
 										atomicOr(p.err, bad & 1 ? 1 : 2);
 									}
@@ -1245,8 +1247,13 @@ bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset 
 template <int NEED, bool RAW> static int launch_need(int grid, cudaStream_t st, const DevModel &dm, const ts::Params &p, const CUtensorMap *m)
 {
 	const int smem = ts::Smem::TOTAL;
-	MC2_CUDA(cudaFuncSetAttribute(ts::tile_sweep_kernel<NEED, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	ts::tile_sweep_kernel<NEED, RAW><<<grid, ts::THREADS, smem, st>>>(dm, p, m[0], m[1], m[2], m[3]);
+	if (p.n_slabs == 1) {
+		MC2_CUDA(cudaFuncSetAttribute(ts::tile_sweep_kernel<NEED, RAW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		ts::tile_sweep_kernel<NEED, RAW, true><<<grid, ts::THREADS, smem, st>>>(dm, p, m[0], m[1], m[2], m[3]);
+	} else {
+		MC2_CUDA(cudaFuncSetAttribute(ts::tile_sweep_kernel<NEED, RAW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		ts::tile_sweep_kernel<NEED, RAW, false><<<grid, ts::THREADS, smem, st>>>(dm, p, m[0], m[1], m[2], m[3]);
+	}
 	return MC2_OK;
 }
 
