@@ -378,7 +378,10 @@ def run_ours(args, rank, world, local_rank):
     tile = eb in (1, 2) and 5 <= k <= 8          # the synthetic sets fit the tile form (counts below 256, sums in 16 bits)
     kernel_name = "tile_sweep_kernel<NEED_DOT|NEED_EMD> (TMA ring + tcgen05 u8 MMA + VIMNMX.U16x2/IDP.2A EMD), %d slab%s per row" % (
         N // 1024, "" if k == 5 else "s") if tile else "sweep_wide_kernel<u16,NEED_DOT|NEED_EMD>"
-    prof = profile_entry("tile_sweep_kernel") if (tile and k == 5) else ({} if tile else profile_entry("sweep_wide_kernel"))
+    if tile:
+        prof = profile_entry("tile_sweep_kernel") if k == 5 else (profile_entry("tile_sweep_kernel<NEED_DOT|NEED_EMD>, 64 slabs") if k == 8 else {})
+    else:
+        prof = profile_entry("sweep_wide_kernel")
     pairs_per_s_kernel = local_pairs / (sweep_ms * 1e-3) if sweep_ms > 0 else 0.0
     try:
         probe = ctx.issue_rate()
