@@ -457,6 +457,10 @@ def run_ours(args, rank, world, local_rank):
                     line["also_cfg2"]["e2e_cluster"] = e2e_cluster_block()
                 except Exception as e:
                     log("[bench] e2e_cluster extra failed: %r" % (e,))
+                try:
+                    line["also_cfg2"]["e2e_fastcar"] = e2e_fastcar_block()
+                except Exception as e:
+                    log("[bench] e2e_fastcar extra failed: %r" % (e,))
         if args.workload == "cfg3":
             try:
                 if world == 1:
@@ -808,6 +812,45 @@ def slow_singles_block(ctx, capi, peak, n=1 << 18):
     out["kernel"] = "pair_generic_kernel<u8> (fp64 log per bin; bound by the fp64 / special-function pipes, not HBM)"
     out["candidates"] = n
     return out
+
+
+def e2e_fastcar_block(n_query=500):
+    """The second consumer of the path as the job it is: the reference's fastcar binary (oracle/_ref/fastcar) next to the
+    same binary with ONE call added to work() (oracle/_ref/fastcar_b200): n_query sequences of
+    the configs[1] set (10k x 1.5 kb) against all of it, classifier read from weights_cfg1_id90.txt (--recover), every host
+    thread; wall clock of the whole process, output lines compared as sorted lists."""
+    import tempfile
+    from meshclust2_b200 import synth
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "fastcar")
+    our_bin = os.path.join(ROOT, "oracle", "_ref", "fastcar_b200")
+    if not (os.path.exists(ref_bin) and os.path.exists(our_bin)):
+        return {"unavailable": "oracle/_ref fastcar binaries not built on this box"}
+    seqs, tids, _, _ = synth.make_config_range("cfg2", 0, None)
+    tmp = tempfile.mkdtemp()
+    db, q = os.path.join(tmp, "db.fa"), os.path.join(tmp, "q.fa")
+    open(db, "w").write(synth.to_fasta(seqs, tids))
+    open(q, "w").write(synth.to_fasta(seqs[:n_query], tids[:n_query]))
+    weights = os.path.join(ROOT, "tests", "golden", "weights_cfg1_id90.txt")
+    threads = os.cpu_count() or 1
+    res = {"workload": "fastcar: %d queries x %d database sequences of 1.5 kb, --id 0.9, --recover weights_cfg1_id90.txt, --threads %d; "
+                       "whole process wall clock" % (n_query, len(seqs), threads)}
+    lines = {}
+    for name, binary in (("reference", ref_bin), ("b200", our_bin)):
+        wd = os.path.join(tmp, name)
+        os.makedirs(wd, exist_ok=True)
+        t0 = time.time()
+        r = subprocess.run([binary, db, "--query", q, "--id", "0.9", "--threads", str(threads), "--output", os.path.join(wd, "out"),
+                            "--recover", weights], cwd=wd, capture_output=True, text=True, timeout=900)
+        res[name + "_s"] = time.time() - t0
+        res[name + "_rc"] = r.returncode
+        if r.returncode != 0:
+            res[name + "_tail"] = (r.stdout + r.stderr)[-300:]
+            return res
+        lines[name] = sorted(open(os.path.join(wd, "out0")).read().splitlines())
+    res["output_lines"] = len(lines["reference"])
+    res["identical_output"] = bool(lines["reference"] == lines["b200"])
+    res["speedup"] = res["reference_s"] / res["b200_s"] if res["b200_s"] > 0 else None
+    return res
 
 
 def e2e_cluster_block(threads_list=None):
