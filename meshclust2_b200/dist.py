@@ -114,7 +114,12 @@ class Comm:
         if self.dist is None:
             return local
         out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        self.dist.all_gather_into_tensor(out, local.contiguous())
+        local = local.contiguous()
+        if local.dtype in (getattr(torch, "uint16", None), getattr(torch, "uint32", None), getattr(torch, "uint64", None)):
+            # NCCL has no unsigned 16 / 32 / 64-bit types: a gather moves bytes
+            self.dist.all_gather_into_tensor(out.view(torch.uint8), local.view(torch.uint8))
+        else:
+            self.dist.all_gather_into_tensor(out, local)
         return out
 
     def all_reduce_sum(self, values, torch, device):
@@ -350,8 +355,8 @@ class GpuEngine:
             if full is not None:
                 full.free()
             full = self._gfull = self.ctx.hset_alloc(rows, self.k, self.eb)
-            ts = {1: "|u1", 2: "<u2", 4: "<u4", 8: "<u8"}[self.eb]
-            self._gt = (torch.as_tensor(self._DevArray(full.device_bins(), (rows, self.N), ts), device=self.device),
+            # the bins as bytes whatever their width: the gather moves bytes, and NCCL has no unsigned 16-bit type
+            self._gt = (torch.as_tensor(self._DevArray(full.device_bins(), (rows, self.N * self.eb), "|u1"), device=self.device),
                         torch.as_tensor(self._DevArray(full.device_sideband(1), (rows,), "<i8"), device=self.device),
                         torch.as_tensor(self._DevArray(full.device_sideband(0), (rows,), "<i8"), device=self.device))
         self.ctx.count_kmers_into_rows(self.seqs, full, comm.rank * self.per)    # synchronises the ctx stream
