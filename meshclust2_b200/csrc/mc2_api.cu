@@ -283,7 +283,7 @@ static void build_screen(DevModel &dm)
 	}
 	double K1 = 0;
 	for (int c = 0; c < MC2_SCR_MAX_COMBOS; c++) {
-		dm.scr_ka[c] = dm.scr_kb[c] = scr_slot(SC_COUNT); // the constant 1
+		dm.scr_ka[c] = dm.scr_kb[c] = scr_slot(dm.need & 7, SC_COUNT); // the constant 1
 		dm.scr_pa2[c] = dm.scr_pb2[c] = 0;
 	}
 	for (int c = 0; c < dm.n_combos; c++) {
@@ -304,7 +304,7 @@ static void build_screen(DevModel &dm)
 			if (pw[k] > 2 || nk == 2) {
 				return; // more than two distinct singles, or one of them beyond its square: outside the screen's form
 			}
-			(nk == 0 ? dm.scr_ka[c] : dm.scr_kb[c]) = scr_slot(k);
+			(nk == 0 ? dm.scr_ka[c] : dm.scr_kb[c]) = scr_slot(dm.need & 7, k);
 			(nk == 0 ? dm.scr_pa2[c] : dm.scr_pb2[c]) = pw[k] == 2;
 			nk++;
 		}

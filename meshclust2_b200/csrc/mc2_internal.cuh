@@ -47,13 +47,28 @@ enum SingleCode : int {
 	SC_COUNT
 };
 
-// slots of the tile sweep's screen scratch: the nine fast singles, densely, then the constant 1
-#define MC2_SCR_SLOTS 10
-__host__ __device__ constexpr int scr_slot(int code)
+// Slots of the tile sweep's screen scratch: the fast singles the kernel instantiation computes (those its reductions
+// `need` give: 1 = sum|p-q|, 2 = sum p*q, 4 = sum|cumP-cumQ|; length_difference always), densely, then the constant 1.
+__host__ __device__ constexpr bool scr_has(int need, int code)
 {
-	return code == SC_MANHATTAN ? 0 : code == SC_EUCLIDEAN ? 1 : code == SC_NORMALIZED_VECTORS ? 2 : code == SC_PEARSON ? 3 :
-	       code == SC_INTERSECTION ? 4 : code == SC_EMD ? 5 : code == SC_LENGTHD ? 6 : code == SC_KULCZYNSKI2 ? 7 :
-	       code == SC_SIMRATIO ? 8 : 9;
+	return (code == SC_MANHATTAN || code == SC_INTERSECTION || code == SC_KULCZYNSKI2) ? (need & 1) != 0 :
+	       (code == SC_EUCLIDEAN || code == SC_NORMALIZED_VECTORS || code == SC_PEARSON || code == SC_SIMRATIO) ? (need & 2) != 0 :
+	       code == SC_EMD ? (need & 4) != 0 : code == SC_LENGTHD;
+}
+__host__ __device__ constexpr int scr_slot(int need, int code)
+{
+	int n = 0;
+	for (int c = 0; c < SC_COUNT; c++) {
+		if (c == code) {
+			return n; // meaningful only for singles the instantiation has
+		}
+		n += scr_has(need, c) ? 1 : 0;
+	}
+	return n; // code == SC_COUNT: the constant 1
+}
+__host__ __device__ constexpr int scr_slots(int need)
+{
+	return scr_slot(need, SC_COUNT) + 1;
 }
 
 #define MC2_SCR_MAX_COMBOS 8

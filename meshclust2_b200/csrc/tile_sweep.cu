@@ -46,17 +46,21 @@ constexpr int KC_U8 = 128;      // bins per ring stage while the u8 rows stream 
 #endif
 constexpr int NCW = MC2_TS_NCW; // compute warps (CTA warps 4 .. 4 + NCW - 1, whole warpgroups): 8 or 16
 constexpr int QN = TQ / (NCW / 4); // query rows per compute thread (x 2 database rows): 32 or 16 accumulator pairs
-// measured on 100 k x 1 kb (bench model): 4 epilogue warps x 4 pairs 95.6 ms per 1.8e9 pairs, 8 x 2: 91.5 ms, 8 x 4 (list
-// flushed at every hit for lack of shared memory): 94.8 ms, 4 x 2: 105.7 ms
+// measured on 100 k x 1 kb (bench model), ms per 1.8e9 pairs: 4 epilogue warps x 4 pairs per thread 95.6, 8 x 2: 91.5,
+// 4 x 2: 105.7
 #ifndef MC2_TS_NEW
 #define MC2_TS_NEW 8
 #endif
-#ifndef MC2_TS_NP
-#define MC2_TS_NP 2
-#endif
 constexpr int NEW = MC2_TS_NEW; // epilogue warps (after the compute warps, whole warpgroups): NEW / 4 per TMEM lane quarter, each
                                 // taking TQ / (NEW / 4) query columns of both regions
-constexpr int NP = MC2_TS_NP;   // pairs a thread of the epilogue screens at a time (query columns per tcgen05.ld)
+// pairs a thread of the epilogue screens at a time (query columns per tcgen05.ld): 4 where the screen's scratch
+// (slots x pairs x 256 threads x 4 bytes) leaves room for a candidate list that is flushed once per tile, else 2
+#ifdef MC2_TS_NP
+constexpr int np_of(int) { return MC2_TS_NP; }
+#else
+constexpr int np_of(int need) { return scr_slots(need) <= 7 ? 4 : 2; }
+#endif
+constexpr int list_cap_of(int need) { return NEW == 8 ? (np_of(need) == 4 ? 192 : 128) : 256; } // candidate records per epilogue warp
 constexpr int QE = TQ / (NEW / 4); // query columns per epilogue warp
 constexpr int THREADS = (4 + NCW + NEW) * 32; // warpgroup 0: TMA producer, MMA issuer, two idle warps
 // setmaxnreg per warpgroup.  The pool is what the launch allocated (threads x launch registers, at most 64 K): the
@@ -72,8 +76,7 @@ constexpr int D_BYTES = TD * 128;        // 32 KB, SWIZZLE_128B
 constexpr int Q_BYTES = TQ * 128;        //  8 KB
 constexpr int STAGE_BYTES = D_BYTES + Q_BYTES; // 40 KB
 constexpr int STAGES = 4;
-constexpr int MAX_SUPER = (NEW == 8 && NP == 4) ? 512 : 1024; // entries of the tile schedule's prefix array (shared memory is tight with the large scratch)
-constexpr int LIST_CAP = NEW == 8 ? 128 : 256; // candidate records per epilogue warp
+constexpr int MAX_SUPER = 1024;          // entries of the tile schedule's prefix array
 // TMEM columns (512 allocated): Gram accumulators double buffered, EMD / SAD sums single buffered
 constexpr u32 TM_DOT = 0;                // + buf * 128 + region * 64
 constexpr u32 TM_EMD = 256;              // + ebuf * 128 + region * 64 (double buffered when no SAD sums are needed)
@@ -96,6 +99,7 @@ struct Params {
 	u32 n_slabs;            // bins per row / 1024 (1 for k = 5, 64 for k = 8)
 	const u32 *sched;       // [n_super + 1] exclusive prefix of items per super-row (device)
 	int no_screen;          // experiments: skip the screen and the exact path (main-loop cost only)
+	int no_compute;         // experiments: the compute warps skip their arithmetic (epilogue cost only; results are wrong)
 	u32 sleep_ctrl, sleep_comp, sleep_epi; // experiments: back-off of the three roles' barrier waits (ns)
 	// raw mode (tests): dense (q1-q0) x (d1-d0) matrices of the reductions instead of scoring
 	u32 *raw_dot, *raw_emd, *raw_sad;
@@ -406,7 +410,7 @@ __device__ __forceinline__ u32 screen_pairs(const DevModel &dm, float *sx, const
 		_Pragma("unroll") for (int t = 0; t < NP; t++)                                   \
 		{                                                                                \
 			const float x_ = __fmaf_rn(a_, (RAW), b_);                               \
-			sx[(scr_slot(CODE) * NP + t) * ET] = x_;                                           \
+			sx[(scr_slot(NEED & 7, CODE) * NP + t) * ET] = x_;                                           \
 			m[t] = fmaxf(m[t], used_ ? fabsf(x_) : 0.0f);                            \
 		}                                                                                \
 	}
@@ -476,19 +480,20 @@ struct Cand {
 	u32 dot, emd, sad;
 };
 
-struct Smem {
+template <int NEED> struct Smem {
+	static constexpr int NP = np_of(NEED & 7), LIST_CAP = list_cap_of(NEED & 7);
 	static constexpr int RING = 0;
 	static constexpr int LIST = STAGES * STAGE_BYTES;                         // Cand[NEW][LIST_CAP]
-	static constexpr int SCRX = LIST + NEW * LIST_CAP * (int)sizeof(Cand);    // float [MC2_SCR_SLOTS][NP][NEW * 32]: the screen's scratch
-	static constexpr int ROWQ = SCRX + MC2_SCR_SLOTS * NP * NEW * 32 * 4;     // RowF[2][TQ]
+	static constexpr int SCRX = LIST + NEW * LIST_CAP * (int)sizeof(Cand);    // float [slots][NP][NEW * 32]: the screen's scratch
+	static constexpr int ROWQ = SCRX + scr_slots(NEED & 7) * NP * NEW * 32 * 4; // RowF[2][TQ]
 	static constexpr int WINQ = ROWQ + 2 * TQ * (int)sizeof(RowF);            // u64 window [2][TQ][2]
 	static constexpr int WIN32 = WINQ + 2 * TQ * 16;                          // uint2 window [2][TQ], saturated to 32 bits
 	static constexpr int SCHED = WIN32 + 2 * TQ * 8;                          // u32 [MAX_SUPER + 1]
 	static constexpr int BARS = SCHED + (MAX_SUPER + 1) * 4 + 4;              // mbarriers
 	static constexpr int MISC = BARS + 32 * 8;                                // tmem base
 	static constexpr int TOTAL = MISC + 64 + 1024;                            // + alignment slack
+	static_assert(TOTAL <= 232448, "shared memory per CTA");
 };
-static_assert(Smem::TOTAL <= 232448, "shared memory per CTA");
 
 // ONE: rows of one 1 KiB slab (k = 5), stage counts known at compile time; otherwise Params::n_slabs slabs per row
 template <int NEED, bool RAW, bool ONE>
@@ -497,7 +502,8 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 		  const __grid_constant__ CUtensorMap mapCumQ, const __grid_constant__ CUtensorMap mapU8D,
 		  const __grid_constant__ CUtensorMap mapU8Q)
 {
-	using L = Smem;
+	using L = Smem<NEED>;
+	constexpr int NP = L::NP, LIST_CAP = L::LIST_CAP;
 	constexpr bool DOT = (NEED & NEED_DOT) != 0, EMD = (NEED & NEED_EMD) != 0, MIN = (NEED & NEED_MIN) != 0;
 	constexpr bool U8_PHASE = DOT || MIN;
 	constexpr bool CUDA_RED = EMD || MIN;             // compute warps produce sums for the epilogue
@@ -651,7 +657,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 #pragma unroll 1
 				for (int c = 0; c < N_U8 + N_CUM; c++) {
 					mbar_wait(bar_full + s * 8, ph, p.err, p.sleep_comp);
-					if (c % 3 != 2) {
+					if (c % 3 != 2 && !p.no_compute) {
 						stage_compute<true>(smem + s * STAGE_BYTES, lane_row, qsel, acc);
 					}
 					__syncwarp();
@@ -752,7 +758,7 @@ tile_sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ P
 		float *sx = reinterpret_cast<float *>(smem + L::SCRX) + etid;
 #pragma unroll
 		for (int t = 0; t < NP; t++) {
-			sx[(scr_slot(SC_COUNT) * NP + t) * (NEW * 32)] = 1.0f;
+			sx[(scr_slot(NEED & 7, SC_COUNT) * NP + t) * (NEW * 32)] = 1.0f;
 		}
 		const int qc0 = (ew >> 2) * QE; // this warp's query columns: qc0 .. qc0 + QE - 1
 		u32 it = 0;
@@ -1246,7 +1252,7 @@ bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset 
 
 template <int NEED, bool RAW> static int launch_need(int grid, cudaStream_t st, const DevModel &dm, const ts::Params &p, const CUtensorMap *m)
 {
-	const int smem = ts::Smem::TOTAL;
+	const int smem = ts::Smem<NEED>::TOTAL;
 	if (p.n_slabs == 1) {
 		MC2_CUDA(cudaFuncSetAttribute(ts::tile_sweep_kernel<NEED, RAW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 		ts::tile_sweep_kernel<NEED, RAW, true><<<grid, ts::THREADS, smem, st>>>(dm, p, m[0], m[1], m[2], m[3]);
@@ -1301,6 +1307,7 @@ int launch_tile_sweep(mc2_ctx *ctx, const DevModel &dm, int need, const mc2_hset
 	p.n_slabs = (u32)(q->N / 1024);
 	p.sched = d_sched;
 	p.no_screen = getenv("MC2_TS_NOSCREEN") != nullptr;
+	p.no_compute = getenv("MC2_TS_NOCOMPUTE") != nullptr;
 	p.sleep_ctrl = getenv("MC2_TS_SLEEP_CTRL") ? (u32)atoi(getenv("MC2_TS_SLEEP_CTRL")) : 0;
 	p.sleep_comp = getenv("MC2_TS_SLEEP_COMP") ? (u32)atoi(getenv("MC2_TS_SLEEP_COMP")) : 0;
 	p.sleep_epi = getenv("MC2_TS_SLEEP_EPI") ? (u32)atoi(getenv("MC2_TS_SLEEP_EPI")) : 0;
