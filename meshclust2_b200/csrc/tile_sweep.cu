@@ -401,17 +401,16 @@ __device__ __forceinline__ u32 screen_pairs(const DevModel &dm, float *sx, const
 	for (int t = 0; t < NP; t++) {
 		m[t] = 0.0f;
 	}
-	// one single: x = a * raw + b -> scratch; max |x| over the singles the model uses.  Branch-free: singles the model
-	// does not use are computed into slots nobody reads.
+	// one single: x = a * raw + b -> scratch; max |x| over the singles the model uses.  The model is the same for the
+	// whole grid, so skipping a single it does not use is a uniform branch.
 #define MC2_SCR(CODE, RAW)                                                                       \
-	{                                                                                        \
+	if (dm.slot[CODE] >= 0) {                                                                \
 		const float a_ = dm.scr_a[CODE], b_ = dm.scr_b[CODE];                            \
-		const bool used_ = dm.slot[CODE] >= 0;                                           \
 		_Pragma("unroll") for (int t = 0; t < NP; t++)                                   \
 		{                                                                                \
 			const float x_ = __fmaf_rn(a_, (RAW), b_);                               \
-			sx[(scr_slot(NEED & 7, CODE) * NP + t) * ET] = x_;                                           \
-			m[t] = fmaxf(m[t], used_ ? fabsf(x_) : 0.0f);                            \
+			sx[(scr_slot(NEED & 7, CODE) * NP + t) * ET] = x_;                       \
+			m[t] = fmaxf(m[t], fabsf(x_));                                           \
 		}                                                                                \
 	}
 	if constexpr ((NEED & NEED_DOT) != 0) {
