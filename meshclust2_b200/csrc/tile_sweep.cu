@@ -1,4 +1,5 @@
-// tile_sweep.cu — K2, all-pairs tile form: query x database sweep over 1 KiB uint8 histograms (k = 5) on sm_100a.
+// tile_sweep.cu — K2, all-pairs tile form: query x database sweep over uint8 / uint16 histograms of k = 5 .. 8 (rows of
+// 1 .. 64 slabs of 1 KiB) on sm_100a.
 //
 // fastcar's work() for a whole block (src/fastcar/FC_Runner.cpp:427-470) / the all-pairs sweep of BASELINE configs[2]:
 // every (query, database) pair inside the length window gets the model's reductions, the GLM score and the cutoff
@@ -6,9 +7,11 @@
 //
 // One persistent CTA per SM (28 warps, warp specialised, registers re-dealt per warpgroup with setmaxnreg) walks
 // 64 (query) x 256 (database) pair tiles in the order of a precomputed schedule (database-tile major inside super-rows
-// of query tiles, so concurrently running CTAs share tiles in L2).  Per tile the 1024 bins stream through a 4-stage
+// of query tiles, so concurrently running CTAs share tiles in L2).  Per tile the bins stream through a 4-stage
 // shared-memory ring of 40 KB stages filled by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, one elected producer thread):
-// 16 stages of 64 bins of the u16 cumulative rows and 8 stages of 128 bins of the u8 rows, interleaved 2 : 1.
+// per 1024 bins 16 stages of 64 bins of the u16 cumulative rows and 8 stages of 128 bins of the u8 rows, interleaved 2 : 1.
+// Rows of several slabs (k >= 6) and uint16 bins: the cumulative rows are those of (bin - pseudo-count), which keeps them
+// in 16 bits without changing any difference cumP - cumQ, and uint16 bins below 256 travel as a byte plane (cum_wide_kernel).
 //   S_pq  = sum p*q              tcgen05.mma kind::i8 (u8 x u8 -> s32, exact) issued by one thread straight from the
 //                                ring: two 128 x 64 accumulators (database rows = TMEM lanes) per tile, double buffered in
 //                                TMEM so the next tile's MMAs overlap the epilogue.
@@ -21,11 +24,12 @@
 //                                The sums go to TMEM (tcgen05.st) for the epilogue warps, double buffered.
 //   S_sad = sum |p - q|          VABSDIFF4.U8.ACC on the u8 stages (4 bins / instruction) -> S_min = (sumP+sumQ-S_sad)/2
 // Epilogue (8 warps, thread = TMEM lane, two warps per lane quarter splitting the query columns; one warp per scheduler
-// is latency bound and stalls the compute warps at the tile hand-over): tcgen05.ld of 2 query columns at a time; length window
+// is latency bound and stalls the compute warps at the tile hand-over): tcgen05.ld of 4 (or 2) query columns at a time; length window
 // (FC_Runner.cpp:435-444) in 32 bits with an exact 64-bit path for lengths >= 2^32; an fp32 evaluation of the GLM sum
 // with a rigorous host-derived error bound that can only REJECT (sum + bound < -1e-6 => not close whatever the
 // rounding); the rest is ballot-compacted into a per-warp list and goes, one pair per lane, through the exact fp64
 // epilogue shared with the other pair kernels (eval_pair_fast), so scores and decisions are the same bits as theirs.
+// The screen is for 1024-bin rows; wider rows send every in-window pair through the exact epilogue.
 #include "mc2_internal.cuh"
 #include "pair_eval.cuh"
 #include <cuda.h>
