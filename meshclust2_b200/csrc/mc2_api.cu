@@ -1832,7 +1832,7 @@ int mc2_get_close_as(mc2_ctx *ctx, const mc2_model *model, const mc2_hset *set_q
 // the launch path.  MC2_NO_SCAN_SERVER=1 (read per call, so tests can compare both paths in one process) turns it off.
 static bool scan_server_eligible(const mc2_model *model, const mc2_hset *set_q, const mc2_hset *set_c, uint64_t n_cand)
 {
-	// measured from C++ (tools/call_latency.cpp): 8.7 us at <= 16 candidates, 12 us at 64, 17 us at 192; the launch path
+	// measured from C++ (tools/call_latency.cpp): 9.3 us at <= 16 candidates, 11 us at 64, 17 us at 192; the launch path
 	// costs 32 us whatever the count
 	if (n_cand > 192 || getenv("MC2_NO_SCAN_SERVER")) {
 		return false;
@@ -1897,23 +1897,27 @@ static int scan_server_call(mc2_ctx *ctx, const mc2_model *model, const mc2_hset
 	cu.d = cutoff;
 	volatile unsigned long long *w = mb->w;
 	w[1] = q; w[2] = q_mag; w[3] = q_len; w[4] = cand_begin; w[5] = cu.u;
-	w[6] = (unsigned long long)(unsigned)n_cand | ((unsigned long long)(cand != nullptr) << 32) | ((unsigned long long)(ovr != 0) << 33);
+	// up to MC2_SCAN_INLINE ids of 32 bits ride in the header itself: one read of host memory fewer for the server
+	bool ids_inline = cand != nullptr && n_cand <= MC2_SCAN_INLINE && set_c->n <= (1ull << 32);
+	w[6] = (unsigned long long)(unsigned)n_cand | ((unsigned long long)(cand != nullptr) << 32) | ((unsigned long long)(ovr != 0) << 33) |
+	       ((unsigned long long)ids_inline << 34);
 	w[8] = (unsigned long long)set_q->bins; w[9] = (unsigned long long)set_c->bins;
 	w[10] = (unsigned long long)set_q->mag; w[11] = (unsigned long long)set_q->sum;
 	w[12] = (unsigned long long)set_q->sumsq; w[13] = (unsigned long long)set_q->len; w[14] = set_q->N;
 	w[16] = (unsigned long long)set_c->mag; w[17] = (unsigned long long)set_c->sum;
 	w[18] = (unsigned long long)set_c->sumsq; w[19] = (unsigned long long)set_c->len;
 	if (cand) {
-		if (n_cand <= MC2_SCAN_INLINE) {
-			for (u64 j = 0; j < n_cand; j++) {
-				w[j < 3 ? 20 + j : 24 + (j - 3)] = cand[j];
+		if (ids_inline) {
+			for (u64 j = 0; j < n_cand; j += 2) {
+				const unsigned long long lo = cand[j], hi = j + 1 < n_cand ? cand[j + 1] : 0;
+				w[scan_id_word((int)(j >> 1))] = lo | (hi << 32);
 			}
 		} else {
 			memcpy(mb->cand, cand, n_cand * 8);
 		}
 	}
 	std::atomic_thread_fence(std::memory_order_seq_cst);
-	w[15] = seq; w[23] = seq; w[31] = seq;
+	w[15] = seq; w[23] = seq; w[31] = seq; w[47] = seq; w[63] = seq;
 	std::atomic_thread_fence(std::memory_order_seq_cst);
 	w[0] = seq;
 	std::atomic_thread_fence(std::memory_order_seq_cst);

@@ -115,16 +115,20 @@ struct DevModel {
 // `seq`; a resident CTA polls it, scores the candidates, reduces the arg-max and writes the answer back; the host polls
 // `seq_done`.  No launch, no memcpy, no stream synchronisation per call.
 #define MC2_SCAN_CAP 512        // longer candidate lists take the launch path
-#define MC2_SCAN_INLINE 10      // candidates that travel inside the request header
+#define MC2_SCAN_INLINE 80      // candidates that travel inside the request header (32-bit row numbers, two per word)
+// the header word that holds inline ids 2k and 2k + 1 (the words between the fixed fields and the sequence copies)
+__host__ __device__ constexpr int scan_id_word(int k) { return k < 3 ? 20 + k : k < 10 ? 24 + (k - 3) : k < 25 ? 32 + (k - 10) : 48 + (k - 25); }
 #define MC2_SCAN_MARKS_INLINE 192 // marks that travel inside the answer line (one bit each)
 struct ScanMailbox {
-	// Request header: 32 words = four 64-byte lines, fetched by the server with ONE coalesced read per poll.  The host
-	// writes word 0 (the sequence number) last and repeats it in the last word of lines 1-3, so a header whose four
-	// copies agree is complete even if the lines were fetched separately.
-	//  [0] seq  [1] q_row  [2] q_mag  [3] q_len  [4] cand_begin  [5] cutoff (double bits)  [6] n_cand | has_list << 32 | ovr << 33
-	//  [7] quit  [8] binsQ  [9] binsC  [10] magQ  [11] sumQ  [12] sumsqQ  [13] lenQ  [14] N  [15] seq
-	//  [16] magC  [17] sumC  [18] sumsqC  [19] lenC  [20..22] cand 0-2  [23] seq  [24..30] cand 3-9  [31] seq
-	volatile unsigned long long w[32];
+	// Request header: 64 words = four 128-byte lines, fetched by the server with ONE coalesced read per poll (16 bytes per
+	// lane).  The host writes word 0 (the sequence number) last and repeats it in words 15, 23, 31, 47 and 63, so a header
+	// whose copies agree is complete even if the lines were fetched separately.
+	//  [0] seq  [1] q_row  [2] q_mag  [3] q_len  [4] cand_begin  [5] cutoff (double bits)
+	//  [6] n_cand | has_list << 32 | ovr << 33 | ids inline << 34   [7] quit
+	//  [8] binsQ  [9] binsC  [10] magQ  [11] sumQ  [12] sumsqQ  [13] lenQ  [14] N  [15] seq
+	//  [16] magC  [17] sumC  [18] sumsqC  [19] lenC  [20..22] ids 0-5  [23] seq  [24..30] ids 6-19  [31] seq
+	//  [32..46] ids 20-49  [47] seq  [48..62] ids 50-79  [63] seq
+	volatile unsigned long long w[64];
 	unsigned long long cand[MC2_SCAN_CAP];      // the whole list when it is longer than MC2_SCAN_INLINE
 	// answer (written by the device with one eight-lane store): one 64-byte line, the sequence number closing both halves
 	//  [0] best  [1] best_dist (double bits)  [2] is_min | err << 32  [3] seq_done  [4..6] mark bits of the first 192 candidates
@@ -134,7 +138,7 @@ struct ScanMailbox {
 	int pad1[15];
 	unsigned char marks[MC2_SCAN_CAP];          // all marks when there are more than MC2_SCAN_MARKS_INLINE candidates
 };
-static_assert(offsetof(ScanMailbox, cand) == 256, "the scan server reads the request header as 32 eight-byte words");
+static_assert(offsetof(ScanMailbox, cand) == 512, "the scan server reads the request header as 64 eight-byte words");
 
 // side-band SoA of a histogram set (device pointers)
 struct Sideband {

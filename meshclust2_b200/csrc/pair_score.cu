@@ -2205,7 +2205,7 @@ __device__ __forceinline__ unsigned long long global_ns()
 template <typename T>
 __global__ void __launch_bounds__(512, 1) scan_server_kernel(const __grid_constant__ DevModel dm, ScanMailbox *mb, u64 first_seq)
 {
-	__shared__ unsigned long long s_hdr[32];      // the request header
+	__shared__ unsigned long long s_hdr[64];      // the request header
 	__shared__ unsigned long long s_cand[MC2_SCAN_CAP];
 	__shared__ double s_dist[MC2_SCAN_CAP];
 	__shared__ unsigned char s_flag[MC2_SCAN_CAP]; // 1 close, 2 skipped / not scored
@@ -2217,20 +2217,24 @@ __global__ void __launch_bounds__(512, 1) scan_server_kernel(const __grid_consta
 	u64 last = first_seq - 1;
 	for (;;) {
 		if (warp == 0) {
-			// every poll fetches the whole header with one coalesced read; it is taken when its four sequence copies agree
+			// every poll fetches the whole header with one coalesced read (16 bytes per lane); it is taken when its six
+			// sequence copies agree
 			const unsigned long long t0 = global_ns();
 			int go = 0;
 			for (;;) {
-				const unsigned long long v = ld_sys_u64(&mb->w[lane]);
-				const unsigned long long s0 = __shfl_sync(0xffffffffu, v, 0);
-				const bool whole = __shfl_sync(0xffffffffu, v, 15) == s0 && __shfl_sync(0xffffffffu, v, 23) == s0 &&
-						   __shfl_sync(0xffffffffu, v, 31) == s0;
+				unsigned long long vx, vy;
+				asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(vx), "=l"(vy) : "l"(&mb->w[2 * lane]) : "memory");
+				const unsigned long long s0 = __shfl_sync(0xffffffffu, vx, 0);
+				const bool whole = __shfl_sync(0xffffffffu, vy, 7) == s0 && __shfl_sync(0xffffffffu, vy, 11) == s0 &&
+						   __shfl_sync(0xffffffffu, vy, 15) == s0 && __shfl_sync(0xffffffffu, vy, 23) == s0 &&
+						   __shfl_sync(0xffffffffu, vy, 31) == s0;
 				if (s0 != last && whole) {
-					s_hdr[lane] = v;
+					s_hdr[2 * lane] = vx;
+					s_hdr[2 * lane + 1] = vy;
 					go = 1;
 					break;
 				}
-				if (__shfl_sync(0xffffffffu, v, 7) != 0 || global_ns() - t0 > MC2_SCAN_IDLE_NS) {
+				if (__shfl_sync(0xffffffffu, vy, 3) != 0 || global_ns() - t0 > MC2_SCAN_IDLE_NS) {
 					break;
 				}
 			}
@@ -2249,9 +2253,10 @@ __global__ void __launch_bounds__(512, 1) scan_server_kernel(const __grid_consta
 		const bool has_list = (s_hdr[6] >> 32) & 1, ovr = (s_hdr[6] >> 33) & 1;
 		const double cutoff = __longlong_as_double((long long)s_hdr[5]);
 		if (has_list) {
-			if (n <= MC2_SCAN_INLINE) {
+			if ((s_hdr[6] >> 34) & 1) { // the ids travel in the header, two 32-bit row numbers per word
 				if (threadIdx.x < n) {
-					s_cand[threadIdx.x] = threadIdx.x < 3 ? s_hdr[20 + threadIdx.x] : s_hdr[24 + threadIdx.x - 3];
+					const unsigned long long wv = s_hdr[scan_id_word((int)threadIdx.x >> 1)];
+					s_cand[threadIdx.x] = (threadIdx.x & 1) ? (wv >> 32) : (wv & 0xFFFFFFFFull);
 				}
 			} else {
 				for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
