@@ -252,11 +252,19 @@ static void build_screen(DevModel &dm)
 {
 	dm.scr_ok = 0;
 	dm.scr_k1 = dm.scr_k0 = 0;
+	dm.scr_thr = 0;
 	memset(dm.scr_a, 0, sizeof dm.scr_a);
 	memset(dm.scr_b, 0, sizeof dm.scr_b);
 	memset(dm.scr_w, 0, sizeof dm.scr_w);
-	if (!dm.fast_epi || dm.regression || dm.bias != 0.0 || dm.n_combos > MC2_SCR_MAX_COMBOS || (dm.need & NEED_LOG)) {
+	// close <=> round(logistic(sum) + bias) > 0 <=> logistic(sum) >= 0.5 - bias (Predictor.cpp:323-333): a threshold on the
+	// sum while 0.5 - bias lies strictly inside (0, 1); outside it every pair (or none) is close and nothing can be screened
+	if (!dm.fast_epi || dm.regression || !(dm.bias > -0.499999 && dm.bias < 0.499999) || dm.n_combos > MC2_SCR_MAX_COMBOS ||
+	    (dm.need & NEED_LOG)) {
 		return;
+	}
+	{
+		const double pth = 0.5 - dm.bias, t = log(pth / (1.0 - pth));
+		dm.scr_thr = nextafterf((float)(t - 1e-6 - fabs(t) * 1e-6), -INFINITY);
 	}
 	const double eps = 1.1920928955078125e-07;
 	double beta = 0;

@@ -107,6 +107,7 @@ struct DevModel {
 	float scr_w[MC2_SCR_MAX_COMBOS + 1];
 	int scr_ka[MC2_SCR_MAX_COMBOS], scr_kb[MC2_SCR_MAX_COMBOS], scr_pa2[MC2_SCR_MAX_COMBOS], scr_pb2[MC2_SCR_MAX_COMBOS];
 	float scr_k1, scr_k0;
+	float scr_thr;                // a pair whose fp32 sum + bound stays below this is not close: logit(0.5 - bias) - margin
 };
 
 // Mailbox of the resident scan server: the accumulate stage of the mean-shift driver issues one Trainer::get_close per

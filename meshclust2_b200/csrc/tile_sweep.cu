@@ -26,8 +26,8 @@
 // Epilogue (8 warps, thread = TMEM lane, two warps per lane quarter splitting the query columns; one warp per scheduler
 // is latency bound and stalls the compute warps at the tile hand-over): tcgen05.ld of 4 (or 2) query columns at a time; length window
 // (FC_Runner.cpp:435-444) in 32 bits with an exact 64-bit path for lengths >= 2^32; an fp32 evaluation of the GLM sum
-// with a rigorous host-derived error bound that can only REJECT (sum + bound < -1e-6 => not close whatever the
-// rounding); the rest is ballot-compacted into a per-warp list and goes, one pair per lane, through the exact fp64
+// with a rigorous host-derived error bound that can only REJECT (sum + bound < logit(0.5 - bias) - 1e-6 => not close
+// whatever the rounding); the rest is ballot-compacted into a per-warp list and goes, one pair per lane, through the exact fp64
 // epilogue shared with the other pair kernels (eval_pair_fast), so scores and decisions are the same bits as theirs.
 // The screen is for 1024-bin rows; wider rows send every in-window pair through the exact epilogue.
 #include "mc2_internal.cuh"
@@ -469,7 +469,7 @@ __device__ __forceinline__ u32 screen_pairs(const DevModel &dm, float *sx, const
 	for (int t = 0; t < NP; t++) {
 		const float u = (1.0f + m[t]) * 1.001f, u2 = u * u;
 		const float e = __fmaf_rn(dm.scr_k1, u2 * u2, dm.scr_k0);
-		const bool reject = (e < 1.0f) && (s[t] + e < -1.0e-6f);
+		const bool reject = (e < 1.0f) && (s[t] + e < dm.scr_thr);
 		maybe |= reject ? 0u : (1u << t);
 	}
 	return maybe;
@@ -1249,7 +1249,7 @@ bool tile_sweep_supported(const DevModel &dm, const mc2_hset *q, const mc2_hset 
 	if (off) {
 		return false;
 	}
-	const bool model = dm.fast_epi && !dm.regression && dm.bias == 0.0 && !(dm.need & NEED_LOG) && (dm.need & 7) != 0;
+	const bool model = dm.fast_epi && !dm.regression && !(dm.need & NEED_LOG) && (dm.need & 7) != 0;
 	return model && tile_sweep_shape_ok(q, d);
 }
 

@@ -228,3 +228,31 @@ def test_tile_sweep_declines_unfit_rows(built_lib, ctx):
         assert r["n_scored"] == scored
         edge = {kk for kk, s in want.items() if abs(s - 0.5) <= 1e-9}
         assert set(got) - edge == set(want) - edge
+
+
+@pytest.mark.parametrize("bias", [0.3, -0.3, 0.6, -0.7])
+def test_tile_sweep_with_a_bias(built_lib, ctx, bias):
+    """--bias moves the decision to logistic(sum) >= 0.5 - bias (Predictor.cpp:323-333): the screen's threshold follows it;
+    at |bias| >= 0.5 every pair (or none) is close and all of them take the exact epilogue"""
+    from meshclust2_b200 import capi
+    rng = np.random.default_rng(3)
+    n = 300
+    H = synth_hist(rng, n, 5, 1, hi=6)
+    ln = rng.integers(900, 1100, n).astype(np.uint64)
+    mag = H.sum(axis=1, dtype=np.uint64)
+    om = port.Model.from_text(weights_text("weights_cfg1_id90"))
+    om.bias = bias
+    hs = ctx.hset_from_host(H, 5, mag=None, length=ln)
+    gm = ctx.model(to_desc(capi, om))
+    r = ctx.all_pairs(gm, hs, hs, 0.9, upper_only=True, max_out=n * n)
+    want, scored = _oracle_sweep(om, H, mag, ln, 0.9, (0, n), (0, n), True)
+    got = {(int(q), int(d)): s for q, d, s in zip(r["q"], r["d"], r["score"])}
+    assert r["n_scored"] == scored
+    edge = {k for k, s in want.items() if abs(s - 0.5) <= 1e-9}
+    assert set(got) - edge == set(want) - edge
+    for k in set(got) & set(want):
+        assert abs(got[k] - want[k]) <= 1e-9
+    if bias >= 0.5:
+        assert len(want) == scored
+    if bias <= -0.5:
+        assert len(want) == 0
