@@ -130,8 +130,11 @@ def main():
             print("[rank %d] update stage center %d MISMATCH: next %d vs %d, good %d vs %d, merge %d vs %d" % (
                 rank, c, nxt[c], want_next, ng[c], want_good, mg[c], want_merge), flush=True)
             bad += 1
-    if n_moved == 0 or (rank == 0 and n_merged == 0):
-        print("[rank %d] update stage check is vacuous (moved %d, merged %d)" % (rank, n_moved, n_merged), flush=True)
+    # every rank looked at a stride of the centers: the check is vacuous only if NO rank saw a move or a merge
+    tot_moved, tot_merged = comm.all_reduce_sum([int(n_moved), int(n_merged)], torch, eng.device)
+    if tot_moved == 0 or tot_merged == 0:
+        if rank == 0:
+            print("[rank 0] update stage check is vacuous (moved %d, merged %d over all ranks)" % (tot_moved, tot_merged), flush=True)
         bad += 1
     tot_bad = comm.all_reduce_sum([bad], torch, eng.device)[0]
     if rank == 0:
